@@ -1,0 +1,166 @@
+/*
+ * b200bda.h -- C ABI of libb200bda.so, the B200-native (sm_100a) ILU0-BiCGSTAB backend for
+ * OPM Flow's per-Newton-step linear solve (3x3-block BSR, fp64) plus the standard-well apply.
+ *
+ * Drop-in boundary.  The entry points below are exactly what a `bda::BdaSolver<3>` subclass and
+ * an `Opm::WellContributions`-compatible container need; each one names the reference interface
+ * it replaces (paths relative to the reference tree, opm/simulators/linalg/bda/).  The C++ shim
+ * that binds them (b200SolverBackend<block_size>) is in opm-autodiff_b200/hostcpp/ and the two
+ * string-chain patches a maintainer adds to the reference are shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no CUDA / torch types.  All `*_host` pointers are host
+ * memory owned by the caller and not retained after the call returns (except for an optional
+ * cudaHostRegister pin of `vals`/`b`, released in b200_destroy).  Functions return a
+ * b200_status; on anything but B200_SUCCESS b200_last_error() describes the failure.  There is
+ * no CPU fallback anywhere in the library: without a usable sm_100 device every entry point that
+ * computes fails loudly.
+ */
+#ifndef B200BDA_H
+#define B200BDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bda::SolverStatus, BdaSolver.hpp:32-37 (same order, same meaning). */
+typedef enum {
+    B200_SUCCESS = 0,                       /* BDA_SOLVER_SUCCESS */
+    B200_ANALYSIS_FAILED = 1,               /* BDA_SOLVER_ANALYSIS_FAILED */
+    B200_CREATE_PRECONDITIONER_FAILED = 2,  /* BDA_SOLVER_CREATE_PRECONDITIONER_FAILED */
+    B200_UNKNOWN_ERROR = 3                  /* BDA_SOLVER_UNKNOWN_ERROR (also: bad arguments, CUDA errors) */
+} b200_status;
+
+/* bda::BdaResult, BdaResult.hpp:28-40 (first five fields, same meaning), followed by extras. */
+typedef struct {
+    int    iterations;   /* (int) min(it, maxit), as cusparseSolverBackend.cu:172 */
+    double reduction;    /* norm / norm0 */
+    int    converged;    /* norm < tolerance * norm0 reached within maxit */
+    double conv_rate;    /* reduction^(1/it) */
+    double elapsed;      /* seconds, whole solve_system call */
+    /* extras (not in BdaResult) */
+    double it;           /* Dune/cusparse half-step counter at exit: 0.5, 1.0, 1.5, ... */
+    double norm0;
+    double norm;
+    int    breakdown;    /* 1 if a Dune SolverAbort guard (|rho|,|omega|,|h| tiny) fired */
+    int    num_levels;   /* level sets of the ILU0 dependency DAG */
+    double t_analysis;   /* seconds: sparsity analysis (first call only, else 0) */
+    double t_copy;       /* seconds: host->device upload (GPU time) */
+    double t_factor;     /* seconds: permutation + ILU0 factorisation (GPU time) */
+    double t_krylov;     /* seconds: BiCGSTAB loop (GPU time) */
+} b200_result;
+
+typedef struct b200_solver b200_solver;   /* one per BdaSolver<3> object */
+typedef struct b200_wells  b200_wells;    /* one per Opm::WellContributions object */
+
+/* ---- solver: replaces cusparseSolverBackend<3> behind BdaSolver<3> ------------------------ */
+
+/* BdaSolver ctor (BdaSolver.hpp:78): verbosity, maxit, tolerance, deviceID.  Selects the device
+ * (cusparseSolverBackend.cu:201) and creates the stream.  NULL on failure. */
+b200_solver* b200_create(int verbosity, int maxit, double tolerance, unsigned int device_id);
+
+/* ~cusparseSolverBackend / finalize (cusparseSolverBackend.cu:54-57,249-279). */
+void b200_destroy(b200_solver* s);
+
+/* Options the reference fixes at compile time or takes from the FlexibleSolver JSON tree:
+ *   "relaxation"  ILU0 relaxation w (setupPropertyTree.cpp:175-188; cusparse uses 1.0)  default 1.0
+ *   "tolerance", "maxit", "verbosity"   override the constructor values
+ *   "pin_host"    1: cudaHostRegister the caller's vals/b once and reuse   default 1
+ *   "use_graph"   1: replay the BiCGSTAB iteration as a CUDA graph                        default 1
+ *   "lookahead"   iterations enqueued ahead of the convergence read-back                  default 2
+ *   "profile"     1: time every kernel with CUDA events (no graph), see b200_kernel_stats default 0
+ * Unknown keys return B200_UNKNOWN_ERROR. */
+b200_status b200_set_option(b200_solver* s, const char* key, double value);
+
+/* BdaSolver<3>::solve_system (BdaSolver.hpp:86-88; cusparseSolverBackend.cu:480-499).
+ *   N    scalar rows (= 3*Nb), nnz scalar nonzeros (= 9*nnzb), dim = 3
+ *   vals_host  nnz doubles, row-major 3x3 blocks in BSR order (BdaBridge.cpp:231-232)
+ *   rows_host  Nb+1 ints, cols_host nnzb ints (0-based, ascending per row, diagonal present;
+ *              BdaBridge.cpp:167-189); read on the first call only (sparsity is fixed after it,
+ *              cusparseSolverBackend.cu:312)
+ *   b_host     N doubles; the initial guess is 0 (cusparseSolverBackend.cu:301)
+ *   wells      may be NULL or hold zero wells
+ * Synchronous: returns after the solve finished on the device (cusparseSolverBackend.cu:456).
+ * Non-convergence is not an error: status SUCCESS with res->converged == 0. */
+b200_status b200_solve_system(b200_solver* s, int N, int nnz, int dim,
+                              const double* vals_host, const int* rows_host, const int* cols_host,
+                              const double* b_host, b200_wells* wells, b200_result* res);
+
+/* BdaSolver<3>::get_result (BdaSolver.hpp:90; cusparseSolverBackend.cu:464-475): N doubles D2H.
+ * Always safe to call after a solve (the reference tests call it unconditionally). */
+b200_status b200_get_result(b200_solver* s, double* x_host);
+
+/* Same solve with the system already resident in HBM (uploaded by the last b200_solve_system or
+ * b200_upload_system): repeats permutation + ILU0 + BiCGSTAB without any host<->device copy of
+ * the matrix.  This is the device-resident leg the benchmark's `value` is measured on. */
+b200_status b200_upload_system(b200_solver* s, int N, int nnz, int dim,
+                               const double* vals_host, const int* rows_host, const int* cols_host,
+                               const double* b_host, b200_wells* wells);
+b200_status b200_solve_resident(b200_solver* s, b200_result* res);
+
+const char* b200_last_error(void);
+
+/* ---- standard wells: replaces Opm::WellContributions (WellContributions.hpp:60-214) -------- */
+
+typedef enum { B200_WELL_C = 0, B200_WELL_D = 1, B200_WELL_B = 2 } b200_well_matrix; /* MatrixType, :69-73 */
+
+/* WellContributions ctor (WellContributions.cpp:31-49): accepts "b200" (and the reference's own
+ * mode strings); anything else fails with "Invalid accelerator mode". */
+b200_wells* b200_wells_create(const char* accelerator_mode, int use_well_conn);
+void        b200_wells_destroy(b200_wells* w);
+/* setBlockSize (WellContributions.cpp:215-225): fails unless dim == 3 and dim_wells == 4. */
+b200_status b200_wells_set_block_size(b200_wells* w, unsigned int dim, unsigned int dim_wells);
+/* addNumBlocks (:227-234): fails after alloc. */
+b200_status b200_wells_add_num_blocks(b200_wells* w, unsigned int num_blocks);
+/* alloc (:236-259). */
+b200_status b200_wells_alloc(b200_wells* w);
+/* addMatrix (:152-213): per well C, then D, then B; fails before alloc.  col_indices ignored for D. */
+b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const int* col_indices,
+                                  const double* values, unsigned int val_size);
+unsigned int b200_wells_get_num_wells(const b200_wells* w);   /* getNumWells (:152-154 of the .hpp) */
+
+/* ---- kernel-level entry points (parity tests, roofline measurement) ------------------------ */
+
+/* All operate on the system uploaded by the last solve/upload call; vectors are host arrays of
+ * N doubles in the caller's natural ordering (the library permutes to its level ordering). */
+b200_status b200_spmv(b200_solver* s, const double* x_host, double* y_host);            /* y = A x */
+b200_status b200_well_apply(b200_solver* s, const double* x_host, double* y_inout_host); /* y -= C^T D^-1 B x */
+b200_status b200_ilu0_factorize(b200_solver* s);                                        /* LU <- ILU0(A) */
+b200_status b200_ilu0_apply(b200_solver* s, const double* d_host, double* v_host);      /* v = w (LU)^-1 d */
+/* LU in the caller's pattern (nnz doubles): L blocks below the diagonal, U above, the diagonal
+ * block holding the INVERSE of the pivot, as ParallelOverlappingILU0.hpp:440-494 leaves it. */
+b200_status b200_get_ilu0(b200_solver* s, double* lu_vals_host);
+/* Level scheduling of the pattern (bda/Reorder.cpp:266-318): to_order/from_order hold Nb ints,
+ * rows_per_level up to Nb ints; returns the level count through num_levels. */
+b200_status b200_get_level_schedule(b200_solver* s, int* to_order, int* from_order,
+                                    int* rows_per_level, int* num_levels);
+/* Host-only analysis (no device needed): same outputs from a raw pattern. */
+b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, int* to_order,
+                                     int* from_order, int* rows_per_level, int* num_levels);
+
+/* Time `reps` back-to-back launches of one kernel with CUDA events on the solver's stream.
+ * which: "spmv", "ilu_apply", "ilu_lower", "ilu_upper", "ilu_factor", "vec_p", "vec_xr1", "vec_xr2",
+ * "well_apply", "permute".  Returns the mean milliseconds per launch and the ALGORITHMIC bytes one
+ * launch moves.  flush_l2 != 0 writes a >L2 scratch buffer before every launch. */
+b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int flush_l2,
+                             double* ms_per_launch, double* algorithmic_bytes);
+
+/* Per-kernel totals accumulated over the solves run with option "profile" = 1.
+ * Returns B200_UNKNOWN_ERROR for an unknown name. */
+b200_status b200_kernel_stats(b200_solver* s, const char* which, long long* launches,
+                              double* total_ms, double* algorithmic_bytes_per_launch);
+void        b200_reset_stats(b200_solver* s);
+/* Number of kernels this library launched since creation / since b200_reset_stats. */
+long long   b200_launch_count(b200_solver* s);
+
+/* 1 if a CUDA device with compute capability 10.x is visible, else 0 (never throws). */
+int b200_device_available(void);
+/* Library version string. */
+const char* b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BDA_H */

@@ -1,0 +1,474 @@
+"""Host-side mirror of the reference's accelerator-bridge interface for the B200 backend.
+
+Same names, argument meaning and error behaviour as the reference classes, bound to the C ABI of
+``libb200bda.so`` (``include/b200bda.h``) with ctypes:
+
+  ``SolverStatus``            bda::SolverStatus            bda/BdaSolver.hpp:32-37
+  ``BdaResult``               bda::BdaResult               bda/BdaResult.hpp:28-40
+  ``WellContributions``       Opm::WellContributions       bda/WellContributions.hpp:60-214, .cpp:31-259
+  ``B200SolverBackend``       bda::BdaSolver<3> subclass   bda/BdaSolver.hpp:86-90 (cf. cusparseSolverBackend)
+  ``BdaBridge``               Opm::BdaBridge<M,V,3>        bda/BdaBridge.cpp:56-121,192-263
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100 device is visible, the
+constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200bda.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+
+class SolverStatus(enum.IntEnum):
+    BDA_SOLVER_SUCCESS = 0
+    BDA_SOLVER_ANALYSIS_FAILED = 1
+    BDA_SOLVER_CREATE_PRECONDITIONER_FAILED = 2
+    BDA_SOLVER_UNKNOWN_ERROR = 3
+
+
+class _CResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("reduction", C.c_double), ("converged", C.c_int),
+                ("conv_rate", C.c_double), ("elapsed", C.c_double), ("it", C.c_double),
+                ("norm0", C.c_double), ("norm", C.c_double), ("breakdown", C.c_int),
+                ("num_levels", C.c_int), ("t_analysis", C.c_double), ("t_copy", C.c_double),
+                ("t_factor", C.c_double), ("t_krylov", C.c_double)]
+
+
+@dataclass
+class BdaResult:
+    """bda/BdaResult.hpp:32-36 (first five fields) + extras filled by this backend."""
+    iterations: int = 0
+    reduction: float = 0.0
+    converged: bool = False
+    conv_rate: float = 0.0
+    elapsed: float = 0.0
+    it: float = 0.0
+    norm0: float = 0.0
+    norm: float = 0.0
+    breakdown: bool = False
+    num_levels: int = 0
+    t_analysis: float = 0.0
+    t_copy: float = 0.0
+    t_factor: float = 0.0
+    t_krylov: float = 0.0
+
+    def _fill(self, r: _CResult) -> None:
+        for name, _ in _CResult._fields_:
+            v = getattr(r, name)
+            setattr(self, name, bool(v) if name in ("converged", "breakdown") else v)
+
+
+def build(force: bool = False) -> None:
+    """Compile libb200bda.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "b200bda.h"))
+    newest = max(os.path.getmtime(f) for f in srcs)
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it was never built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libb200bda.so is not built (run __graft_entry__.build()); "
+                               "this backend has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, ip = C.c_void_p, C.c_int
+        L.b200_create.argtypes = [ip, ip, C.c_double, C.c_uint]
+        L.b200_create.restype = vp
+        L.b200_destroy.argtypes = [vp]
+        L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+        L.b200_solve_system.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp, C.POINTER(_CResult)]
+        L.b200_upload_system.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp]
+        L.b200_solve_resident.argtypes = [vp, C.POINTER(_CResult)]
+        L.b200_get_result.argtypes = [vp, vp]
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_version.restype = C.c_char_p
+        L.b200_wells_create.argtypes = [C.c_char_p, ip]
+        L.b200_wells_create.restype = vp
+        L.b200_wells_destroy.argtypes = [vp]
+        L.b200_wells_set_block_size.argtypes = [vp, C.c_uint, C.c_uint]
+        L.b200_wells_add_num_blocks.argtypes = [vp, C.c_uint]
+        L.b200_wells_alloc.argtypes = [vp]
+        L.b200_wells_add_matrix.argtypes = [vp, ip, vp, vp, C.c_uint]
+        L.b200_wells_get_num_wells.argtypes = [vp]
+        L.b200_wells_get_num_wells.restype = C.c_uint
+        L.b200_spmv.argtypes = [vp, _f64p, _f64p]
+        L.b200_well_apply.argtypes = [vp, _f64p, _f64p]
+        L.b200_ilu0_factorize.argtypes = [vp]
+        L.b200_ilu0_apply.argtypes = [vp, _f64p, _f64p]
+        L.b200_get_ilu0.argtypes = [vp, _f64p]
+        L.b200_get_level_schedule.argtypes = [vp, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
+        L.b200_level_schedule_host.argtypes = [ip, _i32p, _i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
+        L.b200_time_kernel.argtypes = [vp, C.c_char_p, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.b200_kernel_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]
+        L.b200_reset_stats.argtypes = [vp]
+        L.b200_launch_count.argtypes = [vp]
+        L.b200_launch_count.restype = C.c_longlong
+        L.b200_device_available.restype = ip
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "b200_create", "b200_destroy", "b200_set_option", "b200_solve_system", "b200_get_result",
+    "b200_upload_system", "b200_solve_resident", "b200_last_error", "b200_wells_create",
+    "b200_wells_destroy", "b200_wells_set_block_size", "b200_wells_add_num_blocks", "b200_wells_alloc",
+    "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_spmv", "b200_well_apply",
+    "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
+    "b200_level_schedule_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
+    "b200_launch_count", "b200_device_available", "b200_version",
+]
+
+
+def last_error() -> str:
+    return lib().b200_last_error().decode()
+
+
+def device_available() -> bool:
+    return bool(lib().b200_device_available())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class WellContributions:
+    """Opm::WellContributions (standard wells only).  Three phases, as the reference:
+    setBlockSize + addNumBlocks per well, alloc, then per well addMatrix C, D, B
+    (bda/WellContributions.cpp:152-259; fill order wells/StandardWellEval.cpp:1202-1251)."""
+
+    class MatrixType(enum.IntEnum):
+        C = 0
+        D = 1
+        B = 2
+
+    def __init__(self, accelerator_mode: str, useWellConn: bool):
+        self._h = lib().b200_wells_create(accelerator_mode.encode(), int(bool(useWellConn)))
+        if not self._h:
+            raise ValueError(last_error())       # std::logic_error("Invalid accelerator mode")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.b200_wells_destroy(h)
+
+    def _check(self, st):
+        if st != 0:
+            raise ValueError(last_error())       # OPM_THROW(std::logic_error, ...)
+
+    def setBlockSize(self, dim: int, dim_wells: int) -> None:
+        self._check(lib().b200_wells_set_block_size(self._h, dim, dim_wells))
+
+    def addNumBlocks(self, numBlocks: int) -> None:
+        self._check(lib().b200_wells_add_num_blocks(self._h, numBlocks))
+
+    def alloc(self) -> None:
+        self._check(lib().b200_wells_alloc(self._h))
+
+    def addMatrix(self, type, colIndices, values, val_size: int) -> None:
+        ci = None if colIndices is None else np.ascontiguousarray(colIndices, dtype=np.int32)
+        va = np.ascontiguousarray(values, dtype=np.float64)
+        self._check(lib().b200_wells_add_matrix(self._h, int(type), _ptr(ci), _ptr(va), int(val_size)))
+
+    def getNumWells(self) -> int:
+        return int(lib().b200_wells_get_num_wells(self._h))
+
+    @classmethod
+    def from_arrays(cls, val_pointers, Bcols, Ccols, B, C, Dinv, accelerator_mode="b200"):
+        """Convenience: fill from CSR-over-wells arrays exactly as BlackoilWellModel::getWellContributions
+        (wells/BlackoilWellModel_impl.hpp:1061-1099) would."""
+        w = cls(accelerator_mode, False)
+        nw = len(val_pointers) - 1
+        if nw == 0:
+            return w
+        w.setBlockSize(3, 4)
+        for i in range(nw):
+            w.addNumBlocks(int(val_pointers[i + 1] - val_pointers[i]))
+        w.alloc()
+        B = np.asarray(B, dtype=np.float64).reshape(-1, 12)
+        Cm = np.asarray(C, dtype=np.float64).reshape(-1, 12)
+        Dinv = np.asarray(Dinv, dtype=np.float64).reshape(-1, 16)
+        for i in range(nw):
+            s, e = int(val_pointers[i]), int(val_pointers[i + 1])
+            w.addMatrix(cls.MatrixType.C, Ccols[s:e], Cm[s:e], e - s)
+            w.addMatrix(cls.MatrixType.D, np.zeros(1, np.int32), Dinv[i], 1)
+            w.addMatrix(cls.MatrixType.B, Bcols[s:e], B[s:e], e - s)
+        return w
+
+
+class B200SolverBackend:
+    """bda::BdaSolver<3> implementation backed by libb200bda.so (cf. cusparseSolverBackend<3>)."""
+
+    def __init__(self, linear_solver_verbosity: int, maxit: int, tolerance: float, deviceID: int = 0):
+        self.verbosity, self.maxit, self.tolerance, self.deviceID = linear_solver_verbosity, maxit, tolerance, deviceID
+        self._h = lib().b200_create(int(linear_solver_verbosity), int(maxit), float(tolerance), int(deviceID))
+        if not self._h:
+            raise RuntimeError(last_error())     # OPM_THROW(std::logic_error) in cuda_header.hpp:34-44
+        self.N = 0
+        self._keep = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.b200_destroy(h)
+
+    def set_option(self, key: str, value: float) -> None:
+        if lib().b200_set_option(self._h, key.encode(), float(value)) != 0:
+            raise ValueError(last_error())
+
+    @staticmethod
+    def _arrs(vals, rows, cols, b):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        rows = None if rows is None else np.ascontiguousarray(rows, dtype=np.int32)
+        cols = None if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        return vals, rows, cols, b
+
+    def solve_system(self, N, nnz, dim, vals, rows, cols, b, wellContribs: Optional[WellContributions],
+                     res: BdaResult) -> SolverStatus:
+        vals, rows, cols, b = self._arrs(vals, rows, cols, b)
+        self._keep = (vals, rows, cols, b)       # pinned by the library until the next call
+        r = _CResult()
+        st = lib().b200_solve_system(self._h, int(N), int(nnz), int(dim), _ptr(vals), _ptr(rows), _ptr(cols),
+                                     _ptr(b), wellContribs._h if wellContribs is not None else None, C.byref(r))
+        res._fill(r)
+        self.N = int(N)
+        if st == SolverStatus.BDA_SOLVER_UNKNOWN_ERROR:
+            raise RuntimeError(last_error())     # device/runtime errors throw in the reference
+        return SolverStatus(st)
+
+    def get_result(self, x: np.ndarray) -> None:
+        assert x.dtype == np.float64 and x.flags.c_contiguous and x.size >= self.N
+        if lib().b200_get_result(self._h, _ptr(x)) != 0:
+            raise RuntimeError(last_error())
+
+    # -- device-resident leg and kernel-level entry points (benchmark / parity tests) --
+    def upload_system(self, N, nnz, dim, vals, rows, cols, b, wellContribs=None) -> None:
+        vals, rows, cols, b = self._arrs(vals, rows, cols, b)
+        self._keep = (vals, rows, cols, b)
+        st = lib().b200_upload_system(self._h, int(N), int(nnz), int(dim), _ptr(vals), _ptr(rows), _ptr(cols),
+                                      _ptr(b), wellContribs._h if wellContribs is not None else None)
+        self.N = int(N)
+        if st != 0:
+            raise RuntimeError(last_error())
+
+    def solve_resident(self, res: BdaResult) -> SolverStatus:
+        r = _CResult()
+        st = lib().b200_solve_resident(self._h, C.byref(r))
+        res._fill(r)
+        if st == SolverStatus.BDA_SOLVER_UNKNOWN_ERROR:
+            raise RuntimeError(last_error())
+        return SolverStatus(st)
+
+    def _chk(self, st):
+        if st != 0:
+            raise RuntimeError(last_error())
+
+    def spmv(self, x):
+        y = np.empty(self.N)
+        self._chk(lib().b200_spmv(self._h, np.ascontiguousarray(x, dtype=np.float64).reshape(-1), y))
+        return y
+
+    def well_apply(self, x, y):
+        y = np.array(y, dtype=np.float64).reshape(-1).copy()
+        self._chk(lib().b200_well_apply(self._h, np.ascontiguousarray(x, dtype=np.float64).reshape(-1), y))
+        return y
+
+    def ilu0_factorize(self) -> SolverStatus:
+        st = lib().b200_ilu0_factorize(self._h)
+        if st == SolverStatus.BDA_SOLVER_UNKNOWN_ERROR:
+            raise RuntimeError(last_error())
+        return SolverStatus(st)
+
+    def ilu0_apply(self, d):
+        v = np.empty(self.N)
+        self._chk(lib().b200_ilu0_apply(self._h, np.ascontiguousarray(d, dtype=np.float64).reshape(-1), v))
+        return v
+
+    def get_ilu0(self, nnzb: int):
+        lu = np.empty(nnzb * 9)
+        self._chk(lib().b200_get_ilu0(self._h, lu))
+        return lu.reshape(-1, 3, 3)
+
+    def get_level_schedule(self):
+        Nb = self.N // 3
+        to, fr, rpl = np.zeros(Nb, np.int32), np.zeros(Nb, np.int32), np.zeros(Nb, np.int32)
+        n = C.c_int(0)
+        self._chk(lib().b200_get_level_schedule(self._h, to, fr, rpl, C.byref(n)))
+        return to, fr, rpl[:n.value].copy()
+
+    def time_kernel(self, which: str, reps: int = 20, flush_l2: bool = True):
+        ms, by = C.c_double(0), C.c_double(0)
+        self._chk(lib().b200_time_kernel(self._h, which.encode(), int(reps), int(flush_l2), C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+    def kernel_stats(self, which: str):
+        n, ms, by = C.c_longlong(0), C.c_double(0), C.c_double(0)
+        self._chk(lib().b200_kernel_stats(self._h, which.encode(), C.byref(n), C.byref(ms), C.byref(by)))
+        return n.value, ms.value, by.value
+
+    def reset_stats(self) -> None:
+        lib().b200_reset_stats(self._h)
+
+    def launch_count(self) -> int:
+        return int(lib().b200_launch_count(self._h))
+
+
+def level_schedule_host(rows, cols):
+    """Host-only level scheduling of a pattern (no device).  bda/Reorder.cpp:266-318."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    Nb = len(rows) - 1
+    to, fr, rpl = np.zeros(Nb, np.int32), np.zeros(Nb, np.int32), np.zeros(Nb, np.int32)
+    n = C.c_int(0)
+    if lib().b200_level_schedule_host(Nb, rows, cols, to, fr, rpl, C.byref(n)) != 0:
+        raise RuntimeError(last_error())
+    return to, fr, rpl[:n.value].copy()
+
+
+@dataclass
+class BsrMatrix:
+    """What BdaBridge sees of a Dune::BCRSMatrix<MatrixBlock<double,3,3>>: N() block rows, the
+    contiguous row-major block array and (once) the sparsity pattern (BdaBridge.cpp:167-189)."""
+    rows: np.ndarray     # int32 [Nb+1]
+    cols: np.ndarray     # int32 [nnzb]
+    vals: np.ndarray     # float64 [nnzb,3,3]
+
+    def __post_init__(self):
+        self.rows = np.ascontiguousarray(self.rows, dtype=np.int32)
+        self.cols = np.ascontiguousarray(self.cols, dtype=np.int32)
+        self.vals = np.ascontiguousarray(self.vals, dtype=np.float64).reshape(-1, 3, 3)
+
+    def N(self) -> int:
+        return len(self.rows) - 1
+
+    def nonzeroes(self) -> int:
+        return int(self.rows[-1])
+
+    @property
+    def block_dim(self) -> int:
+        return self.vals.shape[1]
+
+
+@dataclass
+class InverseOperatorResult:
+    """Dune::InverseOperatorResult fields BdaBridge fills (BdaBridge.cpp:247-251)."""
+    iterations: int = 0
+    reduction: float = 0.0
+    converged: bool = False
+    conv_rate: float = 0.0
+    elapsed: float = 0.0
+
+
+class BdaBridge:
+    """Opm::BdaBridge<BridgeMatrix, BridgeVector, 3> restricted to the new accelerator mode.
+
+    Constructor signature as BdaBridge.cpp:56-63; accepts accelerator_mode "b200" (the branch a
+    maintainer adds next to "cusparse"/"opencl") or "none".  Any other mode
+    raises like the reference's final else branch (:118-120)."""
+
+    def __init__(self, accelerator_mode: str, fpga_bitstream: str = "", linear_solver_verbosity: int = 0,
+                 maxit: int = 200, tolerance: float = 1e-2, platformID: int = 0, deviceID: int = 0,
+                 opencl_ilu_reorder: str = "none"):
+        self.verbosity = linear_solver_verbosity
+        self.accelerator_mode = accelerator_mode
+        self.use_gpu = False
+        self.backend = None
+        self._h_rows = None
+        self._h_cols = None
+        self._diag_indices = None
+        self.last_result = BdaResult()
+        if accelerator_mode == "b200":
+            self.use_gpu = True
+            self.backend = B200SolverBackend(linear_solver_verbosity, maxit, tolerance, deviceID)
+        elif accelerator_mode == "none":
+            self.use_gpu = False
+        else:
+            raise ValueError("Error unknown value for parameter 'AcceleratorMode', should be passed like "
+                             "'--accelerator-mode=[none|cusparse|opencl|fpga|amgcl|b200]")
+
+    def getUseGpu(self) -> bool:
+        return self.use_gpu
+
+    def checkZeroDiagonal(self, mat: BsrMatrix) -> int:
+        """BdaBridge.cpp:125-161: exact zeros on the diagonal of diagonal blocks become 1e-15 in the
+        CALLER's matrix; diagonal offsets cached on the first call."""
+        if self._diag_indices is None:
+            Nb = mat.N()
+            rowid = np.repeat(np.arange(Nb, dtype=np.int64), np.diff(mat.rows))
+            idx = np.nonzero(mat.cols == rowid)[0]
+            if len(idx) != Nb:
+                raise AssertionError("diagonal block missing")
+            self._diag_indices = idx
+        d = mat.vals[self._diag_indices]
+        ii = np.arange(3)
+        dd = d[:, ii, ii]
+        zeros = dd == 0.0
+        n = int(zeros.sum())
+        if n:
+            dd[zeros] = 1e-15
+            d[:, ii, ii] = dd
+            mat.vals[self._diag_indices] = d
+        return n
+
+    def solve_system(self, mat: BsrMatrix, b: np.ndarray, wellContribs: Optional[WellContributions],
+                     res: InverseOperatorResult) -> None:
+        """BdaBridge.cpp:192-255."""
+        if not self.use_gpu:
+            res.converged = False
+            return
+        result = BdaResult()
+        result.converged = False
+        dim = mat.block_dim
+        Nb = mat.N()
+        N = Nb * dim
+        nnzb = mat.nonzeroes() if self._h_rows is None else int(self._h_rows[-1])
+        nnz = nnzb * dim * dim
+        if dim != 3:
+            import warnings
+            warnings.warn("BdaSolver only accepts blocksize = 3 at this time, will use Dune for the remainder of the program")
+            self.use_gpu = False
+            return
+        if self._h_rows is None:
+            self._h_rows, self._h_cols = mat.rows.copy(), mat.cols.copy()
+            if int(self._h_rows[Nb]) != mat.nonzeroes():
+                raise ValueError("Error size of rows do not sum to number of nonzeroes in BdaBridge::getSparsityPattern()")
+        self.checkZeroDiagonal(mat)
+        status = self.backend.solve_system(N, nnz, dim, mat.vals, self._h_rows, self._h_cols, b, wellContribs, result)
+        if status != SolverStatus.BDA_SOLVER_SUCCESS:
+            import warnings
+            warnings.warn({SolverStatus.BDA_SOLVER_ANALYSIS_FAILED:
+                           "BdaSolver could not analyse level information of matrix, perhaps there is still a 0.0 on the diagonal of a block on the diagonal",
+                           SolverStatus.BDA_SOLVER_CREATE_PRECONDITIONER_FAILED:
+                           "BdaSolver could not create preconditioner, perhaps there is still a 0.0 on the diagonal of a block on the diagonal"}
+                          .get(status, "BdaSolver returned unknown status code"))
+        res.iterations = result.iterations
+        res.reduction = result.reduction
+        res.converged = result.converged
+        res.conv_rate = result.conv_rate
+        res.elapsed = result.elapsed
+        self.last_result = result
+
+    def get_result(self, x: np.ndarray) -> None:
+        """BdaBridge.cpp:258-263."""
+        if self.use_gpu:
+            self.backend.get_result(x)

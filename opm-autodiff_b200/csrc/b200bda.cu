@@ -1,0 +1,918 @@
+// b200bda.cu -- solver object + C ABI (include/b200bda.h) of the B200-native ILU0-BiCGSTAB backend.
+//
+// State machine of b200_solve_system == cusparseSolverBackend<3>::solve_system
+// (bda/cusparseSolverBackend.cu:480-499): first call initialize + copy_system_to_gpu + analyse_matrix,
+// later calls update_system_on_gpu (values and rhs only); every call: new ILU0, BiCGSTAB, sync.
+// There is no CPU fallback: without a CUDA device every computing entry point fails.
+#include "../../include/b200bda.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "analysis.hpp"
+#include "kernels.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + " (" +   \
+                            __FILE__ + ":" + std::to_string(__LINE__) + ")");                      \
+    } while (0)
+
+static double wall()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+        if (count <= n && p) return;
+        release();
+        CUDA_OK(cudaMalloc((void**) &p, std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+enum Kind { K_PERMUTE, K_INIT, K_FACTOR, K_LOWER, K_UPPER, K_SPMV, K_WELL, K_VEC_P, K_VEC_XR1, K_VEC_XR2,
+            K_UNPERMUTE, K_MISC, K_COUNT };
+static const char* kKindNames[K_COUNT] = {"permute", "init", "ilu_factor", "ilu_lower", "ilu_upper", "spmv",
+                                          "well_apply", "vec_p", "vec_xr1", "vec_xr2", "unpermute", "misc"};
+
+struct KStat {
+    long long launches = 0;
+    double ms = 0.0;
+};
+
+// Host-side well container: mirrors the three-phase fill of Opm::WellContributions
+// (bda/WellContributions.cpp:152-259).  Device copies live in the solver (persistent across solves).
+struct Wells {
+    bool allocated = false;
+    unsigned dim = 0, dim_wells = 0, num_blocks = 0, num_std_wells = 0;
+    unsigned num_blocks_so_far = 0, num_std_wells_so_far = 0;
+    std::vector<unsigned> val_pointers;
+    std::vector<int> Ccols, Bcols;
+    std::vector<double> Cnnzs, Dnnzs, Bnnzs;
+};
+
+struct Solver {
+    int verbosity = 0, maxit = 200, device = 0;
+    double tolerance = 1e-2, relaxation = 1.0;
+    bool pin_host = true, use_graph = true, profile = false;
+    int lookahead = 2;
+
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    int trsv_blocks = 0, vec_blocks = 0;
+
+    bool analysed = false, have_system = false, have_factor = false;
+    int N = 0, Nb = 0;
+    long long nnz = 0, nnzb = 0;
+    Analysis an;
+
+    DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_chunks;
+    DevBuf<double> d_stage, d_bstage, d_A, d_LU;
+    DevBuf<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_w, d_xnat, d_tmp1, d_tmp2;
+    DevBuf<double> d_partials;
+    DevBuf<unsigned> d_ticket;
+    DevBuf<Scalars> d_S;
+    Scalars* h_S = nullptr;       // pinned
+    DevBuf<double> d_flush;
+
+    // wells (device, p-space columns)
+    int nwells = 0, nwblocks = 0, nucells = 0;
+    DevBuf<unsigned> d_wptr;
+    DevBuf<int> d_Bcols, d_ucell, d_uptr, d_ublock, d_uwell;
+    DevBuf<double> d_B, d_C, d_Dinv, d_z2;
+
+    // pinned-host registration of the caller's arrays
+    const void* reg_vals = nullptr; size_t reg_vals_bytes = 0;
+    const void* reg_b = nullptr; size_t reg_b_bytes = 0;
+
+    KStat stats[K_COUNT];
+    long long launch_count = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;   // (kind, pool index)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+
+    ~Solver()
+    {
+        if (reg_vals) cudaHostUnregister((void*) reg_vals);
+        if (reg_b) cudaHostUnregister((void*) reg_b);
+        for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (cudaEvent_t e : {ev_a, ev_b, ev_c, ev_d}) if (e) cudaEventDestroy(e);
+        if (h_S) cudaFreeHost(h_S);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // ---- launch bookkeeping ------------------------------------------------------------------
+    int prof_begin(int kind)
+    {
+        stats[kind].launches++;
+        launch_count++;
+        if (!profile) return -1;
+        if (ev_used.size() >= ev_pool.size()) {
+            cudaEvent_t a, b;
+            CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+            ev_pool.emplace_back(a, b);
+        }
+        int idx = (int) ev_used.size();
+        ev_used.emplace_back(kind, idx);
+        CUDA_OK(cudaEventRecord(ev_pool[idx].first, stream));
+        return idx;
+    }
+    void prof_end(int idx)
+    {
+        if (idx >= 0) CUDA_OK(cudaEventRecord(ev_pool[idx].second, stream));
+    }
+    void prof_collect()
+    {
+        if (!profile) return;
+        CUDA_OK(cudaStreamSynchronize(stream));
+        for (auto& u : ev_used) {
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, ev_pool[u.second].first, ev_pool[u.second].second));
+            stats[u.first].ms += ms;
+        }
+        ev_used.clear();
+    }
+
+    double alg_bytes(int kind) const
+    {
+        const double nb = (double) Nb, nz = (double) nnzb;
+        double nnzL = 0;
+        if (analysed) nnzL = (double) ((nnzb - Nb) / 2);
+        switch (kind) {
+            case K_SPMV: return 76.0 * nz + 52.0 * nb;
+            case K_LOWER: return 76.0 * nnzL + 52.0 * nb;
+            case K_UPPER: return 76.0 * (nz - nnzL) + 52.0 * nb;
+            case K_FACTOR: return 148.0 * nz + 8.0 * nb;
+            case K_VEC_P: return 96.0 * nb;
+            case K_VEC_XR1: return 144.0 * nb;
+            case K_VEC_XR2: return 168.0 * nb;
+            case K_WELL: return 272.0 * nwblocks + 128.0 * nwells;
+            case K_PERMUTE: return 148.0 * nz;
+            default: return 0.0;
+        }
+    }
+
+    // ---- setup ---------------------------------------------------------------------------------
+    void init_device()
+    {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                            "); this backend has no CPU fallback");
+        if (device >= ndev) throw CudaError("device id " + std::to_string(device) + " out of range");
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw CudaError(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                            std::to_string(prop.minor) + "; this library is built for sm_100a only");
+        num_sms = prop.multiProcessorCount;
+        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaMallocHost((void**) &h_S, sizeof(Scalars)));
+        memset(h_S, 0, sizeof(Scalars));
+        d_S.alloc(1);
+        d_partials.alloc(3 * kMaxPartials);
+        d_ticket.alloc(1);
+        CUDA_OK(cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned), stream));
+        CUDA_OK(cudaMemsetAsync(d_S.p, 0, sizeof(Scalars), stream));
+        for (cudaEvent_t* e2 : {&ev_a, &ev_b, &ev_c, &ev_d}) CUDA_OK(cudaEventCreate(e2));
+        int occ = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trsv<true>, kTrsvThreads, 0));
+        int occ2 = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trsv<false>, kTrsvThreads, 0));
+        occ = std::min(occ, occ2);
+        if (occ < 1) throw CudaError("triangular-solve kernel does not fit on an SM");
+        trsv_blocks = num_sms * occ;                       // every CTA resident: required by the dataflow sweep
+        vec_blocks = std::min(num_sms * 8, kMaxPartials);
+        if (verbosity > 0)
+            fprintf(stderr, "[b200bda] device %d: %s, %d SMs, trsv grid %d x %d, vec grid %d x %d\n", device, prop.name,
+                    num_sms, trsv_blocks, kTrsvThreads, vec_blocks, kVecThreads);
+    }
+
+    void analyse(int N_, long long nnz_, const int* rows, const int* cols)
+    {
+        Nb = N_ / 3; N = N_; nnz = nnz_; nnzb = nnz_ / 9;
+        if (rows[Nb] != nnzb) throw std::runtime_error("rows[Nb] != nnz / 9");
+        an = b200::analyse(Nb, rows, cols);
+        d_prow.alloc(Nb + 1); d_pcol.alloc(nnzb); d_pdiag.alloc(Nb); d_srcblk.alloc(nnzb); d_perm.alloc(Nb);
+        d_chunks.alloc(an.chunks.size());
+        CUDA_OK(cudaMemcpyAsync(d_prow.p, an.prow.data(), sizeof(int) * (Nb + 1), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_pcol.p, an.pcol.data(), sizeof(int) * nnzb, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_pdiag.p, an.pdiag.data(), sizeof(int) * Nb, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_srcblk.p, an.srcblk.data(), sizeof(int) * nnzb, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_perm.p, an.perm.data(), sizeof(int) * Nb, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_chunks.p, an.chunks.data(), sizeof(int) * an.chunks.size(), cudaMemcpyHostToDevice, stream));
+        d_stage.alloc(nnz); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
+        for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) v->alloc(N);
+        CUDA_OK(cudaMemsetAsync(d_xnat.p, 0, sizeof(double) * N, stream));
+        CUDA_OK(cudaMemsetAsync(d_v.p, 0, sizeof(double) * N, stream));
+        CUDA_OK(cudaMemsetAsync(d_p.p, 0, sizeof(double) * N, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        analysed = true;
+    }
+
+    void maybe_register(const void*& reg, size_t& reg_bytes, const void* ptr, size_t bytes)
+    {
+        if (!pin_host) return;
+        if (reg == ptr && reg_bytes == bytes) return;
+        if (reg) { cudaHostUnregister((void*) reg); reg = nullptr; reg_bytes = 0; }
+        cudaError_t e = cudaHostRegister((void*) ptr, bytes, cudaHostRegisterDefault);
+        if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
+        if (e != cudaSuccess) { cudaGetLastError(); return; }   // pageable copy still works
+        reg = ptr; reg_bytes = bytes;
+    }
+
+    void upload_wells(const Wells* w)
+    {
+        nwells = 0; nwblocks = 0; nucells = 0;
+        if (!w || w->num_std_wells == 0) return;
+        if (w->num_std_wells_so_far != w->num_std_wells || w->num_blocks_so_far != w->num_blocks)
+            throw std::runtime_error("WellContributions incomplete: every well needs addMatrix C, D and B");
+        nwells = (int) w->num_std_wells; nwblocks = (int) w->num_blocks;
+        std::vector<int> bc(nwblocks), cc(nwblocks);
+        for (int p = 0; p < nwblocks; ++p) {
+            if (w->Bcols[p] < 0 || w->Bcols[p] >= Nb || w->Ccols[p] < 0 || w->Ccols[p] >= Nb)
+                throw std::runtime_error("well column index out of range");
+            bc[p] = an.iperm[w->Bcols[p]];
+            cc[p] = an.iperm[w->Ccols[p]];
+        }
+        // unique perforated cells (by C column) with their contribution lists
+        std::vector<int> order(nwblocks), well_of(nwblocks);
+        for (int wi = 0; wi < nwells; ++wi)
+            for (unsigned p = w->val_pointers[wi]; p < w->val_pointers[wi + 1]; ++p) well_of[p] = wi;
+        for (int p = 0; p < nwblocks; ++p) order[p] = p;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cc[a] < cc[b]; });
+        std::vector<int> ucell, uptr, ublock(nwblocks), uwell(nwblocks);
+        for (int e = 0; e < nwblocks; ++e) {
+            int p = order[e];
+            if (e == 0 || cc[p] != ucell.back()) { ucell.push_back(cc[p]); uptr.push_back(e); }
+            ublock[e] = p; uwell[e] = well_of[p];
+        }
+        uptr.push_back(nwblocks);
+        nucells = (int) ucell.size();
+        d_wptr.alloc(nwells + 1); d_Bcols.alloc(nwblocks); d_ucell.alloc(nucells); d_uptr.alloc(nucells + 1);
+        d_ublock.alloc(nwblocks); d_uwell.alloc(nwblocks);
+        d_B.alloc((size_t) nwblocks * 12); d_C.alloc((size_t) nwblocks * 12); d_Dinv.alloc((size_t) nwells * 16);
+        d_z2.alloc((size_t) nwells * 4);
+        auto H2D = [&](void* d, const void* h, size_t bytes) { CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
+        H2D(d_wptr.p, w->val_pointers.data(), sizeof(unsigned) * (nwells + 1));
+        H2D(d_Bcols.p, bc.data(), sizeof(int) * nwblocks);
+        H2D(d_ucell.p, ucell.data(), sizeof(int) * nucells);
+        H2D(d_uptr.p, uptr.data(), sizeof(int) * (nucells + 1));
+        H2D(d_ublock.p, ublock.data(), sizeof(int) * nwblocks);
+        H2D(d_uwell.p, uwell.data(), sizeof(int) * nwblocks);
+        H2D(d_B.p, w->Bnnzs.data(), sizeof(double) * nwblocks * 12);
+        H2D(d_C.p, w->Cnnzs.data(), sizeof(double) * nwblocks * 12);
+        H2D(d_Dinv.p, w->Dnnzs.data(), sizeof(double) * nwells * 16);
+        CUDA_OK(cudaStreamSynchronize(stream));   // the host vectors above are temporaries
+    }
+
+    // H2D of values + rhs (+ pattern and analysis on the first call)
+    double upload(int N_, int nnz_, int dim, const double* vals, const int* rows, const int* cols, const double* b,
+                  const Wells* wells, double* t_analysis)
+    {
+        if (dim != 3) throw std::runtime_error("only 3x3 blocks are supported (dim == 3), as BdaBridge.cpp:207-211");
+        if (N_ <= 0 || N_ % 3 != 0 || nnz_ <= 0 || nnz_ % 9 != 0) throw std::runtime_error("N must be 3*Nb and nnz 9*nnzb");
+        if (!vals || !b) throw std::runtime_error("null vals / b");
+        *t_analysis = 0.0;
+        if (!analysed) {
+            if (!rows || !cols) throw std::runtime_error("null rows / cols on the first call");
+            double t0 = wall();
+            analyse(N_, nnz_, rows, cols);
+            *t_analysis = wall() - t0;
+        } else if (N_ != N || nnz_ != nnz) {
+            throw std::runtime_error("sparsity pattern changed after the first call (fixed, cusparseSolverBackend.cu:312)");
+        }
+        maybe_register(reg_vals, reg_vals_bytes, vals, sizeof(double) * nnz);
+        maybe_register(reg_b, reg_b_bytes, b, sizeof(double) * N);
+        CUDA_OK(cudaEventRecord(ev_a, stream));
+        CUDA_OK(cudaMemcpyAsync(d_stage.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_bstage.p, b, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaEventRecord(ev_b, stream));
+        upload_wells(wells);
+        have_system = true; have_factor = false;
+        CUDA_OK(cudaEventSynchronize(ev_b));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, ev_a, ev_b));
+        return ms * 1e-3;
+    }
+
+    // ---- kernels ------------------------------------------------------------------------------
+    int blocks_for(long long n, int threads, int cap) const
+    {
+        long long b = (n + threads - 1) / threads;
+        return (int) std::max<long long>(1, std::min<long long>(b, cap));
+    }
+
+    void permute_values()
+    {
+        int id = prof_begin(K_PERMUTE);
+        k_permute_vals<<<blocks_for(nnz, 256, num_sms * 16), 256, 0, stream>>>(d_stage.p, d_srcblk.p, d_A.p, nnz);
+        prof_end(id);
+    }
+
+    void factorize()
+    {
+        CUDA_OK(cudaMemsetAsync(&d_S.p->singular, 0, sizeof(int), stream));
+        for (int l = 0; l < an.nlev; ++l) {
+            int row0 = an.levelPtr[l], nrows = an.levelPtr[l + 1] - row0;
+            int id = prof_begin(K_FACTOR);
+            k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, row0, nrows, d_S.p);
+            prof_end(id);
+        }
+        have_factor = true;
+    }
+
+    void trsv_lower(const double* rhs, double* out, Scalars* S)
+    {
+        int id = prof_begin(K_LOWER);
+        k_trsv<true><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
+                                                              (int) an.chunks.size(), rhs, out, nullptr, 1.0, S);
+        prof_end(id);
+    }
+    void trsv_upper(const double* rhs, double* out, double* rearm, Scalars* S)
+    {
+        int id = prof_begin(K_UPPER);
+        k_trsv<false><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
+                                                               (int) an.chunks.size(), rhs, out, rearm, relaxation, S);
+        prof_end(id);
+    }
+    template <int MODE>
+    void spmv(const double* x, double* y, const double* d1)
+    {
+        int id = prof_begin(K_SPMV);
+        k_spmv<MODE><<<blocks_for(N, kVecThreads, kMaxPartials), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
+                                                                                          d_partials.p, d_ticket.p);
+        prof_end(id);
+    }
+    template <int MODE>
+    void wells_apply(const double* x, double* y, const double* d1)
+    {
+        if (nwells == 0) return;
+        int id = prof_begin(K_WELL);
+        k_wells<MODE><<<1, 1024, 0, stream>>>(nwells, d_wptr.p, d_Bcols.p, d_B.p, d_C.p, d_Dinv.p, nucells, d_ucell.p, d_uptr.p,
+                                              d_ublock.p, d_uwell.p, d_z2.p, x, y, d1, d_S.p);
+        prof_end(id);
+    }
+
+    void enqueue_iteration()
+    {
+        int id;
+        id = prof_begin(K_VEC_P);
+        k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
+        prof_end(id);
+        trsv_lower(d_p.p, d_w.p, d_S.p);
+        trsv_upper(d_w.p, d_y.p, d_w.p, d_S.p);
+        spmv<1>(d_y.p, d_v.p, d_rt.p);
+        wells_apply<1>(d_y.p, d_v.p, d_rt.p);
+        id = prof_begin(K_VEC_XR1);
+        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p);
+        prof_end(id);
+        trsv_lower(d_r.p, d_w.p, d_S.p);
+        trsv_upper(d_w.p, d_y.p, d_w.p, d_S.p);
+        spmv<2>(d_y.p, d_t.p, d_r.p);
+        wells_apply<2>(d_y.p, d_t.p, d_r.p);
+        id = prof_begin(K_VEC_XR2);
+        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p);
+        prof_end(id);
+    }
+
+    // permutation + ILU0 + BiCGSTAB on the resident system
+    void solve_resident(b200_result* res)
+    {
+        if (!have_system) throw std::runtime_error("no system uploaded");
+        const double t0 = wall();
+        CUDA_OK(cudaEventRecord(ev_a, stream));
+        permute_values();
+        factorize();
+        CUDA_OK(cudaEventRecord(ev_b, stream));
+        int id = prof_begin(K_INIT);
+        k_init<<<vec_blocks, kVecThreads, 0, stream>>>(d_bstage.p, d_perm.p, d_r.p, d_rt.p, d_x.p, d_w.p, d_y.p, N, d_S.p,
+                                                        d_partials.p, d_ticket.p, tolerance, 2 * maxit);
+        prof_end(id);
+        int enq = 0;
+        while (true) {
+            enqueue_iteration();
+            ++enq;
+            CUDA_OK(cudaMemcpyAsync(h_S, d_S.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(cudaStreamSynchronize(stream));
+            if (verbosity > 1)
+                fprintf(stderr, "[b200bda] it %.1f norm %.6e\n", 0.5 * h_S->it_half, h_S->norm);
+            if (h_S->done || h_S->singular || h_S->trsv_timeout || enq >= maxit) break;
+        }
+        id = prof_begin(K_UNPERMUTE);
+        k_scatter_vec<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d_x.p, d_perm.p, d_xnat.p, N);
+        prof_end(id);
+        CUDA_OK(cudaEventRecord(ev_c, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        CUDA_OK(cudaGetLastError());
+        prof_collect();
+        float ms_f = 0.f, ms_k = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms_f, ev_a, ev_b));
+        CUDA_OK(cudaEventElapsedTime(&ms_k, ev_b, ev_c));
+        const Scalars& S = *h_S;
+        const double it = std::min(0.5 * S.it_half, (double) maxit);
+        res->it = it;
+        res->iterations = (int) it;                                   // cusparseSolverBackend.cu:172
+        res->norm0 = S.norm0; res->norm = S.norm;
+        res->reduction = S.norm0 > 0.0 ? S.norm / S.norm0 : 0.0;      // :173
+        res->conv_rate = it > 0.0 ? std::pow(res->reduction, 1.0 / it) : 0.0;
+        res->converged = S.converged;
+        res->breakdown = S.breakdown;
+        res->num_levels = an.nlev;
+        res->t_factor = ms_f * 1e-3; res->t_krylov = ms_k * 1e-3;
+        res->elapsed = wall() - t0;
+        if (verbosity > 0)
+            fprintf(stderr, "[b200bda] converged %d, it %.1f, reduction %.3e, factor %.3f ms, krylov %.3f ms\n", S.converged, it,
+                    res->reduction, ms_f, ms_k);
+        if (S.trsv_timeout) throw std::runtime_error("triangular-solve dataflow wait timed out");
+    }
+
+    // natural-order host vector -> p-space device vector and back (kernel-level API)
+    void to_device_p(const double* h, double* d_p_out)
+    {
+        CUDA_OK(cudaMemcpyAsync(d_tmp1.p, h, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
+        k_gather_vec<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d_tmp1.p, d_perm.p, d_p_out, N);
+        launch_count++;
+    }
+    void to_host_nat(const double* d_p_in, double* h)
+    {
+        k_scatter_vec<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d_p_in, d_perm.p, d_tmp1.p, N);
+        launch_count++;
+        CUDA_OK(cudaMemcpyAsync(h, d_tmp1.p, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        CUDA_OK(cudaGetLastError());
+    }
+    void fill(double* d, double v)
+    {
+        k_fill<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d, v, N);
+        launch_count++;
+    }
+    void ensure_factor()
+    {
+        if (!have_system) throw std::runtime_error("no system uploaded");
+        if (!have_factor) { permute_values(); factorize(); }
+    }
+};
+
+template <class F>
+static b200_status guarded(F&& f, b200_status on_error = B200_UNKNOWN_ERROR)
+{
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return on_error;
+    } catch (...) {
+        g_last_error = "unknown exception";
+        return on_error;
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_solver : b200::Solver {};
+struct b200_wells : b200::Wells {};
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+const char* b200_version(void) { return "b200bda 0.1 (sm_100a)"; }
+
+int b200_device_available(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return p.major == 10 ? 1 : 0;
+}
+
+b200_solver* b200_create(int verbosity, int maxit, double tolerance, unsigned int device_id)
+{
+    b200_solver* s = nullptr;
+    try {
+        s = new b200_solver();
+        s->verbosity = verbosity; s->maxit = maxit; s->tolerance = tolerance; s->device = (int) device_id;
+        s->init_device();
+        return s;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        delete s;
+        return nullptr;
+    }
+}
+
+void b200_destroy(b200_solver* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+b200_status b200_set_option(b200_solver* s, const char* key, double value)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !key) throw std::runtime_error("null argument");
+        std::string k(key);
+        if (k == "relaxation") s->relaxation = value;
+        else if (k == "tolerance") s->tolerance = value;
+        else if (k == "maxit") s->maxit = (int) value;
+        else if (k == "verbosity") s->verbosity = (int) value;
+        else if (k == "pin_host") s->pin_host = value != 0.0;
+        else if (k == "use_graph") s->use_graph = value != 0.0;
+        else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
+        else if (k == "profile") s->profile = value != 0.0;
+        else throw std::runtime_error("unknown option '" + k + "'");
+        return B200_SUCCESS;
+    });
+}
+
+static b200_status solve_common(b200_solver* s, b200_result* res, double t_analysis, double t_copy)
+{
+    memset(res, 0, sizeof *res);
+    s->solve_resident(res);
+    res->t_analysis = t_analysis; res->t_copy = t_copy;
+    if (s->h_S->singular) {
+        g_last_error = "ILU0: singular or non-finite pivot block";
+        return B200_CREATE_PRECONDITIONER_FAILED;
+    }
+    return B200_SUCCESS;
+}
+
+b200_status b200_solve_system(b200_solver* s, int N, int nnz, int dim, const double* vals, const int* rows, const int* cols,
+                              const double* b, b200_wells* wells, b200_result* res)
+{
+    if (!s || !res) { g_last_error = "null solver / result"; return B200_UNKNOWN_ERROR; }
+    const double t0 = wall();
+    bool in_analysis = !s->analysed;
+    b200_status st = guarded([&]() -> b200_status {
+        CUDA_OK(cudaSetDevice(s->device));
+        double t_an = 0.0;
+        double t_copy = s->upload(N, nnz, dim, vals, rows, cols, b, wells, &t_an);
+        in_analysis = false;
+        b200_status r = solve_common(s, res, t_an, t_copy);
+        res->elapsed = wall() - t0;
+        return r;
+    });
+    if (st == B200_UNKNOWN_ERROR && in_analysis && s->analysed == false && dim == 3 && vals && b && rows && cols)
+        return B200_ANALYSIS_FAILED;
+    return st;
+}
+
+b200_status b200_upload_system(b200_solver* s, int N, int nnz, int dim, const double* vals, const int* rows, const int* cols,
+                               const double* b, b200_wells* wells)
+{
+    if (!s) { g_last_error = "null solver"; return B200_UNKNOWN_ERROR; }
+    return guarded([&]() -> b200_status {
+        CUDA_OK(cudaSetDevice(s->device));
+        double t_an = 0.0;
+        s->upload(N, nnz, dim, vals, rows, cols, b, wells, &t_an);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_solve_resident(b200_solver* s, b200_result* res)
+{
+    if (!s || !res) { g_last_error = "null solver / result"; return B200_UNKNOWN_ERROR; }
+    return guarded([&]() -> b200_status {
+        CUDA_OK(cudaSetDevice(s->device));
+        return solve_common(s, res, 0.0, 0.0);
+    });
+}
+
+b200_status b200_get_result(b200_solver* s, double* x)
+{
+    if (!s || !x) { g_last_error = "null argument"; return B200_UNKNOWN_ERROR; }
+    return guarded([&]() -> b200_status {
+        if (!s->analysed) throw std::runtime_error("get_result before any solve");
+        CUDA_OK(cudaSetDevice(s->device));
+        CUDA_OK(cudaMemcpyAsync(x, s->d_xnat.p, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        return B200_SUCCESS;
+    });
+}
+
+// ---- wells -----------------------------------------------------------------------------------------
+
+b200_wells* b200_wells_create(const char* mode, int use_well_conn)
+{
+    std::string m = mode ? mode : "";
+    // WellContributions.cpp:31-49
+    if (m == "b200" || m == "cusparse" || m == "opencl" || m == "fpga") return new b200_wells();
+    if (m == "amgcl") {
+        if (!use_well_conn) { g_last_error = "Error amgcl requires --matrix-add-well-contributions=true"; return nullptr; }
+        return new b200_wells();
+    }
+    g_last_error = "Invalid accelerator mode";
+    return nullptr;
+}
+void b200_wells_destroy(b200_wells* w) { delete w; }
+
+b200_status b200_wells_set_block_size(b200_wells* w, unsigned int dim, unsigned int dim_wells)
+{
+    return guarded([&]() -> b200_status {
+        if (!w) throw std::runtime_error("null wells");
+        w->dim = dim; w->dim_wells = dim_wells;
+        if (dim != 3 || dim_wells != 4)
+            throw std::runtime_error("WellContributions::setBlockSize error: dim and dim_wells must be equal to 3 and 4");
+        return B200_SUCCESS;
+    });
+}
+b200_status b200_wells_add_num_blocks(b200_wells* w, unsigned int n)
+{
+    return guarded([&]() -> b200_status {
+        if (!w) throw std::runtime_error("null wells");
+        if (w->allocated) throw std::runtime_error("Error cannot add more sizes after allocated in WellContributions");
+        w->num_blocks += n; w->num_std_wells++;
+        return B200_SUCCESS;
+    });
+}
+b200_status b200_wells_alloc(b200_wells* w)
+{
+    return guarded([&]() -> b200_status {
+        if (!w) throw std::runtime_error("null wells");
+        if (w->num_std_wells > 0) {
+            if (w->dim != 3 || w->dim_wells != 4) throw std::runtime_error("setBlockSize(3, 4) must precede alloc");
+            w->val_pointers.assign(w->num_std_wells + 1, 0);
+            w->Ccols.resize(w->num_blocks); w->Bcols.resize(w->num_blocks);
+            w->Cnnzs.resize((size_t) w->num_blocks * 12); w->Bnnzs.resize((size_t) w->num_blocks * 12);
+            w->Dnnzs.resize((size_t) w->num_std_wells * 16);
+            w->allocated = true;
+        }
+        return B200_SUCCESS;
+    });
+}
+b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const int* colIndices, const double* values, unsigned int val_size)
+{
+    return guarded([&]() -> b200_status {
+        if (!w) throw std::runtime_error("null wells");
+        if (!w->allocated) throw std::runtime_error("Error cannot add wellcontribution before allocating memory in WellContributions");
+        if (w->num_std_wells_so_far >= w->num_std_wells) throw std::runtime_error("more wells added than announced with addNumBlocks");
+        const unsigned off = w->num_blocks_so_far;
+        switch (type) {
+            case B200_WELL_C:
+            case B200_WELL_B:
+                if (off + val_size > w->num_blocks) throw std::runtime_error("more blocks added than announced with addNumBlocks");
+                if (!colIndices || !values) throw std::runtime_error("null colIndices / values");
+                if (type == B200_WELL_C) {
+                    memcpy(w->Cnnzs.data() + (size_t) off * 12, values, sizeof(double) * val_size * 12);
+                    memcpy(w->Ccols.data() + off, colIndices, sizeof(int) * val_size);
+                } else {
+                    memcpy(w->Bnnzs.data() + (size_t) off * 12, values, sizeof(double) * val_size * 12);
+                    memcpy(w->Bcols.data() + off, colIndices, sizeof(int) * val_size);
+                    w->val_pointers[w->num_std_wells_so_far] = off;
+                    w->num_blocks_so_far += val_size;          // WellContributions.cpp:205-208
+                    w->num_std_wells_so_far++;
+                    w->val_pointers[w->num_std_wells_so_far] = w->num_blocks_so_far;
+                }
+                break;
+            case B200_WELL_D:
+                if (!values) throw std::runtime_error("null values");
+                memcpy(w->Dnnzs.data() + (size_t) w->num_std_wells_so_far * 16, values, sizeof(double) * 16);
+                break;
+            default:
+                throw std::runtime_error("Error unsupported matrix ID for WellContributions::addMatrix()");
+        }
+        return B200_SUCCESS;
+    });
+}
+unsigned int b200_wells_get_num_wells(const b200_wells* w) { return w ? w->num_std_wells : 0; }
+
+// ---- kernel-level entry points --------------------------------------------------------------------
+
+b200_status b200_spmv(b200_solver* s, const double* x, double* y)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !x || !y) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (!s->have_system) throw std::runtime_error("no system uploaded");
+        if (!s->have_factor) s->permute_values();
+        s->to_device_p(x, s->d_tmp2.p);
+        s->spmv<0>(s->d_tmp2.p, s->d_t.p, nullptr);
+        s->to_host_nat(s->d_t.p, y);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_well_apply(b200_solver* s, const double* x, double* y)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !x || !y) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (!s->have_system) throw std::runtime_error("no system uploaded");
+        s->to_device_p(x, s->d_tmp2.p);
+        s->to_device_p(y, s->d_t.p);
+        s->wells_apply<0>(s->d_tmp2.p, s->d_t.p, nullptr);
+        s->to_host_nat(s->d_t.p, y);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_ilu0_factorize(b200_solver* s)
+{
+    return guarded([&]() -> b200_status {
+        if (!s) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (!s->have_system) throw std::runtime_error("no system uploaded");
+        s->permute_values();
+        s->factorize();
+        CUDA_OK(cudaMemcpyAsync(s->h_S, s->d_S.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        CUDA_OK(cudaGetLastError());
+        if (s->h_S->singular) {
+            g_last_error = "ILU0: singular or non-finite pivot block";
+            return B200_CREATE_PRECONDITIONER_FAILED;
+        }
+        return B200_SUCCESS;
+    });
+}
+
+static double host_sentinel()
+{
+    double v;
+    unsigned long long u = kSentinel;
+    memcpy(&v, &u, sizeof v);
+    return v;
+}
+
+b200_status b200_ilu0_apply(b200_solver* s, const double* d, double* v)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !d || !v) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        s->ensure_factor();
+        s->to_device_p(d, s->d_tmp2.p);
+        s->fill(s->d_w.p, host_sentinel());
+        s->fill(s->d_y.p, host_sentinel());
+        s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr);
+        s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr);
+        s->to_host_nat(s->d_y.p, v);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_get_ilu0(b200_solver* s, double* lu)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !lu) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        s->ensure_factor();
+        std::vector<double> tmp((size_t) s->nnz);
+        CUDA_OK(cudaMemcpyAsync(tmp.data(), s->d_LU.p, sizeof(double) * s->nnz, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        for (long long q = 0; q < s->nnzb; ++q)
+            memcpy(lu + (size_t) s->an.srcblk[q] * 9, tmp.data() + (size_t) q * 9, 9 * sizeof(double));
+        return B200_SUCCESS;
+    });
+}
+
+static void export_schedule(const LevelSchedule& S, int Nb, int* to, int* from, int* rpl, int* nlev)
+{
+    if (to) memcpy(to, S.toOrder.data(), sizeof(int) * Nb);
+    if (from) memcpy(from, S.fromOrder.data(), sizeof(int) * Nb);
+    if (rpl) for (int l = 0; l < S.nlev; ++l) rpl[l] = S.levelPtr[l + 1] - S.levelPtr[l];
+    if (nlev) *nlev = S.nlev;
+}
+
+b200_status b200_get_level_schedule(b200_solver* s, int* to, int* from, int* rpl, int* nlev)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !s->analysed) throw std::runtime_error("no analysed system");
+        export_schedule(s->an.sched, s->Nb, to, from, rpl, nlev);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, int* to, int* from, int* rpl, int* nlev)
+{
+    return guarded([&]() -> b200_status {
+        if (Nb <= 0 || !rows || !cols) throw std::runtime_error("bad arguments");
+        LevelSchedule S = level_schedule(Nb, rows, cols);
+        export_schedule(S, Nb, to, from, rpl, nlev);
+        return B200_SUCCESS;
+    }, B200_ANALYSIS_FAILED);
+}
+
+static int kind_of(const std::string& k)
+{
+    if (k == "ilu_apply") return -2;
+    for (int i = 0; i < K_COUNT; ++i) if (k == kKindNames[i]) return i;
+    return -1;
+}
+
+b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int flush_l2, double* ms_out, double* bytes_out)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !which || reps <= 0) throw std::runtime_error("bad arguments");
+        CUDA_OK(cudaSetDevice(s->device));
+        const int kind = kind_of(which);
+        if (kind == -1) throw std::runtime_error(std::string("unknown kernel '") + which + "'");
+        s->ensure_factor();
+        const int N = s->N;
+        const long long flush_n = 64ll << 20;                    // 512 MB > 126 MB L2
+        if (flush_l2) s->d_flush.alloc(flush_n);
+        // operands: any finite data will do for timing; r as input vector
+        CUDA_OK(cudaMemcpyAsync(s->d_tmp2.p, s->d_bstage.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
+        Scalars hs; memset(&hs, 0, sizeof hs);
+        hs.rho = hs.rho_new = hs.alpha = hs.omega = hs.h = hs.tr = hs.tt = 1.0; hs.norm0 = 1.0; hs.tol = 0.0; hs.max_half = 1 << 30;
+        const bool saved_profile = s->profile;
+        s->profile = false;
+        double total_ms = 0.0;
+        for (int it = -2; it < reps; ++it) {                      // two warm-up launches
+            CUDA_OK(cudaMemcpyAsync(s->d_S.p, &hs, sizeof hs, cudaMemcpyHostToDevice, s->stream));
+            if (kind == K_LOWER || kind == -2) s->fill(s->d_w.p, host_sentinel());
+            if (kind == K_UPPER || kind == -2) s->fill(s->d_y.p, host_sentinel());
+            if (kind == K_UPPER) CUDA_OK(cudaMemcpyAsync(s->d_w.p, s->d_tmp2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
+            if (kind == K_VEC_XR1 || kind == K_VEC_XR2 || kind == K_WELL || kind == K_SPMV)
+                CUDA_OK(cudaMemcpyAsync(s->d_y.p, s->d_tmp2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
+            if (flush_l2) {
+                k_flush_l2<<<s->num_sms * 8, 256, 0, s->stream>>>(s->d_flush.p, flush_n, (double) it);
+                s->launch_count++;
+            }
+            CUDA_OK(cudaEventRecord(s->ev_c, s->stream));
+            switch (kind) {
+                case K_SPMV: s->spmv<0>(s->d_y.p, s->d_t.p, nullptr); break;
+                case K_LOWER: s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr); break;
+                case K_UPPER: s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr); break;
+                case -2: s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr); s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr); break;
+                case K_FACTOR: s->factorize(); break;
+                case K_PERMUTE: s->permute_values(); break;
+                case K_VEC_P: s->stats[K_VEC_P].launches++; s->launch_count++;
+                    k_vec_p<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_tmp2.p, s->d_p.p, s->d_v.p, N, s->d_S.p); break;
+                case K_VEC_XR1: s->stats[K_VEC_XR1].launches++; s->launch_count++;
+                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p); break;
+                case K_VEC_XR2: s->stats[K_VEC_XR2].launches++; s->launch_count++;
+                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p); break;
+                case K_WELL: s->wells_apply<0>(s->d_y.p, s->d_t.p, nullptr); break;
+                default: throw std::runtime_error(std::string("kernel '") + which + "' cannot be timed in isolation");
+            }
+            CUDA_OK(cudaEventRecord(s->ev_d, s->stream));
+            CUDA_OK(cudaEventSynchronize(s->ev_d));
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, s->ev_c, s->ev_d));
+            if (it >= 0) total_ms += ms;
+        }
+        CUDA_OK(cudaGetLastError());
+        s->profile = saved_profile;
+        s->have_factor = (kind == K_PERMUTE) ? false : s->have_factor;   // A refreshed, LU stale only if values changed (they did not)
+        s->have_factor = true;
+        if (ms_out) *ms_out = total_ms / reps;
+        if (bytes_out) *bytes_out = kind == -2 ? s->alg_bytes(K_LOWER) + s->alg_bytes(K_UPPER) : s->alg_bytes(kind);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_kernel_stats(b200_solver* s, const char* which, long long* launches, double* total_ms, double* bytes)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !which) throw std::runtime_error("bad arguments");
+        const int kind = kind_of(which);
+        if (kind < 0) throw std::runtime_error(std::string("unknown kernel '") + which + "'");
+        if (launches) *launches = s->stats[kind].launches;
+        if (total_ms) *total_ms = s->stats[kind].ms;
+        if (bytes) *bytes = s->alg_bytes(kind);
+        return B200_SUCCESS;
+    });
+}
+
+void b200_reset_stats(b200_solver* s)
+{
+    if (!s) return;
+    for (auto& k : s->stats) k = KStat();
+    s->launch_count = 0;
+}
+
+long long b200_launch_count(b200_solver* s) { return s ? s->launch_count : 0; }
+
+}  // extern "C"

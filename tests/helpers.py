@@ -1,0 +1,48 @@
+"""Shared test helpers (dense restatements with numpy for tiny cases)."""
+import numpy as np
+
+
+def oracle_wells(w):
+    from oracle import oracle
+    if w is None:
+        return None
+    return oracle.Wells(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv)
+
+
+def bridge_wells(w, mode="b200"):
+    from opm_autodiff_b200 import bridge
+    if w is None:
+        return bridge.WellContributions(mode, False)
+    return bridge.WellContributions.from_arrays(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv, mode)
+
+
+def dense_from_bsr(rows, cols, vals):
+    Nb = len(rows) - 1
+    A = np.zeros((3 * Nb, 3 * Nb))
+    vals = np.asarray(vals).reshape(-1, 3, 3)
+    for i in range(Nb):
+        for k in range(rows[i], rows[i + 1]):
+            A[3 * i:3 * i + 3, 3 * cols[k]:3 * cols[k] + 3] = vals[k]
+    return A
+
+
+def dense_well_operator(w, Nb):
+    """C^T D^-1 B as a dense (3Nb x 3Nb) matrix."""
+    M = np.zeros((3 * Nb, 3 * Nb))
+    if w is None:
+        return M
+    for i in range(len(w.val_pointers) - 1):
+        s, e = int(w.val_pointers[i]), int(w.val_pointers[i + 1])
+        Bd = np.zeros((4, 3 * Nb))
+        Cd = np.zeros((4, 3 * Nb))
+        for p in range(s, e):
+            Bd[:, 3 * w.Bcols[p]:3 * w.Bcols[p] + 3] += np.asarray(w.B[p]).reshape(4, 3)
+            Cd[:, 3 * w.Ccols[p]:3 * w.Ccols[p] + 3] += np.asarray(w.C[p]).reshape(4, 3)
+        M += Cd.T @ np.asarray(w.Dinv[i]).reshape(4, 4) @ Bd
+    return M
+
+
+def relerr(a, b):
+    a = np.asarray(a).reshape(-1)
+    b = np.asarray(b).reshape(-1)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

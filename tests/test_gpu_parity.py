@@ -1,0 +1,253 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.helpers import bridge_wells, oracle_wells, relerr
+from tests.patterns import grid_pattern
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    from opm_autodiff_b200 import bridge, synth
+    from oracle import oracle
+    if not bridge.device_available():
+        pytest.fail("GPU tests need a B200; the product has no CPU fallback")
+    return bridge, synth, oracle
+
+
+def _solve(bridge, s, tol=1e-10, maxit=200, wells=True, relaxation=1.0, opts=None):
+    be = bridge.B200SolverBackend(0, maxit, tol, 0)
+    be.set_option("relaxation", relaxation)
+    for k, v in (opts or {}).items():
+        be.set_option(k, v)
+    res = bridge.BdaResult()
+    wc = bridge_wells(s.wells if wells else None)
+    st = be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, wc, res)
+    x = np.zeros(3 * s.Nb)
+    be.get_result(x)
+    return be, st, res, x
+
+
+def test_matr33_golden_through_bridge(mods, matr33):
+    """The reference's own boundary test (tests/test_cusparseSolver.cpp:49-112): same call sequence,
+    tol/maxiter from options_flexiblesolver.json (0.5 / 20), empty WellContributions; expected x is the
+    CPU golden of tests/test_flexiblesolver.cpp:114-116 (the GPU-test goldens are not solutions)."""
+    bridge, synth, oracle = mods
+    g = matr33
+    br = bridge.BdaBridge("b200", "empty", 10 * 0, 20, 0.5, 0, 0, "none")
+    wc = bridge.WellContributions("b200", False)
+    res = bridge.InverseOperatorResult()
+    mat = bridge.BsrMatrix(g["rows"], g["cols"], g["vals"].copy())
+    br.solve_system(mat, g["b"].copy(), wc, res)
+    x = np.zeros(9)
+    br.get_result(x)
+    assert res.converged and br.last_result.it == 0.5
+    assert np.max(np.abs(x / g["x_golden"] - 1.0)) < 1e-5           # BOOST_CHECK_CLOSE(.., 1e-3) percent
+    ref = oracle.solve(g["rows"], g["cols"], g["vals"], g["b"], tol=0.5, maxit=20)
+    assert relerr(x, ref.x) < 1e-9
+
+
+@pytest.mark.parametrize("shape,faults", [((7, 6, 5), ()), ((12, 10, 8), ((6, 1),)), ((1, 1, 17), ()), ((33, 1, 1), ()),
+                                           ((20, 16, 12), ((7, 2), (13, 1)))])
+def test_kernels_vs_oracle(mods, shape, faults):
+    bridge, synth, oracle = mods
+    s = synth.small(*shape, faults=faults, nwells=2 if shape[0] >= 7 else 0, nperf=3)
+    be = bridge.B200SolverBackend(0, 10, 1e-2, 0)
+    be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(s.wells))
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=3 * s.Nb) * np.tile([1e5, 1.0, 1.0], s.Nb)
+    # SpMV: same products, different summation order inside a row -> a few ulp
+    y = be.spmv(x)
+    yo = oracle.spmv(s.rows, s.cols, s.vals, x)
+    assert relerr(y, yo) < 1e-14
+    # wells
+    if s.wells is not None:
+        y0 = rng.normal(size=3 * s.Nb)
+        assert relerr(be.well_apply(x, y0), oracle.well_apply(oracle_wells(s.wells), x, y0)) < 1e-13
+    # ILU0 factors in the caller's pattern
+    assert be.ilu0_factorize() == bridge.SolverStatus.BDA_SOLVER_SUCCESS
+    LU = be.get_ilu0(s.nnzb)
+    LUo, diag, st = oracle.ilu0(s.rows, s.cols, s.vals)
+    assert st == 0
+    scale = np.abs(LUo).reshape(-1, 9).max(axis=1)[:, None, None]
+    assert np.max(np.abs(LU - LUo) / scale) < 1e-9
+    # ILU0 apply
+    d = rng.normal(size=3 * s.Nb)
+    v = be.ilu0_apply(d)
+    vo = oracle.ilu0_apply(s.rows, s.cols, diag, LUo, d)
+    assert relerr(v, vo) < 1e-9
+    # level schedule of the uploaded pattern == oracle restatement of Reorder.cpp:266-318
+    to, fr, rpl = be.get_level_schedule()
+    oto, ofr, olp = oracle.level_schedule(s.rows, s.cols)
+    assert np.array_equal(to, oto) and np.array_equal(fr, ofr) and np.array_equal(rpl, np.diff(olp))
+
+
+@pytest.mark.parametrize("shape,faults,nwells,nperf", [((12, 10, 8), ((6, 1),), 3, 4), ((24, 20, 16), (), 0, 0),
+                                                        ((30, 24, 20), ((10, 1), (20, 2)), 6, 15)])
+def test_solve_parity_small(mods, shape, faults, nwells, nperf):
+    """north_star parity: ||x - x_ref|| / ||x_ref|| <= 1e-6 at 1e-10 relative residual, iterations +-10%."""
+    bridge, synth, oracle = mods
+    s = synth.small(*shape, faults=faults, nwells=nwells, nperf=nperf)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200)
+    be, st, res, x = _solve(bridge, s)
+    assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and res.converged and ref.converged
+    assert relerr(x, ref.x) <= 1e-6
+    assert abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
+    assert res.reduction < 1e-10
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells)) < 2e-10
+    assert res.iterations == int(res.it)                              # cusparseSolverBackend.cu:172
+    # relaxation 0.9 (Flow's CPU default, FlowLinearSolverParameters.hpp:146-150): same solution
+    ref9 = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200, relaxation=0.9)
+    _, _, res9, x9 = _solve(bridge, s, relaxation=0.9)
+    assert res9.converged and relerr(x9, ref9.x) <= 1e-6 and abs(res9.it - ref9.it) <= max(1.0, 0.1 * ref9.it)
+
+
+def test_solve_parity_c2_norne_size(mods):
+    """BASELINE.json configs[1]: Norne-sized 36x56x22 with NNC faults, full size (oracle: < 1 s)."""
+    bridge, synth, oracle = mods
+    s = synth.full_system("c2")
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, None, tol=1e-10, maxit=2000)
+    be, st, res, x = _solve(bridge, s, maxit=2000)
+    assert res.converged and relerr(x, ref.x) <= 1e-6
+    assert abs(res.it - ref.it) <= 0.1 * ref.it
+    # production setting (reduction 1e-2, maxit 200; FlowLinearSolverParameters.hpp:141-154)
+    refp = oracle.solve(s.rows, s.cols, s.vals, s.b, None, tol=1e-2, maxit=200)
+    _, _, resp, xp = _solve(bridge, s, tol=1e-2, maxit=200)
+    assert resp.converged and resp.it == refp.it and relerr(xp, refp.x) < 1e-6
+
+
+def test_full_size_c3_properties(mods):
+    """BASELINE.json configs[2] at full size (1M cells, 50 wells x 20 perforations): size-independent
+    checks -- true residual of the returned x (oracle operator), error against the generator's x_true,
+    repeatability, and iteration count against the oracle's partial history."""
+    bridge, synth, oracle = mods
+    s = synth.full_system("c3")
+    be, st, res, x = _solve(bridge, s, maxit=2000)
+    assert res.converged and res.reduction < 1e-10
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells)) < 2e-10
+    assert relerr(x, s.x_true) < 1e-5
+    res2 = bridge.BdaResult()
+    be.solve_resident(res2)
+    x2 = np.zeros_like(x)
+    be.get_result(x2)
+    assert res2.it == res.it and np.array_equal(x, x2)                # deterministic reductions
+    # first 6 half steps of the oracle (about 2 s of CPU): same residual history to 1e-6 relative
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-30, maxit=3, threads=oracle.max_threads())
+    be3 = bridge.B200SolverBackend(0, 3, 1e-30, 0)
+    r3 = bridge.BdaResult()
+    be3.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(s.wells), r3)
+    assert not r3.converged and r3.it == 3.0
+    assert abs(r3.norm / ref.norm - 1.0) < 1e-5 and abs(r3.norm0 / ref.norm0 - 1.0) < 1e-12
+
+
+def test_wells_edge_cases(mods):
+    """> 10 perforations (the reference GPU kernels truncate there, WellContributions.cu:115-124), two
+    wells sharing cells, B and C with different column lists, zero wells."""
+    bridge, synth, oracle = mods
+    s = synth.small(10, 8, 6)
+    rng = np.random.default_rng(9)
+    P = 23
+    c0 = rng.permutation(s.Nb)[:P].astype(np.int32)
+    c1 = np.concatenate([c0[:4], rng.permutation(s.Nb)[:5]]).astype(np.int32)
+    cb = np.concatenate([c0, c1])
+    cc = np.concatenate([c0[::-1], c1])                               # C columns differ from B columns
+    sc = 1e-3
+    from opm_autodiff_b200.synth import WellData
+    w = WellData(np.array([0, P, P + len(c1)], np.uint32), cb, cc, sc * rng.normal(size=(len(cb), 4, 3)),
+                 sc * rng.normal(size=(len(cb), 4, 3)), np.stack([np.eye(4) + 0.1 * rng.normal(size=(4, 4))] * 2))
+    be = bridge.B200SolverBackend(0, 200, 1e-10, 0)
+    wc = bridge_wells(w)
+    assert wc.getNumWells() == 2
+    be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, wc)
+    x = rng.normal(size=3 * s.Nb)
+    y0 = rng.normal(size=3 * s.Nb)
+    assert relerr(be.well_apply(x, y0), oracle.well_apply(oracle_wells(w), x, y0)) < 1e-13
+    res = bridge.BdaResult()
+    be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, wc, res)
+    xs = np.zeros(3 * s.Nb)
+    be.get_result(xs)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(w), tol=1e-10, maxit=200)
+    assert res.converged and relerr(xs, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
+    # NULL wells and an empty container give the plain-matrix solve
+    res0 = bridge.BdaResult()
+    be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None, res0)
+    x0 = np.zeros(3 * s.Nb)
+    be.get_result(x0)
+    ref0 = oracle.solve(s.rows, s.cols, s.vals, s.b, None, tol=1e-10, maxit=200)
+    assert relerr(x0, ref0.x) <= 1e-6
+
+
+def test_state_machine_and_errors(mods):
+    """cusparseSolverBackend.cu:480-499: pattern analysed once, values/rhs change per call; dim != 3 and a
+    changed pattern are errors; singular pivot -> CREATE_PRECONDITIONER_FAILED; maxit -> converged False."""
+    bridge, synth, oracle = mods
+    s = synth.small(9, 8, 7)
+    be = bridge.B200SolverBackend(0, 200, 1e-10, 0)
+    res = bridge.BdaResult()
+    be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None, res)
+    assert res.converged and res.t_analysis > 0 and res.num_levels == 9 + 8 + 7 - 2
+    # second Newton step: new values and rhs, rows/cols not needed any more
+    s2 = synth.small(9, 8, 7, seed=8)
+    be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s2.vals, None, None, s2.b, None, res)
+    x = np.zeros(3 * s.Nb)
+    be.get_result(x)
+    ref = oracle.solve(s2.rows, s2.cols, s2.vals, s2.b, None, tol=1e-10, maxit=200)
+    assert res.converged and res.t_analysis == 0 and relerr(x, ref.x) <= 1e-6
+    with pytest.raises(RuntimeError, match="pattern changed"):
+        be.solve_system(3 * (s.Nb - 1), 9 * s.nnzb, 3, s.vals, None, None, s.b, None, res)
+    with pytest.raises(RuntimeError, match="3x3"):
+        bridge.B200SolverBackend(0, 10, 1e-2, 0).solve_system(2 * s.Nb, 4 * s.nnzb, 2, s.vals, s.rows, s.cols, s.b, None, res)
+    # non-convergence
+    be2 = bridge.B200SolverBackend(0, 2, 1e-14, 0)
+    st = be2.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None, res)
+    assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and not res.converged and res.it == 2.0 and res.iterations == 2
+    # singular pivot block
+    bad = s.vals.copy()
+    d5 = int(np.nonzero(s.cols[s.rows[5]:s.rows[6]] == 5)[0][0]) + s.rows[5]
+    bad[d5] = 0.0
+    be3 = bridge.B200SolverBackend(0, 5, 1e-2, 0)
+    st = be3.solve_system(3 * s.Nb, 9 * s.nnzb, 3, bad, s.rows, s.cols, s.b, None, res)
+    assert st == bridge.SolverStatus.BDA_SOLVER_CREATE_PRECONDITIONER_FAILED
+    # missing diagonal -> analysis failure (BdaSolver.hpp:34)
+    rows = np.array([0, 1, 2], np.int32); cols = np.array([0, 0], np.int32)
+    be4 = bridge.B200SolverBackend(0, 5, 1e-2, 0)
+    st = be4.solve_system(6, 18, 3, np.tile(np.eye(3), (2, 1, 1)), rows, cols, np.ones(6), None, res)
+    assert st == bridge.SolverStatus.BDA_SOLVER_ANALYSIS_FAILED
+
+
+def test_zero_rhs_and_single_row(mods):
+    bridge, synth, oracle = mods
+    s = synth.small(5, 4, 3)
+    be, st, res, x = _solve(bridge, s)
+    be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, None, None, np.zeros(3 * s.Nb), None, res)
+    be.get_result(x)
+    assert res.converged and res.it == 0.0 and not np.any(x)          # Dune: norm0 < 1e-30 -> 0 iterations
+    one = bridge.B200SolverBackend(0, 5, 1e-10, 0)
+    blk = np.array([[[2.0, 1, 0], [0, 3, 1], [1, 0, 4]]])
+    r = bridge.BdaResult()
+    one.solve_system(3, 9, 3, blk, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([1.0, 2, 3]), None, r)
+    x1 = np.zeros(3)
+    one.get_result(x1)
+    assert r.converged and relerr(x1, np.linalg.solve(blk[0], [1.0, 2, 3])) < 1e-12
+
+
+def test_bridge_zero_diagonal_fixup_feeds_backend(mods):
+    """BdaBridge::checkZeroDiagonal (BdaBridge.cpp:125-161) mutates the caller's matrix before the solve."""
+    bridge, synth, oracle = mods
+    s = synth.small(6, 5, 4)
+    vals = s.vals.copy()
+    d = int(np.nonzero(s.cols[s.rows[7]:s.rows[8]] == 7)[0][0]) + s.rows[7]
+    vals[d, 0, 0] = 0.0
+    vo = vals.copy()
+    oracle.check_zero_diagonal(s.rows, s.cols, vo)
+    ref = oracle.solve(s.rows, s.cols, vo, s.b, None, tol=1e-10, maxit=200)
+    br = bridge.BdaBridge("b200", "", 0, 200, 1e-10, 0, 0, "none")
+    mat = bridge.BsrMatrix(s.rows, s.cols, vals)
+    res = bridge.InverseOperatorResult()
+    br.solve_system(mat, s.b, None, res)
+    x = np.zeros(3 * s.Nb)
+    br.get_result(x)
+    assert mat.vals[d, 0, 0] == 1e-15
+    assert res.converged == ref.converged and relerr(x, ref.x) <= 1e-6
