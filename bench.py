@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ILU0-BiCGSTAB backend.
+
+  python bench.py --gpus N --steps K --warmup W [--workload c3] [--impl reference]
+
+A "step" is one converged linear solve (permutation into level order + ILU0 factorisation +
+BiCGSTAB to a 1e-10 relative residual, wells applied) of BASELINE.json's synthetic black-oil
+Jacobian.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+
+  value   solves/s with values+rhs already resident in HBM (b200_solve_resident), device time from
+          CUDA events on the solver's stream, max over ranks
+  e2e     solves/s through the reference-facing call a BdaBridge makes (b200_solve_system +
+          b200_get_result) with HOST buffers: H2D of values+rhs+wells and D2H of x inside the timing
+  roofline  dominant kernel of the step: algorithmic bytes / mean launch duration (CUDA events around
+          every launch in a separate profiled solve) against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the CPU oracle (port of the reference's ISTL path) on this box's host cores, bounded sample
+
+--impl reference times the reference's own CPU algorithm (the oracle port: the Dune/ISTL path does
+not compile in this image) with all host threads, one block-Jacobi ILU0 partition per
+thread -- the semantics of `mpirun -np P flow`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "converged ILU0-BiCGSTAB solves/sec (3x3 BSR fp64, 1e-10 relative residual, wells applied)"
+TOL = 1e-10
+MAXIT = 2000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", help="c2 | c3 | c4 | c5 | nx,ny,nz")
+    ap.add_argument("--cpu-sample-iters", type=int, default=12, help="BiCGSTAB iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def get_cfg(name):
+    from opm_autodiff_b200 import synth
+    if name in synth.CONFIGS:
+        return synth.CONFIGS[name]
+    nx, ny, nz = (int(t) for t in name.split(","))
+    return synth.GridConfig("custom-%dx%dx%d" % (nx, ny, nz), nx, ny, nz)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def oracle_wells(w):
+    from oracle import oracle
+    return None if w is None else oracle.Wells(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv)
+
+
+def cpu_sample(system, iters, threads, nparts, gpu_it):
+    """Bounded CPU sample: factorisation + `iters` BiCGSTAB iterations of the oracle, scaled to the
+    iteration count of the converged solve."""
+    from oracle import oracle
+    Nb = system.Nb
+    part = None
+    if nparts > 1:
+        plane = system.cfg.nx * system.cfg.ny
+        nz = Nb // plane
+        part = np.array([plane * ((nz * p) // nparts) for p in range(nparts)] + [Nb], np.int32)
+    r = oracle.solve(system.rows, system.cols, system.vals, system.b, oracle_wells(system.wells), tol=1e-30,
+                     maxit=iters, part_ptr=part, threads=threads)
+    per_it = r.t_solve / max(r.it, 0.5)
+    return r, per_it, r.t_decomp + per_it * gpu_it
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm (oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from opm_autodiff_b200 import synth
+    from oracle import oracle
+    cfg = get_cfg(args.workload)
+    system = synth.full_system(cfg)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, oracle.max_threads(), 32, cfg.nz // 2))
+    times, its = [], []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        part = None
+        plane = cfg.nx * cfg.ny
+        if threads > 1:
+            part = np.array([plane * ((cfg.nz * p) // threads) for p in range(threads)] + [system.Nb], np.int32)
+        # bounded sample: at most --cpu-sample-iters iterations, scaled to the converged count below
+        r = oracle.solve(system.rows, system.cols, system.vals, system.b, oracle_wells(system.wells), tol=TOL,
+                         maxit=args.cpu_sample_iters, part_ptr=part, threads=threads)
+        if step >= args.warmup:
+            times.append((r.t_decomp, r.t_solve, r.it))
+    # one full converged solve (outside the timed steps) fixes the iteration count of this partitioning
+    rfull = oracle.solve(system.rows, system.cols, system.vals, system.b, oracle_wells(system.wells), tol=TOL, maxit=MAXIT,
+                         part_ptr=part, threads=threads) if args.steps <= 3 or cfg.ncells <= 2_000_000 else None
+    conv_it = rfull.it if rfull is not None else float("nan")
+    per_solve = float(np.mean([d + s / max(i, 0.5) * conv_it for (d, s, i) in times]))
+    value = 1.0 / per_solve
+    sample = ("ILU0 factorisation + %d BiCGSTAB iterations per step of the same %s system, %d block-Jacobi partitions on "
+              "%d threads, scaled to the %.1f iterations this partitioning needs to reach 1e-10"
+              % (args.cpu_sample_iters, cfg.name, threads, threads, conv_it))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_solve, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg.name, "cells": cfg.ncells, "tolerance": TOL},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cpus": cores,
+    }))
+
+
+def run_b200_single(args):
+    from opm_autodiff_b200 import bridge, synth
+    if not bridge.device_available():
+        raise SystemExit("bench.py needs a B200 (sm_100); the backend has no CPU fallback")
+    cfg = get_cfg(args.workload)
+    t0 = time.perf_counter()
+    system = synth.full_system(cfg)
+    t_gen = time.perf_counter() - t0
+    N, nnz = 3 * system.Nb, 9 * system.nnzb
+    w = system.wells
+    wc = bridge.WellContributions("b200", False) if w is None else \
+        bridge.WellContributions.from_arrays(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv)
+    be = bridge.B200SolverBackend(0, MAXIT, TOL, 0)
+    res = bridge.BdaResult()
+    x = np.zeros(N)
+
+    # ---- e2e: the call a BdaBridge makes, host buffers, copies inside the timed region -----------------
+    for _ in range(args.warmup):
+        be.solve_system(N, nnz, 3, system.vals, system.rows, system.cols, system.b, wc, res)
+        be.get_result(x)
+    assert res.converged, "solve did not converge"
+    t_analysis = res.t_analysis
+    t0 = time.perf_counter()
+    e2e_parts = []
+    for _ in range(args.steps):
+        be.solve_system(N, nnz, 3, system.vals, system.rows, system.cols, system.b, wc, res)
+        be.get_result(x)
+        e2e_parts.append((res.t_copy, res.t_factor, res.t_krylov))
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h2d = system.vals.nbytes + system.b.nbytes + (0 if w is None else w.B.nbytes + w.C.nbytes + w.Dinv.nbytes + 8 * len(w.Bcols))
+    d2h = x.nbytes
+    xerr = float(np.linalg.norm(x - system.x_true) / np.linalg.norm(system.x_true))
+
+    # ---- value: system resident in HBM, device time (CUDA events on the solver stream) -----------------
+    be.upload_system(N, nnz, 3, system.vals, system.rows, system.cols, system.b, wc)
+    for _ in range(args.warmup):
+        be.solve_resident(res)
+    be.reset_stats()
+    clocks = ClockSampler(0)
+    clocks.start()
+    be.timer_start()
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        be.solve_resident(res)
+    dev_ms = be.timer_stop()
+    wall_ms = 1e3 * (time.perf_counter() - tw0)
+    clk = clocks.stop()
+    launches = be.launch_count()
+    assert res.converged
+    ms_per_step = dev_ms / args.steps
+    gpu_it = res.it
+
+    # ---- roofline: every kernel timed with CUDA events in one profiled solve ----------------------------
+    be.set_option("profile", 1)
+    be.reset_stats()
+    be.solve_resident(res)
+    be.set_option("profile", 0)
+    peak, peak_src = measured_peak()
+    kernels = {}
+    total_ms = 0.0
+    for k in ("permute", "ilu_factor", "ilu_lower", "ilu_upper", "spmv", "well_apply", "vec_p", "vec_xr1", "vec_xr2", "init", "unpermute"):
+        n, ms, by = be.kernel_stats(k)
+        if n:
+            kernels[k] = {"launches": n, "ms_total": round(ms, 4), "us_per_launch": round(1e3 * ms / n, 3),
+                          "alg_bytes_per_launch": by, "gbs": round(by / (ms / n) * 1e-6, 1) if ms > 0 and by > 0 else None}
+            total_ms += ms
+    for k in kernels:
+        kernels[k]["share"] = round(kernels[k]["ms_total"] / total_ms, 4)
+    # ILU apply = lower + upper sweep (one preconditioner application); SURVEY 8d counts it as one kernel
+    ilu_ms = kernels["ilu_lower"]["ms_total"] + kernels["ilu_upper"]["ms_total"]
+    ilu_n = kernels["ilu_lower"]["launches"]
+    ilu_bytes = kernels["ilu_lower"]["alg_bytes_per_launch"] + kernels["ilu_upper"]["alg_bytes_per_launch"]
+    cand = {"ilu_apply": (ilu_ms, ilu_n, ilu_bytes), "spmv": (kernels["spmv"]["ms_total"], kernels["spmv"]["launches"],
+                                                            kernels["spmv"]["alg_bytes_per_launch"])}
+    dom = max(cand, key=lambda k: cand[k][0])
+    dms, dn, dby = cand[dom]
+    achieved = dby / (dms / dn) * 1e-6
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(cfg.name, {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": round(dms / total_ms, 4),
+                "spmv_gbs": kernels["spmv"]["gbs"], "spmv_frac": round(kernels["spmv"]["gbs"] / peak, 4),
+                "ilu_apply_gbs": round(ilu_bytes / (ilu_ms / ilu_n) * 1e-6, 1)}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, per_it, per_solve = cpu_sample(system, args.cpu_sample_iters, 1, 1, gpu_it)
+        cpu = {"value": 1.0 / per_solve, "unit": "solves/s", "cores": 1, "kind": "port",
+               "sample": "oracle (CPU port of the reference ISTL path, 1 thread = 1 MPI rank): ILU0 factorisation %.2f s + %d "
+                         "BiCGSTAB iterations at %.3f s/iteration, scaled to the %.1f iterations of the converged solve"
+                         % (r.t_decomp, args.cpu_sample_iters, per_it, gpu_it),
+               "host_cpus": os.cpu_count()}
+
+    out = {
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "solves/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg.name, "cells": cfg.ncells, "nnz_blocks": system.nnzb, "wells": cfg.nwells,
+                   "perforations_per_well": cfg.nperf if cfg.nwells else 0, "tolerance": TOL, "relaxation": 1.0,
+                   "iterations": gpu_it, "levels": res.num_levels, "x_error_vs_generator": xerr,
+                   "l2": "inputs larger than L2 (matrix %.0f MB + factor %.0f MB vs 126 MB L2), no flush needed"
+                         % (system.vals.nbytes / 1e6, system.vals.nbytes / 1e6) if system.vals.nbytes > 2.5e8
+                         else "matrix fits L2: steps re-stream it from the staging copy, see DESIGN.md",
+                   "analysis_s_excluded": t_analysis, "generate_s": t_gen},
+        "clocks": clk,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s, "copy_ms": 1e3 * float(np.mean([p[0] for p in e2e_parts])),
+                "factor_ms": 1e3 * float(np.mean([p[1] for p in e2e_parts])),
+                "krylov_ms": 1e3 * float(np.mean([p[2] for p in e2e_parts]))},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    import __graft_entry__ as ge
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ge.build()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus == 1 and world == 1:
+        run_b200_single(args)
+    else:
+        from opm_autodiff_b200 import dist_bench
+        dist_bench.run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -155,6 +155,12 @@ void        b200_reset_stats(b200_solver* s);
 /* Number of kernels this library launched since creation / since b200_reset_stats. */
 long long   b200_launch_count(b200_solver* s);
 
+/* Device-side stopwatch on the solver's own stream (CUDA events): start records an event, stop
+ * records a second one, waits for it and returns the milliseconds in between -- the timed region of
+ * the benchmark, immune to host jitter. */
+b200_status b200_timer_start(b200_solver* s);
+b200_status b200_timer_stop(b200_solver* s, double* ms);
+
 /* 1 if a CUDA device with compute capability 10.x is visible, else 0 (never throws). */
 int b200_device_available(void);
 /* Library version string. */

@@ -123,6 +123,8 @@ def lib():
         L.b200_reset_stats.argtypes = [vp]
         L.b200_launch_count.argtypes = [vp]
         L.b200_launch_count.restype = C.c_longlong
+        L.b200_timer_start.argtypes = [vp]
+        L.b200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200_device_available.restype = ip
         _lib = L
     return _lib
@@ -135,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_spmv", "b200_well_apply",
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
     "b200_level_schedule_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
-    "b200_launch_count", "b200_device_available", "b200_version",
+    "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
 ]
 
 
@@ -331,6 +333,14 @@ class B200SolverBackend:
 
     def launch_count(self) -> int:
         return int(lib().b200_launch_count(self._h))
+
+    def timer_start(self) -> None:
+        self._chk(lib().b200_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0)
+        self._chk(lib().b200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
 
 def level_schedule_host(rows, cols):

@@ -83,10 +83,11 @@ struct Solver {
     double tolerance = 1e-2, relaxation = 1.0;
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
+    int trsv_blocks_per_sm = 2, trsv_sleep_ns = 0;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
-    int trsv_blocks = 0, vec_blocks = 0;
+    int trsv_blocks = 0, vec_blocks = 0, trsv_occ = 1;
 
     bool analysed = false, have_system = false, have_factor = false;
     int N = 0, Nb = 0;
@@ -116,14 +117,14 @@ struct Solver {
     long long launch_count = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     std::vector<std::pair<int, int>> ev_used;   // (kind, pool index)
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
 
     ~Solver()
     {
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_b) cudaHostUnregister((void*) reg_b);
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-        for (cudaEvent_t e : {ev_a, ev_b, ev_c, ev_d}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {ev_a, ev_b, ev_c, ev_d, ev_t0, ev_t1}) if (e) cudaEventDestroy(e);
         if (h_S) cudaFreeHost(h_S);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -210,7 +211,8 @@ struct Solver {
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trsv<false>, kTrsvThreads, 0));
         occ = std::min(occ, occ2);
         if (occ < 1) throw CudaError("triangular-solve kernel does not fit on an SM");
-        trsv_blocks = num_sms * occ;                       // every CTA resident: required by the dataflow sweep
+        trsv_occ = occ;
+        trsv_blocks = num_sms * std::min(occ, trsv_blocks_per_sm);   // every CTA resident: required by the dataflow sweep
         vec_blocks = std::min(num_sms * 8, kMaxPartials);
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] device %d: %s, %d SMs, trsv grid %d x %d, vec grid %d x %d\n", device, prop.name,
@@ -355,14 +357,14 @@ struct Solver {
     {
         int id = prof_begin(K_LOWER);
         k_trsv<true><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
-                                                              (int) an.chunks.size(), rhs, out, nullptr, 1.0, S);
+                                                              (int) an.chunks.size(), rhs, out, nullptr, 1.0, S, trsv_sleep_ns);
         prof_end(id);
     }
     void trsv_upper(const double* rhs, double* out, double* rearm, Scalars* S)
     {
         int id = prof_begin(K_UPPER);
         k_trsv<false><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
-                                                               (int) an.chunks.size(), rhs, out, rearm, relaxation, S);
+                                                               (int) an.chunks.size(), rhs, out, rearm, relaxation, S, trsv_sleep_ns);
         prof_end(id);
     }
     template <int MODE>
@@ -553,6 +555,8 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "trsv_blocks_per_sm") { s->trsv_blocks_per_sm = std::max(1, (int) value); s->trsv_blocks = s->num_sms * std::min(s->trsv_occ, s->trsv_blocks_per_sm); }
+        else if (k == "trsv_sleep_ns") s->trsv_sleep_ns = std::max(0, (int) value);
         else throw std::runtime_error("unknown option '" + k + "'");
         return B200_SUCCESS;
     });
@@ -914,5 +918,30 @@ void b200_reset_stats(b200_solver* s)
 }
 
 long long b200_launch_count(b200_solver* s) { return s ? s->launch_count : 0; }
+
+b200_status b200_timer_start(b200_solver* s)
+{
+    return guarded([&]() -> b200_status {
+        if (!s) throw std::runtime_error("null solver");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (!s->ev_t0) { CUDA_OK(cudaEventCreate(&s->ev_t0)); CUDA_OK(cudaEventCreate(&s->ev_t1)); }
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        CUDA_OK(cudaEventRecord(s->ev_t0, s->stream));
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_timer_stop(b200_solver* s, double* ms)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !ms || !s->ev_t0) throw std::runtime_error("timer not started");
+        CUDA_OK(cudaEventRecord(s->ev_t1, s->stream));
+        CUDA_OK(cudaEventSynchronize(s->ev_t1));
+        float f = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&f, s->ev_t0, s->ev_t1));
+        *ms = f;
+        return B200_SUCCESS;
+    });
+}
 
 }  // extern "C"

@@ -155,10 +155,11 @@ __global__ void __launch_bounds__(kVecThreads) k_init(const double* __restrict__
         S->norm0 = sqrt(tot[0]); S->norm = S->norm0; S->rho_new = tot[0];
         S->rho = 1.0; S->alpha = 1.0; S->omega = 1.0; S->h = 0.0; S->tr = 0.0; S->tt = 0.0;
         S->tol = tol; S->it_half = 0; S->converged = 0; S->breakdown = 0; S->first = 1;
-        S->max_half = max_half; S->trsv_timeout = 0; S->singular = 0;
+        S->max_half = max_half; S->trsv_timeout = 0;
         // Dune: norm0 already below the absolute floor -> converged with 0 iterations
         S->done = (S->norm0 < 1e-30) ? 1 : 0;
         if (S->done) S->converged = 1;
+        if (S->singular) S->done = 1;      // factorisation failed: skip the Krylov loop
     }
 }
 
@@ -245,48 +246,115 @@ __global__ void __launch_bounds__(256) k_ilu_factor_level(const int* __restrict_
 // for L, backward for U.  A dependency x_j is consumed straight from `out`, which the producer of
 // row j overwrites (relaxed gpu-scope 8-byte stores) after it was armed with a NaN sentinel: the
 // value is its own ready flag, so the critical path per level is one L2 round trip and there is no
-// grid-wide barrier between the ~nx+ny+nz levels.  `rearm` (may be null) is re-armed for the
-// next sweep that uses it as an output.
+// grid-wide barrier between the ~nx+ny+nz levels.  Everything that does not depend on other rows
+// (chunk descriptor, row pointers, column indices, factor values, rhs) is loaded BEFORE the wait,
+// the descriptors one chunk ahead, so only the poll -> fma -> store chain is exposed.  While
+// waiting a warp polls a single value per row (the last component of its highest-numbered
+// dependency) and validates the rest once that one has landed.  `rearm` (may be null) is re-armed
+// for the next sweep that uses it as an output.
+constexpr int kTrsvBatch = 4;      // dependencies held in registers at a time
+
 template <bool LOWER>
 __global__ void __launch_bounds__(kTrsvThreads) k_trsv(const int* __restrict__ prow, const int* __restrict__ pcol,
                                                        const int* __restrict__ pdiag, const double* __restrict__ LU,
                                                        const int* __restrict__ chunks, int nchunks,
                                                        const double* __restrict__ rhs, double* out, double* rearm,
-                                                       double relax, Scalars* S)
+                                                       double relax, Scalars* S, int sleep_ns)
 {
     if (S != nullptr && S->done) return;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int W = (gridDim.x * blockDim.x) >> 5;
     const int q = lane / 3, comp = lane - 3 * q;
+    if (gw >= nchunks) return;
+
+    auto chunk_at = [&](int c) { return chunks[LOWER ? c : nchunks - 1 - c]; };
+    // descriptor pipeline: enc (chunk c), then its row bounds; next chunk's enc is fetched one trip early
+    int enc = chunk_at(gw);
+    int enc_next = gw + W < nchunks ? chunk_at(gw + W) : 0;
+    int kb = 0, ke = 0, kd = 0;
+    {
+        const int i0 = (enc >> 4) + q;
+        if (q < (enc & 15)) { kd = pdiag[i0]; kb = LOWER ? prow[i0] : kd + 1; ke = LOWER ? kd : prow[i0 + 1]; }
+    }
     for (int c = gw; c < nchunks; c += W) {
-        const int enc = chunks[LOWER ? c : nchunks - 1 - c];
         const int start = enc >> 4, count = enc & 15;
         const bool act = q < count;
         const int i = start + q;
-        int kb = 0, ke = 0, kd = 0;
-        double acc = 0.0;
-        if (act) {
-            kd = pdiag[i];
-            kb = LOWER ? prow[i] : kd + 1;
-            ke = LOWER ? kd : prow[i + 1];
-            acc = rhs[3 * i + comp];
+        const int nk = act ? ke - kb : 0;
+        double acc = act ? rhs[3 * i + comp] : 0.0;
+        double inv0 = 0.0, inv1 = 0.0, inv2 = 0.0;
+        if (!LOWER && act) {
+            const double* inv = LU + (size_t) kd * 9 + comp * 3;
+            inv0 = inv[0]; inv1 = inv[1]; inv2 = inv[2];
         }
-        for (int k = kb; __any_sync(kFull, act && k < ke); ++k) {
-            if (act && k < ke) {
-                const int col = pcol[k];
-                const double* a = LU + (size_t) k * 9 + comp * 3;
-                const double a0 = a[0], a1 = a[1], a2 = a[2];
-                const double* xp = out + 3 * (size_t) col;
-                double x0, x1, x2;
-                int spins = 0;
-                while (true) {
-                    x0 = ld_relaxed(xp); x1 = ld_relaxed(xp + 1); x2 = ld_relaxed(xp + 2);
-                    if (!(is_sentinel(x0) || is_sentinel(x1) || is_sentinel(x2))) break;
-                    if (++spins > (1 << 22)) { if (S != nullptr) S->trsv_timeout = 1; break; }
+        // first batch of this chunk: columns + factor values into registers
+        int col[kTrsvBatch];
+        double a[kTrsvBatch][3];
+#pragma unroll
+        for (int j = 0; j < kTrsvBatch; ++j) {
+            const bool on = j < nk;
+            const int k = on ? kb + j : 0;
+            col[j] = on ? pcol[k] : -1;
+            const double* ap = LU + (size_t) k * 9 + comp * 3;
+            a[j][0] = on ? ap[0] : 0.0; a[j][1] = on ? ap[1] : 0.0; a[j][2] = on ? ap[2] : 0.0;
+        }
+        // descriptors of the NEXT chunk of this warp (consumed after the wait below)
+        int nkb = 0, nke = 0, nkd = 0;
+        const int enc_cur_next = enc_next;
+        if (c + W < nchunks) {
+            const int i1 = (enc_cur_next >> 4) + q;
+            if (q < (enc_cur_next & 15)) { nkd = pdiag[i1]; nkb = LOWER ? prow[i1] : nkd + 1; nke = LOWER ? nkd : prow[i1 + 1]; }
+            enc_next = c + 2 * W < nchunks ? chunk_at(c + 2 * W) : 0;
+        }
+        for (int k0 = 0; __any_sync(kFull, k0 < nk); k0 += kTrsvBatch) {
+            if (k0 > 0) {
+#pragma unroll
+                for (int j = 0; j < kTrsvBatch; ++j) {
+                    const bool on = k0 + j < nk;
+                    const int k = on ? kb + k0 + j : 0;
+                    col[j] = on ? pcol[k] : -1;
+                    const double* ap = LU + (size_t) k * 9 + comp * 3;
+                    a[j][0] = on ? ap[0] : 0.0; a[j][1] = on ? ap[1] : 0.0; a[j][2] = on ? ap[2] : 0.0;
                 }
-                acc -= a0 * x0 + a1 * x1 + a2 * x2;
             }
+            // cheap wait: one 8-byte poll per row on the dependency most likely to land last
+            int watch = -1;
+#pragma unroll
+            for (int j = 0; j < kTrsvBatch; ++j) watch = max(watch, col[j]);
+            if (!LOWER) {            // backward sweep: the lowest-numbered dependency is produced last
+                watch = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < kTrsvBatch; ++j) if (col[j] >= 0) watch = min(watch, col[j]);
+                if (watch == 0x7fffffff) watch = -1;
+            }
+            int spins = 0;
+            if (watch >= 0) {
+                const double* wp = out + 3 * (size_t) watch + 2;
+                while (is_sentinel(ld_relaxed(wp))) {
+                    if (++spins > (1 << 22)) { if (S != nullptr) S->trsv_timeout = 1; break; }
+                    if (sleep_ns > 0) __nanosleep(sleep_ns);
+                }
+            }
+            // validate + fetch everything (normally a single pass)
+            double x[kTrsvBatch][3];
+            while (true) {
+                bool ready = true;
+#pragma unroll
+                for (int j = 0; j < kTrsvBatch; ++j) {
+                    if (col[j] >= 0) {
+                        const double* xp = out + 3 * (size_t) col[j];
+                        x[j][0] = ld_relaxed(xp); x[j][1] = ld_relaxed(xp + 1); x[j][2] = ld_relaxed(xp + 2);
+                        ready = ready && !(is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2]));
+                    } else {
+                        x[j][0] = 0.0; x[j][1] = 0.0; x[j][2] = 0.0;
+                    }
+                }
+                if (ready) break;
+                if (++spins > (1 << 22)) { if (S != nullptr) S->trsv_timeout = 1; break; }
+            }
+#pragma unroll
+            for (int j = 0; j < kTrsvBatch; ++j) acc -= a[j][0] * x[j][0] + a[j][1] * x[j][1] + a[j][2] * x[j][2];
         }
         if (LOWER) {
             if (act) st_relaxed(out + 3 * i + comp, acc);
@@ -295,12 +363,10 @@ __global__ void __launch_bounds__(kTrsvThreads) k_trsv(const int* __restrict__ p
             const double s0 = __shfl_sync(kFull, acc, base);
             const double s1 = __shfl_sync(kFull, acc, base + 1);
             const double s2 = __shfl_sync(kFull, acc, base + 2);
-            if (act) {
-                const double* inv = LU + (size_t) kd * 9 + comp * 3;
-                st_relaxed(out + 3 * i + comp, (inv[0] * s0 + inv[1] * s1 + inv[2] * s2) * relax);
-            }
+            if (act) st_relaxed(out + 3 * i + comp, (inv0 * s0 + inv1 * s1 + inv2 * s2) * relax);
         }
         if (rearm != nullptr && act) rearm[3 * i + comp] = sentinel();
+        enc = enc_cur_next; kb = nkb; ke = nke; kd = nkd;
     }
 }
 

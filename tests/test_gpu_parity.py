@@ -153,9 +153,10 @@ def test_wells_edge_cases(mods):
     c1 = np.concatenate([c0[:4], rng.permutation(s.Nb)[:5]]).astype(np.int32)
     cb = np.concatenate([c0, c1])
     cc = np.concatenate([c0[::-1], c1])                               # C columns differ from B columns
-    sc = 1e-3
+    sc = 0.05
+    cs = np.array([1e-7, 1.0, 1.0])                                   # pressure column scaled like the matrix blocks
     from opm_autodiff_b200.synth import WellData
-    w = WellData(np.array([0, P, P + len(c1)], np.uint32), cb, cc, sc * rng.normal(size=(len(cb), 4, 3)),
+    w = WellData(np.array([0, P, P + len(c1)], np.uint32), cb, cc, sc * rng.normal(size=(len(cb), 4, 3)) * cs,
                  sc * rng.normal(size=(len(cb), 4, 3)), np.stack([np.eye(4) + 0.1 * rng.normal(size=(4, 4))] * 2))
     be = bridge.B200SolverBackend(0, 200, 1e-10, 0)
     wc = bridge_wells(w)
@@ -205,8 +206,8 @@ def test_state_machine_and_errors(mods):
     assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and not res.converged and res.it == 2.0 and res.iterations == 2
     # singular pivot block
     bad = s.vals.copy()
-    d5 = int(np.nonzero(s.cols[s.rows[5]:s.rows[6]] == 5)[0][0]) + s.rows[5]
-    bad[d5] = 0.0
+    bad[0] = 0.0                      # row 0 has no lower entries: its pivot is never updated, so it stays singular
+    assert s.cols[0] == 0 and oracle.ilu0(s.rows, s.cols, bad)[2] == 2
     be3 = bridge.B200SolverBackend(0, 5, 1e-2, 0)
     st = be3.solve_system(3 * s.Nb, 9 * s.nnzb, 3, bad, s.rows, s.cols, s.b, None, res)
     assert st == bridge.SolverStatus.BDA_SOLVER_CREATE_PRECONDITIONER_FAILED
