@@ -71,6 +71,8 @@ void b200_destroy(b200_solver* s);
  *   "use_graph"   1: replay the BiCGSTAB iteration as a CUDA graph                        default 1
  *   "lookahead"   iterations enqueued ahead of the convergence read-back                  default 2
  *   "profile"     1: time every kernel with CUDA events (no graph), see b200_kernel_stats default 0
+ *   "sweep_parts", "sweep_warps", "sweep_slots", "sweep_stage_bytes", "sweep_window"
+ *                 schedule of the triangular sweeps (parts <= SMs; set before the first solve)
  * Unknown keys return B200_UNKNOWN_ERROR. */
 b200_status b200_set_option(b200_solver* s, const char* key, double value);
 
@@ -139,6 +141,15 @@ b200_status b200_get_level_schedule(b200_solver* s, int* to_order, int* from_ord
 /* Host-only analysis (no device needed): same outputs from a raw pattern. */
 b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, int* to_order,
                                      int* from_order, int* rows_per_level, int* num_levels);
+
+/* Host-only check of the triangular-sweep schedule this library would run for a pattern (no device
+ * needed): emulates the packed pencil streams chunk by chunk with random factor values and compares
+ * with the sequential natural-order substitution (ParallelOverlappingILU0.hpp:867-895).  parts /
+ * stage_bytes / window <= 0 select the defaults.  stats (12 values, may be NULL): parts, lines, strips,
+ * stages L, stages U, chunks L, shared-memory deps L, global deps L, max meta ints, max value doubles,
+ * max rhs rows, reference levels.  Fails with B200_ANALYSIS_FAILED if the schedule could deadlock. */
+b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int stage_bytes,
+                                           int window, unsigned int seed, double* max_rel_err, long long* stats);
 
 /* Time `reps` back-to-back launches of one kernel with CUDA events on the solver's stream.
  * which: "spmv", "ilu_apply", "ilu_lower", "ilu_upper", "ilu_factor", "vec_p", "vec_xr1", "vec_xr2",

@@ -117,6 +117,8 @@ def lib():
         L.b200_get_ilu0.argtypes = [vp, _f64p]
         L.b200_get_level_schedule.argtypes = [vp, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
         L.b200_level_schedule_host.argtypes = [ip, _i32p, _i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
+        L.b200_sweep_schedule_check_host.argtypes = [ip, _i32p, _i32p, ip, ip, ip, C.c_uint, C.POINTER(C.c_double),
+                                                     np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
         L.b200_time_kernel.argtypes = [vp, C.c_char_p, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200_kernel_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]
@@ -136,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "b200_wells_destroy", "b200_wells_set_block_size", "b200_wells_add_num_blocks", "b200_wells_alloc",
     "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_spmv", "b200_well_apply",
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
-    "b200_level_schedule_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
+    "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
 ]
 
@@ -353,6 +355,22 @@ def level_schedule_host(rows, cols):
     if lib().b200_level_schedule_host(Nb, rows, cols, to, fr, rpl, C.byref(n)) != 0:
         raise RuntimeError(last_error())
     return to, fr, rpl[:n.value].copy()
+
+
+SWEEP_STAT_NAMES = ("parts", "lines", "strips", "stages_L", "stages_U", "chunks_L", "window_deps_L", "global_deps_L",
+                    "max_meta_ints", "max_vals_doubles", "max_rhs_rows", "levels")
+
+
+def sweep_schedule_check_host(rows, cols, parts=0, stage_bytes=0, window=0, seed=1):
+    """Host-only emulation of the triangular-sweep schedule of a pattern (no device): returns the largest
+    error against the sequential natural-order substitution (relative to max|x|) and the schedule statistics."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    err = C.c_double(0)
+    stats = np.zeros(12, np.int64)
+    if lib().b200_sweep_schedule_check_host(len(rows) - 1, rows, cols, parts, stage_bytes, window, seed, C.byref(err), stats) != 0:
+        raise RuntimeError(last_error())
+    return err.value, dict(zip(SWEEP_STAT_NAMES, (int(v) for v in stats)))
 
 
 @dataclass

@@ -1,13 +1,31 @@
 // analysis.hpp -- host-side sparsity analysis for the B200 ILU0-BiCGSTAB backend.
 //
 // Replaces, for this backend, what the reference does in BILU0::init (bda/BILU0.cpp:50-158) and
-// cusparseSolverBackend::analyse_matrix (bda/cusparseSolverBackend.cu:348-422): it derives the
-// level sets of the lower-triangular dependency DAG (bda/Reorder.cpp:266-318), a symmetric
-// permutation P into level order, the permuted BSR pattern of P A P^T and the work-chunk table
-// of the triangular-solve kernels.  Done once per sparsity pattern, O(nnzb) work.
+// cusparseSolverBackend::analyse_matrix (bda/cusparseSolverBackend.cu:348-422).  Done once per
+// sparsity pattern, O(nnzb log) work.  It produces
+//   (1) the reference's level sets of the lower-triangular dependency DAG, exactly as
+//       bda::findLevelScheduling returns them (bda/Reorder.cpp:266-318) -- exported for parity and used
+//       (on the symmetrised pattern) as the global topological key of everything below;
+//   (2) the PENCIL schedule the triangular sweeps run.  Inter-SM signalling through L2 costs
+//       0.25-0.46 us per hop on B200 (profiles/r1_pingpong_latency.txt): a sweep that crosses the chip
+//       once per level set (298 of them for 100^3 cells) is latency bound at 1-3 us per level, 20x off
+//       the HBM roofline.  So the rows are cut into P parts (P = resident CTAs, one per SM), each a
+//       bundle of grid LINES (maximal runs r, r+1, ... of mutually dependent rows): a pencil.  Inside a
+//       pencil consecutive level sets hand values over through SHARED memory (one named barrier per
+//       level, ~0.1 us); only dependencies that leave the pencil travel through L2, and any dependency
+//       path crosses few pencils, so the exposed hops drop from #levels to ~#pencils on a diagonal.
+//       Mathematically nothing changes: any topological order of the DAG gives the same ILU0 factors
+//       and the same triangular solves as the sequential reference (natural ordering).
+//   (3) "p-space": rows renumbered part by part, inside a part by (global level, natural index) -- the
+//       processing order, so every CTA streams its factor slice, its rhs and its output linearly --
+//       the BSR pattern of the row-permuted matrix, and the packed lane-major streams of both sweeps.
 #pragma once
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -15,6 +33,7 @@
 namespace b200 {
 
 constexpr int kRowsPerWarp = 10;   // 3 lanes per block row -> 30 active lanes per warp
+constexpr int kPadCol = INT_MIN;   // padded dependency slot of a chunk (factor value 0)
 
 struct LevelSchedule {
     int nlev = 0;
@@ -38,7 +57,6 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
     S.level.assign(Nb, -1);
     S.toOrder.assign(Nb, -1);
     S.fromOrder.assign(Nb, -1);
-    // CSC pattern (rows that hold an entry in each column, ascending)
     std::vector<int> cptr(Nb + 1, 0), crow(std::max<int64_t>(nnzb, 1));
     for (int64_t k = 0; k < nnzb; ++k) {
         if (cols[k] < 0 || cols[k] >= Nb) throw std::runtime_error("column index out of range");
@@ -50,7 +68,6 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
         for (int r = 0; r < Nb; ++r)
             for (int k = rows[r]; k < rows[r + 1]; ++k) crow[fill[cols[k]]++] = r;
     }
-    // remaining lower dependencies per row
     std::vector<int> pending(Nb, 0);
     for (int r = 0; r < Nb; ++r) {
         int n = 0;
@@ -63,15 +80,11 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
         if (pending[r] == 0) { S.fromOrder[next] = r; S.toOrder[r] = next; S.level[r] = 0; ++next; }
     S.levelPtr.push_back(next);
     int active = 0;
-    // A row joins level L when its LAST dependency sits in level L-1.  The reference appends it at
-    // the first scanned row for which canBeStarted() holds, i.e. when all dependencies are in
-    // levels < L -- it is first *seen ready* while scanning its earliest dependent predecessor of
-    // the previous level.  Counting down `pending` over all previous-level predecessors and
-    // appending at the first scanned one reproduces that order: every predecessor in the previous
-    // level is scanned in this sweep, and predecessors in older levels were counted earlier.
-    std::vector<int> seen(Nb, -1);          // level sweep in which the row was first met
-    std::vector<int> cand;                  // rows met in this sweep, in first-met order
-    std::vector<int> hits(Nb, 0);
+    // A row joins a level when all of its lower dependencies are done; the reference appends it the
+    // first time it is visited in that state while scanning the previous level, which is its first
+    // visit of the sweep because readiness does not change during a sweep (doneRows is updated only
+    // after the scan, Reorder.cpp:303-311).
+    std::vector<int> seen(Nb, -1), hits(Nb, 0), cand;
     while (next < Nb) {
         const int lev = (int) S.levelPtr.size() - 1;
         const int start = next;
@@ -85,13 +98,8 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
                 ++hits[r];
             }
         }
-        // The reference tests canBeStarted(r) at EVERY visit; r becomes eligible in this sweep iff
-        // all its dependencies are done, and then it is appended at its first visit.
-        for (int r : cand) {
-            if (hits[r] == pending[r]) {
-                S.fromOrder[next] = r; S.toOrder[r] = next; S.level[r] = lev; ++next;
-            }
-        }
+        for (int r : cand)
+            if (hits[r] == pending[r]) { S.fromOrder[next] = r; S.toOrder[r] = next; S.level[r] = lev; ++next; }
         for (int r : cand) {
             if (S.level[r] < 0) pending[r] -= hits[r];
             hits[r] = 0;
@@ -103,75 +111,530 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
     return S;
 }
 
+// ---- packed sweep streams -------------------------------------------------------------------------
+//
+// A sweep (forward over L, backward over U) is cut, per part, into STAGES: a few KB of consecutive
+// work the producer warp of the CTA fetches with three bulk copies (meta ints, factor values, rhs
+// rows) into one slot of a shared-memory ring.  A stage holds CHUNKS of <= 10 rows of one level
+// (3 lanes per row), grouped into ENTRIES (runs of chunks of the same level inside the stage).
+//
+//   meta blob (ints, 16-byte multiple):
+//     [0] nentries  [1] nchunks  [2] g_lo (even-aligned first p-row of the stage's rhs copy)  [3] rhs rows copied
+//     entries  : nentries x {chunk_begin | barrier << 31, nchunks}    barrier: all rows of earlier levels must be visible
+//     chunks   : nchunks x {g0, count | nd << 8, cols_off, vals_off}  (16-byte aligned; offsets relative to the blobs)
+//     cols     : per chunk nd x count ints: >= 0 position (processing order) inside the part -> shared-memory window,
+//                < 0 and != kPadCol: -(p-row + 1) -> polled in global memory, kPadCol: no dependency
+//   vals blob (doubles, 16-byte multiple): per chunk (nd [+1 inverse pivot for U]) x 3 x (3 count) doubles,
+//     value ((j*3 + v) * 3 count + 3 q + comp) = LU[block j of row q][comp][v]  (lane-major: conflict-free, coalesced)
+//   row q of a chunk is p-row g0 + q (lower sweep) or g0 - q (upper sweep).
+struct StageRef {
+    long long meta_off;    // ints into SweepPlan::meta
+    long long vals_off;    // doubles into the sweep's value stream (even)
+    int meta_ints, vals_doubles;
+    int g_lo, g_rows;      // rhs copy: rows [g_lo, g_lo + g_rows), both even
+};
+struct PartRef { int stage_begin, stage_end, row0, nrows; };
+struct BuildRef {          // one per chunk: where the factor values of the chunk come from
+    long long vals_off;    // doubles into the value stream
+    int src_off;           // into SweepPlan::src: nd_eff x count p-space block indices (-1: padding)
+    int count, nd_eff, pad;
+};
+
+struct SweepPlan {
+    std::vector<int> meta;
+    std::vector<StageRef> stages;
+    std::vector<PartRef> parts;
+    std::vector<BuildRef> build;
+    std::vector<int> src;
+    long long nvals = 0;
+    int maxMetaInts = 4, maxValsDoubles = 2, maxRhsRows = 2;
+    long long nchunks = 0, nentries = 0, nExternal = 0, nWindow = 0;
+};
+
 struct Analysis {
     int Nb = 0;
     int64_t nnzb = 0;
-    int nlev = 0;
+    int nlev = 0;                     // reference level sets (lower-triangular DAG)
     LevelSchedule sched;              // reference-identical schedule (exported for parity)
-    std::vector<int> perm;            // p-space row -> natural row (levels ascending, rows sorted inside a level)
+    std::vector<int> perm;            // p-space row -> natural row
     std::vector<int> iperm;           // natural row -> p-space row
-    std::vector<int> levelPtr;        // nlev + 1, in p-space rows
-    std::vector<int> prow, pcol;      // pattern of P A P^T (columns ascending)
+    std::vector<int> prow, pcol;      // pattern of the permuted matrix; entries of a row keep their NATURAL column order
     std::vector<int> pdiag;           // index of the diagonal block of each p-space row
     std::vector<int> srcblk;          // p-space block -> natural block index
-    std::vector<int> chunks;          // trisolve work chunks: start * 16 + count, never crossing a level
+    // factorisation schedule: p-space rows grouped by global level of the symmetrised pattern
+    int nflev = 0;
+    std::vector<int> flevPtr, flevRows;
+    // triangular sweeps
+    int nparts = 0, nlines = 0, window = 0;
+    int nstrips = 0;
+    std::vector<int> partPtr;         // nparts + 1, p-space rows
+    std::vector<int> partMaxStep;     // rows in the largest level step of each part
+    SweepPlan L, U;
+    int64_t nnzL = 0;                 // strictly lower blocks
     int maxRowLen = 0;
 };
 
-inline Analysis analyse(int Nb, const int* rows, const int* cols)
+struct AnalysisOptions {
+    int parts = 148;            // resident CTAs of the sweep kernels
+    int stageBytes = 16384;     // meta + values + rhs of one ring slot
+    int window = 2048;          // rows of the part kept in the shared-memory window (power of two)
+};
+
+namespace detail {
+
+inline void build_sweep(const Analysis& A, const int* rows, const int* cols, const std::vector<int>& glev,
+                        const std::vector<int>& partOf, bool lower, const AnalysisOptions& opt, SweepPlan& S)
+{
+    const int W = A.window;
+    S.parts.resize(A.nparts);
+    struct TmpChunk { int g0, count, nd, level; std::vector<int> cols, src; };
+    for (int p = 0; p < A.nparts; ++p) {
+        const int row0 = A.partPtr[p], nrows = A.partPtr[p + 1] - row0;
+        const int slack = W - A.partMaxStep[p];
+        S.parts[p].stage_begin = (int) S.stages.size();
+        S.parts[p].row0 = row0;
+        S.parts[p].nrows = nrows;
+        std::vector<TmpChunk> st;       // pending stage
+        int st_bytes = 0, st_glo = 0, st_ghi = 0;
+        int prev_level = -1;            // level of the last chunk emitted in this part
+        auto flush = [&]() {
+            if (st.empty()) return;
+            std::vector<std::pair<int, int>> entries;   // (chunk_begin | barrier, nchunks): runs of equal level
+            for (size_t c = 0; c < st.size();) {
+                size_t e = c;
+                while (e < st.size() && st[e].level == st[c].level) ++e;
+                const bool barrier = prev_level >= 0 && st[c].level != prev_level;
+                entries.emplace_back((int) c | (barrier ? (int) 0x80000000u : 0), (int) (e - c));
+                prev_level = st[c].level;
+                c = e;
+            }
+            const int nent = (int) entries.size(), nch = (int) st.size();
+            const int off_chunks = (4 + 2 * nent + 3) & ~3;
+            const int off_cols = off_chunks + 4 * nch;
+            int ncols = 0;
+            for (auto& c : st) ncols += c.nd * c.count;
+            const int meta_ints = (off_cols + ncols + 3) & ~3;
+            StageRef R{};
+            R.meta_off = (long long) S.meta.size();
+            R.meta_ints = meta_ints;
+            R.vals_off = S.nvals;
+            const int glo_al = st_glo & ~1, ghi_al = (st_ghi + 1) & ~1;
+            R.g_lo = glo_al;
+            R.g_rows = ghi_al - glo_al;
+            S.meta.resize(S.meta.size() + meta_ints, 0);
+            int* m = S.meta.data() + R.meta_off;
+            m[0] = nent; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows;
+            for (int e = 0; e < nent; ++e) { m[4 + 2 * e] = entries[e].first; m[5 + 2 * e] = entries[e].second; }
+            int co = off_cols;
+            long long vo = 0;
+            for (int c = 0; c < nch; ++c) {
+                const TmpChunk& t = st[c];
+                const int nd_eff = t.nd + (lower ? 0 : 1);
+                m[off_chunks + 4 * c + 0] = t.g0;
+                m[off_chunks + 4 * c + 1] = t.count | (t.nd << 8);
+                m[off_chunks + 4 * c + 2] = co;
+                m[off_chunks + 4 * c + 3] = (int) vo;
+                std::copy(t.cols.begin(), t.cols.end(), m + co);
+                co += t.nd * t.count;
+                BuildRef B{};
+                B.vals_off = R.vals_off + vo;
+                B.src_off = (int) S.src.size();
+                B.count = t.count;
+                B.nd_eff = nd_eff;
+                S.src.insert(S.src.end(), t.src.begin(), t.src.end());
+                S.build.push_back(B);
+                vo += (long long) nd_eff * 9 * t.count;
+            }
+            vo = (vo + 1) & ~1LL;
+            if (vo > INT_MAX || S.src.size() > (size_t) INT_MAX) throw std::runtime_error("sweep stage too large");
+            R.vals_doubles = (int) vo;
+            S.nvals += vo;
+            S.maxMetaInts = std::max(S.maxMetaInts, meta_ints);
+            S.maxValsDoubles = std::max(S.maxValsDoubles, R.vals_doubles);
+            S.maxRhsRows = std::max(S.maxRhsRows, R.g_rows);
+            S.nchunks += nch;
+            S.nentries += nent;
+            S.stages.push_back(R);
+            st.clear();
+            st_bytes = 0;
+        };
+        // walk the part in processing order: positions 0..nrows-1 (lower) or reversed (upper)
+        auto g_of = [&](int ps) { return lower ? row0 + ps : row0 + nrows - 1 - ps; };
+        int pos = 0;
+        while (pos < nrows) {
+            const int lev = glev[A.perm[g_of(pos)]];
+            int end = pos;
+            while (end < nrows && glev[A.perm[g_of(end)]] == lev) ++end;
+            for (int s = pos; s < end; s += kRowsPerWarp) {
+                TmpChunk t;
+                t.count = std::min(kRowsPerWarp, end - s);
+                t.g0 = g_of(s);
+                t.level = lev;
+                t.nd = 0;
+                for (int q = 0; q < t.count; ++q) {
+                    const int r = A.perm[g_of(s + q)];
+                    int n = 0;
+                    for (int k = rows[r]; k < rows[r + 1]; ++k) n += lower ? cols[k] < r : cols[k] > r;
+                    t.nd = std::max(t.nd, n);
+                }
+                if (t.nd > 0xffff) throw std::runtime_error("block row too long for the sweep chunk descriptor");
+                const int nd_eff = t.nd + (lower ? 0 : 1);
+                t.cols.assign((size_t) t.nd * t.count, kPadCol);
+                t.src.assign((size_t) nd_eff * t.count, -1);
+                for (int q = 0; q < t.count; ++q) {
+                    const int ps = s + q, g = g_of(ps), r = A.perm[g];
+                    int j = 0;
+                    for (int k = rows[r]; k < rows[r + 1]; ++k) {
+                        const int c = cols[k];
+                        if (lower ? c < r : c > r) {
+                            const int gd = A.iperm[c];
+                            int code = -(gd + 1);
+                            if (partOf[c] == p) {
+                                const int pd = lower ? gd - row0 : row0 + nrows - 1 - gd;      // processing position of the dependency
+                                if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
+                                if (ps - pd <= slack) { code = pd; S.nWindow++; }
+                            }
+                            if (code < 0) S.nExternal++;
+                            t.cols[(size_t) j * t.count + q] = code;
+                            t.src[(size_t) j * t.count + q] = A.prow[g] + (k - rows[r]);
+                            ++j;
+                        }
+                    }
+                    if (!lower) t.src[(size_t) t.nd * t.count + q] = A.pdiag[g];
+                }
+                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8;
+                if (!st.empty() && st_bytes + bytes > opt.stageBytes) flush();
+                if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 64; }
+                const int glo = lower ? t.g0 : t.g0 - t.count + 1, ghi = lower ? t.g0 + t.count : t.g0 + 1;
+                st_glo = std::min(st_glo, glo); st_ghi = std::max(st_ghi, ghi);
+                st_bytes += bytes;
+                st.push_back(std::move(t));
+            }
+            pos = end;
+        }
+        flush();
+        S.parts[p].stage_end = (int) S.stages.size();
+    }
+}
+
+}  // namespace detail
+
+inline Analysis analyse(int Nb, const int* rows, const int* cols, const AnalysisOptions& opt = AnalysisOptions())
 {
     Analysis A;
     A.Nb = Nb;
     A.nnzb = rows[Nb];
     if (rows[0] != 0) throw std::runtime_error("rows[0] must be 0");
+    if (Nb >= (1 << 30)) throw std::runtime_error("Nb too large");
+    if (opt.window < 64 || (opt.window & (opt.window - 1))) throw std::runtime_error("window must be a power of two >= 64");
+    A.window = opt.window;
     for (int r = 0; r < Nb; ++r) {
         bool diag = false;
         for (int k = rows[r]; k < rows[r + 1]; ++k) {
             if (k > rows[r] && cols[k] <= cols[k - 1]) throw std::runtime_error("columns must be strictly ascending in every row");
             diag |= (cols[k] == r);
+            A.nnzL += cols[k] < r;
         }
         if (!diag) throw std::runtime_error("diagonal block missing in block row " + std::to_string(r));
+        A.maxRowLen = std::max(A.maxRowLen, rows[r + 1] - rows[r]);
     }
     A.sched = level_schedule(Nb, rows, cols);
     A.nlev = A.sched.nlev;
-    A.levelPtr = A.sched.levelPtr;
-    // own ordering: same level sets, rows ascending inside a level (gather locality)
+
+    // symmetrised lower adjacency: for row i all j < i with A_ij != 0 or A_ji != 0.  Levels taken on it
+    // are valid for BOTH sweeps (forward over L ascending, backward over U descending) even if the
+    // pattern is not structurally symmetric; for symmetric patterns they are the reference's level sets.
+    std::vector<int> sptr(Nb + 1, 0), sadj;
+    {
+        std::vector<int> cnt(Nb, 0);
+        for (int r = 0; r < Nb; ++r)
+            for (int k = rows[r]; k < rows[r + 1]; ++k) {
+                const int c = cols[k];
+                if (c < r) cnt[r]++;
+                else if (c > r) cnt[c]++;        // transpose entry (c, r) with r < c
+            }
+        for (int r = 0; r < Nb; ++r) sptr[r + 1] = sptr[r] + cnt[r];
+        sadj.resize(std::max(sptr[Nb], 1));
+        std::vector<int> fill(sptr.begin(), sptr.end() - 1);
+        for (int r = 0; r < Nb; ++r)
+            for (int k = rows[r]; k < rows[r + 1]; ++k) {
+                const int c = cols[k];
+                if (c < r) sadj[fill[r]++] = c;
+                else if (c > r) sadj[fill[c]++] = r;
+            }
+        // duplicates (entry present in both triangles) are harmless for max-level computations
+    }
+    std::vector<int> glev(Nb, 0);
+    int ng = 0;
+    for (int r = 0; r < Nb; ++r) {
+        int l = 0;
+        for (int k = sptr[r]; k < sptr[r + 1]; ++k) l = std::max(l, glev[sadj[k]] + 1);
+        glev[r] = l;
+        ng = std::max(ng, l + 1);
+    }
+    A.nflev = ng;
+
+    // ---- lines: maximal runs of consecutive rows each depending on its predecessor ---------------------
+    const int Preq = std::max(1, opt.parts);
+    const int lineCap = std::max(16, (Nb + Preq - 1) / Preq);
+    std::vector<int> lineOf(Nb), lineStart;
+    {
+        int len = 0;
+        for (int r = 0; r < Nb; ++r) {
+            bool chained = false;
+            if (r > 0 && len < lineCap)
+                for (int k = sptr[r]; k < sptr[r + 1]; ++k) chained |= (sadj[k] == r - 1);
+            if (!chained) { lineStart.push_back(r); len = 0; }
+            lineOf[r] = (int) lineStart.size() - 1;
+            ++len;
+        }
+    }
+    const int nlines = (int) lineStart.size();
+    lineStart.push_back(Nb);
+    A.nlines = nlines;
+    std::vector<double> lweight(nlines, 0.0);
+    std::vector<int> lfar(nlines, 0);       // largest line-index distance to a lower neighbour line
+    for (int r = 0; r < Nb; ++r) {
+        const int l = lineOf[r];
+        lweight[l] += (double) (rows[r + 1] - rows[r]) + 1.0;
+        for (int k = sptr[r]; k < sptr[r + 1]; ++k) lfar[l] = std::max(lfar[l], l - lineOf[sadj[k]]);
+    }
+    // lines per "plane": the typical far offset (median over the lines that have one)
+    int perPlane = 1;
+    {
+        std::vector<int> far;
+        for (int l = 0; l < nlines; ++l) if (lfar[l] > 1) far.push_back(lfar[l]);
+        if ((int64_t) far.size() * 10 >= nlines && !far.empty()) {
+            std::nth_element(far.begin(), far.begin() + far.size() / 2, far.end());
+            perPlane = far[far.size() / 2];
+        }
+    }
+    const int P = std::min(Preq, nlines);
+    const int nplanes = std::max(1, nlines / std::max(1, perPlane));
+    const double T = (double) nlines / P;                       // lines per part
+    int tk = (int) std::lround(std::sqrt(T));
+    tk = std::max(1, std::min(tk, nplanes));
+    int G = (int) std::lround((double) nplanes / tk);
+    G = std::max(1, std::min(G, P));
+    A.nstrips = G;
+    // strips: consecutive lines in natural order, equal weight
+    double totalw = 0.0;
+    for (double w : lweight) totalw += w;
+    std::vector<int> stripOf(nlines);
+    std::vector<double> stripw(G, 0.0);
+    {
+        double cum = 0.0;
+        for (int l = 0; l < nlines; ++l) {
+            int s = (int) ((cum + 0.5 * lweight[l]) * G / totalw);
+            s = std::max(0, std::min(G - 1, s));
+            stripOf[l] = s;
+            stripw[s] += lweight[l];
+            cum += lweight[l];
+        }
+    }
+    // bands per strip: P shared out in proportion to strip weight (largest remainder), at least 1 where lines exist
+    std::vector<int> bands(G, 0);
+    {
+        std::vector<std::pair<double, int>> rem;
+        int used = 0;
+        for (int s = 0; s < G; ++s) {
+            const double share = stripw[s] / totalw * P;
+            bands[s] = (int) share;
+            if (bands[s] == 0 && stripw[s] > 0.0) bands[s] = 1;
+            used += bands[s];
+            rem.emplace_back(share - (int) share, s);
+        }
+        std::sort(rem.begin(), rem.end(), [](auto& a, auto& b) { return a.first > b.first; });
+        for (size_t i = 0; used < P && !rem.empty(); ++i, ++used) bands[rem[i % rem.size()].second]++;
+        while (used > P) {                                 // the >= 1 floor may overshoot
+            int big = (int) (std::max_element(bands.begin(), bands.end()) - bands.begin());
+            if (bands[big] <= 1) break;
+            bands[big]--; used--;
+        }
+    }
+    // inside a strip: lines ordered by the level of their first row (a diagonal band), cut by weight
+    std::vector<int> partOfLine(nlines, -1);
+    int nparts = 0;
+    {
+        std::vector<std::vector<int>> linesOf(G);
+        for (int l = 0; l < nlines; ++l) linesOf[stripOf[l]].push_back(l);
+        for (int s = 0; s < G; ++s) {
+            auto& v = linesOf[s];
+            if (v.empty()) continue;
+            std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return glev[lineStart[a]] < glev[lineStart[b]]; });
+            const int B = std::max(1, std::min<int>(bands[s], (int) v.size()));
+            double cum = 0.0;
+            int lastBand = -1;
+            const int base = nparts;
+            for (int l : v) {
+                int b = (int) ((cum + 0.5 * lweight[l]) * B / stripw[s]);
+                b = std::max(0, std::min(B - 1, b));
+                if (b > lastBand + 1) b = lastBand + 1;     // no empty bands
+                if (b > lastBand) lastBand = b;
+                partOfLine[l] = base + b;
+                cum += lweight[l];
+            }
+            nparts = base + lastBand + 1;
+        }
+    }
+    A.nparts = nparts;
+    std::vector<int> partOf(Nb);
+    for (int r = 0; r < Nb; ++r) partOf[r] = partOfLine[lineOf[r]];
+
+    // ---- p-space: part-major, then (global level, natural row) -----------------------------------------
+    A.partPtr.assign(nparts + 1, 0);
+    for (int r = 0; r < Nb; ++r) A.partPtr[partOf[r] + 1]++;
+    for (int p = 0; p < nparts; ++p) A.partPtr[p + 1] += A.partPtr[p];
     A.perm.resize(Nb);
     A.iperm.resize(Nb);
     {
-        std::vector<int> fill(A.levelPtr.begin(), A.levelPtr.end() - 1);
-        for (int r = 0; r < Nb; ++r) A.perm[fill[A.sched.level[r]]++] = r;
+        std::vector<int> fill(A.partPtr.begin(), A.partPtr.end() - 1);
+        for (int r = 0; r < Nb; ++r) A.perm[fill[partOf[r]]++] = r;
+        for (int p = 0; p < nparts; ++p)
+            std::stable_sort(A.perm.begin() + A.partPtr[p], A.perm.begin() + A.partPtr[p + 1],
+                             [&](int a, int b) { return glev[a] < glev[b]; });
         for (int q = 0; q < Nb; ++q) A.iperm[A.perm[q]] = q;
     }
+    A.partMaxStep.assign(nparts, 0);
+    for (int p = 0; p < nparts; ++p) {
+        int run = 0;
+        for (int q = A.partPtr[p]; q < A.partPtr[p + 1]; ++q) {
+            run = (q > A.partPtr[p] && glev[A.perm[q]] == glev[A.perm[q - 1]]) ? run + 1 : 1;
+            A.partMaxStep[p] = std::max(A.partMaxStep[p], run);
+        }
+    }
+
+    // permuted BSR pattern: rows permuted, every row keeps its entries in natural column order (so the
+    // left-looking elimination order and the L/U split are exactly those of the natural-order reference)
     A.prow.resize((size_t) Nb + 1);
     A.pcol.resize(A.nnzb);
-    A.srcblk.resize(A.nnzb);
     A.pdiag.resize(Nb);
+    A.srcblk.resize(A.nnzb);
     A.prow[0] = 0;
     for (int q = 0; q < Nb; ++q) {
         const int r = A.perm[q];
         A.prow[q + 1] = A.prow[q] + (rows[r + 1] - rows[r]);
-        A.maxRowLen = std::max(A.maxRowLen, rows[r + 1] - rows[r]);
     }
-    std::vector<std::pair<int, int>> tmp;
     for (int q = 0; q < Nb; ++q) {
         const int r = A.perm[q];
-        tmp.clear();
-        for (int k = rows[r]; k < rows[r + 1]; ++k) tmp.emplace_back(A.iperm[cols[k]], k);
-        std::sort(tmp.begin(), tmp.end());
         int o = A.prow[q];
-        for (auto& e : tmp) {
-            A.pcol[o] = e.first;
-            A.srcblk[o] = e.second;
-            if (e.first == q) A.pdiag[q] = o;
-            ++o;
+        for (int k = rows[r]; k < rows[r + 1]; ++k, ++o) {
+            A.pcol[o] = A.iperm[cols[k]];
+            A.srcblk[o] = k;
+            if (cols[k] == r) A.pdiag[q] = o;
         }
     }
-    for (int l = 0; l < A.nlev; ++l)
-        for (int s = A.levelPtr[l]; s < A.levelPtr[l + 1]; s += kRowsPerWarp)
-            A.chunks.push_back(s * 16 + std::min(kRowsPerWarp, A.levelPtr[l + 1] - s));
-    if (Nb >= (1 << 27)) throw std::runtime_error("Nb too large for the chunk encoding");
+    // factorisation schedule in p-space rows
+    A.flevPtr.assign(ng + 1, 0);
+    for (int r = 0; r < Nb; ++r) A.flevPtr[glev[r] + 1]++;
+    for (int l = 0; l < ng; ++l) A.flevPtr[l + 1] += A.flevPtr[l];
+    A.flevRows.resize(Nb);
+    {
+        std::vector<int> fill(A.flevPtr.begin(), A.flevPtr.end() - 1);
+        for (int q = 0; q < Nb; ++q) A.flevRows[fill[glev[A.perm[q]]]++] = q;
+    }
+    detail::build_sweep(A, rows, cols, glev, partOf, true, opt, A.L);
+    detail::build_sweep(A, rows, cols, glev, partOf, false, opt, A.U);
     return A;
+}
+
+// ---- host emulation of the sweep kernels (schedule verification without a GPU) ---------------------
+//
+// Interprets the packed streams exactly as k_sweep does, one chunk at a time, round-robin over the
+// parts; a chunk whose out-of-window dependency has not been produced yet makes its part yield.
+// Returns false if a full round makes no progress (the schedule would deadlock on the device).
+inline void fill_stream_host(const SweepPlan& S, const double* LU, std::vector<double>& vals)
+{
+    vals.assign((size_t) std::max<long long>(S.nvals, 1), 0.0);
+    for (const BuildRef& B : S.build)
+        for (int j = 0; j < B.nd_eff; ++j)
+            for (int q = 0; q < B.count; ++q) {
+                const int k = S.src[B.src_off + j * B.count + q];
+                for (int comp = 0; comp < 3; ++comp)
+                    for (int v = 0; v < 3; ++v)
+                        vals[B.vals_off + (size_t) (j * 3 + v) * 3 * B.count + 3 * q + comp] = k >= 0 ? LU[(size_t) k * 9 + comp * 3 + v] : 0.0;
+            }
+}
+
+inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, const std::vector<double>& vals, const double* rhs,
+                          double* out, double relax)
+{
+    const int W = A.window;
+    const double NaN = std::nan("");
+    for (int i = 0; i < 3 * A.Nb; ++i) out[i] = NaN;
+    struct Cursor { int stage, entry, chunk; std::vector<double> win; };
+    std::vector<Cursor> cur(A.nparts);
+    for (int p = 0; p < A.nparts; ++p) cur[p] = {S.parts[p].stage_begin, 0, 0, std::vector<double>((size_t) 3 * W, NaN)};
+    int remaining = A.nparts;
+    std::vector<char> done(A.nparts, 0);
+    while (remaining > 0) {
+        bool progress = false;
+        for (int p = 0; p < A.nparts; ++p) {
+            if (done[p]) continue;
+            Cursor& c = cur[p];
+            const PartRef& P = S.parts[p];
+            while (true) {
+                if (c.stage >= P.stage_end) { done[p] = 1; --remaining; progress = true; break; }
+                const StageRef& R = S.stages[c.stage];
+                const int* m = S.meta.data() + R.meta_off;
+                const int nent = m[0];
+                if (c.entry >= nent) { c.stage++; c.entry = 0; c.chunk = 0; continue; }
+                const int cb = m[4 + 2 * c.entry] & 0x7fffffff, nc = m[5 + 2 * c.entry];
+                if (c.chunk >= nc) { c.entry++; c.chunk = 0; continue; }
+                const int off_chunks = (4 + 2 * nent + 3) & ~3;
+                const int* d = m + off_chunks + 4 * (cb + c.chunk);
+                const int g0 = d[0], count = d[1] & 255, nd = d[1] >> 8, co = d[2], vo = d[3];
+                const double* v = vals.data() + R.vals_off + vo;
+                bool ready = true;
+                for (int j = 0; j < nd && ready; ++j)
+                    for (int q = 0; q < count; ++q) {
+                        const int code = m[co + j * count + q];
+                        if (code < 0 && code != kPadCol && std::isnan(out[3 * (size_t) (-(code + 1))])) { ready = false; break; }
+                    }
+                if (!ready) break;      // yield to the next part
+                double res[kRowsPerWarp][3];
+                for (int q = 0; q < count; ++q) {
+                    const int g = lower ? g0 + q : g0 - q;
+                    if (g < R.g_lo || g >= R.g_lo + R.g_rows) throw std::runtime_error("emulate: row outside the stage's rhs window");
+                    double acc[3];
+                    for (int comp = 0; comp < 3; ++comp) {
+                        double a = rhs[3 * (size_t) g + comp];
+                        for (int j = 0; j < nd; ++j) {
+                            const int code = m[co + j * count + q];
+                            if (code == kPadCol) continue;
+                            const double* x = code >= 0 ? c.win.data() + 3 * (size_t) (code & (W - 1)) : out + 3 * (size_t) (-(code + 1));
+                            for (int e = 0; e < 3; ++e) {
+                                if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
+                                a -= v[(size_t) (j * 3 + e) * 3 * count + 3 * q + comp] * x[e];
+                            }
+                        }
+                        acc[comp] = a;
+                    }
+                    for (int comp = 0; comp < 3; ++comp) {
+                        double r = acc[comp];
+                        if (!lower) {
+                            r = 0.0;
+                            for (int e = 0; e < 3; ++e) r += v[(size_t) (nd * 3 + e) * 3 * count + 3 * q + comp] * acc[e];
+                            r *= relax;
+                        }
+                        res[q][comp] = r;
+                    }
+                }
+                for (int q = 0; q < count; ++q) {
+                    const int g = lower ? g0 + q : g0 - q;
+                    const int pos = lower ? g - P.row0 : P.row0 + P.nrows - 1 - g;
+                    for (int comp = 0; comp < 3; ++comp) {
+                        c.win[3 * (size_t) (pos & (W - 1)) + comp] = res[q][comp];
+                        out[3 * (size_t) g + comp] = res[q][comp];
+                    }
+                }
+                c.chunk++;
+                progress = true;
+            }
+        }
+        if (!progress) return false;
+    }
+    return true;
 }
 
 }  // namespace b200

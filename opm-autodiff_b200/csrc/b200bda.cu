@@ -57,9 +57,9 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-enum Kind { K_PERMUTE, K_INIT, K_FACTOR, K_LOWER, K_UPPER, K_SPMV, K_WELL, K_VEC_P, K_VEC_XR1, K_VEC_XR2,
+enum Kind { K_PERMUTE, K_INIT, K_FACTOR, K_SLICES, K_LOWER, K_UPPER, K_SPMV, K_WELL, K_VEC_P, K_VEC_XR1, K_VEC_XR2,
             K_UNPERMUTE, K_MISC, K_COUNT };
-static const char* kKindNames[K_COUNT] = {"permute", "init", "ilu_factor", "ilu_lower", "ilu_upper", "spmv",
+static const char* kKindNames[K_COUNT] = {"permute", "init", "ilu_factor", "ilu_stream", "ilu_lower", "ilu_upper", "spmv",
                                           "well_apply", "vec_p", "vec_xr1", "vec_xr2", "unpermute", "misc"};
 
 struct KStat {
@@ -83,18 +83,26 @@ struct Solver {
     double tolerance = 1e-2, relaxation = 1.0;
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
-    int trsv_blocks_per_sm = 2, trsv_sleep_ns = 0;
+    // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
+    int sweep_parts = 0, sweep_warps = 8, sweep_slots = 6, sweep_stage_bytes = 16384, sweep_window = 2048;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
-    int trsv_blocks = 0, vec_blocks = 0, trsv_occ = 1;
+    int vec_blocks = 0;
+    size_t smem_optin = 0, sweep_smem = 0;
+    int sweep_metaCap = 0, sweep_valsCap = 0, sweep_rhsCap = 0;
 
     bool analysed = false, have_system = false, have_factor = false;
     int N = 0, Nb = 0;
     long long nnz = 0, nnzb = 0;
     Analysis an;
 
-    DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_chunks;
+    DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows;
+    DevBuf<StageD> d_stagesL, d_stagesU;
+    DevBuf<PartD> d_partsL, d_partsU;
+    DevBuf<BuildD> d_buildL, d_buildU;
+    DevBuf<int> d_metaL, d_metaU, d_srcL, d_srcU;
+    DevBuf<double> d_valL, d_valU;
     DevBuf<double> d_stage, d_bstage, d_A, d_LU;
     DevBuf<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_w, d_xnat, d_tmp1, d_tmp2;
     DevBuf<double> d_partials;
@@ -205,35 +213,74 @@ struct Solver {
         CUDA_OK(cudaMemsetAsync(d_ticket.p, 0, sizeof(unsigned), stream));
         CUDA_OK(cudaMemsetAsync(d_S.p, 0, sizeof(Scalars), stream));
         for (cudaEvent_t* e2 : {&ev_a, &ev_b, &ev_c, &ev_d}) CUDA_OK(cudaEventCreate(e2));
-        int occ = 0;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trsv<true>, kTrsvThreads, 0));
-        int occ2 = 0;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_trsv<false>, kTrsvThreads, 0));
-        occ = std::min(occ, occ2);
-        if (occ < 1) throw CudaError("triangular-solve kernel does not fit on an SM");
-        trsv_occ = occ;
-        trsv_blocks = num_sms * std::min(occ, trsv_blocks_per_sm);   // every CTA resident: required by the dataflow sweep
+        smem_optin = prop.sharedMemPerBlockOptin;
         vec_blocks = std::min(num_sms * 8, kMaxPartials);
         if (verbosity > 0)
-            fprintf(stderr, "[b200bda] device %d: %s, %d SMs, trsv grid %d x %d, vec grid %d x %d\n", device, prop.name,
-                    num_sms, trsv_blocks, kTrsvThreads, vec_blocks, kVecThreads);
+            fprintf(stderr, "[b200bda] device %d: %s, %d SMs, %zu B smem/CTA, vec grid %d x %d\n", device, prop.name,
+                    num_sms, smem_optin, vec_blocks, kVecThreads);
     }
 
     void analyse(int N_, long long nnz_, const int* rows, const int* cols)
     {
         Nb = N_ / 3; N = N_; nnz = nnz_; nnzb = nnz_ / 9;
         if (rows[Nb] != nnzb) throw std::runtime_error("rows[Nb] != nnz / 9");
-        an = b200::analyse(Nb, rows, cols);
-        d_prow.alloc(Nb + 1); d_pcol.alloc(nnzb); d_pdiag.alloc(Nb); d_srcblk.alloc(nnzb); d_perm.alloc(Nb);
-        d_chunks.alloc(an.chunks.size());
-        CUDA_OK(cudaMemcpyAsync(d_prow.p, an.prow.data(), sizeof(int) * (Nb + 1), cudaMemcpyHostToDevice, stream));
-        CUDA_OK(cudaMemcpyAsync(d_pcol.p, an.pcol.data(), sizeof(int) * nnzb, cudaMemcpyHostToDevice, stream));
-        CUDA_OK(cudaMemcpyAsync(d_pdiag.p, an.pdiag.data(), sizeof(int) * Nb, cudaMemcpyHostToDevice, stream));
-        CUDA_OK(cudaMemcpyAsync(d_srcblk.p, an.srcblk.data(), sizeof(int) * nnzb, cudaMemcpyHostToDevice, stream));
-        CUDA_OK(cudaMemcpyAsync(d_perm.p, an.perm.data(), sizeof(int) * Nb, cudaMemcpyHostToDevice, stream));
-        CUDA_OK(cudaMemcpyAsync(d_chunks.p, an.chunks.data(), sizeof(int) * an.chunks.size(), cudaMemcpyHostToDevice, stream));
+        AnalysisOptions opt;
+        opt.parts = sweep_parts > 0 ? std::min(sweep_parts, num_sms) : num_sms;      // every CTA of a sweep must be resident
+        opt.stageBytes = sweep_stage_bytes;
+        opt.window = sweep_window;
+        an = b200::analyse(Nb, rows, cols, opt);
+        static_assert(sizeof(StageD) == sizeof(StageRef) && sizeof(PartD) == sizeof(PartRef) && sizeof(BuildD) == sizeof(BuildRef),
+                      "device/host sweep descriptor mismatch");
+        auto up = [&](auto& dbuf, const auto& hvec) {
+            dbuf.alloc(hvec.size());
+            if (!hvec.empty())
+                CUDA_OK(cudaMemcpyAsync(dbuf.p, hvec.data(), sizeof(hvec[0]) * hvec.size(), cudaMemcpyHostToDevice, stream));
+        };
+        up(d_prow, an.prow); up(d_pcol, an.pcol); up(d_pdiag, an.pdiag); up(d_srcblk, an.srcblk); up(d_perm, an.perm);
+        up(d_flevRows, an.flevRows);
+        up(d_metaL, an.L.meta); up(d_metaU, an.U.meta); up(d_srcL, an.L.src); up(d_srcU, an.U.src);
+        d_stagesL.alloc(an.L.stages.size()); d_stagesU.alloc(an.U.stages.size());
+        d_partsL.alloc(an.nparts); d_partsU.alloc(an.nparts);
+        d_buildL.alloc(an.L.build.size()); d_buildU.alloc(an.U.build.size());
+        auto upraw = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
+        upraw(d_stagesL.p, an.L.stages.data(), sizeof(StageRef) * an.L.stages.size());
+        upraw(d_stagesU.p, an.U.stages.data(), sizeof(StageRef) * an.U.stages.size());
+        upraw(d_partsL.p, an.L.parts.data(), sizeof(PartRef) * an.nparts);
+        upraw(d_partsU.p, an.U.parts.data(), sizeof(PartRef) * an.nparts);
+        upraw(d_buildL.p, an.L.build.data(), sizeof(BuildRef) * an.L.build.size());
+        upraw(d_buildU.p, an.U.build.data(), sizeof(BuildRef) * an.U.build.size());
+        d_valL.alloc((size_t) an.L.nvals + 2); d_valU.alloc((size_t) an.U.nvals + 2);
+        // sweep launch shape: one CTA per part, ring of `slots` stages + the row window in shared memory
+        sweep_metaCap = std::max(an.L.maxMetaInts, an.U.maxMetaInts);
+        sweep_valsCap = std::max(an.L.maxValsDoubles, an.U.maxValsDoubles);
+        sweep_rhsCap = std::max(an.L.maxRhsRows, an.U.maxRhsRows);
+        const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
+        sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
+        while (sweep_slots > 2 && 128 + (size_t) sweep_window * 24 + sweep_slots * slotBytes > smem_optin) --sweep_slots;
+        sweep_smem = 128 + (size_t) sweep_window * 24 + sweep_slots * slotBytes;
+        if (sweep_smem > smem_optin)
+            throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
+                                     std::to_string(slotBytes) + " B per stage)");
+        if (an.nparts > num_sms) throw std::runtime_error("internal: more sweep parts than SMs");
+        CUDA_OK(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
+        CUDA_OK(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
+        int occ = 0, occ2 = 0;
+        const int threads = (sweep_warps + 1) * 32;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<true>, threads, sweep_smem));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_sweep<false>, threads, sweep_smem));
+        if (std::min(occ, occ2) < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
+        if (verbosity > 0)
+            fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts; "
+                            "L: %zu stages %lld chunks (%lld window / %lld global deps), U: %zu stages; sweep grid %d x %d, "
+                            "%d slots x %zu B + window %d rows = %zu B smem\n",
+                    Nb, (long long) nnzb, an.nlev, an.nlines, an.nstrips, an.nparts, an.L.stages.size(), an.L.nchunks, an.L.nWindow,
+                    an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, slotBytes, sweep_window, sweep_smem);
         d_stage.alloc(nnz); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
-        for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) v->alloc(N);
+        // + 8 doubles: the sweeps' 16-byte aligned rhs copies may read one row past the end
+        for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) {
+            v->alloc(N + 8);
+            CUDA_OK(cudaMemsetAsync(v->p, 0, sizeof(double) * (N + 8), stream));
+        }
         CUDA_OK(cudaMemsetAsync(d_xnat.p, 0, sizeof(double) * N, stream));
         CUDA_OK(cudaMemsetAsync(d_v.p, 0, sizeof(double) * N, stream));
         CUDA_OK(cudaMemsetAsync(d_p.p, 0, sizeof(double) * N, stream));
@@ -344,27 +391,47 @@ struct Solver {
     void factorize()
     {
         CUDA_OK(cudaMemsetAsync(&d_S.p->singular, 0, sizeof(int), stream));
-        for (int l = 0; l < an.nlev; ++l) {
-            int row0 = an.levelPtr[l], nrows = an.levelPtr[l + 1] - row0;
+        for (int l = 0; l < an.nflev; ++l) {
+            int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
             int id = prof_begin(K_FACTOR);
-            k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, row0, nrows, d_S.p);
+            k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             prof_end(id);
         }
+        int id = prof_begin(K_SLICES);
+        k_fill_stream<<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+            d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p);
+        prof_end(id);
+        id = prof_begin(K_SLICES);
+        k_fill_stream<<<blocks_for((long long) an.U.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+            d_buildU.p, (int) an.U.build.size(), d_srcU.p, d_LU.p, d_valU.p);
+        prof_end(id);
         have_factor = true;
     }
 
-    void trsv_lower(const double* rhs, double* out, Scalars* S)
+    SweepArgs sweep_args(bool lower, const double* rhs, double* out, double* rearm, bool check_done) const
+    {
+        SweepArgs a;
+        a.stages = lower ? d_stagesL.p : d_stagesU.p;
+        a.parts = lower ? d_partsL.p : d_partsU.p;
+        a.meta = lower ? d_metaL.p : d_metaU.p;
+        a.vals = lower ? d_valL.p : d_valU.p;
+        a.rhs = rhs; a.out = out; a.rearm = rearm; a.S = d_S.p;
+        a.relax = lower ? 1.0 : relaxation;
+        a.nparts = an.nparts; a.nslots = sweep_slots; a.window = sweep_window;
+        a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap;
+        a.check_done = check_done ? 1 : 0;
+        return a;
+    }
+    void trsv_lower(const double* rhs, double* out, bool check_done)
     {
         int id = prof_begin(K_LOWER);
-        k_trsv<true><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
-                                                              (int) an.chunks.size(), rhs, out, nullptr, 1.0, S, trsv_sleep_ns);
+        k_sweep<true><<<an.nparts, (sweep_warps + 1) * 32, sweep_smem, stream>>>(sweep_args(true, rhs, out, nullptr, check_done));
         prof_end(id);
     }
-    void trsv_upper(const double* rhs, double* out, double* rearm, Scalars* S)
+    void trsv_upper(const double* rhs, double* out, double* rearm, bool check_done)
     {
         int id = prof_begin(K_UPPER);
-        k_trsv<false><<<trsv_blocks, kTrsvThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, d_chunks.p,
-                                                               (int) an.chunks.size(), rhs, out, rearm, relaxation, S, trsv_sleep_ns);
+        k_sweep<false><<<an.nparts, (sweep_warps + 1) * 32, sweep_smem, stream>>>(sweep_args(false, rhs, out, rearm, check_done));
         prof_end(id);
     }
     template <int MODE>
@@ -391,15 +458,15 @@ struct Solver {
         id = prof_begin(K_VEC_P);
         k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
-        trsv_lower(d_p.p, d_w.p, d_S.p);
-        trsv_upper(d_w.p, d_y.p, d_w.p, d_S.p);
+        trsv_lower(d_p.p, d_w.p, true);
+        trsv_upper(d_w.p, d_y.p, d_w.p, true);
         spmv<1>(d_y.p, d_v.p, d_rt.p);
         wells_apply<1>(d_y.p, d_v.p, d_rt.p);
         id = prof_begin(K_VEC_XR1);
         k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p);
         prof_end(id);
-        trsv_lower(d_r.p, d_w.p, d_S.p);
-        trsv_upper(d_w.p, d_y.p, d_w.p, d_S.p);
+        trsv_lower(d_r.p, d_w.p, true);
+        trsv_upper(d_w.p, d_y.p, d_w.p, true);
         spmv<2>(d_y.p, d_t.p, d_r.p);
         wells_apply<2>(d_y.p, d_t.p, d_r.p);
         id = prof_begin(K_VEC_XR2);
@@ -555,8 +622,15 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
-        else if (k == "trsv_blocks_per_sm") { s->trsv_blocks_per_sm = std::max(1, (int) value); s->trsv_blocks = s->num_sms * std::min(s->trsv_occ, s->trsv_blocks_per_sm); }
-        else if (k == "trsv_sleep_ns") s->trsv_sleep_ns = std::max(0, (int) value);
+        else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window") {
+            if (s->analysed) throw std::runtime_error(k + " must be set before the first solve");
+            const int v = (int) value;
+            if (k == "sweep_parts") s->sweep_parts = std::max(0, v);
+            else if (k == "sweep_warps") s->sweep_warps = std::min(15, std::max(1, v));
+            else if (k == "sweep_slots") s->sweep_slots = std::min(kSweepMaxSlots, std::max(2, v));
+            else if (k == "sweep_stage_bytes") s->sweep_stage_bytes = std::max(1024, v);
+            else s->sweep_window = v;
+        }
         else throw std::runtime_error("unknown option '" + k + "'");
         return B200_SUCCESS;
     });
@@ -779,8 +853,8 @@ b200_status b200_ilu0_apply(b200_solver* s, const double* d, double* v)
         s->to_device_p(d, s->d_tmp2.p);
         s->fill(s->d_w.p, host_sentinel());
         s->fill(s->d_y.p, host_sentinel());
-        s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr);
-        s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr);
+        s->trsv_lower(s->d_tmp2.p, s->d_w.p, false);
+        s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, false);
         s->to_host_nat(s->d_y.p, v);
         return B200_SUCCESS;
     });
@@ -828,6 +902,70 @@ b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, i
     }, B200_ANALYSIS_FAILED);
 }
 
+// Host-only verification of the sweep schedule (no device): analyse the pattern, fill L/U with random
+// values, run the packed streams through the chunk-by-chunk emulator and compare with the sequential
+// natural-order substitution.  stats: [nparts, nlines, nstrips, stagesL, stagesU, chunksL, windowDepsL, globalDepsL,
+// maxMetaInts, maxValsDoubles, maxRhsRows, levels].
+b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int stage_bytes, int window,
+                                           unsigned seed, double* max_rel_err, long long* stats)
+{
+    return guarded([&]() -> b200_status {
+        if (Nb <= 0 || !rows || !cols) throw std::runtime_error("bad arguments");
+        AnalysisOptions opt;
+        if (parts > 0) opt.parts = parts;
+        if (stage_bytes > 0) opt.stageBytes = stage_bytes;
+        if (window > 0) opt.window = window;
+        Analysis A = analyse(Nb, rows, cols, opt);
+        const long long nnzb = rows[Nb];
+        // pseudo-random factor in the permuted pattern: small off-diagonal blocks, well-conditioned "inverse pivots"
+        std::vector<double> LU((size_t) nnzb * 9);
+        unsigned long long st = seed * 2654435761ull + 88172645463325252ull;
+        auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double) (st >> 11) / 9007199254740992.0 - 0.5; };
+        for (int q = 0; q < Nb; ++q)
+            for (int k = A.prow[q]; k < A.prow[q + 1]; ++k)
+                for (int e = 0; e < 9; ++e)
+                    LU[(size_t) k * 9 + e] = (k == A.pdiag[q] ? (e % 4 == 0 ? 1.0 : 0.0) : 0.0) + 0.3 * rnd();
+        std::vector<double> rhs((size_t) 3 * Nb + 8), y((size_t) 3 * Nb + 8), x((size_t) 3 * Nb + 8), yr((size_t) 3 * Nb), xr((size_t) 3 * Nb);
+        for (int i = 0; i < 3 * Nb; ++i) rhs[i] = rnd();
+        // sequential reference in NATURAL order on p-space storage
+        for (int r = 0; r < Nb; ++r) {
+            const int q = A.iperm[r];
+            double acc[3] = {rhs[3 * q], rhs[3 * q + 1], rhs[3 * q + 2]};
+            for (int k = A.prow[q]; k < A.pdiag[q]; ++k)
+                for (int c = 0; c < 3; ++c)
+                    for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * yr[3 * (size_t) A.pcol[k] + e];
+            for (int c = 0; c < 3; ++c) yr[3 * (size_t) q + c] = acc[c];
+        }
+        for (int r = Nb - 1; r >= 0; --r) {
+            const int q = A.iperm[r];
+            double acc[3] = {yr[3 * q], yr[3 * q + 1], yr[3 * q + 2]};
+            for (int k = A.pdiag[q] + 1; k < A.prow[q + 1]; ++k)
+                for (int c = 0; c < 3; ++c)
+                    for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * xr[3 * (size_t) A.pcol[k] + e];
+            const double* d = LU.data() + (size_t) A.pdiag[q] * 9;
+            for (int c = 0; c < 3; ++c) xr[3 * (size_t) q + c] = d[c * 3] * acc[0] + d[c * 3 + 1] * acc[1] + d[c * 3 + 2] * acc[2];
+        }
+        std::vector<double> vL, vU;
+        fill_stream_host(A.L, LU.data(), vL);
+        fill_stream_host(A.U, LU.data(), vU);
+        if (!emulate_sweep(A, A.L, true, vL, rhs.data(), y.data(), 1.0)) throw std::runtime_error("lower sweep schedule deadlocks");
+        if (!emulate_sweep(A, A.U, false, vU, y.data(), x.data(), 1.0)) throw std::runtime_error("upper sweep schedule deadlocks");
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < 3 * Nb; ++i) {
+            num = std::max(num, std::fabs(x[i] - xr[i]) + std::fabs(y[i] - yr[i]));
+            den = std::max(den, std::fabs(xr[i]));
+        }
+        if (max_rel_err) *max_rel_err = den > 0.0 ? num / den : num;
+        if (stats) {
+            const long long v[12] = {A.nparts, A.nlines, A.nstrips, (long long) A.L.stages.size(), (long long) A.U.stages.size(), A.L.nchunks,
+                                     A.L.nWindow, A.L.nExternal, std::max(A.L.maxMetaInts, A.U.maxMetaInts),
+                                     std::max(A.L.maxValsDoubles, A.U.maxValsDoubles), std::max(A.L.maxRhsRows, A.U.maxRhsRows), A.nlev};
+            memcpy(stats, v, sizeof v);
+        }
+        return B200_SUCCESS;
+    }, B200_ANALYSIS_FAILED);
+}
+
 static int kind_of(const std::string& k)
 {
     if (k == "ilu_apply") return -2;
@@ -867,9 +1005,9 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
             CUDA_OK(cudaEventRecord(s->ev_c, s->stream));
             switch (kind) {
                 case K_SPMV: s->spmv<0>(s->d_y.p, s->d_t.p, nullptr); break;
-                case K_LOWER: s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr); break;
-                case K_UPPER: s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr); break;
-                case -2: s->trsv_lower(s->d_tmp2.p, s->d_w.p, nullptr); s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, nullptr); break;
+                case K_LOWER: s->trsv_lower(s->d_tmp2.p, s->d_w.p, false); break;
+                case K_UPPER: s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, false); break;
+                case -2: s->trsv_lower(s->d_tmp2.p, s->d_w.p, false); s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, false); break;
                 case K_FACTOR: s->factorize(); break;
                 case K_PERMUTE: s->permute_values(); break;
                 case K_VEC_P: s->stats[K_VEC_P].launches++; s->launch_count++;

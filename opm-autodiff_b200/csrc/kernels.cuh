@@ -22,7 +22,7 @@ namespace b200 {
 constexpr unsigned long long kSentinel = 0x7FF8DEADBEEF0B20ULL;   // quiet-NaN payload: "not computed yet"
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kVecThreads = 256;
-constexpr int kTrsvThreads = 256;
+constexpr int kPadColD = (int) 0x80000000;   // == analysis.hpp kPadCol (INT_MIN)
 constexpr int kMaxPartials = 4096;     // per reduced quantity
 
 // Device-resident Krylov state: scalars never round-trip through the host inside the loop.
@@ -184,17 +184,18 @@ __device__ __forceinline__ bool inv3(const double* m, double* inv)
     return det != 0.0 && isfinite(det);
 }
 
-// One warp factorises one block row of the level [row0, row0+nrows): copies the row of A into LU,
-// eliminates the lower entries in ascending column order (rows of earlier levels are final),
-// inverts the pivot.  Lanes 0..8 own one scalar of the 3x3 block being produced.
+// One warp factorises one block row of the level (p-space rows rowlist[0..nrows)): copies the row of A
+// into LU, eliminates the lower entries in ascending NATURAL column order (the order the entries of a
+// p-space row are stored in; rows of earlier levels are final), inverts the pivot.  Lanes 0..8 own one
+// scalar of the 3x3 block being produced.
 __global__ void __launch_bounds__(256) k_ilu_factor_level(const int* __restrict__ prow, const int* __restrict__ pcol,
                                                           const int* __restrict__ pdiag, const double* __restrict__ A,
-                                                          double* LU, int row0, int nrows, Scalars* S)
+                                                          double* LU, const int* __restrict__ rowlist, int nrows, Scalars* S)
 {
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= nrows) return;
-    const int i = row0 + wid;
+    const int i = rowlist[wid];
     const int rs = prow[i], re = prow[i + 1], di = pdiag[i];
     for (int q = rs * 9 + lane; q < re * 9; q += 32) LU[q] = A[q];
     __syncwarp();
@@ -239,134 +240,258 @@ __global__ void __launch_bounds__(256) k_ilu_factor_level(const int* __restrict_
     }
 }
 
-// ---- triangular solves (sync-free, dataflow through the output vector) -------------------------
+// ---- triangular solves: pencil-pipelined sweeps -----------------------------------------------------
+//
+// Device mirrors of analysis.hpp's StageRef / PartRef / BuildRef (layout checked by static_assert in
+// b200bda.cu).
+struct StageD { long long meta_off, vals_off; int meta_ints, vals_doubles, g_lo, g_rows; };
+struct PartD { int stage_begin, stage_end, row0, nrows; };
+struct BuildD { long long vals_off; int src_off, count, nd_eff, pad; };
 
-// Persistent kernel, every warp resident.  A warp owns chunks of <= 10 rows of ONE level
-// (3 lanes per block row, lane = 3*row + component) and walks the chunk list round-robin, forward
-// for L, backward for U.  A dependency x_j is consumed straight from `out`, which the producer of
-// row j overwrites (relaxed gpu-scope 8-byte stores) after it was armed with a NaN sentinel: the
-// value is its own ready flag, so the critical path per level is one L2 round trip and there is no
-// grid-wide barrier between the ~nx+ny+nz levels.  Everything that does not depend on other rows
-// (chunk descriptor, row pointers, column indices, factor values, rhs) is loaded BEFORE the wait,
-// the descriptors one chunk ahead, so only the poll -> fma -> store chain is exposed.  While
-// waiting a warp polls a single value per row (the last component of its highest-numbered
-// dependency) and validates the rest once that one has landed.  `rearm` (may be null) is re-armed
-// for the next sweep that uses it as an output.
-constexpr int kTrsvBatch = 4;      // dependencies held in registers at a time
-
-template <bool LOWER>
-__global__ void __launch_bounds__(kTrsvThreads) k_trsv(const int* __restrict__ prow, const int* __restrict__ pcol,
-                                                       const int* __restrict__ pdiag, const double* __restrict__ LU,
-                                                       const int* __restrict__ chunks, int nchunks,
-                                                       const double* __restrict__ rhs, double* out, double* rearm,
-                                                       double relax, Scalars* S, int sleep_ns)
+// Scatter the BSR factor (p-space) into the lane-major value stream of one sweep: one warp per chunk,
+// stream value ((j*3 + v) * 3 count + 3 q + comp) = LU[src(j, q)][comp][v].
+__global__ void __launch_bounds__(256) k_fill_stream(const BuildD* __restrict__ build, int nchunks, const int* __restrict__ src,
+                                                     const double* __restrict__ LU, double* __restrict__ vals)
 {
-    if (S != nullptr && S->done) return;
     const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int W = (gridDim.x * blockDim.x) >> 5;
-    const int q = lane / 3, comp = lane - 3 * q;
-    if (gw >= nchunks) return;
-
-    auto chunk_at = [&](int c) { return chunks[LOWER ? c : nchunks - 1 - c]; };
-    // descriptor pipeline: enc (chunk c), then its row bounds; next chunk's enc is fetched one trip early
-    int enc = chunk_at(gw);
-    int enc_next = gw + W < nchunks ? chunk_at(gw + W) : 0;
-    int kb = 0, ke = 0, kd = 0;
-    {
-        const int i0 = (enc >> 4) + q;
-        if (q < (enc & 15)) { kd = pdiag[i0]; kb = LOWER ? prow[i0] : kd + 1; ke = LOWER ? kd : prow[i0 + 1]; }
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nchunks; c += (gridDim.x * blockDim.x) >> 5) {
+        const BuildD b = build[c];
+        const int per_j = 9 * b.count, total = b.nd_eff * per_j, lanes = 3 * b.count;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int j = idx / per_j, rem = idx - j * per_j;
+            const int v = rem / lanes, l = rem - v * lanes;
+            const int q = l / 3, comp = l - 3 * q;
+            const int k = src[b.src_off + j * b.count + q];
+            vals[b.vals_off + idx] = k >= 0 ? LU[(size_t) k * 9 + comp * 3 + v] : 0.0;
+        }
     }
-    for (int c = gw; c < nchunks; c += W) {
-        const int start = enc >> 4, count = enc & 15;
-        const bool act = q < count;
-        const int i = start + q;
-        const int nk = act ? ke - kb : 0;
-        double acc = act ? rhs[3 * i + comp] : 0.0;
-        double inv0 = 0.0, inv1 = 0.0, inv2 = 0.0;
-        if (!LOWER && act) {
-            const double* inv = LU + (size_t) kd * 9 + comp * 3;
-            inv0 = inv[0]; inv1 = inv[1]; inv2 = inv[2];
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// suspends the warp in hardware until the phase with the given parity has completed
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int kSweepBatch = 3;         // dependency slots kept in registers (7-point stencils need 3)
+constexpr int kSweepMaxSlots = 8;      // ring slots (full + empty mbarriers fit the 128-byte header)
+
+struct SweepArgs {
+    const StageD* stages;
+    const PartD* parts;
+    const int* meta;
+    const double* vals;
+    const double* rhs;
+    double* out;
+    double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
+    Scalars* S;
+    double relax;
+    int nparts, nslots, window, metaCap, valsCap, rhsCap, check_done;
+};
+
+// One triangular sweep.  One persistent CTA per PART (pencil of grid lines, analysis.hpp), all resident.
+//   producer warp : walks the part's stages and fetches each one -- meta ints, lane-major factor values,
+//                   rhs rows, all contiguous in processing order -- with three bulk copies (TMA unit,
+//                   UBLKCP) into a ring of shared-memory slots, several stages ahead of the consumers:
+//                   HBM latency never sits on the dependency chain;
+//   consumer warps: a chunk = <= 10 rows of one level, 3 lanes per row.  Dependencies inside the part are
+//                   read from a shared-memory WINDOW of the most recent rows (written by the consumers,
+//                   ~30 cycles), levels are separated by one named barrier; dependencies on other parts
+//                   are read from global `out`, which every sweep finds armed with a NaN sentinel and every
+//                   producer overwrites with relaxed gpu-scope 8-byte stores -- the value is its own
+//                   ready flag, one L2 hop (0.25-0.46 us) and only on pencil faces.
+// Parts process their rows in ascending (descending for U) global level, a topological order of the
+// whole DAG, so the waits cannot cycle as long as every CTA is resident (grid <= SMs).
+template <bool LOWER>
+__global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
+{
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
+    if (P.check_done && P.S->done) return;
+    const int part = blockIdx.x;
+    if (part >= P.nparts) return;
+    const PartD pr = P.parts[part];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
+    unsigned long long* empty = full + kSweepMaxSlots;
+    double* win = reinterpret_cast<double*>(sweep_smem + 128);
+    unsigned char* slots = reinterpret_cast<unsigned char*>(win + 3 * (size_t) P.window);
+    const size_t metaBytes = (size_t) P.metaCap * 4, valsBytes = (size_t) P.valsCap * 8, rhsBytes = (size_t) P.rhsCap * 24;
+    const size_t slotBytes = metaBytes + valsBytes + rhsBytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NW = (blockDim.x >> 5) - 1;          // consumer warps; the last warp is the producer
+    const int nslots = P.nslots;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int nst = pr.stage_end - pr.stage_begin;
+
+    if (warp == NW) {                               // ---- producer ----
+        if (lane == 0) {
+            for (int i = 0; i < nst; ++i) {
+                const int s = i % nslots;
+                if (i >= nslots) mbar_wait(empty + s, ((i / nslots) - 1) & 1);
+                const StageD R = P.stages[pr.stage_begin + i];
+                unsigned char* base = slots + (size_t) s * slotBytes;
+                const unsigned bm = (unsigned) R.meta_ints * 4, bv = (unsigned) R.vals_doubles * 8, br = (unsigned) R.g_rows * 24;
+                mbar_expect_tx(full + s, bm + bv + br);
+                bulk_g2s(base, P.meta + R.meta_off, bm, full + s);
+                if (bv) bulk_g2s(base + metaBytes, P.vals + R.vals_off, bv, full + s);
+                bulk_g2s(base + metaBytes + valsBytes, P.rhs + 3 * (size_t) R.g_lo, br, full + s);
+            }
         }
-        // first batch of this chunk: columns + factor values into registers
-        int col[kTrsvBatch];
-        double a[kTrsvBatch][3];
+        return;
+    }
+
+    // ---- consumers ----
+    const int q = lane / 3, comp = lane - 3 * q;
+    const int wmask = P.window - 1;
+    const int nthreads = NW * 32;
+    for (int i = 0; i < nst; ++i) {
+        const int s = i % nslots;
+        mbar_wait(full + s, (i / nslots) & 1);
+        const unsigned char* base = slots + (size_t) s * slotBytes;
+        const int* m = reinterpret_cast<const int*>(base);
+        const double* vv = reinterpret_cast<const double*>(base + metaBytes);
+        const double* rr = reinterpret_cast<const double*>(base + metaBytes + valsBytes);
+        const int nent = m[0], g_lo = m[2];
+        const int off_chunks = (4 + 2 * nent + 3) & ~3;
+        for (int e = 0; e < nent; ++e) {
+            const int e0 = m[4 + 2 * e], nc = m[5 + 2 * e];
+            const int cb = e0 & 0x7fffffff;
+            bool synced = e0 >= 0;                  // sign bit: a barrier separates this entry from earlier levels
+            for (int c = warp; c < nc; c += NW) {
+                const int4 d = *reinterpret_cast<const int4*>(m + off_chunks + 4 * (cb + c));
+                const int count = d.y & 255, nd = d.y >> 8;
+                const bool act = q < count;
+                const int g = LOWER ? d.x + q : d.x - q;
+                const int lanes = 3 * count;
+                // everything that does not depend on other rows, before the barrier
+                int col[kSweepBatch];
+                double a[kSweepBatch][3], x[kSweepBatch][3];
+                const double* vb = vv + d.w + lane;
 #pragma unroll
-        for (int j = 0; j < kTrsvBatch; ++j) {
-            const bool on = j < nk;
-            const int k = on ? kb + j : 0;
-            col[j] = on ? pcol[k] : -1;
-            const double* ap = LU + (size_t) k * 9 + comp * 3;
-            a[j][0] = on ? ap[0] : 0.0; a[j][1] = on ? ap[1] : 0.0; a[j][2] = on ? ap[2] : 0.0;
-        }
-        // descriptors of the NEXT chunk of this warp (consumed after the wait below)
-        int nkb = 0, nke = 0, nkd = 0;
-        const int enc_cur_next = enc_next;
-        if (c + W < nchunks) {
-            const int i1 = (enc_cur_next >> 4) + q;
-            if (q < (enc_cur_next & 15)) { nkd = pdiag[i1]; nkb = LOWER ? prow[i1] : nkd + 1; nke = LOWER ? nkd : prow[i1 + 1]; }
-            enc_next = c + 2 * W < nchunks ? chunk_at(c + 2 * W) : 0;
-        }
-        for (int k0 = 0; __any_sync(kFull, k0 < nk); k0 += kTrsvBatch) {
-            if (k0 > 0) {
+                for (int j = 0; j < kSweepBatch; ++j) {
+                    const bool on = act && j < nd;
+                    col[j] = on ? m[d.z + j * count + q] : kPadColD;
 #pragma unroll
-                for (int j = 0; j < kTrsvBatch; ++j) {
-                    const bool on = k0 + j < nk;
-                    const int k = on ? kb + k0 + j : 0;
-                    col[j] = on ? pcol[k] : -1;
-                    const double* ap = LU + (size_t) k * 9 + comp * 3;
-                    a[j][0] = on ? ap[0] : 0.0; a[j][1] = on ? ap[1] : 0.0; a[j][2] = on ? ap[2] : 0.0;
+                    for (int v = 0; v < 3; ++v) a[j][v] = on ? vb[(j * 3 + v) * lanes] : 0.0;
                 }
-            }
-            // cheap wait: one 8-byte poll per row on the dependency most likely to land last
-            int watch = -1;
+                double acc = act ? rr[3 * (g - g_lo) + comp] : 0.0;
+                double inv[3] = {0.0, 0.0, 0.0};
+                if (!LOWER && act) {
 #pragma unroll
-            for (int j = 0; j < kTrsvBatch; ++j) watch = max(watch, col[j]);
-            if (!LOWER) {            // backward sweep: the lowest-numbered dependency is produced last
-                watch = 0x7fffffff;
-#pragma unroll
-                for (int j = 0; j < kTrsvBatch; ++j) if (col[j] >= 0) watch = min(watch, col[j]);
-                if (watch == 0x7fffffff) watch = -1;
-            }
-            int spins = 0;
-            if (watch >= 0) {
-                const double* wp = out + 3 * (size_t) watch + 2;
-                while (is_sentinel(ld_relaxed(wp))) {
-                    if (++spins > (1 << 22)) { if (S != nullptr) S->trsv_timeout = 1; break; }
-                    if (sleep_ns > 0) __nanosleep(sleep_ns);
+                    for (int v = 0; v < 3; ++v) inv[v] = vb[(nd * 3 + v) * lanes];
                 }
-            }
-            // validate + fetch everything (normally a single pass)
-            double x[kTrsvBatch][3];
-            while (true) {
-                bool ready = true;
+                // dependencies on other parts: request them now, they land while the warp waits for its level
 #pragma unroll
-                for (int j = 0; j < kTrsvBatch; ++j) {
-                    if (col[j] >= 0) {
-                        const double* xp = out + 3 * (size_t) col[j];
-                        x[j][0] = ld_relaxed(xp); x[j][1] = ld_relaxed(xp + 1); x[j][2] = ld_relaxed(xp + 2);
-                        ready = ready && !(is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2]));
-                    } else {
-                        x[j][0] = 0.0; x[j][1] = 0.0; x[j][2] = 0.0;
+                for (int j = 0; j < kSweepBatch; ++j) {
+                    const bool ext = col[j] < 0 && col[j] != kPadColD;
+                    const double* xp = P.out + 3 * (size_t) (ext ? -(col[j] + 1) : 0);
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) x[j][v] = ext ? ld_relaxed(xp + v) : 0.0;
+                }
+                if (!synced) { named_barrier(1, nthreads); synced = true; }
+                // ---- exposed part: window reads, fma, publish ----
+#pragma unroll
+                for (int j = 0; j < kSweepBatch; ++j) {
+                    const int cj = col[j];
+                    if (cj >= 0) {
+                        const double* xp = win + 3 * (cj & wmask);
+                        x[j][0] = xp[0]; x[j][1] = xp[1]; x[j][2] = xp[2];
+                    } else if (cj != kPadColD) {
+                        int spins = 0;
+                        while (is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2])) {
+                            const double* xp = P.out + 3 * (size_t) (-(cj + 1));
+                            x[j][0] = ld_relaxed(xp); x[j][1] = ld_relaxed(xp + 1); x[j][2] = ld_relaxed(xp + 2);
+                            if ((++spins & 1023) == 0 && (spins > (1 << 21) || *((volatile int*) &P.S->trsv_timeout))) {
+                                P.S->trsv_timeout = 1;
+                                break;
+                            }
+                        }
+                    }
+                    double t = a[j][0] * x[j][0];
+                    t = fma(a[j][1], x[j][1], t);
+                    t = fma(a[j][2], x[j][2], t);
+                    acc -= t;
+                }
+                if (nd > kSweepBatch) {                      // long rows (NNC, wells in the matrix): unpipelined tail
+                    for (int j = kSweepBatch; j < nd; ++j) {
+                        const int cj = act ? m[d.z + j * count + q] : kPadColD;
+                        if (cj == kPadColD) continue;
+                        double x0, x1, x2;
+                        if (cj >= 0) {
+                            const double* xp = win + 3 * (cj & wmask);
+                            x0 = xp[0]; x1 = xp[1]; x2 = xp[2];
+                        } else {
+                            const double* xp = P.out + 3 * (size_t) (-(cj + 1));
+                            int spins = 0;
+                            while (true) {
+                                x0 = ld_relaxed(xp); x1 = ld_relaxed(xp + 1); x2 = ld_relaxed(xp + 2);
+                                if (!(is_sentinel(x0) || is_sentinel(x1) || is_sentinel(x2))) break;
+                                if ((++spins & 1023) == 0 && (spins > (1 << 21) || *((volatile int*) &P.S->trsv_timeout))) {
+                                    P.S->trsv_timeout = 1;
+                                    break;
+                                }
+                            }
+                        }
+                        double t = vb[(j * 3) * lanes] * x0;
+                        t = fma(vb[(j * 3 + 1) * lanes], x1, t);
+                        t = fma(vb[(j * 3 + 2) * lanes], x2, t);
+                        acc -= t;
                     }
                 }
-                if (ready) break;
-                if (++spins > (1 << 22)) { if (S != nullptr) S->trsv_timeout = 1; break; }
+                double res = acc;
+                if (!LOWER) {
+                    const int b3 = act ? 3 * q : 0;
+                    const double s0 = __shfl_sync(kFull, acc, b3);
+                    const double s1 = __shfl_sync(kFull, acc, b3 + 1);
+                    const double s2 = __shfl_sync(kFull, acc, b3 + 2);
+                    res = (inv[0] * s0 + inv[1] * s1 + inv[2] * s2) * P.relax;
+                }
+                if (act) {
+                    const int pos = LOWER ? g - pr.row0 : pr.row0 + pr.nrows - 1 - g;
+                    win[3 * (pos & wmask) + comp] = res;
+                    st_relaxed(P.out + 3 * (size_t) g + comp, res);
+                    if (P.rearm != nullptr) P.rearm[3 * (size_t) g + comp] = sentinel();
+                }
             }
-#pragma unroll
-            for (int j = 0; j < kTrsvBatch; ++j) acc -= a[j][0] * x[j][0] + a[j][1] * x[j][1] + a[j][2] * x[j][2];
+            if (!synced) named_barrier(1, nthreads);        // warps without a chunk of this level still take part
         }
-        if (LOWER) {
-            if (act) st_relaxed(out + 3 * i + comp, acc);
-        } else {
-            const int base = act ? 3 * q : 0;
-            const double s0 = __shfl_sync(kFull, acc, base);
-            const double s1 = __shfl_sync(kFull, acc, base + 1);
-            const double s2 = __shfl_sync(kFull, acc, base + 2);
-            if (act) st_relaxed(out + 3 * i + comp, (inv0 * s0 + inv1 * s1 + inv2 * s2) * relax);
-        }
-        if (rearm != nullptr && act) rearm[3 * i + comp] = sentinel();
-        enc = enc_cur_next; kb = nkb; ke = nke; kd = nkd;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
     }
 }
 

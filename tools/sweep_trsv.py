@@ -1,26 +1,37 @@
 #!/usr/bin/env python
-"""Sweeps the launch knobs of the triangular-solve kernels on one workload (GPU box tool)."""
-import sys, os, json
+"""Sweeps the schedule knobs of the triangular-sweep kernels on one workload (GPU box tool).
+
+  python tools/sweep_trsv.py c3 "parts,warps,slots,stage_bytes[,window];..."
+"""
+import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from opm_autodiff_b200 import bridge, synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-cfg = synth.CONFIGS[name]
+combos = sys.argv[2] if len(sys.argv) > 2 else "148,8,6,16384;148,4,6,16384;148,8,8,8192;148,12,4,32768;74,8,6,16384"
+cfg = synth.CONFIGS[name] if name in synth.CONFIGS else synth.GridConfig("custom", *[int(t) for t in name.split("x")])
 s = synth.full_system(cfg)
-be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
-be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
-be.ilu0_factorize()
-out = []
-for bps in (1, 2, 3, 4, 8):
-    for sl in (0, 32, 100, 300):
-        be.set_option("trsv_blocks_per_sm", bps)
-        be.set_option("trsv_sleep_ns", sl)
+for combo in combos.split(";"):
+    t = [int(v) for v in combo.split(",")]
+    parts, warps, slots, sb = t[:4]
+    window = t[4] if len(t) > 4 else 2048
+    be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
+    for k, v in (("sweep_parts", parts), ("sweep_warps", warps), ("sweep_slots", slots), ("sweep_stage_bytes", sb), ("sweep_window", window)):
+        be.set_option(k, v)
+    t0 = time.time()
+    try:
+        be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
+        t_an = time.time() - t0
+        be.ilu0_factorize()
         lo, byl = be.time_kernel("ilu_lower", 10, True)
         up, byu = be.time_kernel("ilu_upper", 10, True)
-        out.append({"blocks_per_sm": bps, "sleep_ns": sl, "lower_us": round(lo * 1e3, 1), "upper_us": round(up * 1e3, 1),
-                    "apply_gbs": round((byl + byu) / (lo + up) * 1e-6, 1)})
-        print(out[-1], flush=True)
+        print({"parts": parts, "warps": warps, "slots": slots, "stage_bytes": sb, "window": window, "lower_us": round(lo * 1e3, 1),
+               "upper_us": round(up * 1e3, 1), "apply_gbs": round((byl + byu) / (lo + up) * 1e-6, 1), "upload+analysis_s": round(t_an, 2)}, flush=True)
+    except RuntimeError as e:
+        print({"combo": combo, "error": str(e)[:120]}, flush=True)
+    del be
+be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
+be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
 for k in ("spmv", "vec_p", "vec_xr1", "vec_xr2", "permute", "ilu_factor"):
     ms, by = be.time_kernel(k, 10, True)
     print(k, round(ms * 1e3, 1), "us", round(by / ms * 1e-6, 1), "GB/s", flush=True)
