@@ -84,6 +84,7 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
+    int sweep_dbg = 0;
     int sweep_parts = 0, sweep_warps = 8, sweep_slots = 6, sweep_stage_bytes = 16384, sweep_window = 2048;
 
     cudaStream_t stream = nullptr;
@@ -420,6 +421,7 @@ struct Solver {
         a.nparts = an.nparts; a.nslots = sweep_slots; a.window = sweep_window;
         a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap;
         a.check_done = check_done ? 1 : 0;
+        a.dbg = sweep_dbg;
         return a;
     }
     void trsv_lower(const double* rhs, double* out, bool check_done)
@@ -622,6 +624,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "sweep_dbg") s->sweep_dbg = (int) value;
         else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window") {
             if (s->analysed) throw std::runtime_error(k + " must be set before the first solve");
             const int v = (int) value;

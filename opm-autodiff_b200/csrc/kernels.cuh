@@ -318,6 +318,7 @@ struct SweepArgs {
     Scalars* S;
     double relax;
     int nparts, nslots, window, metaCap, valsCap, rhsCap, check_done;
+    int dbg;              // timing experiments only (results are wrong): 1 weak out store, 2 no out store, 4 no level barrier, 8 no wait on other parts
 };
 
 // One triangular sweep.  One persistent CTA per PART (pencil of grid lines, analysis.hpp), all resident.
@@ -359,17 +360,28 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
     const int nst = pr.stage_end - pr.stage_begin;
 
     if (warp == NW) {                               // ---- producer ----
-        if (lane == 0) {
-            for (int i = 0; i < nst; ++i) {
-                const int s = i % nslots;
-                if (i >= nslots) mbar_wait(empty + s, ((i / nslots) - 1) & 1);
-                const StageD R = P.stages[pr.stage_begin + i];
-                unsigned char* base = slots + (size_t) s * slotBytes;
-                const unsigned bm = (unsigned) R.meta_ints * 4, bv = (unsigned) R.vals_doubles * 8, br = (unsigned) R.g_rows * 24;
-                mbar_expect_tx(full + s, bm + bv + br);
-                bulk_g2s(base, P.meta + R.meta_off, bm, full + s);
-                if (bv) bulk_g2s(base + metaBytes, P.vals + R.vals_off, bv, full + s);
-                bulk_g2s(base + metaBytes + valsBytes, P.rhs + 3 * (size_t) R.g_lo, br, full + s);
+        // stage descriptors: one coalesced load per 32 stages (a lane each), the next batch in flight while
+        // this one is issued -- no global-memory latency between two stages
+        StageD cur = {0, 0, 0, 0, 0, 0}, nxt = cur;
+        if (lane < nst) nxt = P.stages[pr.stage_begin + lane];
+        for (int b0 = 0; b0 < nst; b0 += 32) {
+            cur = nxt;
+            if (b0 + 32 + lane < nst) nxt = P.stages[pr.stage_begin + b0 + 32 + lane];
+            const int n = min(32, nst - b0);
+            for (int k = 0; k < n; ++k) {
+                const long long meta_off = __shfl_sync(kFull, cur.meta_off, k), vals_off = __shfl_sync(kFull, cur.vals_off, k);
+                const unsigned bm = (unsigned) __shfl_sync(kFull, cur.meta_ints, k) * 4, bv = (unsigned) __shfl_sync(kFull, cur.vals_doubles, k) * 8;
+                const int g_lo = __shfl_sync(kFull, cur.g_lo, k);
+                const unsigned br = (unsigned) __shfl_sync(kFull, cur.g_rows, k) * 24;
+                if (lane == 0) {
+                    const int i = b0 + k, s = i % nslots;
+                    if (i >= nslots) mbar_wait(empty + s, ((i / nslots) - 1) & 1);
+                    unsigned char* base = slots + (size_t) s * slotBytes;
+                    mbar_expect_tx(full + s, bm + bv + br);
+                    bulk_g2s(base, P.meta + meta_off, bm, full + s);
+                    if (bv) bulk_g2s(base + metaBytes, P.vals + vals_off, bv, full + s);
+                    bulk_g2s(base + metaBytes + valsBytes, P.rhs + 3 * (size_t) g_lo, br, full + s);
+                }
             }
         }
         return;
@@ -423,7 +435,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 #pragma unroll
                     for (int v = 0; v < 3; ++v) x[j][v] = ext ? ld_relaxed(xp + v) : 0.0;
                 }
-                if (!synced) { named_barrier(1, nthreads); synced = true; }
+                if (!synced) { if (!(P.dbg & 4)) named_barrier(1, nthreads); synced = true; }
                 // ---- exposed part: window reads, fma, publish ----
 #pragma unroll
                 for (int j = 0; j < kSweepBatch; ++j) {
@@ -433,7 +445,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                         x[j][0] = xp[0]; x[j][1] = xp[1]; x[j][2] = xp[2];
                     } else if (cj != kPadColD) {
                         int spins = 0;
-                        while (is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2])) {
+                        while (!(P.dbg & 8) && (is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2]))) {
                             const double* xp = P.out + 3 * (size_t) (-(cj + 1));
                             x[j][0] = ld_relaxed(xp); x[j][1] = ld_relaxed(xp + 1); x[j][2] = ld_relaxed(xp + 2);
                             if ((++spins & 1023) == 0 && (spins > (1 << 21) || *((volatile int*) &P.S->trsv_timeout))) {
@@ -484,11 +496,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                 if (act) {
                     const int pos = LOWER ? g - pr.row0 : pr.row0 + pr.nrows - 1 - g;
                     win[3 * (pos & wmask) + comp] = res;
-                    st_relaxed(P.out + 3 * (size_t) g + comp, res);
+                    if (P.dbg & 1) P.out[3 * (size_t) g + comp] = res;
+                    else if (!(P.dbg & 2)) st_relaxed(P.out + 3 * (size_t) g + comp, res);
                     if (P.rearm != nullptr) P.rearm[3 * (size_t) g + comp] = sentinel();
                 }
             }
-            if (!synced) named_barrier(1, nthreads);        // warps without a chunk of this level still take part
+            if (!synced && !(P.dbg & 4)) named_barrier(1, nthreads);        // warps without a chunk of this level still take part
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
