@@ -309,7 +309,7 @@ def main():
         run_b200_single(args)
     else:
         from opm_autodiff_b200 import dist_bench
-        dist_bench.run(args)
+        dist_bench.run(args, METRIC, TOL, MAXIT, get_cfg, ClockSampler, measured_peak)
 
 
 if __name__ == "__main__":

@@ -123,6 +123,44 @@ b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const in
                                   const double* values, unsigned int val_size);
 unsigned int b200_wells_get_num_wells(const b200_wells* w);   /* getNumWells (:152-154 of the .hpp) */
 
+/* ---- multi-GPU: row slabs, halo exchange over NVLink peer memory, NCCL all-reduce ------------ */
+/*
+ * One process and one b200_solver per GPU (rank).  The reference has no multi-GPU accelerator path (it
+ * disables the bridge under MPI, ISTLSolverEbos.hpp:136-141); the semantics implemented here are those of
+ * its MPI CPU path, which is what a lifted ban would have to reproduce:
+ *   - every rank holds the rows it owns, local column numbering with the ghost cells LAST
+ *     (--owner-cells-first, ISTLSolverEbos.hpp:171-180; findOverlapRowsAndColumns.hpp:119-139);
+ *   - operator: owned rows times the (owned + ghost) vector after copyOwnerToAll
+ *     (WellModelGhostLastMatrixAdapter::apply, WellOperators.hpp:200-214);
+ *   - preconditioner: ILU0 of the owned x owned block, no communication (block Jacobi:
+ *     PreconditionerFactory.hpp:237-252, ParallelOverlappingILU0.hpp:440-494,857-895);
+ *   - scalar products: owned entries only, summed over the ranks (Dune::OwnerOverlapCopyCommunication).
+ * In this mode b200_solve_system takes N = 3 * owned rows, a pattern whose column indices run over
+ * owned + n_ghost cells, and b / x of the owned rows only.  Standard wells must lie inside one rank.
+ * Call order: b200_create, b200_dist_init, b200_dist_set_halo, (exchange the IPC handles),
+ * b200_dist_connect_peer per neighbour, then b200_solve_system on every rank collectively.
+ */
+
+/* ncclGetUniqueId: 128 bytes, produced on rank 0 and sent to the other ranks by the host. */
+b200_status b200_dist_unique_id(unsigned char* id128);
+/* Marks the solver as one rank of `world` and joins the NCCL communicator (world == 1: no NCCL needed,
+ * id128 may be NULL). */
+b200_status b200_dist_init(b200_solver* s, int rank, int world, const unsigned char* id128);
+/* Halo plan of this rank.  neigh_rank[n]: ranks exchanged with; send_rows[send_ptr[n] .. send_ptr[n+1]):
+ * owned local rows whose x entries neighbour n needs, in the order n stores them as ghosts;
+ * ghosts [recv_ptr[n], recv_ptr[n+1]) (ghost index = local column - owned rows) are filled by neighbour n.
+ * Allocates the receive block and returns its CUDA IPC handle (64 bytes) for the neighbours. */
+b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const int* neigh_rank, const int* send_ptr,
+                               const int* send_rows, const int* recv_ptr, unsigned char* ipc_handle64);
+/* Maps neighbour neigh_index's receive block.  peer_n_ghost: that rank's ghost count; peer_recv_offset:
+ * first ghost index of MY section there (its recv_ptr[slot]); peer_slot: my index in ITS neighbour list. */
+b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, const unsigned char* peer_ipc_handle64,
+                                   int peer_n_ghost, int peer_recv_offset, int peer_slot);
+/* Collective y_owned = (A [x_owned; x_ghost])_owned on the uploaded system (parity tests). */
+b200_status b200_dist_spmv(b200_solver* s, const double* x_owned_host, double* y_owned_host);
+int b200_dist_rank(const b200_solver* s);
+int b200_dist_world(const b200_solver* s);
+
 /* ---- kernel-level entry points (parity tests, roofline measurement) ------------------------ */
 
 /* All operate on the system uploaded by the last solve/upload call; vectors are host arrays of
@@ -153,7 +191,7 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
 
 /* Time `reps` back-to-back launches of one kernel with CUDA events on the solver's stream.
  * which: "spmv", "ilu_apply", "ilu_lower", "ilu_upper", "ilu_factor", "vec_p", "vec_xr1", "vec_xr2",
- * "well_apply", "permute".  Returns the mean milliseconds per launch and the ALGORITHMIC bytes one
+ * "well_apply", "permute" (b200_kernel_stats also knows "halo_push", "spmv_ghost", "allreduce", "finish").  Returns the mean milliseconds per launch and the ALGORITHMIC bytes one
  * launch moves.  flush_l2 != 0 writes a >L2 scratch buffer before every launch. */
 b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int flush_l2,
                              double* ms_per_launch, double* algorithmic_bytes);

@@ -128,6 +128,13 @@ def lib():
         L.b200_timer_start.argtypes = [vp]
         L.b200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200_device_available.restype = ip
+        L.b200_dist_unique_id.argtypes = [vp]
+        L.b200_dist_init.argtypes = [vp, ip, ip, vp]
+        L.b200_dist_set_halo.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
+        L.b200_dist_connect_peer.argtypes = [vp, ip, vp, ip, ip, ip]
+        L.b200_dist_spmv.argtypes = [vp, _f64p, _f64p]
+        L.b200_dist_rank.argtypes = [vp]
+        L.b200_dist_world.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -140,6 +147,8 @@ EXPORTED_SYMBOLS = [
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
     "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
+    "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_connect_peer", "b200_dist_spmv",
+    "b200_dist_rank", "b200_dist_world",
 ]
 
 
@@ -335,6 +344,33 @@ class B200SolverBackend:
 
     def launch_count(self) -> int:
         return int(lib().b200_launch_count(self._h))
+
+    # -- multi-GPU (one backend per rank; see include/b200bda.h and dist.py) --
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        if lib().b200_dist_unique_id(buf) != 0:
+            raise RuntimeError(last_error())
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: Optional[bytes]) -> None:
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._chk(lib().b200_dist_init(self._h, int(rank), int(world), buf))
+
+    def dist_set_halo(self, n_ghost, neigh_rank, send_ptr, send_rows, recv_ptr) -> bytes:
+        a = [np.ascontiguousarray(v, dtype=np.int32) for v in (neigh_rank, send_ptr, send_rows, recv_ptr)]
+        out = C.create_string_buffer(64)
+        self._chk(lib().b200_dist_set_halo(self._h, int(n_ghost), len(a[0]), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), out))
+        return out.raw
+
+    def dist_connect_peer(self, neigh_index, peer_handle: bytes, peer_n_ghost, peer_recv_offset, peer_slot) -> None:
+        self._chk(lib().b200_dist_connect_peer(self._h, int(neigh_index), C.create_string_buffer(peer_handle, 64),
+                                                int(peer_n_ghost), int(peer_recv_offset), int(peer_slot)))
+
+    def dist_spmv(self, x):
+        y = np.empty(self.N)
+        self._chk(lib().b200_dist_spmv(self._h, np.ascontiguousarray(x, dtype=np.float64).reshape(-1), y))
+        return y
 
     def timer_start(self) -> None:
         self._chk(lib().b200_timer_start(self._h))

@@ -6,6 +6,8 @@
 // There is no CPU fallback: without a CUDA device every computing entry point fails.
 #include "../../include/b200bda.h"
 
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -58,9 +60,66 @@ struct DevBuf {
 };
 
 enum Kind { K_PERMUTE, K_INIT, K_FACTOR, K_SLICES, K_LOWER, K_UPPER, K_SPMV, K_WELL, K_VEC_P, K_VEC_XR1, K_VEC_XR2,
-            K_UNPERMUTE, K_MISC, K_COUNT };
+            K_UNPERMUTE, K_MISC, K_HALO_PUSH, K_SPMV_GHOST, K_ALLREDUCE, K_FINISH, K_COUNT };
 static const char* kKindNames[K_COUNT] = {"permute", "init", "ilu_factor", "ilu_stream", "ilu_lower", "ilu_upper", "spmv",
-                                          "well_apply", "vec_p", "vec_xr1", "vec_xr2", "unpermute", "misc"};
+                                          "well_apply", "vec_p", "vec_xr1", "vec_xr2", "unpermute", "misc",
+                                          "halo_push", "spmv_ghost", "allreduce", "finish"};
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------
+// Only the multi-GPU entry points need NCCL, and a Python host already has torch's libnccl.so.2 mapped:
+// dlopen by soname binds to that copy (one NCCL per process) or, in a plain C++ host, to the system one.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    void load()
+    {
+        if (handle) return;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) throw std::runtime_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+        auto sym = [&](const char* n) {
+            void* f = dlsym(handle, n);
+            if (!f) throw std::runtime_error(std::string("libnccl.so.2 lacks ") + n);
+            return f;
+        };
+        GetUniqueId = (int (*)(NcclId*)) sym("ncclGetUniqueId");
+        CommInitRank = (int (*)(void**, int, NcclId, int)) sym("ncclCommInitRank");
+        CommDestroy = (int (*)(void*)) sym("ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) sym("ncclAllReduce");
+        GetErrorString = (const char* (*)(int)) sym("ncclGetErrorString");
+    }
+};
+static NcclApi g_nccl;
+constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+#define NCCL_OK(expr)                                                                              \
+    do {                                                                                           \
+        int r__ = (expr);                                                                          \
+        if (r__ != 0)                                                                              \
+            throw CudaError(std::string(#expr) + " failed: " + g_nccl.GetErrorString(r__));       \
+    } while (0)
+
+// Multi-GPU state of one rank (row slab with ghosts numbered last).
+struct Dist {
+    bool enabled = false;
+    int rank = 0, world = 1;
+    void* comm = nullptr;
+    // halo plan (host)
+    bool have_halo = false;
+    int n_ghost = 0, nneigh = 0;
+    std::vector<int> neigh_rank, send_ptr, send_rows, recv_ptr;
+    // owned x ghost coupling (built by analyse): boundary rows in p-space
+    int gnrows = 0;
+    long long gnblocks = 0;
+    // peers
+    std::vector<void*> peer_base;           // mapped receive block of each neighbour
+    std::vector<HaloPeerD> peers;
+    unsigned epoch = 0;
+    bool peers_ready = false;
+};
 
 struct KStat {
     long long launches = 0;
@@ -95,8 +154,15 @@ struct Solver {
 
     bool analysed = false, have_system = false, have_factor = false;
     int N = 0, Nb = 0;
-    long long nnz = 0, nnzb = 0;
+    long long nnz = 0, nnzb = 0;              // owned x owned part (what ILU0 and the big SpMV see)
+    long long nnz_stage = 0;                   // the caller's array (owned x (owned + ghost))
     Analysis an;
+
+    Dist dist;
+    DevBuf<unsigned char> d_halo;              // [flags: 64 x u32 | 2 x 3 n_ghost doubles], IPC-exported
+    DevBuf<HaloPeerD> d_peers;
+    DevBuf<int> d_send_prow, d_grow, d_gptr, d_gcol, d_gsrc;
+    DevBuf<unsigned> d_push_tickets;
 
     DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows;
     DevBuf<StageD> d_stagesL, d_stagesU;
@@ -130,6 +196,8 @@ struct Solver {
 
     ~Solver()
     {
+        for (void* p : dist.peer_base) if (p) cudaIpcCloseMemHandle(p);
+        if (dist.comm) g_nccl.CommDestroy(dist.comm);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_b) cudaHostUnregister((void*) reg_b);
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -223,13 +291,52 @@ struct Solver {
 
     void analyse(int N_, long long nnz_, const int* rows, const int* cols)
     {
-        Nb = N_ / 3; N = N_; nnz = nnz_; nnzb = nnz_ / 9;
-        if (rows[Nb] != nnzb) throw std::runtime_error("rows[Nb] != nnz / 9");
+        Nb = N_ / 3; N = N_; nnz_stage = nnz_;
+        const long long nnzb_in = nnz_ / 9;
+        if (rows[Nb] != nnzb_in) throw std::runtime_error("rows[Nb] != nnz / 9");
         AnalysisOptions opt;
         opt.parts = sweep_parts > 0 ? std::min(sweep_parts, num_sms) : num_sms;      // every CTA of a sweep must be resident
         opt.stageBytes = sweep_stage_bytes;
         opt.window = sweep_window;
-        an = b200::analyse(Nb, rows, cols, opt);
+        if (!dist.enabled) {
+            an = b200::analyse(Nb, rows, cols, opt);
+        } else {
+            // Row slab of a partitioned matrix: columns >= Nb are ghosts (numbered last).  The preconditioner is
+            // block-Jacobi ILU0 on the owned x owned block, exactly what the reference's parallel ILU0 does
+            // (ghost_last_bilu0_decomposition, ParallelOverlappingILU0.hpp:440-494 with interiorSize = owned rows);
+            // the owned x ghost blocks only enter the operator (k_spmv_ghost).
+            if (!dist.have_halo) throw std::runtime_error("multi-GPU solver: b200_dist_set_halo must precede the first solve");
+            std::vector<int> sq_rows((size_t) Nb + 1, 0), sq_cols, sq_src, grow_nat, gptr(1, 0), gcol, gsrc;
+            sq_cols.reserve(nnzb_in); sq_src.reserve(nnzb_in);
+            for (int r = 0; r < Nb; ++r) {
+                bool any = false;
+                for (int k = rows[r]; k < rows[r + 1]; ++k) {
+                    const int c = cols[k];
+                    if (c < 0 || c >= Nb + dist.n_ghost) throw std::runtime_error("column index outside owned + ghost range");
+                    if (c < Nb) { sq_cols.push_back(c); sq_src.push_back(k); }
+                    else { gcol.push_back(c - Nb); gsrc.push_back(k); any = true; }
+                }
+                sq_rows[r + 1] = (int) sq_cols.size();
+                if (any) { grow_nat.push_back(r); gptr.push_back((int) gcol.size()); }
+            }
+            an = b200::analyse(Nb, sq_rows.data(), sq_cols.data(), opt);
+            for (auto& b : an.srcblk) b = sq_src[b];            // p-space block -> block of the caller's array
+            dist.gnrows = (int) grow_nat.size();
+            dist.gnblocks = (long long) gcol.size();
+            std::vector<int> grow_p(grow_nat.size()), send_prow(dist.send_rows.size());
+            for (size_t i = 0; i < grow_nat.size(); ++i) grow_p[i] = an.iperm[grow_nat[i]];
+            for (size_t i = 0; i < send_prow.size(); ++i) {
+                if (dist.send_rows[i] < 0 || dist.send_rows[i] >= Nb) throw std::runtime_error("halo send row outside the owned range");
+                send_prow[i] = an.iperm[dist.send_rows[i]];
+            }
+            auto upv = [&](DevBuf<int>& d, const std::vector<int>& h) {
+                d.alloc(h.size());
+                if (!h.empty()) CUDA_OK(cudaMemcpyAsync(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, stream));
+            };
+            upv(d_grow, grow_p); upv(d_gptr, gptr); upv(d_gcol, gcol); upv(d_gsrc, gsrc); upv(d_send_prow, send_prow);
+            CUDA_OK(cudaStreamSynchronize(stream));           // host vectors above are temporaries
+        }
+        nnzb = an.nnzb; nnz = 9 * nnzb;
         static_assert(sizeof(StageD) == sizeof(StageRef) && sizeof(PartD) == sizeof(PartRef) && sizeof(BuildD) == sizeof(BuildRef),
                       "device/host sweep descriptor mismatch");
         auto up = [&](auto& dbuf, const auto& hvec) {
@@ -276,7 +383,7 @@ struct Solver {
                             "%d slots x %zu B + window %d rows = %zu B smem\n",
                     Nb, (long long) nnzb, an.nlev, an.nlines, an.nstrips, an.nparts, an.L.stages.size(), an.L.nchunks, an.L.nWindow,
                     an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, slotBytes, sweep_window, sweep_smem);
-        d_stage.alloc(nnz); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
+        d_stage.alloc(nnz_stage); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
         // + 8 doubles: the sweeps' 16-byte aligned rhs copies may read one row past the end
         for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) {
             v->alloc(N + 8);
@@ -358,13 +465,13 @@ struct Solver {
             double t0 = wall();
             analyse(N_, nnz_, rows, cols);
             *t_analysis = wall() - t0;
-        } else if (N_ != N || nnz_ != nnz) {
+        } else if (N_ != N || nnz_ != nnz_stage) {
             throw std::runtime_error("sparsity pattern changed after the first call (fixed, cusparseSolverBackend.cu:312)");
         }
-        maybe_register(reg_vals, reg_vals_bytes, vals, sizeof(double) * nnz);
+        maybe_register(reg_vals, reg_vals_bytes, vals, sizeof(double) * nnz_stage);
         maybe_register(reg_b, reg_b_bytes, b, sizeof(double) * N);
         CUDA_OK(cudaEventRecord(ev_a, stream));
-        CUDA_OK(cudaMemcpyAsync(d_stage.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(d_stage.p, vals, sizeof(double) * nnz_stage, cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaMemcpyAsync(d_bstage.p, b, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaEventRecord(ev_b, stream));
         upload_wells(wells);
@@ -454,26 +561,85 @@ struct Solver {
         prof_end(id);
     }
 
+    // ---- multi-GPU pieces (no-ops on a single GPU) ------------------------------------------------
+    void allreduce(void* buf, int count, int dtype, int op)
+    {
+        if (!dist.enabled || dist.world == 1) return;
+        int id = prof_begin(K_ALLREDUCE);
+        NCCL_OK(g_nccl.AllReduce(buf, buf, (size_t) count, dtype, op, dist.comm, stream));
+        prof_end(id);
+    }
+    void allreduce_sum(double* buf, int count) { allreduce(buf, count, kNcclFloat64, kNcclSum); }
+    template <int PHASE>
+    void finish()
+    {
+        if (!dist.enabled) return;
+        int id = prof_begin(K_FINISH);
+        k_finish<PHASE><<<1, 32, 0, stream>>>(d_S.p, tolerance, 2 * maxit);
+        prof_end(id);
+    }
+    // boundary entries of y (p-space) -> the neighbours' receive blocks; one epoch per exchange
+    void halo_push(const double* y, bool check_done)
+    {
+        if (!dist.enabled) return;
+        ++dist.epoch;
+        if (dist.nneigh == 0) return;
+        if (!dist.peers_ready) throw std::runtime_error("multi-GPU solver: peers not connected (b200_dist_connect_peer)");
+        int maxsend = 0;
+        for (int n = 0; n < dist.nneigh; ++n) maxsend = std::max(maxsend, dist.send_ptr[n + 1] - dist.send_ptr[n]);
+        const int bx = std::max(1, std::min(32, (3 * maxsend + 2047) / 2048));
+        int id = prof_begin(K_HALO_PUSH);
+        k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, stream>>>(d_peers.p, d_send_prow.p, y, dist.epoch, d_push_tickets.p, d_S.p,
+                                                                check_done ? 1 : 0);
+        prof_end(id);
+    }
+    const double* ghost_x() const
+    {
+        return reinterpret_cast<const double*>(d_halo.p + 256) + (size_t) (dist.epoch & 1u) * 3 * (size_t) dist.n_ghost;
+    }
+    template <int MODE>
+    void spmv_ghost(double* y, const double* d1, bool check_done)
+    {
+        if (!dist.enabled || dist.nneigh == 0 || dist.gnrows == 0) return;
+        int id = prof_begin(K_SPMV_GHOST);
+        const int blocks = blocks_for(3ll * dist.gnrows, kVecThreads, num_sms * 2);
+        k_spmv_ghost<MODE><<<blocks, kVecThreads, 0, stream>>>(dist.gnrows, d_grow.p, d_gptr.p, d_gcol.p, d_gsrc.p, d_stage.p, ghost_x(),
+                                                               reinterpret_cast<const unsigned*>(d_halo.p), dist.nneigh, dist.epoch, y,
+                                                               d1, d_S.p, d_partials.p, d_ticket.p, check_done ? 1 : 0);
+        prof_end(id);
+    }
+
     void enqueue_iteration()
     {
+        const int dm = dist.enabled ? 1 : 0;
         int id;
         id = prof_begin(K_VEC_P);
         k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
         trsv_lower(d_p.p, d_w.p, true);
         trsv_upper(d_w.p, d_y.p, d_w.p, true);
+        halo_push(d_y.p, true);
         spmv<1>(d_y.p, d_v.p, d_rt.p);
         wells_apply<1>(d_y.p, d_v.p, d_rt.p);
+        spmv_ghost<1>(d_v.p, d_rt.p, true);
+        allreduce_sum(&d_S.p->h, 1);
         id = prof_begin(K_VEC_XR1);
-        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p);
+        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
         prof_end(id);
+        allreduce_sum(d_S.p->red, 1);
+        finish<1>();
         trsv_lower(d_r.p, d_w.p, true);
         trsv_upper(d_w.p, d_y.p, d_w.p, true);
+        halo_push(d_y.p, true);
         spmv<2>(d_y.p, d_t.p, d_r.p);
         wells_apply<2>(d_y.p, d_t.p, d_r.p);
+        spmv_ghost<2>(d_t.p, d_r.p, true);
+        allreduce_sum(&d_S.p->tr, 2);
         id = prof_begin(K_VEC_XR2);
-        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p);
+        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
         prof_end(id);
+        allreduce_sum(d_S.p->red, 2);
+        finish<2>();
     }
 
     // permutation + ILU0 + BiCGSTAB on the resident system
@@ -485,10 +651,13 @@ struct Solver {
         permute_values();
         factorize();
         CUDA_OK(cudaEventRecord(ev_b, stream));
+        allreduce(&d_S.p->singular, 1, kNcclInt32, kNcclMax);      // a failed pivot on any rank stops all of them
         int id = prof_begin(K_INIT);
         k_init<<<vec_blocks, kVecThreads, 0, stream>>>(d_bstage.p, d_perm.p, d_r.p, d_rt.p, d_x.p, d_w.p, d_y.p, N, d_S.p,
-                                                        d_partials.p, d_ticket.p, tolerance, 2 * maxit);
+                                                        d_partials.p, d_ticket.p, tolerance, 2 * maxit, dist.enabled ? 1 : 0);
         prof_end(id);
+        allreduce_sum(d_S.p->red, 1);
+        finish<0>();
         int enq = 0;
         while (true) {
             enqueue_iteration();
@@ -790,6 +959,129 @@ b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const in
 }
 unsigned int b200_wells_get_num_wells(const b200_wells* w) { return w ? w->num_std_wells : 0; }
 
+// ---- multi-GPU: one process (and one b200_solver) per GPU ---------------------------------------------
+
+b200_status b200_dist_unique_id(unsigned char* id128)
+{
+    return guarded([&]() -> b200_status {
+        if (!id128) throw std::runtime_error("null argument");
+        g_nccl.load();
+        NcclId id;
+        NCCL_OK(g_nccl.GetUniqueId(&id));
+        memcpy(id128, id.internal, 128);
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_dist_init(b200_solver* s, int rank, int world, const unsigned char* id128)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad arguments");
+        if (s->analysed) throw std::runtime_error("b200_dist_init must precede the first solve");
+        CUDA_OK(cudaSetDevice(s->device));
+        s->dist.enabled = true; s->dist.rank = rank; s->dist.world = world;
+        if (world > 1) {
+            if (!id128) throw std::runtime_error("null NCCL id");
+            g_nccl.load();
+            NcclId id;
+            memcpy(id.internal, id128, 128);
+            NCCL_OK(g_nccl.CommInitRank(&s->dist.comm, world, id, rank));
+        }
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const int* neigh_rank, const int* send_ptr,
+                               const int* send_rows, const int* recv_ptr, unsigned char* ipc_handle64)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || n_ghost < 0 || n_neigh < 0 || n_neigh > 64) throw std::runtime_error("bad arguments");
+        if (!s->dist.enabled) throw std::runtime_error("b200_dist_init first");
+        if (s->analysed) throw std::runtime_error("b200_dist_set_halo must precede the first solve");
+        if (n_neigh > 0 && (!neigh_rank || !send_ptr || !send_rows || !recv_ptr)) throw std::runtime_error("null halo arrays");
+        CUDA_OK(cudaSetDevice(s->device));
+        Dist& D = s->dist;
+        D.n_ghost = n_ghost; D.nneigh = n_neigh;
+        D.neigh_rank.assign(neigh_rank, neigh_rank + n_neigh);
+        D.send_ptr.assign(1, 0); D.recv_ptr.assign(1, 0);
+        if (n_neigh > 0) {
+            D.send_ptr.assign(send_ptr, send_ptr + n_neigh + 1);
+            D.recv_ptr.assign(recv_ptr, recv_ptr + n_neigh + 1);
+            D.send_rows.assign(send_rows, send_rows + send_ptr[n_neigh]);
+            if (D.recv_ptr[n_neigh] != n_ghost) throw std::runtime_error("recv_ptr does not cover the ghost range");
+        } else if (n_ghost != 0) throw std::runtime_error("ghost cells without neighbours");
+        // receive block: flags + two parity buffers; zeroed so that epoch 0 never matches
+        const size_t bytes = 256 + 2 * 3 * (size_t) std::max(n_ghost, 1) * sizeof(double);
+        s->d_halo.alloc(bytes);
+        CUDA_OK(cudaMemset(s->d_halo.p, 0, bytes));
+        s->d_push_tickets.alloc(64);
+        CUDA_OK(cudaMemset(s->d_push_tickets.p, 0, 64 * sizeof(unsigned)));
+        D.peer_base.assign(n_neigh, nullptr);
+        D.peers.assign(n_neigh, HaloPeerD{});
+        D.have_halo = true;
+        D.peers_ready = (n_neigh == 0);
+        if (ipc_handle64) {
+            cudaIpcMemHandle_t h;
+            static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+            CUDA_OK(cudaIpcGetMemHandle(&h, s->d_halo.p));
+            memcpy(ipc_handle64, &h, 64);
+        }
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, const unsigned char* peer_ipc_handle64, int peer_n_ghost,
+                                   int peer_recv_offset, int peer_slot)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !peer_ipc_handle64) throw std::runtime_error("null argument");
+        Dist& D = s->dist;
+        if (!D.have_halo || neigh_index < 0 || neigh_index >= D.nneigh) throw std::runtime_error("bad neighbour index");
+        if (peer_slot < 0 || peer_slot >= 64 || peer_recv_offset < 0 || peer_recv_offset > peer_n_ghost) throw std::runtime_error("bad peer layout");
+        CUDA_OK(cudaSetDevice(s->device));
+        cudaIpcMemHandle_t h;
+        memcpy(&h, peer_ipc_handle64, 64);
+        void* base = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        D.peer_base[neigh_index] = base;
+        HaloPeerD& P = D.peers[neigh_index];
+        P.flag = reinterpret_cast<unsigned*>(base) + peer_slot;
+        P.recv = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(base) + 256) + 3 * (size_t) peer_recv_offset;
+        P.parity_stride = 3ll * peer_n_ghost;
+        P.send_begin = D.send_ptr[neigh_index];
+        P.send_end = D.send_ptr[neigh_index + 1];
+        bool all = true;
+        for (void* p : D.peer_base) all = all && p != nullptr;
+        if (all) {
+            s->d_peers.alloc(D.nneigh);
+            CUDA_OK(cudaMemcpy(s->d_peers.p, D.peers.data(), sizeof(HaloPeerD) * D.nneigh, cudaMemcpyHostToDevice));
+            D.peers_ready = true;
+        }
+        return B200_SUCCESS;
+    });
+}
+
+// y_owned = (A [x_owned; x_ghost])_owned with the halo exchanged over peer memory (collective: every rank calls it)
+b200_status b200_dist_spmv(b200_solver* s, const double* x, double* y)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !x || !y) throw std::runtime_error("null argument");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (!s->dist.enabled) throw std::runtime_error("not a multi-GPU solver");
+        if (!s->have_system) throw std::runtime_error("no system uploaded");
+        if (!s->have_factor) s->permute_values();
+        s->to_device_p(x, s->d_tmp2.p);
+        s->halo_push(s->d_tmp2.p, false);
+        s->spmv<0>(s->d_tmp2.p, s->d_t.p, nullptr);
+        s->spmv_ghost<0>(s->d_t.p, nullptr, false);
+        s->to_host_nat(s->d_t.p, y);
+        return B200_SUCCESS;
+    });
+}
+
+int b200_dist_rank(const b200_solver* s) { return s ? s->dist.rank : 0; }
+int b200_dist_world(const b200_solver* s) { return s ? s->dist.world : 1; }
+
 // ---- kernel-level entry points --------------------------------------------------------------------
 
 b200_status b200_spmv(b200_solver* s, const double* x, double* y)
@@ -869,7 +1161,7 @@ b200_status b200_get_ilu0(b200_solver* s, double* lu)
         if (!s || !lu) throw std::runtime_error("null argument");
         CUDA_OK(cudaSetDevice(s->device));
         s->ensure_factor();
-        std::vector<double> tmp((size_t) s->nnz);
+        std::vector<double> tmp((size_t) s->nnz);     // owned x owned blocks; ghost blocks of lu are left untouched
         CUDA_OK(cudaMemcpyAsync(tmp.data(), s->d_LU.p, sizeof(double) * s->nnz, cudaMemcpyDeviceToHost, s->stream));
         CUDA_OK(cudaStreamSynchronize(s->stream));
         for (long long q = 0; q < s->nnzb; ++q)
@@ -1016,9 +1308,9 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
                 case K_VEC_P: s->stats[K_VEC_P].launches++; s->launch_count++;
                     k_vec_p<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_tmp2.p, s->d_p.p, s->d_v.p, N, s->d_S.p); break;
                 case K_VEC_XR1: s->stats[K_VEC_XR1].launches++; s->launch_count++;
-                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p); break;
+                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0); break;
                 case K_VEC_XR2: s->stats[K_VEC_XR2].launches++; s->launch_count++;
-                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p); break;
+                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0); break;
                 case K_WELL: s->wells_apply<0>(s->d_y.p, s->d_t.p, nullptr); break;
                 default: throw std::runtime_error(std::string("kernel '") + which + "' cannot be timed in isolation");
             }

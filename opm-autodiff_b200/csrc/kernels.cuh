@@ -28,6 +28,7 @@ constexpr int kMaxPartials = 4096;     // per reduced quantity
 // Device-resident Krylov state: scalars never round-trip through the host inside the loop.
 struct Scalars {
     double rho, rho_new, alpha, omega, h, tr, tt, norm, norm0, tol;
+    double red[2];      // multi-GPU: raw local sums waiting for the all-reduce (k_finish consumes them)
     int it_half, done, converged, breakdown, first, max_half, trsv_timeout, singular;
 };
 
@@ -136,11 +137,51 @@ __global__ void __launch_bounds__(256) k_fill(double* __restrict__ a, double v, 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) a[i] = v;
 }
 
+// Scalar epilogues of the three reducing vector phases.  Single GPU: run by the last block of the phase
+// itself.  Multi-GPU: the phase leaves its raw local sums in S->red, an all-reduce sums them over the
+// ranks in place, and k_finish runs the same epilogue -- every rank takes the same decisions from the
+// same bits (cusparseSolverBackend.cu:92-176 for the formulas).
+__device__ __forceinline__ void finish_init(Scalars* S, double rr, double tol, int max_half)
+{
+    S->norm0 = sqrt(rr); S->norm = S->norm0; S->rho_new = rr;
+    S->rho = 1.0; S->alpha = 1.0; S->omega = 1.0; S->h = 0.0; S->tr = 0.0; S->tt = 0.0;
+    S->tol = tol; S->it_half = 0; S->converged = 0; S->breakdown = 0; S->first = 1;
+    S->max_half = max_half; S->trsv_timeout = 0;
+    // Dune: norm0 already below the absolute floor -> converged with 0 iterations
+    S->done = (S->norm0 < 1e-30) ? 1 : 0;
+    if (S->done) S->converged = 1;
+    if (S->singular) S->done = 1;      // factorisation failed: skip the Krylov loop
+}
+__device__ __forceinline__ void finish_xr1(Scalars* S, double rr)
+{
+    S->first = 0;
+    S->norm = sqrt(rr); S->it_half += 1;
+    if (S->norm < S->tol * S->norm0) { S->converged = 1; S->done = 1; }
+}
+__device__ __forceinline__ void finish_xr2(Scalars* S, double rr, double rtr)
+{
+    S->rho = S->rho_new; S->rho_new = rtr;
+    S->norm = sqrt(rr); S->it_half += 1;
+    if (S->norm < S->tol * S->norm0 || S->norm < 1e-30) { S->converged = 1; S->done = 1; }
+    else if (fabs(S->rho) <= 1e-80 || fabs(S->omega) <= 1e-80 || !(S->norm == S->norm)) { S->breakdown = 1; S->done = 1; }
+    else if (S->it_half >= S->max_half) S->done = 1;
+}
+// PHASE 0: after k_init, 1: after k_vec_xr1, 2: after k_vec_xr2 (multi-GPU only, one thread)
+template <int PHASE>
+__global__ void k_finish(Scalars* S, double tol, int max_half)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (PHASE == 0) { finish_init(S, S->red[0], tol, max_half); return; }
+    if (S->done) return;
+    if (PHASE == 1) finish_xr1(S, S->red[0]);
+    if (PHASE == 2) finish_xr2(S, S->red[0], S->red[1]);
+}
+
 // r = rt = P b, x = 0, arm the dataflow arrays, norm0 = ||r||, rho_new = <rt, r>
 __global__ void __launch_bounds__(kVecThreads) k_init(const double* __restrict__ b_nat, const int* __restrict__ perm,
                                                       double* __restrict__ r, double* __restrict__ rt, double* __restrict__ x,
                                                       double* __restrict__ w, double* __restrict__ y, int N, Scalars* S,
-                                                      double* partials, unsigned* ticket, double tol, int max_half)
+                                                      double* partials, unsigned* ticket, double tol, int max_half, int dist)
 {
     double acc[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
@@ -152,14 +193,8 @@ __global__ void __launch_bounds__(kVecThreads) k_init(const double* __restrict__
     }
     double tot[1];
     if (grid_reduce<1>(acc, partials, ticket, tot)) {
-        S->norm0 = sqrt(tot[0]); S->norm = S->norm0; S->rho_new = tot[0];
-        S->rho = 1.0; S->alpha = 1.0; S->omega = 1.0; S->h = 0.0; S->tr = 0.0; S->tt = 0.0;
-        S->tol = tol; S->it_half = 0; S->converged = 0; S->breakdown = 0; S->first = 1;
-        S->max_half = max_half; S->trsv_timeout = 0;
-        // Dune: norm0 already below the absolute floor -> converged with 0 iterations
-        S->done = (S->norm0 < 1e-30) ? 1 : 0;
-        if (S->done) S->converged = 1;
-        if (S->singular) S->done = 1;      // factorisation failed: skip the Krylov loop
+        if (dist) { S->red[0] = tot[0]; S->done = 0; }
+        else finish_init(S, tot[0], tol, max_half);
     }
 }
 
@@ -560,7 +595,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_p(const double* __restrict_
 // x += alpha y; r -= alpha v; norm = ||r||; y is re-armed (its last reader).  alpha = rho_new / h.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ v, int N, Scalars* S, double* partials,
-                                                         unsigned* ticket)
+                                                         unsigned* ticket, int dist)
 {
     if (S->done) return;
     const double h = S->h;
@@ -579,16 +614,16 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
     }
     double tot[1];
     if (grid_reduce<1>(acc, partials, ticket, tot)) {
-        S->alpha = alpha; S->first = 0;
-        S->norm = sqrt(tot[0]); S->it_half += 1;
-        if (S->norm < S->tol * S->norm0) { S->converged = 1; S->done = 1; }
+        S->alpha = alpha;
+        if (dist) S->red[0] = tot[0];
+        else finish_xr1(S, tot[0]);
     }
 }
 
 // x += omega y; r -= omega t; norm = ||r||; rho <- rho_new <- <rt, r>.  omega = tr / tt.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ t, const double* __restrict__ rt, int N,
-                                                         Scalars* S, double* partials, unsigned* ticket)
+                                                         Scalars* S, double* partials, unsigned* ticket, int dist)
 {
     if (S->done) return;
     const double omega = S->tr / S->tt;
@@ -603,11 +638,9 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x,
     }
     double tot[2];
     if (grid_reduce<2>(acc, partials, ticket, tot)) {
-        S->omega = omega; S->rho = S->rho_new; S->rho_new = tot[1];
-        S->norm = sqrt(tot[0]); S->it_half += 1;
-        if (S->norm < S->tol * S->norm0 || S->norm < 1e-30) { S->converged = 1; S->done = 1; }
-        else if (fabs(S->rho) <= 1e-80 || fabs(omega) <= 1e-80 || !(S->norm == S->norm)) { S->breakdown = 1; S->done = 1; }
-        else if (S->it_half >= S->max_half) S->done = 1;
+        S->omega = omega;
+        if (dist) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
+        else finish_xr2(S, tot[0], tot[1]);
     }
 }
 
@@ -676,6 +709,104 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
                 if (MODE == 1) S->h += a;
                 if (MODE == 2) { S->tr += a; S->tt += b; }
             }
+        }
+    }
+}
+
+// ---- multi-GPU: halo exchange over NVLink peer memory -----------------------------------------------
+//
+// Row-slab partition, ghosts numbered last (ISTLSolverEbos.hpp:171-180, findOverlapRowsAndColumns.hpp:119-139).
+// Every rank owns a receive block [flags | 2 x 3 n_ghost doubles] that its neighbours map through CUDA IPC.
+// k_halo_push writes the boundary entries of the SpMV input straight into the neighbours' receive blocks
+// (st over NVLink, no staging, no NCCL) and then raises the neighbour's flag to the epoch of this
+// exchange; k_spmv_ghost, which applies the few owned x ghost blocks after the big owned x owned SpMV
+// has run, is the only kernel that waits for the flags -- the transfer hides behind the owned SpMV.
+// Reference semantics: WellModelGhostLastMatrixAdapter::apply multiplies the interior rows with the
+// full (owned + ghost) vector (WellOperators.hpp:200-214) after the communicator's copyOwnerToAll.
+struct HaloPeerD {
+    double* recv;                // neighbour's receive block: first double of MY section, parity 0
+    unsigned* flag;              // neighbour's flag slot for me
+    long long parity_stride;     // doubles between the neighbour's two parity buffers
+    int send_begin, send_end;    // my entries of send_prow
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid (blocks per neighbour, neighbours).  tickets: one counter per neighbour (self-resetting).
+__global__ void __launch_bounds__(256) k_halo_push(const HaloPeerD* __restrict__ peers, const int* __restrict__ send_prow,
+                                                   const double* __restrict__ y, unsigned epoch, unsigned* tickets, Scalars* S,
+                                                   int check_done)
+{
+    if (check_done && S->done) return;
+    const HaloPeerD P = peers[blockIdx.y];
+    double* dst = P.recv + (epoch & 1u) * P.parity_stride;
+    const int n3 = 3 * (P.send_end - P.send_begin);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+        const int e = i / 3, c = i - 3 * e;
+        dst[i] = y[3 * (size_t) send_prow[P.send_begin + e] + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(tickets + blockIdx.y, 1u) == gridDim.x - 1) {
+            tickets[blockIdx.y] = 0;
+            __threadfence_system();
+            st_release_sys(P.flag, epoch);
+        }
+    }
+}
+
+// y[row] += sum over the ghost blocks of the row of A_og x_ghost, for the boundary rows only; patches the dot
+// products the owned SpMV took (MODE as k_spmv).  3 lanes per boundary row.  Block values are read from the
+// staging copy of the caller's array (gsrc = block index there).
+template <int MODE>
+__global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int* __restrict__ grow, const int* __restrict__ gptr,
+                                                            const int* __restrict__ gcol, const int* __restrict__ gsrc,
+                                                            const double* __restrict__ stage, const double* __restrict__ ghost_x,
+                                                            const unsigned* flags, int nneigh, unsigned epoch, double* y,
+                                                            const double* __restrict__ d1, Scalars* S, double* partials,
+                                                            unsigned* ticket, int check_done)
+{
+    if (check_done && S->done) return;
+    if (threadIdx.x < nneigh) {
+        long long spins = 0;
+        while ((int) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            if ((++spins & 1023) == 0 && (spins > (1ll << 24) || *((volatile int*) &S->trsv_timeout))) {
+                S->trsv_timeout = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    double acc[2] = {0.0, 0.0};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * nrows; t += gridDim.x * blockDim.x) {
+        const int u = t / 3, c = t - 3 * u;
+        double delta = 0.0;
+        for (int e = gptr[u]; e < gptr[u + 1]; ++e) {
+            const double* a = stage + (size_t) gsrc[e] * 9 + c * 3;
+            const double* xx = ghost_x + 3 * (size_t) gcol[e];
+            delta += a[0] * __ldcg(xx) + a[1] * __ldcg(xx + 1) + a[2] * __ldcg(xx + 2);
+        }
+        const size_t idx = 3 * (size_t) grow[u] + c;
+        const double old = y[idx], now = old + delta;
+        y[idx] = now;
+        if (MODE == 1) acc[0] += d1[idx] * delta;
+        if (MODE == 2) { acc[0] += d1[idx] * delta; acc[1] += now * now - old * old; }
+    }
+    if (MODE != 0) {
+        double tot[2];
+        if (grid_reduce<2>(acc, partials, ticket, tot)) {
+            if (MODE == 1) S->h += tot[0];
+            if (MODE == 2) { S->tr += tot[0]; S->tt += tot[1]; }
         }
     }
 }

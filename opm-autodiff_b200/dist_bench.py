@@ -1,0 +1,142 @@
+"""bench.py's N > 1 leg: one rank per GPU under torchrun, row slabs of the same synthetic system.
+
+Every rank generates only its own slab (synth.generate is slab-independent), the set-up exchange (halo
+requests, NCCL id, CUDA-IPC handles) goes through torch.distributed, the data path (halo over peer memory,
+NCCL all-reduce of the dot products) runs inside libb200bda.so.  Timing: barrier + device synchronise on
+both sides, CUDA events on each rank's solver stream, MAX over ranks."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run(args, metric, tol, maxit, get_cfg, ClockSampler, measured_peak):
+    import torch
+    import torch.distributed as td
+    from . import bridge, dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if not bridge.device_available():
+        raise SystemExit("bench.py needs B200s (sm_100); the backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    if not td.is_initialized():
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = get_cfg(args.workload)
+    t0 = time.perf_counter()
+    ls = dist.slab_system(cfg, rank, world)
+    t_gen = time.perf_counter() - t0
+    ds = dist.DistSolver(ls, local, maxit=maxit, tolerance=tol)
+    res = bridge.BdaResult()
+
+    def sync():
+        torch.cuda.synchronize()
+        td.barrier()
+
+    def maxf(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+
+    def sumf(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        return float(t[0])
+
+    # ---- e2e: host buffers, H2D of values + rhs and D2H of x inside the timed region --------------------
+    for _ in range(args.warmup):
+        ds.solve_system(res)
+        x = ds.get_result()
+    assert res.converged, "solve did not converge"
+    t_analysis = res.t_analysis
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ds.solve_system(res)
+        x = ds.get_result()
+    sync()
+    e2e_s = maxf((time.perf_counter() - t0) / args.steps)
+    err2 = sumf(float(np.sum((x - ls.x_true) ** 2)))
+    ref2 = sumf(float(np.sum(ls.x_true ** 2)))
+    w = ls.wells
+    h2d = sumf(ls.vals.nbytes + ls.b.nbytes + (0 if w is None else w.B.nbytes + w.C.nbytes + w.Dinv.nbytes + 8 * len(w.Bcols)))
+    d2h = sumf(x.nbytes)
+
+    # ---- value: system resident in HBM, device time, max over ranks --------------------------------------
+    ds.upload()
+    for _ in range(args.warmup):
+        ds.solve_resident(res)
+    ds.be.reset_stats()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    sync()
+    ds.be.timer_start()
+    for _ in range(args.steps):
+        ds.solve_resident(res)
+    dev_ms = ds.be.timer_stop()
+    sync()
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = maxf(dev_ms / args.steps)
+    launches = sumf(ds.be.launch_count())
+    assert res.converged
+
+    # ---- per-kernel profile of one solve (CUDA events around every launch), rank-local, max over ranks ----
+    ds.be.set_option("profile", 1)
+    ds.be.reset_stats()
+    sync()
+    ds.solve_resident(res)
+    ds.be.set_option("profile", 0)
+    peak, peak_src = measured_peak()
+    kernels, total_ms = {}, 0.0
+    for k in ("permute", "ilu_factor", "ilu_lower", "ilu_upper", "spmv", "spmv_ghost", "halo_push", "allreduce", "finish",
+              "well_apply", "vec_p", "vec_xr1", "vec_xr2", "init", "unpermute"):
+        n, ms, by = ds.be.kernel_stats(k)
+        n, ms = int(maxf(n)), maxf(ms)
+        if n:
+            by = sumf(by)
+            kernels[k] = {"launches": n, "ms_total": round(ms, 4), "us_per_launch": round(1e3 * ms / n, 3),
+                          "alg_bytes_per_launch_all_ranks": by,
+                          "gbs_all_ranks": round(by / (ms / n) * 1e-6, 1) if ms > 0 and by > 0 else None}
+            total_ms += ms
+    for k in kernels:
+        kernels[k]["share"] = round(kernels[k]["ms_total"] / total_ms, 4)
+    if rank != 0:
+        td.barrier()
+        td.destroy_process_group()
+        return
+    ilu_ms = kernels["ilu_lower"]["ms_total"] + kernels["ilu_upper"]["ms_total"]
+    ilu_n = kernels["ilu_lower"]["launches"]
+    ilu_by = kernels["ilu_lower"]["alg_bytes_per_launch_all_ranks"] + kernels["ilu_upper"]["alg_bytes_per_launch_all_ranks"]
+    cand = {"ilu_apply": (ilu_ms, ilu_n, ilu_by),
+            "spmv": (kernels["spmv"]["ms_total"], kernels["spmv"]["launches"], kernels["spmv"]["alg_bytes_per_launch_all_ranks"])}
+    dom = max(cand, key=lambda k: cand[k][0])
+    dms, dn, dby = cand[dom]
+    achieved = dby / world / (dms / dn) * 1e-6          # per GPU, against one GPU's peak
+    out = {
+        "metric": metric, "value": 1e3 / ms_per_step, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg.name, "cells": cfg.ncells, "wells": cfg.nwells, "tolerance": tol, "relaxation": 1.0,
+                   "partition": "%d row slabs along k, ghosts last, block-Jacobi ILU0 per GPU" % world,
+                   "iterations": res.it, "x_error_vs_generator": float(np.sqrt(err2 / ref2)),
+                   "l2": "per-GPU slab (matrix + factor) larger than L2, no flush" if ls.vals.nbytes > 1.3e8
+                         else "per-GPU slab fits L2 at this rank count",
+                   "analysis_s_excluded": t_analysis, "generate_s": t_gen},
+        "clocks": clk,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "note": "per GPU: algorithmic bytes of all ranks / ranks / slowest rank's mean launch time",
+                     "share_of_step": round(dms / total_ms, 4)},
+        "kernels": kernels,
+        "cpu_baseline": None,
+    }
+    print(json.dumps(out), flush=True)
+    td.barrier()
+    td.destroy_process_group()
