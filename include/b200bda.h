@@ -196,6 +196,11 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
 b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int flush_l2,
                              double* ms_per_launch, double* algorithmic_bytes);
 
+/* Debugging aid: with option "sweep_trace" = 1 the triangular sweeps record, per part (148 x) and stage (first 1024),
+ * four SM-clock stamps {consumer starts waiting, data landed, stage done, producer issued}; this copies the trace of the
+ * last sweep (148 * 1024 * 4 values) to the host. */
+b200_status b200_get_sweep_trace(b200_solver* s, long long* out, long long count);
+
 /* Per-kernel totals accumulated over the solves run with option "profile" = 1.
  * Returns B200_UNKNOWN_ERROR for an unknown name. */
 b200_status b200_kernel_stats(b200_solver* s, const char* which, long long* launches,

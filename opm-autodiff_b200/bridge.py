@@ -128,6 +128,7 @@ def lib():
         L.b200_timer_start.argtypes = [vp]
         L.b200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200_device_available.restype = ip
+        L.b200_get_sweep_trace.argtypes = [vp, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_longlong]
         L.b200_dist_unique_id.argtypes = [vp]
         L.b200_dist_init.argtypes = [vp, ip, ip, vp]
         L.b200_dist_set_halo.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
     "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_connect_peer", "b200_dist_spmv",
-    "b200_dist_rank", "b200_dist_world",
+    "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace",
 ]
 
 
@@ -371,6 +372,12 @@ class B200SolverBackend:
         y = np.empty(self.N)
         self._chk(lib().b200_dist_spmv(self._h, np.ascontiguousarray(x, dtype=np.float64).reshape(-1), y))
         return y
+
+    def sweep_trace(self):
+        """[148, 1024, 4] SM-clock stamps of the last traced sweep (option sweep_trace = 1)."""
+        out = np.zeros(148 * 1024 * 4, np.int64)
+        self._chk(lib().b200_get_sweep_trace(self._h, out, out.size))
+        return out.reshape(148, 1024, 4)
 
     def timer_start(self) -> None:
         self._chk(lib().b200_timer_start(self._h))

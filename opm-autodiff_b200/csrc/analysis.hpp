@@ -119,11 +119,19 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
 // (3 lanes per row), grouped into ENTRIES (runs of chunks of the same level inside the stage).
 //
 //   meta blob (ints, 16-byte multiple):
-//     [0] nentries  [1] nchunks  [2] g_lo (even-aligned first p-row of the stage's rhs copy)  [3] rhs rows copied
-//     entries  : nentries x {chunk_begin | barrier << 31, nchunks}    barrier: all rows of earlier levels must be visible
-//     chunks   : nchunks x {g0, count | nd << 8, cols_off, vals_off}  (16-byte aligned; offsets relative to the blobs)
-//     cols     : per chunk nd x count ints: >= 0 position (processing order) inside the part -> shared-memory window,
-//                < 0 and != kPadCol: -(p-row + 1) -> polled in global memory, kPadCol: no dependency
+//     header  [0] nentries [1] nchunks [2] g_lo (even-aligned first p-row of the rhs copy) [3] rhs rows copied
+//             [4] next (external rows of the stage) [5] off_ext [6] off_wl [7] off_chunks
+//     entries : at 8, nentries x {chunk_begin | barrier << 31, nchunks, ext_end, 0}
+//               barrier: a level boundary separates the entry from what precedes it; ext_end: external rows
+//               [0, ext_end) of the stage list must have arrived before the entry runs (cumulative)
+//     chunks  : at off_chunks (16-byte aligned), nchunks x {g0, count | nd << 8, cols_off | vals_off << 16, ext_need}
+//               ext_need = ext_end of its entry if the chunk reads an external row, else 0
+//     cols    : per chunk nd x count ints: >= 0 position (processing order) inside the part -> shared-memory window,
+//               < 0 and != kPadCol: -(index into the stage's external list + 1), kPadCol: no dependency
+//     ext     : at off_ext, next p-rows owned by OTHER parts (or by this part but beyond the window), grouped by the
+//               entry that first needs them; a helper warp polls them in global memory and parks them in the slot
+//     wl      : at off_wl, the static work lists of the W consumer warps: W + 1 offsets (relative to off_wl),
+//               W trailing barrier counts, then the items {chunk index | level barriers to pass first << 16}
 //   vals blob (doubles, 16-byte multiple): per chunk (nd [+1 inverse pivot for U]) x 3 x (3 count) doubles,
 //     value ((j*3 + v) * 3 count + 3 q + comp) = LU[block j of row q][comp][v]  (lane-major: conflict-free, coalesced)
 //   row q of a chunk is p-row g0 + q (lower sweep) or g0 - q (upper sweep).
@@ -147,8 +155,8 @@ struct SweepPlan {
     std::vector<BuildRef> build;
     std::vector<int> src;
     long long nvals = 0;
-    int maxMetaInts = 4, maxValsDoubles = 2, maxRhsRows = 2;
-    long long nchunks = 0, nentries = 0, nExternal = 0, nWindow = 0;
+    int maxMetaInts = 4, maxValsDoubles = 2, maxRhsRows = 2, maxExtRows = 2;
+    long long nchunks = 0, nentries = 0, nExternal = 0, nWindow = 0, nExtRows = 0;
 };
 
 struct Analysis {
@@ -165,7 +173,7 @@ struct Analysis {
     int nflev = 0;
     std::vector<int> flevPtr, flevRows;
     // triangular sweeps
-    int nparts = 0, nlines = 0, window = 0;
+    int nparts = 0, nlines = 0, window = 0, warps = 8;
     int nstrips = 0;
     std::vector<int> partPtr;         // nparts + 1, p-space rows
     std::vector<int> partMaxStep;     // rows in the largest level step of each part
@@ -178,6 +186,7 @@ struct AnalysisOptions {
     int parts = 148;            // resident CTAs of the sweep kernels
     int stageBytes = 16384;     // meta + values + rhs of one ring slot
     int window = 2048;          // rows of the part kept in the shared-memory window (power of two)
+    int warps = 8;              // consumer warps of a sweep CTA (the static work lists are cut for this many)
 };
 
 namespace detail {
@@ -199,6 +208,7 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
         int prev_level = -1;            // level of the last chunk emitted in this part
         auto flush = [&]() {
             if (st.empty()) return;
+            const int NWc = A.warps;
             std::vector<std::pair<int, int>> entries;   // (chunk_begin | barrier, nchunks): runs of equal level
             for (size_t c = 0; c < st.size();) {
                 size_t e = c;
@@ -209,11 +219,52 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                 c = e;
             }
             const int nent = (int) entries.size(), nch = (int) st.size();
-            const int off_chunks = (4 + 2 * nent + 3) & ~3;
+            // external rows of the stage, listed once, grouped by the first entry that needs them
+            std::vector<int> ext, ext_end(nent, 0), need(nch, 0);
+            {
+                std::vector<std::pair<int, int>> seen;      // (p-row, index), kept sorted
+                for (int e = 0; e < nent; ++e) {
+                    const int cb = entries[e].first & 0x7fffffff;
+                    for (int c = cb; c < cb + entries[e].second; ++c) {
+                        bool any = false;
+                        for (int& code : st[c].cols) {
+                            if (code >= 0 || code == kPadCol) continue;
+                            const int gd = -(code + 1);
+                            auto it = std::lower_bound(seen.begin(), seen.end(), std::make_pair(gd, -1));
+                            int idx;
+                            if (it != seen.end() && it->first == gd) idx = it->second;
+                            else { idx = (int) ext.size(); ext.push_back(gd); seen.insert(it, std::make_pair(gd, idx)); }
+                            code = -(idx + 1);
+                            any = true;
+                        }
+                        need[c] = any ? 1 : 0;
+                    }
+                    ext_end[e] = (int) ext.size();
+                    for (int c = cb; c < cb + entries[e].second; ++c) if (need[c]) need[c] = ext_end[e];
+                }
+            }
+            const int next = (int) ext.size();
+            if (next >= 65536 || nch >= 65536 || nent >= 32768) throw std::runtime_error("sweep stage too large");
+            // static work lists: chunk c of an entry goes to warp c % W; every warp passes every level barrier
+            std::vector<std::vector<int>> wl(NWc);
+            std::vector<int> pend(NWc, 0);
+            for (int e = 0; e < nent; ++e) {
+                if (entries[e].first < 0) for (int w = 0; w < NWc; ++w) pend[w]++;
+                const int cb = entries[e].first & 0x7fffffff;
+                for (int c = 0; c < entries[e].second; ++c) {
+                    const int w = c % NWc;
+                    wl[w].push_back((cb + c) | (pend[w] << 16));
+                    pend[w] = 0;
+                }
+            }
+            const int off_chunks = (8 + 4 * nent + 3) & ~3;
             const int off_cols = off_chunks + 4 * nch;
             int ncols = 0;
             for (auto& c : st) ncols += c.nd * c.count;
-            const int meta_ints = (off_cols + ncols + 3) & ~3;
+            const int off_ext = off_cols + ncols;
+            const int off_wl = off_ext + next;
+            const int wl_ints = 2 * NWc + 1 + nch;
+            const int meta_ints = (off_wl + wl_ints + 3) & ~3;
             StageRef R{};
             R.meta_off = (long long) S.meta.size();
             R.meta_ints = meta_ints;
@@ -223,17 +274,20 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             R.g_rows = ghi_al - glo_al;
             S.meta.resize(S.meta.size() + meta_ints, 0);
             int* m = S.meta.data() + R.meta_off;
-            m[0] = nent; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows;
-            for (int e = 0; e < nent; ++e) { m[4 + 2 * e] = entries[e].first; m[5 + 2 * e] = entries[e].second; }
+            m[0] = nent; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows; m[4] = next; m[5] = off_ext; m[6] = off_wl; m[7] = off_chunks;
+            for (int e = 0; e < nent; ++e) {
+                m[8 + 4 * e] = entries[e].first; m[9 + 4 * e] = entries[e].second; m[10 + 4 * e] = ext_end[e]; m[11 + 4 * e] = 0;
+            }
             int co = off_cols;
             long long vo = 0;
             for (int c = 0; c < nch; ++c) {
                 const TmpChunk& t = st[c];
                 const int nd_eff = t.nd + (lower ? 0 : 1);
+                if (co >= 65536 || vo >= 65536) throw std::runtime_error("sweep stage too large for the packed chunk offsets");
                 m[off_chunks + 4 * c + 0] = t.g0;
                 m[off_chunks + 4 * c + 1] = t.count | (t.nd << 8);
-                m[off_chunks + 4 * c + 2] = co;
-                m[off_chunks + 4 * c + 3] = (int) vo;
+                m[off_chunks + 4 * c + 2] = co | ((int) vo << 16);
+                m[off_chunks + 4 * c + 3] = need[c];
                 std::copy(t.cols.begin(), t.cols.end(), m + co);
                 co += t.nd * t.count;
                 BuildRef B{};
@@ -245,6 +299,18 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                 S.build.push_back(B);
                 vo += (long long) nd_eff * 9 * t.count;
             }
+            std::copy(ext.begin(), ext.end(), m + off_ext);
+            {
+                int* w0 = m + off_wl;
+                int o = 2 * NWc + 1;
+                for (int w = 0; w < NWc; ++w) {
+                    w0[w] = o;
+                    std::copy(wl[w].begin(), wl[w].end(), w0 + o);
+                    o += (int) wl[w].size();
+                    w0[NWc + 1 + w] = pend[w];
+                }
+                w0[NWc] = o;
+            }
             vo = (vo + 1) & ~1LL;
             if (vo > INT_MAX || S.src.size() > (size_t) INT_MAX) throw std::runtime_error("sweep stage too large");
             R.vals_doubles = (int) vo;
@@ -252,6 +318,8 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             S.maxMetaInts = std::max(S.maxMetaInts, meta_ints);
             S.maxValsDoubles = std::max(S.maxValsDoubles, R.vals_doubles);
             S.maxRhsRows = std::max(S.maxRhsRows, R.g_rows);
+            S.maxExtRows = std::max(S.maxExtRows, (next + 1) & ~1);
+            S.nExtRows += next;
             S.nchunks += nch;
             S.nentries += nent;
             S.stages.push_back(R);
@@ -302,9 +370,11 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                     }
                     if (!lower) t.src[(size_t) t.nd * t.count + q] = A.pdiag[g];
                 }
-                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8;
+                int nextc = 0;
+                for (int code : t.cols) nextc += (code < 0 && code != kPadCol);
+                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8 + 28 * nextc + 4;
                 if (!st.empty() && st_bytes + bytes > opt.stageBytes) flush();
-                if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 64; }
+                if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 160; }
                 const int glo = lower ? t.g0 : t.g0 - t.count + 1, ghi = lower ? t.g0 + t.count : t.g0 + 1;
                 st_glo = std::min(st_glo, glo); st_ghi = std::max(st_ghi, ghi);
                 st_bytes += bytes;
@@ -328,6 +398,8 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
     if (Nb >= (1 << 30)) throw std::runtime_error("Nb too large");
     if (opt.window < 64 || (opt.window & (opt.window - 1))) throw std::runtime_error("window must be a power of two >= 64");
     A.window = opt.window;
+    if (opt.warps < 1 || opt.warps > 14) throw std::runtime_error("consumer warps must be in 1..14");
+    A.warps = opt.warps;
     for (int r = 0; r < Nb; ++r) {
         bool diag = false;
         for (int k = rows[r]; k < rows[r + 1]; ++k) {
@@ -562,6 +634,34 @@ inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, con
     const int W = A.window;
     const double NaN = std::nan("");
     for (int i = 0; i < 3 * A.Nb; ++i) out[i] = NaN;
+    // the static work lists must cover every chunk exactly once, in entry order per warp, and every warp must pass
+    // the same number of level barriers per stage (the device kernel relies on both)
+    for (const StageRef& R : S.stages) {
+        const int* m = S.meta.data() + R.meta_off;
+        const int nent = m[0], nch = m[1];
+        const int* wl = m + m[6];
+        int nbar = 0;
+        for (int e = 0; e < nent; ++e) nbar += m[8 + 4 * e] < 0;
+        std::vector<int> entry_of(nch, -1), hit(nch, 0);
+        for (int e = 0; e < nent; ++e)
+            for (int c = 0; c < m[9 + 4 * e]; ++c) entry_of[(m[8 + 4 * e] & 0x7fffffff) + c] = e;
+        for (int w = 0; w < A.warps; ++w) {
+            int bars = wl[A.warps + 1 + w], last_entry = -1;
+            for (int t = wl[w]; t < wl[w + 1]; ++t) {
+                const int c = wl[t] & 0xffff, nb = wl[t] >> 16;
+                if (c >= nch || hit[c]++) throw std::runtime_error("emulate: bad sweep work list");
+                if (entry_of[c] < last_entry) throw std::runtime_error("emulate: work list out of order");
+                int expect = 0;
+                for (int e = last_entry + 1; e <= entry_of[c]; ++e) expect += m[8 + 4 * e] < 0;
+                if (last_entry == entry_of[c]) expect = 0;
+                if (nb != expect) throw std::runtime_error("emulate: wrong barrier count in a sweep work list");
+                last_entry = entry_of[c];
+                bars += nb;
+            }
+            if (bars != nbar) throw std::runtime_error("emulate: warps disagree on the barrier count of a stage");
+        }
+        for (int c = 0; c < nch; ++c) if (hit[c] != 1) throw std::runtime_error("emulate: chunk missing from the work lists");
+    }
     struct Cursor { int stage, entry, chunk; std::vector<double> win; };
     std::vector<Cursor> cur(A.nparts);
     for (int p = 0; p < A.nparts; ++p) cur[p] = {S.parts[p].stage_begin, 0, 0, std::vector<double>((size_t) 3 * W, NaN)};
@@ -579,19 +679,16 @@ inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, con
                 const int* m = S.meta.data() + R.meta_off;
                 const int nent = m[0];
                 if (c.entry >= nent) { c.stage++; c.entry = 0; c.chunk = 0; continue; }
-                const int cb = m[4 + 2 * c.entry] & 0x7fffffff, nc = m[5 + 2 * c.entry];
+                const int cb = m[8 + 4 * c.entry] & 0x7fffffff, nc = m[9 + 4 * c.entry], ext_end = m[10 + 4 * c.entry];
                 if (c.chunk >= nc) { c.entry++; c.chunk = 0; continue; }
-                const int off_chunks = (4 + 2 * nent + 3) & ~3;
-                const int* d = m + off_chunks + 4 * (cb + c.chunk);
-                const int g0 = d[0], count = d[1] & 255, nd = d[1] >> 8, co = d[2], vo = d[3];
-                const double* v = vals.data() + R.vals_off + vo;
+                const int* ext = m + m[5];
+                // the helper warp delivers the external rows of an entry as a group: all of them must exist
                 bool ready = true;
-                for (int j = 0; j < nd && ready; ++j)
-                    for (int q = 0; q < count; ++q) {
-                        const int code = m[co + j * count + q];
-                        if (code < 0 && code != kPadCol && std::isnan(out[3 * (size_t) (-(code + 1))])) { ready = false; break; }
-                    }
+                for (int x = 0; x < ext_end && ready; ++x) ready = !std::isnan(out[3 * (size_t) ext[x]]);
                 if (!ready) break;      // yield to the next part
+                const int* d = m + m[7] + 4 * (cb + c.chunk);
+                const int g0 = d[0], count = d[1] & 255, nd = d[1] >> 8, co = d[2] & 0xffff, vo = (int) ((unsigned) d[2] >> 16);
+                const double* v = vals.data() + R.vals_off + vo;
                 double res[kRowsPerWarp][3];
                 for (int q = 0; q < count; ++q) {
                     const int g = lower ? g0 + q : g0 - q;
@@ -602,7 +699,8 @@ inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, con
                         for (int j = 0; j < nd; ++j) {
                             const int code = m[co + j * count + q];
                             if (code == kPadCol) continue;
-                            const double* x = code >= 0 ? c.win.data() + 3 * (size_t) (code & (W - 1)) : out + 3 * (size_t) (-(code + 1));
+                            if (code < 0 && (-(code + 1) >= d[3] || -(code + 1) >= m[4])) throw std::runtime_error("emulate: external index beyond ext_need");
+                            const double* x = code >= 0 ? c.win.data() + 3 * (size_t) (code & (W - 1)) : out + 3 * (size_t) ext[-(code + 1)];
                             for (int e = 0; e < 3; ++e) {
                                 if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
                                 a -= v[(size_t) (j * 3 + e) * 3 * count + 3 * q + comp] * x[e];

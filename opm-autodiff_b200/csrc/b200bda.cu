@@ -143,14 +143,16 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_dbg = 0;
-    int sweep_parts = 0, sweep_warps = 8, sweep_slots = 6, sweep_stage_bytes = 16384, sweep_window = 2048;
+    int sweep_parts = 0, sweep_warps = 8, sweep_helpers = 4, sweep_slots = 4, sweep_stage_bytes = 32768, sweep_window = 2048;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     int vec_blocks = 0;
     size_t smem_optin = 0, sweep_smem = 0;
-    int sweep_metaCap = 0, sweep_valsCap = 0, sweep_rhsCap = 0;
+    int sweep_metaCap = 0, sweep_valsCap = 0, sweep_rhsCap = 0, sweep_extCap = 0;
+    bool sweep_trace = false;
+    static constexpr int kTraceCap = 1024;
+    DevBuf<long long> d_trace;
 
     bool analysed = false, have_system = false, have_factor = false;
     int N = 0, Nb = 0;
@@ -298,6 +300,7 @@ struct Solver {
         opt.parts = sweep_parts > 0 ? std::min(sweep_parts, num_sms) : num_sms;      // every CTA of a sweep must be resident
         opt.stageBytes = sweep_stage_bytes;
         opt.window = sweep_window;
+        opt.warps = sweep_warps;
         if (!dist.enabled) {
             an = b200::analyse(Nb, rows, cols, opt);
         } else {
@@ -362,10 +365,12 @@ struct Solver {
         sweep_metaCap = std::max(an.L.maxMetaInts, an.U.maxMetaInts);
         sweep_valsCap = std::max(an.L.maxValsDoubles, an.U.maxValsDoubles);
         sweep_rhsCap = std::max(an.L.maxRhsRows, an.U.maxRhsRows);
-        const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
+        sweep_extCap = std::max(an.L.maxExtRows, an.U.maxExtRows);
+        const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24 + (size_t) sweep_extCap * 24;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
-        while (sweep_slots > 2 && 128 + (size_t) sweep_window * 24 + sweep_slots * slotBytes > smem_optin) --sweep_slots;
-        sweep_smem = 128 + (size_t) sweep_window * 24 + sweep_slots * slotBytes;
+        while (sweep_slots > 2 && kSweepHeader + (size_t) sweep_window * 24 + sweep_slots * slotBytes > smem_optin) --sweep_slots;
+        sweep_smem = kSweepHeader + (size_t) sweep_window * 24 + sweep_slots * slotBytes;
+        sweep_helpers = std::max(1, std::min(sweep_helpers, 15 - sweep_warps));
         if (sweep_smem > smem_optin)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
@@ -373,16 +378,17 @@ struct Solver {
         CUDA_OK(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
         CUDA_OK(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
         int occ = 0, occ2 = 0;
-        const int threads = (sweep_warps + 1) * 32;
+        const int threads = sweep_threads();
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<true>, threads, sweep_smem));
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_sweep<false>, threads, sweep_smem));
         if (std::min(occ, occ2) < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts; "
                             "L: %zu stages %lld chunks (%lld window / %lld global deps), U: %zu stages; sweep grid %d x %d, "
-                            "%d slots x %zu B + window %d rows = %zu B smem\n",
+                            "%d slots x %zu B + window %d rows = %zu B smem; %lld external rows L (max %d per stage)\n",
                     Nb, (long long) nnzb, an.nlev, an.nlines, an.nstrips, an.nparts, an.L.stages.size(), an.L.nchunks, an.L.nWindow,
-                    an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, slotBytes, sweep_window, sweep_smem);
+                    an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, slotBytes, sweep_window, sweep_smem,
+                    an.L.nExtRows, sweep_extCap);
         d_stage.alloc(nnz_stage); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
         // + 8 doubles: the sweeps' 16-byte aligned rhs copies may read one row past the end
         for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) {
@@ -526,21 +532,24 @@ struct Solver {
         a.rhs = rhs; a.out = out; a.rearm = rearm; a.S = d_S.p;
         a.relax = lower ? 1.0 : relaxation;
         a.nparts = an.nparts; a.nslots = sweep_slots; a.window = sweep_window;
-        a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap;
+        a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extCap = sweep_extCap;
+        a.nwarps = sweep_warps; a.nhalo = sweep_helpers;
         a.check_done = check_done ? 1 : 0;
-        a.dbg = sweep_dbg;
+        a.trace = sweep_trace ? d_trace.p : nullptr;
+        a.trace_cap = kTraceCap;
         return a;
     }
+    int sweep_threads() const { return (sweep_warps + 1 + sweep_helpers) * 32; }
     void trsv_lower(const double* rhs, double* out, bool check_done)
     {
         int id = prof_begin(K_LOWER);
-        k_sweep<true><<<an.nparts, (sweep_warps + 1) * 32, sweep_smem, stream>>>(sweep_args(true, rhs, out, nullptr, check_done));
+        k_sweep<true><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(sweep_args(true, rhs, out, nullptr, check_done));
         prof_end(id);
     }
     void trsv_upper(const double* rhs, double* out, double* rearm, bool check_done)
     {
         int id = prof_begin(K_UPPER);
-        k_sweep<false><<<an.nparts, (sweep_warps + 1) * 32, sweep_smem, stream>>>(sweep_args(false, rhs, out, rearm, check_done));
+        k_sweep<false><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(sweep_args(false, rhs, out, rearm, check_done));
         prof_end(id);
     }
     template <int MODE>
@@ -793,12 +802,16 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
-        else if (k == "sweep_dbg") s->sweep_dbg = (int) value;
-        else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window") {
+        else if (k == "sweep_trace") {
+            s->sweep_trace = value != 0.0;
+            if (s->sweep_trace) { s->d_trace.alloc((size_t) 148 * 4 * b200::Solver::kTraceCap); CUDA_OK(cudaMemset(s->d_trace.p, 0, sizeof(long long) * s->d_trace.n)); }
+        }
+        else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_helpers" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window") {
             if (s->analysed) throw std::runtime_error(k + " must be set before the first solve");
             const int v = (int) value;
             if (k == "sweep_parts") s->sweep_parts = std::max(0, v);
-            else if (k == "sweep_warps") s->sweep_warps = std::min(15, std::max(1, v));
+            else if (k == "sweep_warps") s->sweep_warps = std::min(14, std::max(1, v));
+            else if (k == "sweep_helpers") s->sweep_helpers = std::min(8, std::max(1, v));
             else if (k == "sweep_slots") s->sweep_slots = std::min(kSweepMaxSlots, std::max(2, v));
             else if (k == "sweep_stage_bytes") s->sweep_stage_bytes = std::max(1024, v);
             else s->sweep_window = v;
@@ -1259,6 +1272,19 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
         }
         return B200_SUCCESS;
     }, B200_ANALYSIS_FAILED);
+}
+
+// Debugging aid: stage timeline of the last traced sweep (option "sweep_trace" = 1): per part (148) and stage
+// (first 1024) four SM-clock stamps {consumer starts waiting, data landed, stage done, producer issued}.
+b200_status b200_get_sweep_trace(b200_solver* s, long long* out, long long count)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !out || !s->d_trace.p) throw std::runtime_error("no trace (set option sweep_trace first)");
+        CUDA_OK(cudaSetDevice(s->device));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        CUDA_OK(cudaMemcpy(out, s->d_trace.p, sizeof(long long) * std::min<size_t>((size_t) count, s->d_trace.n), cudaMemcpyDeviceToHost));
+        return B200_SUCCESS;
+    });
 }
 
 static int kind_of(const std::string& k)

@@ -340,7 +340,8 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
 }
 
 constexpr int kSweepBatch = 3;         // dependency slots kept in registers (7-point stencils need 3)
-constexpr int kSweepMaxSlots = 8;      // ring slots (full + empty mbarriers fit the 128-byte header)
+constexpr int kSweepMaxSlots = 8;      // ring slots (full + empty mbarriers and the ext flags fit the 256-byte header)
+constexpr int kSweepHeader = 256;
 
 struct SweepArgs {
     const StageD* stages;
@@ -352,8 +353,29 @@ struct SweepArgs {
     double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
     Scalars* S;
     double relax;
-    int nparts, nslots, window, metaCap, valsCap, rhsCap, check_done;
-    int dbg;              // timing experiments only (results are wrong): 1 weak out store, 2 no out store, 4 no level barrier, 8 no wait on other parts
+    int nparts, nslots, window, metaCap, valsCap, rhsCap, extCap, nwarps, nhalo, check_done;
+    long long* trace;     // debugging aid (may be null): per part and stage {wait begin, data landed, stage done, issued} in SM cycles
+    int trace_cap;
+};
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p)
+{
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_s32(int* p, int v)
+{
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// One decoded chunk: everything a consumer warp can fetch BEFORE the level barrier that releases the chunk.
+struct ChunkRegs {
+    int g, pos, count, nd, lanes, cols_off, vals_off, need, nbar;
+    int col[kSweepBatch];
+    double a[kSweepBatch][3];
+    double acc, inv[3];
+    bool act;
 };
 
 // One triangular sweep.  One persistent CTA per PART (pencil of grid lines, analysis.hpp), all resident.
@@ -361,14 +383,21 @@ struct SweepArgs {
 //                   rhs rows, all contiguous in processing order -- with three bulk copies (TMA unit,
 //                   UBLKCP) into a ring of shared-memory slots, several stages ahead of the consumers:
 //                   HBM latency never sits on the dependency chain;
-//   consumer warps: a chunk = <= 10 rows of one level, 3 lanes per row.  Dependencies inside the part are
-//                   read from a shared-memory WINDOW of the most recent rows (written by the consumers,
-//                   ~30 cycles), levels are separated by one named barrier; dependencies on other parts
-//                   are read from global `out`, which every sweep finds armed with a NaN sentinel and every
-//                   producer overwrites with relaxed gpu-scope 8-byte stores -- the value is its own
-//                   ready flag, one L2 hop (0.25-0.46 us) and only on pencil faces.
+//   helper warps  : rows owned by OTHER parts are the only values that travel through L2 (every sweep finds
+//                   `out` armed with a NaN sentinel, producers overwrite it with relaxed gpu-scope 8-byte
+//                   stores: the value is its own ready flag).  Helper warp h takes the stages i = h (mod H):
+//                   as soon as the stage's meta has landed it polls the stage's external rows, entry by
+//                   entry, and parks them in the slot -- one L2 round trip (0.4-0.9 us) per level, but
+//                   several stages AHEAD of the consumers and off their critical path; it publishes a
+//                   per-slot counter the consumers check (shared memory, ~30 cycles);
+//   consumer warps: a chunk = <= 10 rows of one level, 3 lanes per row; each warp walks its own static
+//                   work list of the stage and decodes chunk t+1 (descriptor, columns, factor values,
+//                   rhs) before it waits for the level barrier of chunk t, so that between two level
+//                   barriers only the dependent part is left: window reads (values of earlier rows of this
+//                   part, written by the consumers), 9 fma, window store.
 // Parts process their rows in ascending (descending for U) global level, a topological order of the
-// whole DAG, so the waits cannot cycle as long as every CTA is resident (grid <= SMs).
+// whole DAG, and an entry only ever waits for rows of earlier levels, so the waits cannot cycle as long
+// as every CTA is resident (grid <= SMs).
 template <bool LOWER>
 __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 {
@@ -379,15 +408,16 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
     const PartD pr = P.parts[part];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
     unsigned long long* empty = full + kSweepMaxSlots;
-    double* win = reinterpret_cast<double*>(sweep_smem + 128);
+    int* ext_ready = reinterpret_cast<int*>(sweep_smem + 128);
+    double* win = reinterpret_cast<double*>(sweep_smem + kSweepHeader);
     unsigned char* slots = reinterpret_cast<unsigned char*>(win + 3 * (size_t) P.window);
     const size_t metaBytes = (size_t) P.metaCap * 4, valsBytes = (size_t) P.valsCap * 8, rhsBytes = (size_t) P.rhsCap * 24;
-    const size_t slotBytes = metaBytes + valsBytes + rhsBytes;
+    const size_t slotBytes = metaBytes + valsBytes + rhsBytes + (size_t) P.extCap * 24;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int NW = (blockDim.x >> 5) - 1;          // consumer warps; the last warp is the producer
+    const int NW = P.nwarps, NH = P.nhalo;
     const int nslots = P.nslots;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW + 1); ext_ready[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -395,8 +425,6 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
     const int nst = pr.stage_end - pr.stage_begin;
 
     if (warp == NW) {                               // ---- producer ----
-        // stage descriptors: one coalesced load per 32 stages (a lane each), the next batch in flight while
-        // this one is issued -- no global-memory latency between two stages
         StageD cur = {0, 0, 0, 0, 0, 0}, nxt = cur;
         if (lane < nst) nxt = P.stages[pr.stage_begin + lane];
         for (int b0 = 0; b0 < nst; b0 += 32) {
@@ -411,6 +439,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                 if (lane == 0) {
                     const int i = b0 + k, s = i % nslots;
                     if (i >= nslots) mbar_wait(empty + s, ((i / nslots) - 1) & 1);
+                    if (P.trace && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 3] = clock64();
                     unsigned char* base = slots + (size_t) s * slotBytes;
                     mbar_expect_tx(full + s, bm + bv + br);
                     bulk_g2s(base, P.meta + meta_off, bm, full + s);
@@ -422,123 +451,152 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
         return;
     }
 
+    if (warp > NW) {                                // ---- helpers: external rows ----
+        const int h = warp - NW - 1;
+        for (int i = h; i < nst; i += NH) {
+            const int s = i % nslots;
+            mbar_wait(full + s, (i / nslots) & 1);
+            unsigned char* base = slots + (size_t) s * slotBytes;
+            const int* m = reinterpret_cast<const int*>(base);
+            double* ex = reinterpret_cast<double*>(base + metaBytes + valsBytes + rhsBytes);
+            const int nent = m[0], next = m[4];
+            const int* extl = m + m[5];
+            const int tag = (i + 1) << 16;
+            int e0 = 0;
+            for (int e = 0; e < nent && e0 < next; ++e) {
+                const int eend = m[10 + 4 * e];
+                if (eend == e0) continue;
+                while (e0 < eend) {
+                    const int idx = e0 + lane;
+                    const bool on = idx < eend;
+                    const double* xp = P.out + 3 * (size_t) (on ? extl[idx] : 0);
+                    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+                    bool ok = !on;
+                    int spins = 0;
+                    while (true) {
+                        if (!ok) {
+                            x0 = ld_relaxed(xp); x1 = ld_relaxed(xp + 1); x2 = ld_relaxed(xp + 2);
+                            ok = !(is_sentinel(x0) || is_sentinel(x1) || is_sentinel(x2));
+                        }
+                        if (__all_sync(kFull, ok)) break;
+                        if ((++spins & 255) == 0 && (spins > (1 << 20) || *((volatile int*) &P.S->trsv_timeout))) {
+                            P.S->trsv_timeout = 1;
+                            break;
+                        }
+                        __nanosleep(40);
+                    }
+                    if (on) { ex[3 * idx] = x0; ex[3 * idx + 1] = x1; ex[3 * idx + 2] = x2; }
+                    e0 = min(e0 + 32, eend);
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) st_volatile_s32(ext_ready + s, tag + eend);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+        return;
+    }
+
     // ---- consumers ----
     const int q = lane / 3, comp = lane - 3 * q;
     const int wmask = P.window - 1;
     const int nthreads = NW * 32;
+    const bool tracing = P.trace != nullptr && threadIdx.x == 0;
     for (int i = 0; i < nst; ++i) {
         const int s = i % nslots;
+        if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 0] = clock64();
         mbar_wait(full + s, (i / nslots) & 1);
+        if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 1] = clock64();
         const unsigned char* base = slots + (size_t) s * slotBytes;
         const int* m = reinterpret_cast<const int*>(base);
         const double* vv = reinterpret_cast<const double*>(base + metaBytes);
         const double* rr = reinterpret_cast<const double*>(base + metaBytes + valsBytes);
-        const int nent = m[0], g_lo = m[2];
-        const int off_chunks = (4 + 2 * nent + 3) & ~3;
-        for (int e = 0; e < nent; ++e) {
-            const int e0 = m[4 + 2 * e], nc = m[5 + 2 * e];
-            const int cb = e0 & 0x7fffffff;
-            bool synced = e0 >= 0;                  // sign bit: a barrier separates this entry from earlier levels
-            for (int c = warp; c < nc; c += NW) {
-                const int4 d = *reinterpret_cast<const int4*>(m + off_chunks + 4 * (cb + c));
-                const int count = d.y & 255, nd = d.y >> 8;
-                const bool act = q < count;
-                const int g = LOWER ? d.x + q : d.x - q;
-                const int lanes = 3 * count;
-                // everything that does not depend on other rows, before the barrier
-                int col[kSweepBatch];
-                double a[kSweepBatch][3], x[kSweepBatch][3];
-                const double* vb = vv + d.w + lane;
+        const double* ex = reinterpret_cast<const double*>(base + metaBytes + valsBytes + rhsBytes);
+        const int g_lo = m[2], off_chunks = m[7];
+        const int* wl = m + m[6];
+        const int tb = wl[warp], te = wl[warp + 1], tail = wl[NW + 1 + warp];
+        const int tag = (i + 1) << 16;
+
+        auto decode = [&](int item) {
+            ChunkRegs c;
+            const int4 d = *reinterpret_cast<const int4*>(m + off_chunks + 4 * (item & 0xffff));
+            c.nbar = item >> 16;
+            c.count = d.y & 255; c.nd = d.y >> 8;
+            c.act = q < c.count;
+            c.g = LOWER ? d.x + q : d.x - q;
+            c.pos = LOWER ? c.g - pr.row0 : pr.row0 + pr.nrows - 1 - c.g;
+            c.lanes = 3 * c.count;
+            c.cols_off = d.z & 0xffff; c.vals_off = (int) ((unsigned) d.z >> 16);
+            c.need = d.w;
+            const double* vb = vv + c.vals_off + lane;
 #pragma unroll
-                for (int j = 0; j < kSweepBatch; ++j) {
-                    const bool on = act && j < nd;
-                    col[j] = on ? m[d.z + j * count + q] : kPadColD;
+            for (int j = 0; j < kSweepBatch; ++j) {
+                const bool on = c.act && j < c.nd;
+                c.col[j] = on ? m[c.cols_off + j * c.count + q] : kPadColD;
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) a[j][v] = on ? vb[(j * 3 + v) * lanes] : 0.0;
-                }
-                double acc = act ? rr[3 * (g - g_lo) + comp] : 0.0;
-                double inv[3] = {0.0, 0.0, 0.0};
-                if (!LOWER && act) {
+                for (int v = 0; v < 3; ++v) c.a[j][v] = on ? vb[(j * 3 + v) * c.lanes] : 0.0;
+            }
+            c.acc = c.act ? rr[3 * (c.g - g_lo) + comp] : 0.0;
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) inv[v] = vb[(nd * 3 + v) * lanes];
+            for (int v = 0; v < 3; ++v) c.inv[v] = (!LOWER && c.act) ? vb[(c.nd * 3 + v) * c.lanes] : 0.0;
+            return c;
+        };
+
+        ChunkRegs nx;
+        if (tb < te) nx = decode(wl[tb]);
+        for (int t = tb; t < te; ++t) {
+            const ChunkRegs c = nx;
+            if (t + 1 < te) nx = decode(wl[t + 1]);
+            for (int b = 0; b < c.nbar; ++b) named_barrier(1, nthreads);
+            if (c.need) {                                   // external rows of this level: parked by a helper warp
+                int spins = 0;
+                while (ld_volatile_s32(ext_ready + s) - (tag + c.need) < 0) {
+                    if ((++spins & 4095) == 0 && *((volatile int*) &P.S->trsv_timeout)) break;
                 }
-                // dependencies on other parts: request them now, they land while the warp waits for its level
+                __threadfence_block();
+            }
+            // ---- exposed part: window / parked reads, fma, publish ----
+            double acc = c.acc;
 #pragma unroll
-                for (int j = 0; j < kSweepBatch; ++j) {
-                    const bool ext = col[j] < 0 && col[j] != kPadColD;
-                    const double* xp = P.out + 3 * (size_t) (ext ? -(col[j] + 1) : 0);
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) x[j][v] = ext ? ld_relaxed(xp + v) : 0.0;
-                }
-                if (!synced) { if (!(P.dbg & 4)) named_barrier(1, nthreads); synced = true; }
-                // ---- exposed part: window reads, fma, publish ----
-#pragma unroll
-                for (int j = 0; j < kSweepBatch; ++j) {
-                    const int cj = col[j];
-                    if (cj >= 0) {
-                        const double* xp = win + 3 * (cj & wmask);
-                        x[j][0] = xp[0]; x[j][1] = xp[1]; x[j][2] = xp[2];
-                    } else if (cj != kPadColD) {
-                        int spins = 0;
-                        while (!(P.dbg & 8) && (is_sentinel(x[j][0]) || is_sentinel(x[j][1]) || is_sentinel(x[j][2]))) {
-                            const double* xp = P.out + 3 * (size_t) (-(cj + 1));
-                            x[j][0] = ld_relaxed(xp); x[j][1] = ld_relaxed(xp + 1); x[j][2] = ld_relaxed(xp + 2);
-                            if ((++spins & 1023) == 0 && (spins > (1 << 21) || *((volatile int*) &P.S->trsv_timeout))) {
-                                P.S->trsv_timeout = 1;
-                                break;
-                            }
-                        }
-                    }
-                    double t = a[j][0] * x[j][0];
-                    t = fma(a[j][1], x[j][1], t);
-                    t = fma(a[j][2], x[j][2], t);
-                    acc -= t;
-                }
-                if (nd > kSweepBatch) {                      // long rows (NNC, wells in the matrix): unpipelined tail
-                    for (int j = kSweepBatch; j < nd; ++j) {
-                        const int cj = act ? m[d.z + j * count + q] : kPadColD;
-                        if (cj == kPadColD) continue;
-                        double x0, x1, x2;
-                        if (cj >= 0) {
-                            const double* xp = win + 3 * (cj & wmask);
-                            x0 = xp[0]; x1 = xp[1]; x2 = xp[2];
-                        } else {
-                            const double* xp = P.out + 3 * (size_t) (-(cj + 1));
-                            int spins = 0;
-                            while (true) {
-                                x0 = ld_relaxed(xp); x1 = ld_relaxed(xp + 1); x2 = ld_relaxed(xp + 2);
-                                if (!(is_sentinel(x0) || is_sentinel(x1) || is_sentinel(x2))) break;
-                                if ((++spins & 1023) == 0 && (spins > (1 << 21) || *((volatile int*) &P.S->trsv_timeout))) {
-                                    P.S->trsv_timeout = 1;
-                                    break;
-                                }
-                            }
-                        }
-                        double t = vb[(j * 3) * lanes] * x0;
-                        t = fma(vb[(j * 3 + 1) * lanes], x1, t);
-                        t = fma(vb[(j * 3 + 2) * lanes], x2, t);
-                        acc -= t;
-                    }
-                }
-                double res = acc;
-                if (!LOWER) {
-                    const int b3 = act ? 3 * q : 0;
-                    const double s0 = __shfl_sync(kFull, acc, b3);
-                    const double s1 = __shfl_sync(kFull, acc, b3 + 1);
-                    const double s2 = __shfl_sync(kFull, acc, b3 + 2);
-                    res = (inv[0] * s0 + inv[1] * s1 + inv[2] * s2) * P.relax;
-                }
-                if (act) {
-                    const int pos = LOWER ? g - pr.row0 : pr.row0 + pr.nrows - 1 - g;
-                    win[3 * (pos & wmask) + comp] = res;
-                    if (P.dbg & 1) P.out[3 * (size_t) g + comp] = res;
-                    else if (!(P.dbg & 2)) st_relaxed(P.out + 3 * (size_t) g + comp, res);
-                    if (P.rearm != nullptr) P.rearm[3 * (size_t) g + comp] = sentinel();
+            for (int j = 0; j < kSweepBatch; ++j) {
+                const int cj = c.col[j];
+                const double* xp = cj >= 0 ? win + 3 * (cj & wmask) : ex + 3 * (cj == kPadColD ? 0 : -(cj + 1));
+                const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+                double tt = c.a[j][0] * x0;
+                tt = fma(c.a[j][1], x1, tt);
+                tt = fma(c.a[j][2], x2, tt);
+                acc -= (cj == kPadColD) ? 0.0 : tt;
+            }
+            if (c.nd > kSweepBatch) {                       // long rows (NNC, wells in the matrix): unpipelined tail
+                const double* vb = vv + c.vals_off + lane;
+                for (int j = kSweepBatch; j < c.nd; ++j) {
+                    const int cj = c.act ? m[c.cols_off + j * c.count + q] : kPadColD;
+                    if (cj == kPadColD) continue;
+                    const double* xp = cj >= 0 ? win + 3 * (cj & wmask) : ex + 3 * (-(cj + 1));
+                    double tt = vb[(j * 3) * c.lanes] * xp[0];
+                    tt = fma(vb[(j * 3 + 1) * c.lanes], xp[1], tt);
+                    tt = fma(vb[(j * 3 + 2) * c.lanes], xp[2], tt);
+                    acc -= tt;
                 }
             }
-            if (!synced && !(P.dbg & 4)) named_barrier(1, nthreads);        // warps without a chunk of this level still take part
+            double res = acc;
+            if (!LOWER) {
+                const int b3 = c.act ? 3 * q : 0;
+                const double s0 = __shfl_sync(kFull, acc, b3);
+                const double s1 = __shfl_sync(kFull, acc, b3 + 1);
+                const double s2 = __shfl_sync(kFull, acc, b3 + 2);
+                res = (c.inv[0] * s0 + c.inv[1] * s1 + c.inv[2] * s2) * P.relax;
+            }
+            if (c.act) {
+                win[3 * (c.pos & wmask) + comp] = res;
+                st_relaxed(P.out + 3 * (size_t) c.g + comp, res);
+                if (P.rearm != nullptr) P.rearm[3 * (size_t) c.g + comp] = sentinel();
+            }
         }
+        for (int b = 0; b < tail; ++b) named_barrier(1, nthreads);
         __syncwarp();
+        if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 2] = clock64();
         if (lane == 0) mbar_arrive(empty + s);
     }
 }

@@ -14,20 +14,21 @@ def run(shape, label, **opts):
     lo, _ = be.time_kernel("ilu_lower", 10, False)
     up, _ = be.time_kernel("ilu_upper", 10, False)
     nlev = sum(shape) - 2
-    print("%-40s grid %-12s %-50s lower %8.1f us upper %8.1f us  (%d levels -> %.3f us/level lower)"
+    print("%-28s grid %-12s %-60s lower %8.1f us upper %8.1f us  (%d levels -> %.3f us/level lower)"
           % (label, "x".join(map(str, shape)), opts, lo * 1e3, up * 1e3, nlev, lo * 1e3 / nlev), flush=True)
 
-for dbg in (0, 1, 2, 4, 6, 8, 14):
-    run((4000, 1, 1), "1-D chain, one part", parts=1, dbg=dbg)
-for dbg in (0, 1, 2, 4, 6, 14):
-    run((200, 8, 8), "one pencil 8x8", parts=1, dbg=dbg)
-run((200, 8, 8), "one pencil 8x8, 32K stages", parts=1, stage_bytes=32768, slots=4)
-run((200, 8, 8), "one pencil 8x8, 8K stages", parts=1, stage_bytes=8192, slots=8)
-run((200, 8, 8), "pencil 8x8 cut in 4 parts", parts=4)
-run((200, 32, 32), "4x4 pencils", parts=16)
-for dbg in (0, 1, 2, 4, 8, 9, 14):
-    run((100, 100, 100), "c3 shape default", parts=148, dbg=dbg)
-run((100, 100, 100), "c3 shape 32K/12 warps", parts=148, stage_bytes=32768, slots=4, warps=12)
-run((100, 100, 100), "c3 shape 32K/12 warps weak store", parts=148, stage_bytes=32768, slots=4, warps=12, dbg=1)
-run((100, 100, 100), "c3 shape 8K/8 slots", parts=148, stage_bytes=8192, slots=8, warps=8)
-run((100, 100, 100), "c3 shape 8K/8 slots weak store", parts=148, stage_bytes=8192, slots=8, warps=8, dbg=1)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "micro"):
+    run((4000, 1, 1), "1-D chain, one part", parts=1)
+    run((200, 8, 8), "one pencil 8x8", parts=1)
+    run((200, 8, 8), "one pencil 8x8, 32K", parts=1, stage_bytes=32768, slots=4)
+    run((200, 8, 8), "pencil 8x8 cut in 4 parts", parts=4)
+    run((200, 32, 32), "4x4 pencils", parts=16)
+if which in ("all", "c3"):
+    run((100, 100, 100), "c3 default", parts=148)
+    run((100, 100, 100), "c3 helpers 2", parts=148, helpers=2)
+    run((100, 100, 100), "c3 helpers 6", parts=148, helpers=6)
+    run((100, 100, 100), "c3 32K/4 slots", parts=148, stage_bytes=32768, slots=4)
+    run((100, 100, 100), "c3 32K/4 slots 12 warps/3", parts=148, stage_bytes=32768, slots=4, warps=12, helpers=3)
+    run((100, 100, 100), "c3 8K/8 slots", parts=148, stage_bytes=8192, slots=8)
+    run((100, 100, 100), "c3 4 warps", parts=148, warps=4)
