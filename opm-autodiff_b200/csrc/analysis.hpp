@@ -116,25 +116,30 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
 // A sweep (forward over L, backward over U) is cut, per part, into STAGES: a few KB of consecutive
 // work the producer warp of the CTA fetches with three bulk copies (meta ints, factor values, rhs
 // rows) into one slot of a shared-memory ring.  A stage holds CHUNKS of <= 10 rows of one level
-// (3 lanes per row), grouped into ENTRIES (runs of chunks of the same level inside the stage).
+// (3 lanes per row).  Chunk c of a level belongs to consumer warp c % W; every warp walks its own
+// static WORK LIST and passes every level barrier of the stage.
+//
+// Shared-memory value space of a part ("xwin", rows of 3 doubles): [0, window) the most recent rows of
+// the part (position in processing order & (window - 1)), [window, window + extWindow) a ring of rows
+// owned by other parts, parked there by helper warps, and one all-zero row at window + extWindow that
+// padded dependency slots point to.  A dependency code is simply the xwin row to read.
 //
 //   meta blob (ints, 16-byte multiple):
-//     header  [0] nentries [1] nchunks [2] g_lo (even-aligned first p-row of the rhs copy) [3] rhs rows copied
-//             [4] next (external rows of the stage) [5] off_ext [6] off_wl [7] off_chunks
-//     entries : at 8, nentries x {chunk_begin | barrier << 31, nchunks, ext_end, 0}
-//               barrier: a level boundary separates the entry from what precedes it; ext_end: external rows
-//               [0, ext_end) of the stage list must have arrived before the entry runs (cumulative)
-//     chunks  : at off_chunks (16-byte aligned), nchunks x {g0, count | nd << 8, cols_off | vals_off << 16, ext_need}
-//               ext_need = ext_end of its entry if the chunk reads an external row, else 0
-//     cols    : per chunk nd x count ints: >= 0 position (processing order) inside the part -> shared-memory window,
-//               < 0 and != kPadCol: -(index into the stage's external list + 1), kPadCol: no dependency
-//     ext     : at off_ext, next p-rows owned by OTHER parts (or by this part but beyond the window), grouped by the
-//               entry that first needs them; a helper warp polls them in global memory and parks them in the slot
-//     wl      : at off_wl, the static work lists of the W consumer warps: W + 1 offsets (relative to off_wl),
-//               W trailing barrier counts, then the items {chunk index | level barriers to pass first << 16}
+//     header  [0] ngroups [1] nchunks [2] g_lo (even-aligned first p-row of the rhs copy) [3] rhs rows copied
+//             [4] next (external rows of the stage) [5] off_ext [6] off_wl [7] off_items
+//             [8] ext_base (external rows of the part before this stage) [9] level barriers in the stage
+//     groups  : at 12, ngroups cumulative ends: the external rows [0, end) of the stage list are needed by the
+//               levels up to the group's; a helper warp delivers them group by group
+//     cols    : per chunk nd x count ints, xwin rows (see above)
+//     ext     : at off_ext, next p-rows (rows of other parts, or of this part beyond the window), in group order;
+//               row k of the list is parked at xwin row window + ((ext_base + k) & (extWindow - 1))
+//     wl      : at off_wl, W + 1 item offsets (per warp, in items) then W trailing barrier counts
+//     items   : at off_items (16-byte aligned), one int4 per chunk, grouped by warp in processing order:
+//               {g0, count | nd << 4 | barriers to pass first << 16, cols_off | vals_off << 16, wpos0 | ext_need << 16}
+//               row q of the chunk is p-row g0 + q (lower sweep) or g0 - q (upper sweep) and is written to
+//               xwin row (wpos0 + q) & (window - 1); ext_need: external rows [0, ext_need) must be parked
 //   vals blob (doubles, 16-byte multiple): per chunk (nd [+1 inverse pivot for U]) x 3 x (3 count) doubles,
 //     value ((j*3 + v) * 3 count + 3 q + comp) = LU[block j of row q][comp][v]  (lane-major: conflict-free, coalesced)
-//   row q of a chunk is p-row g0 + q (lower sweep) or g0 - q (upper sweep).
 struct StageRef {
     long long meta_off;    // ints into SweepPlan::meta
     long long vals_off;    // doubles into the sweep's value stream (even)
@@ -173,7 +178,7 @@ struct Analysis {
     int nflev = 0;
     std::vector<int> flevPtr, flevRows;
     // triangular sweeps
-    int nparts = 0, nlines = 0, window = 0, warps = 8;
+    int nparts = 0, nlines = 0, window = 0, warps = 8, extWindow = 1024;
     int nstrips = 0;
     std::vector<int> partPtr;         // nparts + 1, p-space rows
     std::vector<int> partMaxStep;     // rows in the largest level step of each part
@@ -187,6 +192,7 @@ struct AnalysisOptions {
     int stageBytes = 16384;     // meta + values + rhs of one ring slot
     int window = 2048;          // rows of the part kept in the shared-memory window (power of two)
     int warps = 8;              // consumer warps of a sweep CTA (the static work lists are cut for this many)
+    int extWindow = 1024;       // rows of the external-row ring (power of two); bounds ring slots x external rows per stage
 };
 
 namespace detail {
@@ -194,9 +200,11 @@ namespace detail {
 inline void build_sweep(const Analysis& A, const int* rows, const int* cols, const std::vector<int>& glev,
                         const std::vector<int>& partOf, bool lower, const AnalysisOptions& opt, SweepPlan& S)
 {
-    const int W = A.window;
+    const int W = A.window, EW = A.extWindow, NWc = A.warps;
+    const int zrow = W + EW;
     S.parts.resize(A.nparts);
-    struct TmpChunk { int g0, count, nd, level; std::vector<int> cols, src; };
+    // cols of a TmpChunk: >= 0 xwin row of the window, kPadCol padding, otherwise -(p-row + 1) of an external row
+    struct TmpChunk { int g0, count, nd, level, ps0; std::vector<int> cols, src; };
     for (int p = 0; p < A.nparts; ++p) {
         const int row0 = A.partPtr[p], nrows = A.partPtr[p + 1] - row0;
         const int slack = W - A.partMaxStep[p];
@@ -206,65 +214,56 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
         std::vector<TmpChunk> st;       // pending stage
         int st_bytes = 0, st_glo = 0, st_ghi = 0;
         int prev_level = -1;            // level of the last chunk emitted in this part
+        long long ext_base = 0;         // external rows of the part before the pending stage
         auto flush = [&]() {
             if (st.empty()) return;
-            const int NWc = A.warps;
-            std::vector<std::pair<int, int>> entries;   // (chunk_begin | barrier, nchunks): runs of equal level
-            for (size_t c = 0; c < st.size();) {
-                size_t e = c;
-                while (e < st.size() && st[e].level == st[c].level) ++e;
-                const bool barrier = prev_level >= 0 && st[c].level != prev_level;
-                entries.emplace_back((int) c | (barrier ? (int) 0x80000000u : 0), (int) (e - c));
-                prev_level = st[c].level;
-                c = e;
-            }
-            const int nent = (int) entries.size(), nch = (int) st.size();
-            // external rows of the stage, listed once, grouped by the first entry that needs them
-            std::vector<int> ext, ext_end(nent, 0), need(nch, 0);
+            const int nch = (int) st.size();
+            // external rows of the stage, listed once, grouped by the first level that needs them
+            std::vector<int> ext, gend, need(nch, 0);
+            std::vector<std::vector<int>> wl(NWc);          // chunk indices per warp
+            std::vector<std::vector<int>> wbar(NWc);        // barriers before each of them
+            std::vector<int> pend(NWc, 0);
+            int nbar_total = 0;
             {
                 std::vector<std::pair<int, int>> seen;      // (p-row, index), kept sorted
-                for (int e = 0; e < nent; ++e) {
-                    const int cb = entries[e].first & 0x7fffffff;
-                    for (int c = cb; c < cb + entries[e].second; ++c) {
+                for (int c = 0; c < nch;) {
+                    int e = c;
+                    while (e < nch && st[e].level == st[c].level) ++e;
+                    if (prev_level >= 0 && st[c].level != prev_level) { for (int w = 0; w < NWc; ++w) pend[w]++; nbar_total++; }
+                    prev_level = st[c].level;
+                    for (int k = c; k < e; ++k) {
                         bool any = false;
-                        for (int& code : st[c].cols) {
+                        for (int& code : st[k].cols) {
                             if (code >= 0 || code == kPadCol) continue;
                             const int gd = -(code + 1);
                             auto it = std::lower_bound(seen.begin(), seen.end(), std::make_pair(gd, -1));
                             int idx;
                             if (it != seen.end() && it->first == gd) idx = it->second;
                             else { idx = (int) ext.size(); ext.push_back(gd); seen.insert(it, std::make_pair(gd, idx)); }
-                            code = -(idx + 1);
+                            code = W + (int) ((ext_base + idx) & (EW - 1));
                             any = true;
                         }
-                        need[c] = any ? 1 : 0;
+                        need[k] = any ? 1 : 0;
+                        const int w = (k - c) % NWc;
+                        wl[w].push_back(k);
+                        wbar[w].push_back(pend[w]);
+                        pend[w] = 0;
                     }
-                    ext_end[e] = (int) ext.size();
-                    for (int c = cb; c < cb + entries[e].second; ++c) if (need[c]) need[c] = ext_end[e];
+                    if (gend.empty() || (int) ext.size() != gend.back()) { if (!ext.empty()) gend.push_back((int) ext.size()); }
+                    for (int k = c; k < e; ++k) if (need[k]) need[k] = (int) ext.size();
+                    c = e;
                 }
             }
-            const int next = (int) ext.size();
-            if (next >= 65536 || nch >= 65536 || nent >= 32768) throw std::runtime_error("sweep stage too large");
-            // static work lists: chunk c of an entry goes to warp c % W; every warp passes every level barrier
-            std::vector<std::vector<int>> wl(NWc);
-            std::vector<int> pend(NWc, 0);
-            for (int e = 0; e < nent; ++e) {
-                if (entries[e].first < 0) for (int w = 0; w < NWc; ++w) pend[w]++;
-                const int cb = entries[e].first & 0x7fffffff;
-                for (int c = 0; c < entries[e].second; ++c) {
-                    const int w = c % NWc;
-                    wl[w].push_back((cb + c) | (pend[w] << 16));
-                    pend[w] = 0;
-                }
-            }
-            const int off_chunks = (8 + 4 * nent + 3) & ~3;
-            const int off_cols = off_chunks + 4 * nch;
+            for (auto& c : st) for (int& code : c.cols) if (code == kPadCol) code = zrow;
+            const int next = (int) ext.size(), ngroups = (int) gend.size();
+            if (next >= 65536 || nch >= 65536 || nbar_total >= 32768 || next > EW) throw std::runtime_error("sweep stage too large");
+            const int off_cols = 12 + ngroups;
             int ncols = 0;
             for (auto& c : st) ncols += c.nd * c.count;
             const int off_ext = off_cols + ncols;
             const int off_wl = off_ext + next;
-            const int wl_ints = 2 * NWc + 1 + nch;
-            const int meta_ints = (off_wl + wl_ints + 3) & ~3;
+            const int off_items = (off_wl + 2 * NWc + 1 + 3) & ~3;
+            const int meta_ints = off_items + 4 * nch;
             StageRef R{};
             R.meta_off = (long long) S.meta.size();
             R.meta_ints = meta_ints;
@@ -274,20 +273,17 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             R.g_rows = ghi_al - glo_al;
             S.meta.resize(S.meta.size() + meta_ints, 0);
             int* m = S.meta.data() + R.meta_off;
-            m[0] = nent; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows; m[4] = next; m[5] = off_ext; m[6] = off_wl; m[7] = off_chunks;
-            for (int e = 0; e < nent; ++e) {
-                m[8 + 4 * e] = entries[e].first; m[9 + 4 * e] = entries[e].second; m[10 + 4 * e] = ext_end[e]; m[11 + 4 * e] = 0;
-            }
+            m[0] = ngroups; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows; m[4] = next; m[5] = off_ext; m[6] = off_wl; m[7] = off_items;
+            m[8] = (int) (ext_base & (EW - 1)); m[9] = nbar_total;
+            std::copy(gend.begin(), gend.end(), m + 12);
+            std::vector<int> cols_off(nch), vals_off(nch);
             int co = off_cols;
             long long vo = 0;
             for (int c = 0; c < nch; ++c) {
                 const TmpChunk& t = st[c];
                 const int nd_eff = t.nd + (lower ? 0 : 1);
                 if (co >= 65536 || vo >= 65536) throw std::runtime_error("sweep stage too large for the packed chunk offsets");
-                m[off_chunks + 4 * c + 0] = t.g0;
-                m[off_chunks + 4 * c + 1] = t.count | (t.nd << 8);
-                m[off_chunks + 4 * c + 2] = co | ((int) vo << 16);
-                m[off_chunks + 4 * c + 3] = need[c];
+                cols_off[c] = co; vals_off[c] = (int) vo;
                 std::copy(t.cols.begin(), t.cols.end(), m + co);
                 co += t.nd * t.count;
                 BuildRef B{};
@@ -302,11 +298,18 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             std::copy(ext.begin(), ext.end(), m + off_ext);
             {
                 int* w0 = m + off_wl;
-                int o = 2 * NWc + 1;
+                int o = 0;
                 for (int w = 0; w < NWc; ++w) {
                     w0[w] = o;
-                    std::copy(wl[w].begin(), wl[w].end(), w0 + o);
-                    o += (int) wl[w].size();
+                    for (size_t t = 0; t < wl[w].size(); ++t, ++o) {
+                        const int c = wl[w][t];
+                        const TmpChunk& ch = st[c];
+                        int* it = m + off_items + 4 * o;
+                        it[0] = ch.g0;
+                        it[1] = ch.count | (ch.nd << 4) | (wbar[w][t] << 16);
+                        it[2] = cols_off[c] | (vals_off[c] << 16);
+                        it[3] = (ch.ps0 & (W - 1)) | (need[c] << 16);
+                    }
                     w0[NWc + 1 + w] = pend[w];
                 }
                 w0[NWc] = o;
@@ -318,11 +321,12 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             S.maxMetaInts = std::max(S.maxMetaInts, meta_ints);
             S.maxValsDoubles = std::max(S.maxValsDoubles, R.vals_doubles);
             S.maxRhsRows = std::max(S.maxRhsRows, R.g_rows);
-            S.maxExtRows = std::max(S.maxExtRows, (next + 1) & ~1);
+            S.maxExtRows = std::max(S.maxExtRows, next);
             S.nExtRows += next;
             S.nchunks += nch;
-            S.nentries += nent;
+            S.nentries += nbar_total;
             S.stages.push_back(R);
+            ext_base += next;
             st.clear();
             st_bytes = 0;
         };
@@ -337,6 +341,7 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                 TmpChunk t;
                 t.count = std::min(kRowsPerWarp, end - s);
                 t.g0 = g_of(s);
+                t.ps0 = s;
                 t.level = lev;
                 t.nd = 0;
                 for (int q = 0; q < t.count; ++q) {
@@ -345,10 +350,11 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                     for (int k = rows[r]; k < rows[r + 1]; ++k) n += lower ? cols[k] < r : cols[k] > r;
                     t.nd = std::max(t.nd, n);
                 }
-                if (t.nd > 0xffff) throw std::runtime_error("block row too long for the sweep chunk descriptor");
+                if (t.nd > 0xfff) throw std::runtime_error("block row too long for the sweep chunk descriptor");
                 const int nd_eff = t.nd + (lower ? 0 : 1);
                 t.cols.assign((size_t) t.nd * t.count, kPadCol);
                 t.src.assign((size_t) nd_eff * t.count, -1);
+                int nextc = 0;
                 for (int q = 0; q < t.count; ++q) {
                     const int ps = s + q, g = g_of(ps), r = A.perm[g];
                     int j = 0;
@@ -360,9 +366,9 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                             if (partOf[c] == p) {
                                 const int pd = lower ? gd - row0 : row0 + nrows - 1 - gd;      // processing position of the dependency
                                 if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
-                                if (ps - pd <= slack) { code = pd; S.nWindow++; }
+                                if (ps - pd <= slack) { code = pd & (W - 1); S.nWindow++; }
                             }
-                            if (code < 0) S.nExternal++;
+                            if (code < 0) { S.nExternal++; nextc++; }
                             t.cols[(size_t) j * t.count + q] = code;
                             t.src[(size_t) j * t.count + q] = A.prow[g] + (k - rows[r]);
                             ++j;
@@ -370,9 +376,7 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                     }
                     if (!lower) t.src[(size_t) t.nd * t.count + q] = A.pdiag[g];
                 }
-                int nextc = 0;
-                for (int code : t.cols) nextc += (code < 0 && code != kPadCol);
-                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8 + 28 * nextc + 4;
+                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8 + 4 * nextc + 4;
                 if (!st.empty() && st_bytes + bytes > opt.stageBytes) flush();
                 if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 160; }
                 const int glo = lower ? t.g0 : t.g0 - t.count + 1, ghi = lower ? t.g0 + t.count : t.g0 + 1;
@@ -400,6 +404,8 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
     A.window = opt.window;
     if (opt.warps < 1 || opt.warps > 14) throw std::runtime_error("consumer warps must be in 1..14");
     A.warps = opt.warps;
+    if (opt.extWindow < 64 || (opt.extWindow & (opt.extWindow - 1))) throw std::runtime_error("extWindow must be a power of two >= 64");
+    A.extWindow = opt.extWindow;
     for (int r = 0; r < Nb; ++r) {
         bool diag = false;
         for (int k = rows[r]; k < rows[r + 1]; ++k) {
@@ -631,102 +637,121 @@ inline void fill_stream_host(const SweepPlan& S, const double* LU, std::vector<d
 inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, const std::vector<double>& vals, const double* rhs,
                           double* out, double relax)
 {
-    const int W = A.window;
+    const int W = A.window, EW = A.extWindow, NW = A.warps, zrow = W + EW;
     const double NaN = std::nan("");
     for (int i = 0; i < 3 * A.Nb; ++i) out[i] = NaN;
-    // the static work lists must cover every chunk exactly once, in entry order per warp, and every warp must pass
-    // the same number of level barriers per stage (the device kernel relies on both)
-    for (const StageRef& R : S.stages) {
-        const int* m = S.meta.data() + R.meta_off;
-        const int nent = m[0], nch = m[1];
-        const int* wl = m + m[6];
-        int nbar = 0;
-        for (int e = 0; e < nent; ++e) nbar += m[8 + 4 * e] < 0;
-        std::vector<int> entry_of(nch, -1), hit(nch, 0);
-        for (int e = 0; e < nent; ++e)
-            for (int c = 0; c < m[9 + 4 * e]; ++c) entry_of[(m[8 + 4 * e] & 0x7fffffff) + c] = e;
-        for (int w = 0; w < A.warps; ++w) {
-            int bars = wl[A.warps + 1 + w], last_entry = -1;
-            for (int t = wl[w]; t < wl[w + 1]; ++t) {
-                const int c = wl[t] & 0xffff, nb = wl[t] >> 16;
-                if (c >= nch || hit[c]++) throw std::runtime_error("emulate: bad sweep work list");
-                if (entry_of[c] < last_entry) throw std::runtime_error("emulate: work list out of order");
-                int expect = 0;
-                for (int e = last_entry + 1; e <= entry_of[c]; ++e) expect += m[8 + 4 * e] < 0;
-                if (last_entry == entry_of[c]) expect = 0;
-                if (nb != expect) throw std::runtime_error("emulate: wrong barrier count in a sweep work list");
-                last_entry = entry_of[c];
-                bars += nb;
-            }
-            if (bars != nbar) throw std::runtime_error("emulate: warps disagree on the barrier count of a stage");
-        }
-        for (int c = 0; c < nch; ++c) if (hit[c] != 1) throw std::runtime_error("emulate: chunk missing from the work lists");
+    // One cursor per consumer warp, exactly the control flow of k_sweep: walk the work list, pass `nbar` level
+    // barriers (all W warps must arrive), wait for the parked external rows, compute, finally the trailing barriers.
+    struct Warp { int t, bars, tail_left; bool loaded, in_tail, done, at_bar; };
+    struct Part { int stage; std::vector<Warp> w; int arrivals; std::vector<double> xwin; bool started; };
+    std::vector<Part> parts(A.nparts);
+    for (int p = 0; p < A.nparts; ++p) {
+        parts[p].stage = S.parts[p].stage_begin;
+        parts[p].w.assign(NW, Warp{0, 0, 0, false, false, false, false});
+        parts[p].arrivals = 0;
+        parts[p].xwin.assign((size_t) 3 * (zrow + 1), NaN);
+        for (int e = 0; e < 3; ++e) parts[p].xwin[(size_t) 3 * zrow + e] = 0.0;
+        parts[p].started = false;
     }
-    struct Cursor { int stage, entry, chunk; std::vector<double> win; };
-    std::vector<Cursor> cur(A.nparts);
-    for (int p = 0; p < A.nparts; ++p) cur[p] = {S.parts[p].stage_begin, 0, 0, std::vector<double>((size_t) 3 * W, NaN)};
     int remaining = A.nparts;
-    std::vector<char> done(A.nparts, 0);
+    std::vector<char> finished(A.nparts, 0);
     while (remaining > 0) {
         bool progress = false;
         for (int p = 0; p < A.nparts; ++p) {
-            if (done[p]) continue;
-            Cursor& c = cur[p];
-            const PartRef& P = S.parts[p];
+            if (finished[p]) continue;
+            Part& P = parts[p];
+            const PartRef& PR = S.parts[p];
             while (true) {
-                if (c.stage >= P.stage_end) { done[p] = 1; --remaining; progress = true; break; }
-                const StageRef& R = S.stages[c.stage];
+                if (P.stage >= PR.stage_end) { finished[p] = 1; --remaining; progress = true; break; }
+                const StageRef& R = S.stages[P.stage];
                 const int* m = S.meta.data() + R.meta_off;
-                const int nent = m[0];
-                if (c.entry >= nent) { c.stage++; c.entry = 0; c.chunk = 0; continue; }
-                const int cb = m[8 + 4 * c.entry] & 0x7fffffff, nc = m[9 + 4 * c.entry], ext_end = m[10 + 4 * c.entry];
-                if (c.chunk >= nc) { c.entry++; c.chunk = 0; continue; }
-                const int* ext = m + m[5];
-                // the helper warp delivers the external rows of an entry as a group: all of them must exist
-                bool ready = true;
-                for (int x = 0; x < ext_end && ready; ++x) ready = !std::isnan(out[3 * (size_t) ext[x]]);
-                if (!ready) break;      // yield to the next part
-                const int* d = m + m[7] + 4 * (cb + c.chunk);
-                const int g0 = d[0], count = d[1] & 255, nd = d[1] >> 8, co = d[2] & 0xffff, vo = (int) ((unsigned) d[2] >> 16);
-                const double* v = vals.data() + R.vals_off + vo;
-                double res[kRowsPerWarp][3];
-                for (int q = 0; q < count; ++q) {
-                    const int g = lower ? g0 + q : g0 - q;
-                    if (g < R.g_lo || g >= R.g_lo + R.g_rows) throw std::runtime_error("emulate: row outside the stage's rhs window");
-                    double acc[3];
-                    for (int comp = 0; comp < 3; ++comp) {
-                        double a = rhs[3 * (size_t) g + comp];
-                        for (int j = 0; j < nd; ++j) {
-                            const int code = m[co + j * count + q];
-                            if (code == kPadCol) continue;
-                            if (code < 0 && (-(code + 1) >= d[3] || -(code + 1) >= m[4])) throw std::runtime_error("emulate: external index beyond ext_need");
-                            const double* x = code >= 0 ? c.win.data() + 3 * (size_t) (code & (W - 1)) : out + 3 * (size_t) ext[-(code + 1)];
-                            for (int e = 0; e < 3; ++e) {
-                                if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
-                                a -= v[(size_t) (j * 3 + e) * 3 * count + 3 * q + comp] * x[e];
+                const int* extl = m + m[5];
+                const int* wl = m + m[6];
+                const int* items = m + m[7];
+                const int ext_base = m[8];
+                if (!P.started) {
+                    int nitems = 0;
+                    for (int w = 0; w < NW; ++w) {
+                        P.w[w] = Warp{wl[w], 0, 0, false, false, false, false};
+                        int bars = wl[NW + 1 + w];
+                        for (int t = wl[w]; t < wl[w + 1]; ++t, ++nitems) bars += (items[4 * t + 1] >> 16) & 0xffff;
+                        if (bars != m[9]) throw std::runtime_error("emulate: warps disagree on the barrier count of a stage");
+                    }
+                    if (nitems != m[1]) throw std::runtime_error("emulate: work lists do not cover the chunks of the stage");
+                    if (m[4] > EW) throw std::runtime_error("emulate: external rows of a stage exceed the ring");
+                    P.arrivals = 0;
+                    P.started = true;
+                }
+                bool local = false;
+                int ndone = 0;
+                for (int w = 0; w < NW; ++w) {
+                    Warp& c = P.w[w];
+                    if (c.done) { ++ndone; continue; }
+                    if (c.at_bar) continue;
+                    if (!c.in_tail && !c.loaded) {
+                        if (c.t == wl[w + 1]) { c.in_tail = true; c.bars = wl[NW + 1 + w]; }
+                        else { c.bars = (items[4 * c.t + 1] >> 16) & 0xffff; c.loaded = true; }
+                    }
+                    if (c.bars > 0) { c.at_bar = true; P.arrivals++; local = true; continue; }
+                    if (c.in_tail) { c.done = true; ++ndone; local = true; continue; }
+                    const int* it = items + 4 * c.t;
+                    const int g0 = it[0], count = it[1] & 15, nd = (it[1] >> 4) & 0xfff;
+                    const int co = it[2] & 0xffff, vo = (int) ((unsigned) it[2] >> 16);
+                    const int wpos0 = it[3] & 0xffff, need = (int) ((unsigned) it[3] >> 16);
+                    bool ready = true;
+                    for (int x = 0; x < need && ready; ++x) ready = !std::isnan(out[3 * (size_t) extl[x]]);
+                    if (!ready) continue;                     // the helper warp has not delivered this group yet
+                    const double* v = vals.data() + R.vals_off + vo;
+                    double res[kRowsPerWarp][3];
+                    for (int q = 0; q < count; ++q) {
+                        const int g = lower ? g0 + q : g0 - q;
+                        if (g < R.g_lo || g >= R.g_lo + R.g_rows) throw std::runtime_error("emulate: row outside the stage's rhs window");
+                        double acc[3];
+                        for (int comp = 0; comp < 3; ++comp) {
+                            double a = rhs[3 * (size_t) g + comp];
+                            for (int j = 0; j < nd; ++j) {
+                                const int code = m[co + j * count + q];
+                                if (code < 0 || code > zrow) throw std::runtime_error("emulate: bad dependency code");
+                                const double* x;
+                                if (code >= W && code < zrow) {      // parked external row: map the ring slot back to the list
+                                    const int k = (code - W - ext_base) & (EW - 1);
+                                    if (k >= need) throw std::runtime_error("emulate: external row beyond ext_need");
+                                    x = out + 3 * (size_t) extl[k];
+                                } else x = P.xwin.data() + 3 * (size_t) code;
+                                for (int e = 0; e < 3; ++e) {
+                                    if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
+                                    a -= v[(size_t) (j * 3 + e) * 3 * count + 3 * q + comp] * x[e];
+                                }
                             }
+                            acc[comp] = a;
                         }
-                        acc[comp] = a;
-                    }
-                    for (int comp = 0; comp < 3; ++comp) {
-                        double r = acc[comp];
-                        if (!lower) {
-                            r = 0.0;
-                            for (int e = 0; e < 3; ++e) r += v[(size_t) (nd * 3 + e) * 3 * count + 3 * q + comp] * acc[e];
-                            r *= relax;
+                        for (int comp = 0; comp < 3; ++comp) {
+                            double r = acc[comp];
+                            if (!lower) {
+                                r = 0.0;
+                                for (int e = 0; e < 3; ++e) r += v[(size_t) (nd * 3 + e) * 3 * count + 3 * q + comp] * acc[e];
+                                r *= relax;
+                            }
+                            res[q][comp] = r;
                         }
-                        res[q][comp] = r;
                     }
-                }
-                for (int q = 0; q < count; ++q) {
-                    const int g = lower ? g0 + q : g0 - q;
-                    const int pos = lower ? g - P.row0 : P.row0 + P.nrows - 1 - g;
-                    for (int comp = 0; comp < 3; ++comp) {
-                        c.win[3 * (size_t) (pos & (W - 1)) + comp] = res[q][comp];
-                        out[3 * (size_t) g + comp] = res[q][comp];
+                    for (int q = 0; q < count; ++q) {
+                        const int g = lower ? g0 + q : g0 - q;
+                        for (int comp = 0; comp < 3; ++comp) {
+                            P.xwin[3 * (size_t) ((wpos0 + q) & (W - 1)) + comp] = res[q][comp];
+                            out[3 * (size_t) g + comp] = res[q][comp];
+                        }
                     }
+                    c.t++; c.loaded = false;
+                    local = true;
                 }
-                c.chunk++;
+                if (P.arrivals == NW) {
+                    for (int w = 0; w < NW; ++w) { P.w[w].at_bar = false; P.w[w].bars--; }
+                    P.arrivals = 0;
+                    local = true;
+                }
+                if (ndone == NW) { P.stage++; P.started = false; progress = true; continue; }
+                if (!local) break;          // every warp waits for another part: yield
                 progress = true;
             }
         }

@@ -366,11 +366,15 @@ struct Solver {
         sweep_valsCap = std::max(an.L.maxValsDoubles, an.U.maxValsDoubles);
         sweep_rhsCap = std::max(an.L.maxRhsRows, an.U.maxRhsRows);
         sweep_extCap = std::max(an.L.maxExtRows, an.U.maxExtRows);
-        const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24 + (size_t) sweep_extCap * 24;
+        const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
+        const size_t fixedBytes = kSweepHeader + (size_t) (sweep_window + an.extWindow + 2) * 24;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
-        while (sweep_slots > 2 && kSweepHeader + (size_t) sweep_window * 24 + sweep_slots * slotBytes > smem_optin) --sweep_slots;
-        sweep_smem = kSweepHeader + (size_t) sweep_window * 24 + sweep_slots * slotBytes;
-        sweep_helpers = std::max(1, std::min(sweep_helpers, 15 - sweep_warps));
+        // the stages in flight must fit the shared memory of an SM and their external rows the external ring
+        while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_optin || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
+        sweep_smem = fixedBytes + sweep_slots * slotBytes;
+        if ((long long) sweep_slots * sweep_extCap > an.extWindow)
+            throw std::runtime_error("external-row ring of the triangular sweeps too small (" + std::to_string(sweep_extCap) + " rows per stage)");
+        sweep_helpers = std::max(1, std::min({sweep_helpers, 15 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
         if (sweep_smem > smem_optin)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
@@ -532,7 +536,7 @@ struct Solver {
         a.rhs = rhs; a.out = out; a.rearm = rearm; a.S = d_S.p;
         a.relax = lower ? 1.0 : relaxation;
         a.nparts = an.nparts; a.nslots = sweep_slots; a.window = sweep_window;
-        a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extCap = sweep_extCap;
+        a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extWindow = an.extWindow;
         a.nwarps = sweep_warps; a.nhalo = sweep_helpers;
         a.check_done = check_done ? 1 : 0;
         a.trace = sweep_trace ? d_trace.p : nullptr;

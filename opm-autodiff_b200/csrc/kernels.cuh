@@ -353,7 +353,7 @@ struct SweepArgs {
     double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
     Scalars* S;
     double relax;
-    int nparts, nslots, window, metaCap, valsCap, rhsCap, extCap, nwarps, nhalo, check_done;
+    int nparts, nslots, window, extWindow, metaCap, valsCap, rhsCap, nwarps, nhalo, check_done;
     long long* trace;     // debugging aid (may be null): per part and stage {wait begin, data landed, stage done, issued} in SM cycles
     int trace_cap;
 };
@@ -369,13 +369,11 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v)
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-// One decoded chunk: everything a consumer warp can fetch BEFORE the level barrier that releases the chunk.
+// Everything of one chunk a consumer lane can fetch BEFORE the level barrier that releases the chunk.
 struct ChunkRegs {
-    int g, pos, count, nd, lanes, cols_off, vals_off, need, nbar;
-    int col[kSweepBatch];
-    double a[kSweepBatch][3];
+    int code[kSweepBatch];        // xwin rows of the first three dependencies
+    double a[kSweepBatch][3];     // this lane's row of their factor blocks
     double acc, inv[3];
-    bool act;
 };
 
 // One triangular sweep.  One persistent CTA per PART (pencil of grid lines, analysis.hpp), all resident.
@@ -386,17 +384,18 @@ struct ChunkRegs {
 //   helper warps  : rows owned by OTHER parts are the only values that travel through L2 (every sweep finds
 //                   `out` armed with a NaN sentinel, producers overwrite it with relaxed gpu-scope 8-byte
 //                   stores: the value is its own ready flag).  Helper warp h takes the stages i = h (mod H):
-//                   as soon as the stage's meta has landed it polls the stage's external rows, entry by
-//                   entry, and parks them in the slot -- one L2 round trip (0.4-0.9 us) per level, but
-//                   several stages AHEAD of the consumers and off their critical path; it publishes a
-//                   per-slot counter the consumers check (shared memory, ~30 cycles);
+//                   as soon as the stage's meta has landed it polls the stage's external rows, level group by
+//                   level group, and parks them in the external ring of the shared-memory value space -- one
+//                   L2 round trip per group, but several stages AHEAD of the consumers and off their critical
+//                   path; it publishes a per-slot counter the consumers check (shared memory, ~30 cycles);
 //   consumer warps: a chunk = <= 10 rows of one level, 3 lanes per row; each warp walks its own static
-//                   work list of the stage and decodes chunk t+1 (descriptor, columns, factor values,
-//                   rhs) before it waits for the level barrier of chunk t, so that between two level
-//                   barriers only the dependent part is left: window reads (values of earlier rows of this
-//                   part, written by the consumers), 9 fma, window store.
+//                   work list of the stage, two chunks deep in flight: the item of chunk t+2 and the columns,
+//                   factor values and rhs of chunk t+1 are loaded before the level barrier of chunk t, so
+//                   between two level barriers only the dependent part is left: 9 shared-memory reads of
+//                   earlier rows (window, parked external rows or the zero row: one flat value space, no
+//                   branches), 9 fma, one store.
 // Parts process their rows in ascending (descending for U) global level, a topological order of the
-// whole DAG, and an entry only ever waits for rows of earlier levels, so the waits cannot cycle as long
+// whole DAG, and a level only ever waits for rows of earlier levels, so the waits cannot cycle as long
 // as every CTA is resident (grid <= SMs).
 template <bool LOWER>
 __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
@@ -409,10 +408,11 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
     unsigned long long* empty = full + kSweepMaxSlots;
     int* ext_ready = reinterpret_cast<int*>(sweep_smem + 128);
-    double* win = reinterpret_cast<double*>(sweep_smem + kSweepHeader);
-    unsigned char* slots = reinterpret_cast<unsigned char*>(win + 3 * (size_t) P.window);
+    double* xwin = reinterpret_cast<double*>(sweep_smem + kSweepHeader);
+    const int W = P.window, EW = P.extWindow, zrow = W + EW;
+    unsigned char* slots = reinterpret_cast<unsigned char*>(xwin + 3 * (size_t) (zrow + 2));
     const size_t metaBytes = (size_t) P.metaCap * 4, valsBytes = (size_t) P.valsCap * 8, rhsBytes = (size_t) P.rhsCap * 24;
-    const size_t slotBytes = metaBytes + valsBytes + rhsBytes + (size_t) P.extCap * 24;
+    const size_t slotBytes = metaBytes + valsBytes + rhsBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW = P.nwarps, NH = P.nhalo;
     const int nslots = P.nslots;
@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (threadIdx.x < 6) xwin[3 * (size_t) zrow + threadIdx.x] = 0.0;
     __syncthreads();
     const int nst = pr.stage_end - pr.stage_begin;
 
@@ -453,19 +454,17 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 
     if (warp > NW) {                                // ---- helpers: external rows ----
         const int h = warp - NW - 1;
+        double* ring = xwin + 3 * (size_t) W;
         for (int i = h; i < nst; i += NH) {
             const int s = i % nslots;
             mbar_wait(full + s, (i / nslots) & 1);
-            unsigned char* base = slots + (size_t) s * slotBytes;
-            const int* m = reinterpret_cast<const int*>(base);
-            double* ex = reinterpret_cast<double*>(base + metaBytes + valsBytes + rhsBytes);
-            const int nent = m[0], next = m[4];
+            const int* m = reinterpret_cast<const int*>(slots + (size_t) s * slotBytes);
+            const int ngroups = m[0], ext_base = m[8];
             const int* extl = m + m[5];
             const int tag = (i + 1) << 16;
             int e0 = 0;
-            for (int e = 0; e < nent && e0 < next; ++e) {
-                const int eend = m[10 + 4 * e];
-                if (eend == e0) continue;
+            for (int gi = 0; gi < ngroups; ++gi) {
+                const int eend = m[12 + gi];
                 while (e0 < eend) {
                     const int idx = e0 + lane;
                     const bool on = idx < eend;
@@ -485,7 +484,10 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                         }
                         __nanosleep(40);
                     }
-                    if (on) { ex[3 * idx] = x0; ex[3 * idx + 1] = x1; ex[3 * idx + 2] = x2; }
+                    if (on) {
+                        double* d = ring + 3 * (size_t) ((ext_base + idx) & (EW - 1));
+                        d[0] = x0; d[1] = x1; d[2] = x2;
+                    }
                     e0 = min(e0 + 32, eend);
                 }
                 __syncwarp();
@@ -500,8 +502,9 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 
     // ---- consumers ----
     const int q = lane / 3, comp = lane - 3 * q;
-    const int wmask = P.window - 1;
+    const int wmask = W - 1;
     const int nthreads = NW * 32;
+    const int rhs_lane = LOWER ? lane : comp - 3 * q;         // rhs row of this lane relative to the chunk's first row
     const bool tracing = P.trace != nullptr && threadIdx.x == 0;
     for (int i = 0; i < nst; ++i) {
         const int s = i % nslots;
@@ -510,88 +513,88 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
         if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 1] = clock64();
         const unsigned char* base = slots + (size_t) s * slotBytes;
         const int* m = reinterpret_cast<const int*>(base);
-        const double* vv = reinterpret_cast<const double*>(base + metaBytes);
-        const double* rr = reinterpret_cast<const double*>(base + metaBytes + valsBytes);
-        const double* ex = reinterpret_cast<const double*>(base + metaBytes + valsBytes + rhsBytes);
-        const int g_lo = m[2], off_chunks = m[7];
+        const double* vv = reinterpret_cast<const double*>(base + metaBytes) + lane;
         const int* wl = m + m[6];
+        const int4* items = reinterpret_cast<const int4*>(m + m[7]);
+        const double* rr = reinterpret_cast<const double*>(base + metaBytes + valsBytes) - 3 * m[2] + rhs_lane;
         const int tb = wl[warp], te = wl[warp + 1], tail = wl[NW + 1 + warp];
         const int tag = (i + 1) << 16;
 
-        auto decode = [&](int item) {
+        auto fetch = [&](const int4 it) {
             ChunkRegs c;
-            const int4 d = *reinterpret_cast<const int4*>(m + off_chunks + 4 * (item & 0xffff));
-            c.nbar = item >> 16;
-            c.count = d.y & 255; c.nd = d.y >> 8;
-            c.act = q < c.count;
-            c.g = LOWER ? d.x + q : d.x - q;
-            c.pos = LOWER ? c.g - pr.row0 : pr.row0 + pr.nrows - 1 - c.g;
-            c.lanes = 3 * c.count;
-            c.cols_off = d.z & 0xffff; c.vals_off = (int) ((unsigned) d.z >> 16);
-            c.need = d.w;
-            const double* vb = vv + c.vals_off + lane;
+            const int count = it.y & 15, nd = (it.y >> 4) & 0xfff, lanes = 3 * count;
+            const bool act = q < count;
+            const int* cp = m + (it.z & 0xffff) + q;
+            const double* vb = vv + ((unsigned) it.z >> 16);
 #pragma unroll
             for (int j = 0; j < kSweepBatch; ++j) {
-                const bool on = c.act && j < c.nd;
-                c.col[j] = on ? m[c.cols_off + j * c.count + q] : kPadColD;
+                const bool on = j < nd;                       // warp-uniform
+                c.code[j] = (on && act) ? cp[j * count] : zrow;
 #pragma unroll
-                for (int v = 0; v < 3; ++v) c.a[j][v] = on ? vb[(j * 3 + v) * c.lanes] : 0.0;
+                for (int v = 0; v < 3; ++v) c.a[j][v] = on ? vb[(j * 3 + v) * lanes] : 0.0;
             }
-            c.acc = c.act ? rr[3 * (c.g - g_lo) + comp] : 0.0;
+            c.acc = act ? rr[3 * it.x] : 0.0;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) c.inv[v] = (!LOWER && c.act) ? vb[(c.nd * 3 + v) * c.lanes] : 0.0;
+            for (int v = 0; v < 3; ++v) c.inv[v] = LOWER ? 0.0 : vb[(nd * 3 + v) * lanes];
             return c;
         };
 
-        ChunkRegs nx;
-        if (tb < te) nx = decode(wl[tb]);
+        const int4 none = make_int4(0, 0, 0, 0);
+        int4 it1 = tb < te ? items[tb] : none;                // item of chunk t
+        int4 it2 = tb + 1 < te ? items[tb + 1] : none;        // item of chunk t + 1
+        ChunkRegs nx = fetch(it1);
         for (int t = tb; t < te; ++t) {
+            const int4 it = it1;
             const ChunkRegs c = nx;
-            if (t + 1 < te) nx = decode(wl[t + 1]);
-            for (int b = 0; b < c.nbar; ++b) named_barrier(1, nthreads);
-            if (c.need) {                                   // external rows of this level: parked by a helper warp
+            it1 = it2;
+            if (t + 2 < te) it2 = items[t + 2];
+            if (t + 1 < te) nx = fetch(it1);
+            const int nbar = (it.y >> 16) & 0xffff, need = (int) ((unsigned) it.w >> 16);
+            for (int b = 0; b < nbar; ++b) named_barrier(1, nthreads);
+            if (need) {                                       // external rows of this level: parked by a helper warp
                 int spins = 0;
-                while (ld_volatile_s32(ext_ready + s) - (tag + c.need) < 0) {
+                while (ld_volatile_s32(ext_ready + s) - (tag + need) < 0) {
                     if ((++spins & 4095) == 0 && *((volatile int*) &P.S->trsv_timeout)) break;
                 }
                 __threadfence_block();
             }
-            // ---- exposed part: window / parked reads, fma, publish ----
+            // ---- exposed part: 9 reads of earlier rows, fma, publish ----
             double acc = c.acc;
 #pragma unroll
             for (int j = 0; j < kSweepBatch; ++j) {
-                const int cj = c.col[j];
-                const double* xp = cj >= 0 ? win + 3 * (cj & wmask) : ex + 3 * (cj == kPadColD ? 0 : -(cj + 1));
-                const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
-                double tt = c.a[j][0] * x0;
-                tt = fma(c.a[j][1], x1, tt);
-                tt = fma(c.a[j][2], x2, tt);
-                acc -= (cj == kPadColD) ? 0.0 : tt;
+                const double* xp = xwin + 3 * c.code[j];
+                double tt = c.a[j][0] * xp[0];
+                tt = fma(c.a[j][1], xp[1], tt);
+                tt = fma(c.a[j][2], xp[2], tt);
+                acc -= tt;
             }
-            if (c.nd > kSweepBatch) {                       // long rows (NNC, wells in the matrix): unpipelined tail
-                const double* vb = vv + c.vals_off + lane;
-                for (int j = kSweepBatch; j < c.nd; ++j) {
-                    const int cj = c.act ? m[c.cols_off + j * c.count + q] : kPadColD;
-                    if (cj == kPadColD) continue;
-                    const double* xp = cj >= 0 ? win + 3 * (cj & wmask) : ex + 3 * (-(cj + 1));
-                    double tt = vb[(j * 3) * c.lanes] * xp[0];
-                    tt = fma(vb[(j * 3 + 1) * c.lanes], xp[1], tt);
-                    tt = fma(vb[(j * 3 + 2) * c.lanes], xp[2], tt);
+            const int count = it.y & 15, nd = (it.y >> 4) & 0xfff;
+            const bool act = q < count;
+            if (nd > kSweepBatch) {                           // long rows (NNC, wells in the matrix): unpipelined tail
+                const int lanes = 3 * count;
+                const int* cp = m + (it.z & 0xffff) + q;
+                const double* vb = vv + ((unsigned) it.z >> 16);
+                for (int j = kSweepBatch; j < nd; ++j) {
+                    const double* xp = xwin + 3 * (act ? cp[j * count] : zrow);
+                    double tt = vb[(j * 3) * lanes] * xp[0];
+                    tt = fma(vb[(j * 3 + 1) * lanes], xp[1], tt);
+                    tt = fma(vb[(j * 3 + 2) * lanes], xp[2], tt);
                     acc -= tt;
                 }
             }
             double res = acc;
             if (!LOWER) {
-                const int b3 = c.act ? 3 * q : 0;
+                const int b3 = act ? 3 * q : 0;
                 const double s0 = __shfl_sync(kFull, acc, b3);
                 const double s1 = __shfl_sync(kFull, acc, b3 + 1);
                 const double s2 = __shfl_sync(kFull, acc, b3 + 2);
                 res = (c.inv[0] * s0 + c.inv[1] * s1 + c.inv[2] * s2) * P.relax;
             }
-            if (c.act) {
-                win[3 * (c.pos & wmask) + comp] = res;
-                st_relaxed(P.out + 3 * (size_t) c.g + comp, res);
-                if (P.rearm != nullptr) P.rearm[3 * (size_t) c.g + comp] = sentinel();
+            if (act) {
+                const int g = LOWER ? it.x + q : it.x - q;
+                xwin[3 * (((it.w & 0xffff) + q) & wmask) + comp] = res;
+                st_relaxed(P.out + 3 * (size_t) g + comp, res);
+                if (P.rearm != nullptr) P.rearm[3 * (size_t) g + comp] = sentinel();
             }
         }
         for (int b = 0; b < tail; ++b) named_barrier(1, nthreads);

@@ -1,0 +1,68 @@
+// smlat.cu -- intra-SM latency terms of the triangular-sweep critical path on sm_100a (one CTA, 8 + warps).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o smlat smlat.cu && ./smlat
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void named_barrier(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void st_relaxed(double* p, double v) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+// mode 0: dependent DFMA chain; 1: dependent LDS chain (pointer chase); 2: bar.sync (8 warps, all arrive together);
+// 3: bar.sync where only warp 0 does work between barriers (STS + LDS + 4 DFMA), the others just wait;
+// 4: as 3 plus a st.relaxed.gpu global store before every barrier; 5: as 3 plus a weak global store;
+// 6: as 3 with 13 warps in the CTA of which 8 take part in the barrier (others spin on smem try-wait like producer/helpers)
+__global__ void k(int mode, int iters, double* gout, long long* cycles, double seed)
+{
+    __shared__ double sm[4096];
+    __shared__ int chase[1024];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) chase[i] = (i * 37 + 11) & 1023;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = seed + i;
+    __syncthreads();
+    long long t0 = clock64();
+    double a = seed, b = 1.0000001, c = 0.5;
+    int idx = lane;
+    if (mode == 0) {
+        if (warp == 0) for (int i = 0; i < iters; ++i) a = fma(a, b, c);
+    } else if (mode == 1) {
+        if (warp == 0) for (int i = 0; i < iters; ++i) idx = chase[idx];
+    } else if (mode == 2) {
+        if (warp < 8) for (int i = 0; i < iters; ++i) named_barrier(1, 256);
+    } else if (mode >= 3) {
+        if (warp < 8) {
+            for (int i = 0; i < iters; ++i) {
+                named_barrier(1, 256);
+                if (warp == 0) {
+                    double x0 = sm[(i * 3) & 4095], x1 = sm[(i * 3 + 1) & 4095], x2 = sm[(i * 3 + 2) & 4095];
+                    double t = b * x0; t = fma(c, x1, t); t = fma(b, x2, t); a -= t;
+                    sm[(i * 3 + 3 + lane) & 4095] = a;
+                    if (mode == 4) st_relaxed(gout + ((i * 32 + lane) & 65535), a);
+                    if (mode == 5) gout[(i * 32 + lane) & 65535] = a;
+                }
+            }
+        } else if (mode == 6) {
+            volatile int* flag = chase;
+            while (flag[0] != -12345 && clock64() - t0 < 400000ll) { }
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { cycles[0] = t1 - t0; }
+    if (a == 123.456 || idx == -5) gout[0] = a + idx;
+}
+
+int main()
+{
+    double* gout; long long* cyc;
+    cudaMalloc(&gout, 65536 * 8 + 64); cudaMalloc(&cyc, 64);
+    const char* names[] = {"dependent DFMA", "dependent LDS (pointer chase)", "bar.sync 8 warps, nothing else", "level step: bar + LDS + 4 DFMA + STS (warp 0 works)",
+                           "level step + st.relaxed.gpu", "level step + weak global store", "level step, 5 extra warps spinning"};
+    for (int mode = 0; mode < 7; ++mode) {
+        const int iters = 2000;
+        const int threads = mode == 6 ? 416 : 256;
+        for (int rep = 0; rep < 2; ++rep) k<<<1, threads>>>(mode, iters, gout, cyc, 1.5);
+        cudaDeviceSynchronize();
+        long long h = 0;
+        cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("%-55s %8.1f cycles/iter (%s)\n", names[mode], (double) h / iters, cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
