@@ -113,33 +113,43 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
 
 // ---- packed sweep streams -------------------------------------------------------------------------
 //
-// A sweep (forward over L, backward over U) is cut, per part, into STAGES: a few KB of consecutive
+// A sweep (forward over L, backward over U) is cut, per part, into STAGES: tens of KB of consecutive
 // work the producer warp of the CTA fetches with three bulk copies (meta ints, factor values, rhs
-// rows) into one slot of a shared-memory ring.  A stage holds CHUNKS of <= 10 rows of one level
-// (3 lanes per row).  Chunk c of a level belongs to consumer warp c % W; every warp walks its own
-// static WORK LIST and passes every level barrier of the stage.
+// rows) into one slot of a shared-memory ring.  The unit of work is a RECORD: <= 10 rows of one level
+// (3 lanes per row, lane = 3 q + comp) with up to 3 dependencies each; rows with more dependencies get
+// continuation records (the partial sums stay in registers).  Record c of a level belongs to consumer
+// warp c % W; every warp walks its own static WORK LIST and passes every level barrier of the stage.
+// Everything a lane needs is laid out so that it costs one load with an immediate offset.
 //
 // Shared-memory value space of a part ("xwin", rows of 3 doubles): [0, window) the most recent rows of
 // the part (position in processing order & (window - 1)), [window, window + extWindow) a ring of rows
 // owned by other parts, parked there by helper warps, and one all-zero row at window + extWindow that
-// padded dependency slots point to.  A dependency code is simply the xwin row to read.
+// padded dependency slots point to.
 //
 //   meta blob (ints, 16-byte multiple):
-//     header  [0] ngroups [1] nchunks [2] g_lo (even-aligned first p-row of the rhs copy) [3] rhs rows copied
+//     header  [0] ngroups [1] nrecords [2] g_lo (even-aligned first p-row of the rhs copy) [3] rhs rows copied
 //             [4] next (external rows of the stage) [5] off_ext [6] off_wl [7] off_items
-//             [8] ext_base (external rows of the part before this stage) [9] level barriers in the stage
+//             [8] ext_base (external rows of the part before this stage) [9] level barriers in the stage [10] off_codes
 //     groups  : at 12, ngroups cumulative ends: the external rows [0, end) of the stage list are needed by the
 //               levels up to the group's; a helper warp delivers them group by group
-//     cols    : per chunk nd x count ints, xwin rows (see above)
 //     ext     : at off_ext, next p-rows (rows of other parts, or of this part beyond the window), in group order;
 //               row k of the list is parked at xwin row window + ((ext_base + k) & (extWindow - 1))
-//     wl      : at off_wl, W + 1 item offsets (per warp, in items) then W trailing barrier counts
-//     items   : at off_items (16-byte aligned), one int4 per chunk, grouped by warp in processing order:
-//               {g0, count | nd << 4 | barriers to pass first << 16, cols_off | vals_off << 16, wpos0 | ext_need << 16}
-//               row q of the chunk is p-row g0 + q (lower sweep) or g0 - q (upper sweep) and is written to
-//               xwin row (wpos0 + q) & (window - 1); ext_need: external rows [0, ext_need) must be parked
-//   vals blob (doubles, 16-byte multiple): per chunk (nd [+1 inverse pivot for U]) x 3 x (3 count) doubles,
-//     value ((j*3 + v) * 3 count + 3 q + comp) = LU[block j of row q][comp][v]  (lane-major: conflict-free, coalesced)
+//     wl      : at off_wl, W + 1 record offsets (per warp) then W trailing barrier counts
+//     items   : at off_items (16-byte aligned), one int4 per record, grouped by warp in processing order:
+//               {24 (g0 - g_lo), first | last << 1 | count << 4 | level barriers to pass first << 16, ext_need, 3 g0}
+//               row q is p-row g0 + q (lower sweep) or g0 - q (upper sweep); external rows [0, ext_need) must be parked
+//     codes   : at off_codes (16-byte aligned), per record 32 x int4 (one per lane):
+//               {32 * xwin row of dependency 0, 1, 2, byte offset of the lane's result in xwin or -1 (no store)}
+//   vals blob (doubles): per record NF x 32 doubles, field f of lane l at sweep_vidx(f, l).
+//     lower sweep, NF = 9 : field 3 j + v = L[block j of row q][comp][v]
+//     upper sweep, NF = 12: field 3 j + v = (w D^-1 U)[block j of row q][comp][v], field 9 + v = (w D^-1)[comp][v]
+//     (the inverse pivot and the relaxation factor w are folded into the stream when it is filled, so that the
+//     dependent part of a row is the same 9 fma for both sweeps: x = (w D^-1) y - sum (w D^-1 U) x)
+// position of field f of lane l inside a record of the value stream: doubles are paired so that a lane fetches two with
+// one 16-byte load (lower: 4 pairs + the ninth value alone; upper: 6 pairs)
+inline int sweep_vidx(bool lower, int f, int l) { return (lower && f == 8) ? 256 + l : (f >> 1) * 64 + 2 * l + (f & 1); }
+constexpr int kXwinStride = 4;     // doubles per xwin row (3 used): rows are 32-byte aligned, read as 16 + 8 bytes
+
 struct StageRef {
     long long meta_off;    // ints into SweepPlan::meta
     long long vals_off;    // doubles into the sweep's value stream (even)
@@ -147,10 +157,10 @@ struct StageRef {
     int g_lo, g_rows;      // rhs copy: rows [g_lo, g_lo + g_rows), both even
 };
 struct PartRef { int stage_begin, stage_end, row0, nrows; };
-struct BuildRef {          // one per chunk: where the factor values of the chunk come from
+struct BuildRef {          // one per record: where its factor values come from
     long long vals_off;    // doubles into the value stream
-    int src_off;           // into SweepPlan::src: nd_eff x count p-space block indices (-1: padding)
-    int count, nd_eff, pad;
+    int src_off;           // into SweepPlan::src: 3 x count dependency blocks then count pivot blocks (p-space, -1: none)
+    int count, first;
 };
 
 struct SweepPlan {
@@ -160,6 +170,7 @@ struct SweepPlan {
     std::vector<BuildRef> build;
     std::vector<int> src;
     long long nvals = 0;
+    int nfields = 9;
     int maxMetaInts = 4, maxValsDoubles = 2, maxRhsRows = 2, maxExtRows = 2;
     long long nchunks = 0, nentries = 0, nExternal = 0, nWindow = 0, nExtRows = 0;
 };
@@ -178,7 +189,7 @@ struct Analysis {
     int nflev = 0;
     std::vector<int> flevPtr, flevRows;
     // triangular sweeps
-    int nparts = 0, nlines = 0, window = 0, warps = 8, extWindow = 1024;
+    int nparts = 0, nlines = 0, window = 0, warps = 8, groups = 1, extWindow = 512;
     int nstrips = 0;
     std::vector<int> partPtr;         // nparts + 1, p-space rows
     std::vector<int> partMaxStep;     // rows in the largest level step of each part
@@ -190,9 +201,12 @@ struct Analysis {
 struct AnalysisOptions {
     int parts = 148;            // resident CTAs of the sweep kernels
     int stageBytes = 16384;     // meta + values + rhs of one ring slot
-    int window = 2048;          // rows of the part kept in the shared-memory window (power of two)
+    int window = 0;             // rows of the part kept in the shared-memory window (power of two); 0: four times the largest
+                                // level step of any part, at least 256
     int warps = 8;              // consumer warps of a sweep CTA (the static work lists are cut for this many)
-    int extWindow = 1024;       // rows of the external-row ring (power of two); bounds ring slots x external rows per stage
+    int groups = 1;             // consecutive levels go to different warp groups (warps / groups warps each): while one group
+                                // runs the dependent part of level l, the next ones already hold the operands of l+1, l+2
+    int extWindow = 512;        // rows of the external-row ring (power of two); bounds ring slots x external rows per stage
 };
 
 namespace detail {
@@ -200,70 +214,73 @@ namespace detail {
 inline void build_sweep(const Analysis& A, const int* rows, const int* cols, const std::vector<int>& glev,
                         const std::vector<int>& partOf, bool lower, const AnalysisOptions& opt, SweepPlan& S)
 {
-    const int W = A.window, EW = A.extWindow, NWc = A.warps;
+    const int W = A.window, EW = A.extWindow, NWc = A.warps, NG = A.groups, NWG = A.warps / A.groups;
     const int zrow = W + EW;
+    const int NF = lower ? 9 : 12;
+    S.nfields = NF;
     S.parts.resize(A.nparts);
-    // cols of a TmpChunk: >= 0 xwin row of the window, kPadCol padding, otherwise -(p-row + 1) of an external row
-    struct TmpChunk { int g0, count, nd, level, ps0; std::vector<int> cols, src; };
+    // cols of a TmpRec: >= 0 xwin row of the window, kPadCol padding, otherwise -(p-row + 1) of an external row
+    struct TmpRec { int g0, count, level, ps0, first, last; int cols[3][kRowsPerWarp], src[3][kRowsPerWarp], piv[kRowsPerWarp]; };
     for (int p = 0; p < A.nparts; ++p) {
         const int row0 = A.partPtr[p], nrows = A.partPtr[p + 1] - row0;
         const int slack = W - A.partMaxStep[p];
         S.parts[p].stage_begin = (int) S.stages.size();
         S.parts[p].row0 = row0;
         S.parts[p].nrows = nrows;
-        std::vector<TmpChunk> st;       // pending stage
+        std::vector<TmpRec> st;         // pending stage
         int st_bytes = 0, st_glo = 0, st_ghi = 0;
-        int prev_level = -1;            // level of the last chunk emitted in this part
+        int prev_level = -1;            // level of the last record emitted in this part
+        int level_index = 0;            // levels of the part so far: level l belongs to warp group l % groups
         long long ext_base = 0;         // external rows of the part before the pending stage
         auto flush = [&]() {
             if (st.empty()) return;
-            const int nch = (int) st.size();
+            const int nrec = (int) st.size();
             // external rows of the stage, listed once, grouped by the first level that needs them
-            std::vector<int> ext, gend, need(nch, 0);
-            std::vector<std::vector<int>> wl(NWc);          // chunk indices per warp
-            std::vector<std::vector<int>> wbar(NWc);        // barriers before each of them
+            std::vector<int> ext, gend, need(nrec, 0), order, bars;
+            std::vector<std::vector<int>> wl(NWc), wbar(NWc);
             std::vector<int> pend(NWc, 0);
             int nbar_total = 0;
             {
                 std::vector<std::pair<int, int>> seen;      // (p-row, index), kept sorted
-                for (int c = 0; c < nch;) {
+                for (int c = 0; c < nrec;) {
                     int e = c;
-                    while (e < nch && st[e].level == st[c].level) ++e;
-                    if (prev_level >= 0 && st[c].level != prev_level) { for (int w = 0; w < NWc; ++w) pend[w]++; nbar_total++; }
+                    while (e < nrec && st[e].level == st[c].level) ++e;
+                    if (prev_level >= 0 && st[c].level != prev_level) { for (int w = 0; w < NWc; ++w) pend[w]++; nbar_total++; level_index++; }
                     prev_level = st[c].level;
+                    int chunk = -1;                          // continuation records follow their first record to the same warp
                     for (int k = c; k < e; ++k) {
                         bool any = false;
-                        for (int& code : st[k].cols) {
-                            if (code >= 0 || code == kPadCol) continue;
-                            const int gd = -(code + 1);
-                            auto it = std::lower_bound(seen.begin(), seen.end(), std::make_pair(gd, -1));
-                            int idx;
-                            if (it != seen.end() && it->first == gd) idx = it->second;
-                            else { idx = (int) ext.size(); ext.push_back(gd); seen.insert(it, std::make_pair(gd, idx)); }
-                            code = W + (int) ((ext_base + idx) & (EW - 1));
-                            any = true;
-                        }
+                        for (int j = 0; j < 3; ++j)
+                            for (int q = 0; q < st[k].count; ++q) {
+                                int& code = st[k].cols[j][q];
+                                if (code >= 0 || code == kPadCol) continue;
+                                const int gd = -(code + 1);
+                                auto it = std::lower_bound(seen.begin(), seen.end(), std::make_pair(gd, -1));
+                                int idx;
+                                if (it != seen.end() && it->first == gd) idx = it->second;
+                                else { idx = (int) ext.size(); ext.push_back(gd); seen.insert(it, std::make_pair(gd, idx)); }
+                                code = W + (int) ((ext_base + idx) & (EW - 1));
+                                any = true;
+                            }
                         need[k] = any ? 1 : 0;
-                        const int w = (k - c) % NWc;
+                        if (st[k].first) ++chunk;
+                        const int w = (level_index % NG) * NWG + chunk % NWG;
                         wl[w].push_back(k);
                         wbar[w].push_back(pend[w]);
                         pend[w] = 0;
                     }
-                    if (gend.empty() || (int) ext.size() != gend.back()) { if (!ext.empty()) gend.push_back((int) ext.size()); }
+                    if (!ext.empty() && (gend.empty() || (int) ext.size() != gend.back())) gend.push_back((int) ext.size());
                     for (int k = c; k < e; ++k) if (need[k]) need[k] = (int) ext.size();
                     c = e;
                 }
             }
-            for (auto& c : st) for (int& code : c.cols) if (code == kPadCol) code = zrow;
             const int next = (int) ext.size(), ngroups = (int) gend.size();
-            if (next >= 65536 || nch >= 65536 || nbar_total >= 32768 || next > EW) throw std::runtime_error("sweep stage too large");
-            const int off_cols = 12 + ngroups;
-            int ncols = 0;
-            for (auto& c : st) ncols += c.nd * c.count;
-            const int off_ext = off_cols + ncols;
+            if (next > EW || nbar_total >= 32768) throw std::runtime_error("sweep stage too large");
+            const int off_ext = 12 + ngroups;
             const int off_wl = off_ext + next;
             const int off_items = (off_wl + 2 * NWc + 1 + 3) & ~3;
-            const int meta_ints = off_items + 4 * nch;
+            const int off_codes = off_items + 4 * nrec;
+            const int meta_ints = off_codes + 128 * nrec;
             StageRef R{};
             R.meta_off = (long long) S.meta.size();
             R.meta_ints = meta_ints;
@@ -273,48 +290,44 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             R.g_rows = ghi_al - glo_al;
             S.meta.resize(S.meta.size() + meta_ints, 0);
             int* m = S.meta.data() + R.meta_off;
-            m[0] = ngroups; m[1] = nch; m[2] = glo_al; m[3] = R.g_rows; m[4] = next; m[5] = off_ext; m[6] = off_wl; m[7] = off_items;
-            m[8] = (int) (ext_base & (EW - 1)); m[9] = nbar_total;
+            m[0] = ngroups; m[1] = nrec; m[2] = glo_al; m[3] = R.g_rows; m[4] = next; m[5] = off_ext; m[6] = off_wl; m[7] = off_items;
+            m[8] = (int) (ext_base & (EW - 1)); m[9] = nbar_total; m[10] = off_codes;
             std::copy(gend.begin(), gend.end(), m + 12);
-            std::vector<int> cols_off(nch), vals_off(nch);
-            int co = off_cols;
-            long long vo = 0;
-            for (int c = 0; c < nch; ++c) {
-                const TmpChunk& t = st[c];
-                const int nd_eff = t.nd + (lower ? 0 : 1);
-                if (co >= 65536 || vo >= 65536) throw std::runtime_error("sweep stage too large for the packed chunk offsets");
-                cols_off[c] = co; vals_off[c] = (int) vo;
-                std::copy(t.cols.begin(), t.cols.end(), m + co);
-                co += t.nd * t.count;
-                BuildRef B{};
-                B.vals_off = R.vals_off + vo;
-                B.src_off = (int) S.src.size();
-                B.count = t.count;
-                B.nd_eff = nd_eff;
-                S.src.insert(S.src.end(), t.src.begin(), t.src.end());
-                S.build.push_back(B);
-                vo += (long long) nd_eff * 9 * t.count;
-            }
             std::copy(ext.begin(), ext.end(), m + off_ext);
-            {
-                int* w0 = m + off_wl;
-                int o = 0;
-                for (int w = 0; w < NWc; ++w) {
-                    w0[w] = o;
-                    for (size_t t = 0; t < wl[w].size(); ++t, ++o) {
-                        const int c = wl[w][t];
-                        const TmpChunk& ch = st[c];
-                        int* it = m + off_items + 4 * o;
-                        it[0] = ch.g0;
-                        it[1] = ch.count | (ch.nd << 4) | (wbar[w][t] << 16);
-                        it[2] = cols_off[c] | (vals_off[c] << 16);
-                        it[3] = (ch.ps0 & (W - 1)) | (need[c] << 16);
+            int* w0 = m + off_wl;
+            int o = 0;
+            for (int w = 0; w < NWc; ++w) {
+                w0[w] = o;
+                for (size_t t = 0; t < wl[w].size(); ++t, ++o) {
+                    const TmpRec& rc = st[wl[w][t]];
+                    int* it = m + off_items + 4 * o;
+                    it[0] = 24 * (rc.g0 - glo_al);
+                    it[1] = rc.first | (rc.last << 1) | (rc.count << 4) | (wbar[w][t] << 16);
+                    it[2] = need[wl[w][t]];
+                    it[3] = 3 * rc.g0;
+                    int* cd = m + off_codes + 128 * o;
+                    for (int l = 0; l < 32; ++l) {
+                        const int q = l / 3, comp = l - 3 * q;
+                        const bool act = q < rc.count;
+                        for (int j = 0; j < 3; ++j) {
+                            const int code = act ? rc.cols[j][q] : kPadCol;
+                            cd[4 * l + j] = 8 * kXwinStride * (code == kPadCol ? zrow : code);
+                        }
+                        cd[4 * l + 3] = (act && rc.last) ? 8 * kXwinStride * ((rc.ps0 + q) & (W - 1)) + 8 * comp : -1;
                     }
-                    w0[NWc + 1 + w] = pend[w];
+                    BuildRef B{};
+                    B.vals_off = R.vals_off + (long long) o * NF * 32;
+                    B.src_off = (int) S.src.size();
+                    B.count = rc.count;
+                    B.first = rc.first;
+                    for (int j = 0; j < 3; ++j) for (int q = 0; q < rc.count; ++q) S.src.push_back(rc.src[j][q]);
+                    for (int q = 0; q < rc.count; ++q) S.src.push_back(lower ? -1 : rc.piv[q]);
+                    S.build.push_back(B);
                 }
-                w0[NWc] = o;
+                w0[NWc + 1 + w] = pend[w];
             }
-            vo = (vo + 1) & ~1LL;
+            w0[NWc] = o;
+            const long long vo = (long long) nrec * NF * 32;
             if (vo > INT_MAX || S.src.size() > (size_t) INT_MAX) throw std::runtime_error("sweep stage too large");
             R.vals_doubles = (int) vo;
             S.nvals += vo;
@@ -323,7 +336,7 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             S.maxRhsRows = std::max(S.maxRhsRows, R.g_rows);
             S.maxExtRows = std::max(S.maxExtRows, next);
             S.nExtRows += next;
-            S.nchunks += nch;
+            S.nchunks += nrec;
             S.nentries += nbar_total;
             S.stages.push_back(R);
             ext_base += next;
@@ -338,26 +351,12 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
             int end = pos;
             while (end < nrows && glev[A.perm[g_of(end)]] == lev) ++end;
             for (int s = pos; s < end; s += kRowsPerWarp) {
-                TmpChunk t;
-                t.count = std::min(kRowsPerWarp, end - s);
-                t.g0 = g_of(s);
-                t.ps0 = s;
-                t.level = lev;
-                t.nd = 0;
-                for (int q = 0; q < t.count; ++q) {
-                    const int r = A.perm[g_of(s + q)];
-                    int n = 0;
-                    for (int k = rows[r]; k < rows[r + 1]; ++k) n += lower ? cols[k] < r : cols[k] > r;
-                    t.nd = std::max(t.nd, n);
-                }
-                if (t.nd > 0xfff) throw std::runtime_error("block row too long for the sweep chunk descriptor");
-                const int nd_eff = t.nd + (lower ? 0 : 1);
-                t.cols.assign((size_t) t.nd * t.count, kPadCol);
-                t.src.assign((size_t) nd_eff * t.count, -1);
-                int nextc = 0;
-                for (int q = 0; q < t.count; ++q) {
+                const int count = std::min(kRowsPerWarp, end - s);
+                // dependencies of the rows of this chunk
+                std::vector<int> dcode[kRowsPerWarp], dsrc[kRowsPerWarp];
+                int nd = 0, piv[kRowsPerWarp];
+                for (int q = 0; q < count; ++q) {
                     const int ps = s + q, g = g_of(ps), r = A.perm[g];
-                    int j = 0;
                     for (int k = rows[r]; k < rows[r + 1]; ++k) {
                         const int c = cols[k];
                         if (lower ? c < r : c > r) {
@@ -368,21 +367,40 @@ inline void build_sweep(const Analysis& A, const int* rows, const int* cols, con
                                 if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
                                 if (ps - pd <= slack) { code = pd & (W - 1); S.nWindow++; }
                             }
-                            if (code < 0) { S.nExternal++; nextc++; }
-                            t.cols[(size_t) j * t.count + q] = code;
-                            t.src[(size_t) j * t.count + q] = A.prow[g] + (k - rows[r]);
-                            ++j;
+                            if (code < 0) S.nExternal++;
+                            dcode[q].push_back(code);
+                            dsrc[q].push_back(A.prow[g] + (k - rows[r]));
                         }
                     }
-                    if (!lower) t.src[(size_t) t.nd * t.count + q] = A.pdiag[g];
+                    piv[q] = A.pdiag[g];
+                    nd = std::max(nd, (int) dcode[q].size());
                 }
-                const int bytes = 16 + 4 * t.nd * t.count + 72 * nd_eff * t.count + 24 * t.count + 8 + 4 * nextc + 4;
+                const int npass = std::max(1, (nd + 2) / 3);
+                int bytes = 0;
+                std::vector<TmpRec> recs(npass);
+                for (int r = 0; r < npass; ++r) {
+                    TmpRec& t = recs[r];
+                    t.g0 = g_of(s); t.count = count; t.level = lev; t.ps0 = s; t.first = r == 0; t.last = r == npass - 1;
+                    for (int q = 0; q < kRowsPerWarp; ++q) {
+                        t.piv[q] = q < count ? piv[q] : -1;
+                        for (int j = 0; j < 3; ++j) {
+                            const int d = 3 * r + j;
+                            const bool have = q < count && d < (int) dcode[q].size();
+                            t.cols[j][q] = have ? dcode[q][d] : kPadCol;
+                            t.src[j][q] = have ? dsrc[q][d] : -1;
+                            if (have && dcode[q][d] < 0) bytes += 4;
+                        }
+                    }
+                    bytes += 16 + 512 + NF * 256;
+                }
+                bytes += 24 * count;
                 if (!st.empty() && st_bytes + bytes > opt.stageBytes) flush();
-                if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 160; }
-                const int glo = lower ? t.g0 : t.g0 - t.count + 1, ghi = lower ? t.g0 + t.count : t.g0 + 1;
+                if (st.empty()) { st_glo = INT_MAX; st_ghi = 0; st_bytes = 192; }
+                const int g0 = g_of(s);
+                const int glo = lower ? g0 : g0 - count + 1, ghi = lower ? g0 + count : g0 + 1;
                 st_glo = std::min(st_glo, glo); st_ghi = std::max(st_ghi, ghi);
                 st_bytes += bytes;
-                st.push_back(std::move(t));
+                for (auto& t : recs) st.push_back(t);
             }
             pos = end;
         }
@@ -400,10 +418,12 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
     A.nnzb = rows[Nb];
     if (rows[0] != 0) throw std::runtime_error("rows[0] must be 0");
     if (Nb >= (1 << 30)) throw std::runtime_error("Nb too large");
-    if (opt.window < 64 || (opt.window & (opt.window - 1))) throw std::runtime_error("window must be a power of two >= 64");
+    if (opt.window != 0 && (opt.window < 64 || (opt.window & (opt.window - 1)))) throw std::runtime_error("window must be a power of two >= 64");
     A.window = opt.window;
-    if (opt.warps < 1 || opt.warps > 14) throw std::runtime_error("consumer warps must be in 1..14");
+    if (opt.warps < 1 || opt.warps > 26) throw std::runtime_error("consumer warps must be in 1..26");
+    if (opt.groups < 1 || opt.warps % opt.groups) throw std::runtime_error("consumer warps must be a multiple of the warp groups");
     A.warps = opt.warps;
+    A.groups = opt.groups;
     if (opt.extWindow < 64 || (opt.extWindow & (opt.extWindow - 1))) throw std::runtime_error("extWindow must be a power of two >= 64");
     A.extWindow = opt.extWindow;
     for (int r = 0; r < Nb; ++r) {
@@ -574,12 +594,18 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
         for (int q = 0; q < Nb; ++q) A.iperm[A.perm[q]] = q;
     }
     A.partMaxStep.assign(nparts, 0);
+    int maxStep = 1;
     for (int p = 0; p < nparts; ++p) {
         int run = 0;
         for (int q = A.partPtr[p]; q < A.partPtr[p + 1]; ++q) {
             run = (q > A.partPtr[p] && glev[A.perm[q]] == glev[A.perm[q - 1]]) ? run + 1 : 1;
             A.partMaxStep[p] = std::max(A.partMaxStep[p], run);
         }
+        maxStep = std::max(maxStep, A.partMaxStep[p]);
+    }
+    if (A.window == 0) {
+        A.window = 256;
+        while (A.window < 4 * maxStep && A.window < 4096) A.window *= 2;
     }
 
     // permuted BSR pattern: rows permuted, every row keeps its entries in natural column order (so the
@@ -621,36 +647,51 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
 // Interprets the packed streams exactly as k_sweep does, one chunk at a time, round-robin over the
 // parts; a chunk whose out-of-window dependency has not been produced yet makes its part yield.
 // Returns false if a full round makes no progress (the schedule would deadlock on the device).
-inline void fill_stream_host(const SweepPlan& S, const double* LU, std::vector<double>& vals)
+inline void fill_stream_host(const SweepPlan& S, bool lower, const double* LU, double relax, std::vector<double>& vals)
 {
+    const int NF = S.nfields;
     vals.assign((size_t) std::max<long long>(S.nvals, 1), 0.0);
     for (const BuildRef& B : S.build)
-        for (int j = 0; j < B.nd_eff; ++j)
-            for (int q = 0; q < B.count; ++q) {
-                const int k = S.src[B.src_off + j * B.count + q];
-                for (int comp = 0; comp < 3; ++comp)
-                    for (int v = 0; v < 3; ++v)
-                        vals[B.vals_off + (size_t) (j * 3 + v) * 3 * B.count + 3 * q + comp] = k >= 0 ? LU[(size_t) k * 9 + comp * 3 + v] : 0.0;
+        for (int l = 0; l < 32; ++l) {
+            const int q = l / 3, comp = l - 3 * q;
+            if (q >= B.count) continue;
+            double inv[3] = {0.0, 0.0, 0.0};
+            if (!lower) {
+                const int kp = S.src[B.src_off + 3 * B.count + q];
+                for (int e = 0; e < 3; ++e) inv[e] = relax * LU[(size_t) kp * 9 + comp * 3 + e];
+                if (B.first) for (int v = 0; v < 3; ++v) vals[B.vals_off + sweep_vidx(false, 9 + v, l)] = inv[v];
             }
+            for (int j = 0; j < 3; ++j) {
+                const int k = S.src[B.src_off + j * B.count + q];
+                for (int v = 0; v < 3; ++v) {
+                    double x = 0.0;
+                    if (k >= 0) {
+                        if (lower) x = LU[(size_t) k * 9 + comp * 3 + v];
+                        else x = inv[0] * LU[(size_t) k * 9 + v] + inv[1] * LU[(size_t) k * 9 + 3 + v] + inv[2] * LU[(size_t) k * 9 + 6 + v];
+                    }
+                    vals[B.vals_off + sweep_vidx(lower, 3 * j + v, l)] = x;
+                }
+            }
+        }
 }
 
 inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, const std::vector<double>& vals, const double* rhs,
-                          double* out, double relax)
+                          double* out)
 {
-    const int W = A.window, EW = A.extWindow, NW = A.warps, zrow = W + EW;
+    const int W = A.window, EW = A.extWindow, NW = A.warps, zrow = W + EW, NF = S.nfields;
     const double NaN = std::nan("");
     for (int i = 0; i < 3 * A.Nb; ++i) out[i] = NaN;
     // One cursor per consumer warp, exactly the control flow of k_sweep: walk the work list, pass `nbar` level
     // barriers (all W warps must arrive), wait for the parked external rows, compute, finally the trailing barriers.
-    struct Warp { int t, bars, tail_left; bool loaded, in_tail, done, at_bar; };
+    struct Warp { int t, bars; bool loaded, in_tail, done, at_bar; double carry[32]; };
     struct Part { int stage; std::vector<Warp> w; int arrivals; std::vector<double> xwin; bool started; };
     std::vector<Part> parts(A.nparts);
     for (int p = 0; p < A.nparts; ++p) {
         parts[p].stage = S.parts[p].stage_begin;
-        parts[p].w.assign(NW, Warp{0, 0, 0, false, false, false, false});
+        parts[p].w.assign(NW, Warp{});
         parts[p].arrivals = 0;
-        parts[p].xwin.assign((size_t) 3 * (zrow + 1), NaN);
-        for (int e = 0; e < 3; ++e) parts[p].xwin[(size_t) 3 * zrow + e] = 0.0;
+        parts[p].xwin.assign((size_t) kXwinStride * (zrow + 1), NaN);
+        for (int e = 0; e < 3; ++e) parts[p].xwin[(size_t) kXwinStride * zrow + e] = 0.0;
         parts[p].started = false;
     }
     int remaining = A.nparts;
@@ -668,17 +709,20 @@ inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, con
                 const int* extl = m + m[5];
                 const int* wl = m + m[6];
                 const int* items = m + m[7];
+                const int* codes = m + m[10];
                 const int ext_base = m[8];
                 if (!P.started) {
                     int nitems = 0;
                     for (int w = 0; w < NW; ++w) {
-                        P.w[w] = Warp{wl[w], 0, 0, false, false, false, false};
+                        Warp& c = P.w[w];
+                        c.t = wl[w]; c.bars = 0; c.loaded = c.in_tail = c.done = c.at_bar = false;
                         int bars = wl[NW + 1 + w];
                         for (int t = wl[w]; t < wl[w + 1]; ++t, ++nitems) bars += (items[4 * t + 1] >> 16) & 0xffff;
                         if (bars != m[9]) throw std::runtime_error("emulate: warps disagree on the barrier count of a stage");
                     }
-                    if (nitems != m[1]) throw std::runtime_error("emulate: work lists do not cover the chunks of the stage");
+                    if (nitems != m[1]) throw std::runtime_error("emulate: work lists do not cover the records of the stage");
                     if (m[4] > EW) throw std::runtime_error("emulate: external rows of a stage exceed the ring");
+                    if ((long long) m[1] * NF * 32 != R.vals_doubles) throw std::runtime_error("emulate: value blob size mismatch");
                     P.arrivals = 0;
                     P.started = true;
                 }
@@ -695,52 +739,46 @@ inline bool emulate_sweep(const Analysis& A, const SweepPlan& S, bool lower, con
                     if (c.bars > 0) { c.at_bar = true; P.arrivals++; local = true; continue; }
                     if (c.in_tail) { c.done = true; ++ndone; local = true; continue; }
                     const int* it = items + 4 * c.t;
-                    const int g0 = it[0], count = it[1] & 15, nd = (it[1] >> 4) & 0xfff;
-                    const int co = it[2] & 0xffff, vo = (int) ((unsigned) it[2] >> 16);
-                    const int wpos0 = it[3] & 0xffff, need = (int) ((unsigned) it[3] >> 16);
+                    const int count = (it[1] >> 4) & 15, first = it[1] & 1, last = (it[1] >> 1) & 1, need = it[2], g0 = it[3] / 3;
+                    if (it[0] != 24 * (g0 - R.g_lo) || it[3] != 3 * g0) throw std::runtime_error("emulate: bad record item");
                     bool ready = true;
                     for (int x = 0; x < need && ready; ++x) ready = !std::isnan(out[3 * (size_t) extl[x]]);
                     if (!ready) continue;                     // the helper warp has not delivered this group yet
-                    const double* v = vals.data() + R.vals_off + vo;
-                    double res[kRowsPerWarp][3];
-                    for (int q = 0; q < count; ++q) {
+                    const double* v = vals.data() + R.vals_off + (size_t) c.t * NF * 32;
+                    const int* cd = codes + 128 * c.t;
+                    for (int l = 0; l < 3 * count; ++l) {
+                        const int q = l / 3, comp = l - 3 * q;
                         const int g = lower ? g0 + q : g0 - q;
                         if (g < R.g_lo || g >= R.g_lo + R.g_rows) throw std::runtime_error("emulate: row outside the stage's rhs window");
-                        double acc[3];
-                        for (int comp = 0; comp < 3; ++comp) {
-                            double a = rhs[3 * (size_t) g + comp];
-                            for (int j = 0; j < nd; ++j) {
-                                const int code = m[co + j * count + q];
-                                if (code < 0 || code > zrow) throw std::runtime_error("emulate: bad dependency code");
-                                const double* x;
-                                if (code >= W && code < zrow) {      // parked external row: map the ring slot back to the list
-                                    const int k = (code - W - ext_base) & (EW - 1);
-                                    if (k >= need) throw std::runtime_error("emulate: external row beyond ext_need");
-                                    x = out + 3 * (size_t) extl[k];
-                                } else x = P.xwin.data() + 3 * (size_t) code;
-                                for (int e = 0; e < 3; ++e) {
-                                    if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
-                                    a -= v[(size_t) (j * 3 + e) * 3 * count + 3 * q + comp] * x[e];
-                                }
+                        double acc;
+                        if (!first) acc = c.carry[l];
+                        else if (lower) acc = rhs[3 * (size_t) g + comp];
+                        else acc = v[sweep_vidx(false, 9, l)] * rhs[3 * (size_t) g] + v[sweep_vidx(false, 10, l)] * rhs[3 * (size_t) g + 1] + v[sweep_vidx(false, 11, l)] * rhs[3 * (size_t) g + 2];
+                        for (int j = 0; j < 3; ++j) {
+                            if (cd[4 * l + j] % (8 * kXwinStride)) throw std::runtime_error("emulate: bad dependency code");
+                            const int code = cd[4 * l + j] / (8 * kXwinStride);
+                            if (code < 0 || code > zrow) throw std::runtime_error("emulate: bad dependency code");
+                            const double* x;
+                            if (code >= W && code < zrow) {      // parked external row: map the ring slot back to the list
+                                const int k = (code - W - ext_base) & (EW - 1);
+                                if (k >= need) throw std::runtime_error("emulate: external row beyond ext_need");
+                                x = out + 3 * (size_t) extl[k];
+                            } else x = P.xwin.data() + kXwinStride * (size_t) code;
+                            for (int e = 0; e < 3; ++e) {
+                                if (std::isnan(x[e])) throw std::runtime_error("emulate: read of a value that was not produced yet");
+                                acc -= v[sweep_vidx(lower, 3 * j + e, l)] * x[e];
                             }
-                            acc[comp] = a;
                         }
-                        for (int comp = 0; comp < 3; ++comp) {
-                            double r = acc[comp];
-                            if (!lower) {
-                                r = 0.0;
-                                for (int e = 0; e < 3; ++e) r += v[(size_t) (nd * 3 + e) * 3 * count + 3 * q + comp] * acc[e];
-                                r *= relax;
-                            }
-                            res[q][comp] = r;
-                        }
+                        c.carry[l] = acc;
                     }
-                    for (int q = 0; q < count; ++q) {
+                    for (int l = 0; l < 32; ++l) {
+                        const int wout = cd[4 * l + 3];
+                        if ((wout >= 0) != (last && l < 3 * count)) throw std::runtime_error("emulate: store flag mismatch");
+                        if (wout < 0) continue;
+                        const int q = l / 3, comp = l - 3 * q;
                         const int g = lower ? g0 + q : g0 - q;
-                        for (int comp = 0; comp < 3; ++comp) {
-                            P.xwin[3 * (size_t) ((wpos0 + q) & (W - 1)) + comp] = res[q][comp];
-                            out[3 * (size_t) g + comp] = res[q][comp];
-                        }
+                        P.xwin[(size_t) wout / 8] = c.carry[l];
+                        out[3 * (size_t) g + comp] = c.carry[l];
                     }
                     c.t++; c.loaded = false;
                     local = true;

@@ -143,7 +143,7 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_parts = 0, sweep_warps = 8, sweep_helpers = 4, sweep_slots = 4, sweep_stage_bytes = 32768, sweep_window = 2048;
+    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 81920, sweep_window = 0, sweep_ext_window = 512;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -300,7 +300,9 @@ struct Solver {
         opt.parts = sweep_parts > 0 ? std::min(sweep_parts, num_sms) : num_sms;      // every CTA of a sweep must be resident
         opt.stageBytes = sweep_stage_bytes;
         opt.window = sweep_window;
+        opt.extWindow = sweep_ext_window;
         opt.warps = sweep_warps;
+        opt.groups = sweep_groups;
         if (!dist.enabled) {
             an = b200::analyse(Nb, rows, cols, opt);
         } else {
@@ -367,25 +369,29 @@ struct Solver {
         sweep_rhsCap = std::max(an.L.maxRhsRows, an.U.maxRhsRows);
         sweep_extCap = std::max(an.L.maxExtRows, an.U.maxExtRows);
         const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
-        const size_t fixedBytes = kSweepHeader + (size_t) (sweep_window + an.extWindow + 2) * 24;
+        const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 32 + kSweepTailPad;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_optin || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
         if ((long long) sweep_slots * sweep_extCap > an.extWindow)
             throw std::runtime_error("external-row ring of the triangular sweeps too small (" + std::to_string(sweep_extCap) + " rows per stage)");
-        sweep_helpers = std::max(1, std::min({sweep_helpers, 15 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
+        sweep_helpers = std::max(1, std::min({sweep_helpers, 27 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
         if (sweep_smem > smem_optin)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
         if (an.nparts > num_sms) throw std::runtime_error("internal: more sweep parts than SMs");
-        CUDA_OK(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
-        CUDA_OK(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
-        int occ = 0, occ2 = 0;
+        int occ = 8;
         const int threads = sweep_threads();
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<true>, threads, sweep_smem));
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_sweep<false>, threads, sweep_smem));
-        if (std::min(occ, occ2) < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
+        auto prep = [&](auto kern) {
+            CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
+            int o = 0;
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, sweep_smem));
+            occ = std::min(occ, o);
+        };
+        prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
+        prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
+        if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts; "
                             "L: %zu stages %lld chunks (%lld window / %lld global deps), U: %zu stages; sweep grid %d x %d, "
@@ -516,12 +522,12 @@ struct Solver {
             prof_end(id);
         }
         int id = prof_begin(K_SLICES);
-        k_fill_stream<<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
-            d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p);
+        k_fill_stream<true><<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+            d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p, 1.0);
         prof_end(id);
         id = prof_begin(K_SLICES);
-        k_fill_stream<<<blocks_for((long long) an.U.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
-            d_buildU.p, (int) an.U.build.size(), d_srcU.p, d_LU.p, d_valU.p);
+        k_fill_stream<false><<<blocks_for((long long) an.U.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+            d_buildU.p, (int) an.U.build.size(), d_srcU.p, d_LU.p, d_valU.p, relaxation);
         prof_end(id);
         have_factor = true;
     }
@@ -534,8 +540,7 @@ struct Solver {
         a.meta = lower ? d_metaL.p : d_metaU.p;
         a.vals = lower ? d_valL.p : d_valU.p;
         a.rhs = rhs; a.out = out; a.rearm = rearm; a.S = d_S.p;
-        a.relax = lower ? 1.0 : relaxation;
-        a.nparts = an.nparts; a.nslots = sweep_slots; a.window = sweep_window;
+        a.nparts = an.nparts; a.nslots = sweep_slots; a.window = an.window;
         a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extWindow = an.extWindow;
         a.nwarps = sweep_warps; a.nhalo = sweep_helpers;
         a.check_done = check_done ? 1 : 0;
@@ -544,16 +549,24 @@ struct Solver {
         return a;
     }
     int sweep_threads() const { return (sweep_warps + 1 + sweep_helpers) * 32; }
+    template <bool LOWER>
+    void launch_sweep(const SweepArgs& a)
+    {
+        const bool rearm = a.rearm != nullptr, trace = a.trace != nullptr;
+        auto go = [&](auto kern) { kern<<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a); };
+        if (trace) { if (rearm) go(k_sweep<LOWER, true, true>); else go(k_sweep<LOWER, false, true>); }
+        else { if (rearm) go(k_sweep<LOWER, true, false>); else go(k_sweep<LOWER, false, false>); }
+    }
     void trsv_lower(const double* rhs, double* out, bool check_done)
     {
         int id = prof_begin(K_LOWER);
-        k_sweep<true><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(sweep_args(true, rhs, out, nullptr, check_done));
+        launch_sweep<true>(sweep_args(true, rhs, out, nullptr, check_done));
         prof_end(id);
     }
     void trsv_upper(const double* rhs, double* out, double* rearm, bool check_done)
     {
         int id = prof_begin(K_UPPER);
-        k_sweep<false><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(sweep_args(false, rhs, out, rearm, check_done));
+        launch_sweep<false>(sweep_args(false, rhs, out, rearm, check_done));
         prof_end(id);
     }
     template <int MODE>
@@ -808,16 +821,18 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "profile") s->profile = value != 0.0;
         else if (k == "sweep_trace") {
             s->sweep_trace = value != 0.0;
-            if (s->sweep_trace) { s->d_trace.alloc((size_t) 148 * 4 * b200::Solver::kTraceCap); CUDA_OK(cudaMemset(s->d_trace.p, 0, sizeof(long long) * s->d_trace.n)); }
+            if (s->sweep_trace) { s->d_trace.alloc((size_t) 2 * 148 * 4 * b200::Solver::kTraceCap); CUDA_OK(cudaMemset(s->d_trace.p, 0, sizeof(long long) * s->d_trace.n)); }
         }
-        else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_helpers" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window") {
+        else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_groups" || k == "sweep_helpers" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window" || k == "sweep_ext_window") {
             if (s->analysed) throw std::runtime_error(k + " must be set before the first solve");
             const int v = (int) value;
             if (k == "sweep_parts") s->sweep_parts = std::max(0, v);
-            else if (k == "sweep_warps") s->sweep_warps = std::min(14, std::max(1, v));
+            else if (k == "sweep_warps") s->sweep_warps = std::min(26, std::max(1, v));
+            else if (k == "sweep_groups") s->sweep_groups = std::max(1, v);
             else if (k == "sweep_helpers") s->sweep_helpers = std::min(8, std::max(1, v));
             else if (k == "sweep_slots") s->sweep_slots = std::min(kSweepMaxSlots, std::max(2, v));
             else if (k == "sweep_stage_bytes") s->sweep_stage_bytes = std::max(1024, v);
+            else if (k == "sweep_ext_window") s->sweep_ext_window = v;
             else s->sweep_window = v;
         }
         else throw std::runtime_error("unknown option '" + k + "'");
@@ -1258,10 +1273,10 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
             for (int c = 0; c < 3; ++c) xr[3 * (size_t) q + c] = d[c * 3] * acc[0] + d[c * 3 + 1] * acc[1] + d[c * 3 + 2] * acc[2];
         }
         std::vector<double> vL, vU;
-        fill_stream_host(A.L, LU.data(), vL);
-        fill_stream_host(A.U, LU.data(), vU);
-        if (!emulate_sweep(A, A.L, true, vL, rhs.data(), y.data(), 1.0)) throw std::runtime_error("lower sweep schedule deadlocks");
-        if (!emulate_sweep(A, A.U, false, vU, y.data(), x.data(), 1.0)) throw std::runtime_error("upper sweep schedule deadlocks");
+        fill_stream_host(A.L, true, LU.data(), 1.0, vL);
+        fill_stream_host(A.U, false, LU.data(), 1.0, vU);
+        if (!emulate_sweep(A, A.L, true, vL, rhs.data(), y.data())) throw std::runtime_error("lower sweep schedule deadlocks");
+        if (!emulate_sweep(A, A.U, false, vU, y.data(), x.data())) throw std::runtime_error("upper sweep schedule deadlocks");
         double num = 0.0, den = 0.0;
         for (int i = 0; i < 3 * Nb; ++i) {
             num = std::max(num, std::fabs(x[i] - xr[i]) + std::fabs(y[i] - yr[i]));

@@ -281,23 +281,47 @@ __global__ void __launch_bounds__(256) k_ilu_factor_level(const int* __restrict_
 // b200bda.cu).
 struct StageD { long long meta_off, vals_off; int meta_ints, vals_doubles, g_lo, g_rows; };
 struct PartD { int stage_begin, stage_end, row0, nrows; };
-struct BuildD { long long vals_off; int src_off, count, nd_eff, pad; };
+struct BuildD { long long vals_off; int src_off, count, first; };
 
-// Scatter the BSR factor (p-space) into the lane-major value stream of one sweep: one warp per chunk,
-// stream value ((j*3 + v) * 3 count + 3 q + comp) = LU[src(j, q)][comp][v].
-__global__ void __launch_bounds__(256) k_fill_stream(const BuildD* __restrict__ build, int nchunks, const int* __restrict__ src,
-                                                     const double* __restrict__ LU, double* __restrict__ vals)
+// position of field f of this lane inside a record of the value stream (== analysis.hpp sweep_vidx)
+template <bool LOWER>
+__device__ __forceinline__ int vidx(int f, int lane) { return (LOWER && f == 8) ? 256 + lane : (f >> 1) * 64 + 2 * lane + (f & 1); }
+
+// Scatter the BSR factor (p-space) into the record stream of one sweep (analysis.hpp): one warp per record, one
+// lane per (row q, component comp) of the record.
+//   lower: field 3 j + v = L[block j][comp][v]
+//   upper: field 3 j + v = (w D^-1 U)[block j][comp][v], field 9 + v = (w D^-1)[comp][v]  (first record of a row only)
+template <bool LOWER>
+__global__ void __launch_bounds__(256) k_fill_stream(const BuildD* __restrict__ build, int nrec, const int* __restrict__ src,
+                                                     const double* __restrict__ LU, double* __restrict__ vals, double relax)
 {
     const int lane = threadIdx.x & 31;
-    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nchunks; c += (gridDim.x * blockDim.x) >> 5) {
+    const int q = lane / 3, comp = lane - 3 * q;
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nrec; c += (gridDim.x * blockDim.x) >> 5) {
         const BuildD b = build[c];
-        const int per_j = 9 * b.count, total = b.nd_eff * per_j, lanes = 3 * b.count;
-        for (int idx = lane; idx < total; idx += 32) {
-            const int j = idx / per_j, rem = idx - j * per_j;
-            const int v = rem / lanes, l = rem - v * lanes;
-            const int q = l / 3, comp = l - 3 * q;
-            const int k = src[b.src_off + j * b.count + q];
-            vals[b.vals_off + idx] = k >= 0 ? LU[(size_t) k * 9 + comp * 3 + v] : 0.0;
+        double* out = vals + b.vals_off;
+        const bool act = q < b.count;
+        double inv[3] = {0.0, 0.0, 0.0};
+        if (!LOWER) {
+            if (act) {
+                const double* d = LU + (size_t) src[b.src_off + 3 * b.count + q] * 9 + comp * 3;
+                inv[0] = relax * d[0]; inv[1] = relax * d[1]; inv[2] = relax * d[2];
+            }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) out[vidx<LOWER>(9 + v, lane)] = b.first ? inv[v] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int k = act ? src[b.src_off + j * b.count + q] : -1;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                double x = 0.0;
+                if (k >= 0) {
+                    const double* u = LU + (size_t) k * 9;
+                    x = LOWER ? u[comp * 3 + v] : inv[0] * u[v] + inv[1] * u[3 + v] + inv[2] * u[6 + v];
+                }
+                out[vidx<LOWER>(3 * j + v, lane)] = x;
+            }
         }
     }
 }
@@ -315,18 +339,35 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// suspends the warp in hardware until the phase with the given parity has completed
+// waits until the phase with the given parity has completed.  try_wait with a suspend-time hint parks the warp in
+// hardware instead of spinning: a hot try_wait loop in the producer / helper warps steals issue slots from the
+// consumer warp that shares their scheduler (+50 % on the level step, tools/microbench/smlat.cu).
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+}
+// the same for warps off the critical path (producer, helpers): sleep between two attempts
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+        if (ok) break;
+        __nanosleep(200);
+    }
 }
 // 1-D bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
@@ -339,9 +380,9 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-constexpr int kSweepBatch = 3;         // dependency slots kept in registers (7-point stencils need 3)
 constexpr int kSweepMaxSlots = 8;      // ring slots (full + empty mbarriers and the ext flags fit the 256-byte header)
 constexpr int kSweepHeader = 256;
+constexpr int kSweepTailPad = 512;     // lanes of a partly filled record may read (never use) a few rows past the last rhs copy
 
 struct SweepArgs {
     const StageD* stages;
@@ -352,11 +393,35 @@ struct SweepArgs {
     double* out;
     double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
     Scalars* S;
-    double relax;
     int nparts, nslots, window, extWindow, metaCap, valsCap, rhsCap, nwarps, nhalo, check_done;
     long long* trace;     // debugging aid (may be null): per part and stage {wait begin, data landed, stage done, issued} in SM cycles
     int trace_cap;
 };
+
+// shared-memory accesses by 32-bit shared address: generic pointers into dynamic shared memory make the compiler rebuild
+// the shared window base (S2R SR_CgaCtaId + LEA) next to every use, in the middle of the dependent part of a row
+__device__ __forceinline__ double2 lds_f64x2(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds_s32x4(unsigned a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
 
 __device__ __forceinline__ int ld_volatile_s32(const int* p)
 {
@@ -369,15 +434,8 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v)
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-// Everything of one chunk a consumer lane can fetch BEFORE the level barrier that releases the chunk.
-struct ChunkRegs {
-    int code[kSweepBatch];        // xwin rows of the first three dependencies
-    double a[kSweepBatch][3];     // this lane's row of their factor blocks
-    double acc, inv[3];
-};
-
 // One triangular sweep.  One persistent CTA per PART (pencil of grid lines, analysis.hpp), all resident.
-//   producer warp : walks the part's stages and fetches each one -- meta ints, lane-major factor values,
+//   producer warp : walks the part's stages and fetches each one -- meta ints, record-major factor values,
 //                   rhs rows, all contiguous in processing order -- with three bulk copies (TMA unit,
 //                   UBLKCP) into a ring of shared-memory slots, several stages ahead of the consumers:
 //                   HBM latency never sits on the dependency chain;
@@ -388,17 +446,20 @@ struct ChunkRegs {
 //                   level group, and parks them in the external ring of the shared-memory value space -- one
 //                   L2 round trip per group, but several stages AHEAD of the consumers and off their critical
 //                   path; it publishes a per-slot counter the consumers check (shared memory, ~30 cycles);
-//   consumer warps: a chunk = <= 10 rows of one level, 3 lanes per row; each warp walks its own static
-//                   work list of the stage, two chunks deep in flight: the item of chunk t+2 and the columns,
-//                   factor values and rhs of chunk t+1 are loaded before the level barrier of chunk t, so
-//                   between two level barriers only the dependent part is left: 9 shared-memory reads of
-//                   earlier rows (window, parked external rows or the zero row: one flat value space, no
-//                   branches), 9 fma, one store.
+//   consumer warps: a record = <= 10 rows of one level, 3 lanes per row.  A lone warp issues in order at ~5 cycles
+//                   per instruction (measured: tools/microbench/smlat.cu, profiles/), so the time between two
+//                   level barriers is the INSTRUCTION COUNT of whatever sits between them.  Hence: the record
+//                   layout makes every operand one load with an immediate offset (values in 16-byte pairs,
+//                   32-byte value rows, precomputed byte offsets), the dependent part is 6 shared-memory reads
+//                   of earlier rows (window, parked external rows or the zero row: one flat value space, no
+//                   branches), 9 fma + 3 add and one store, and consecutive levels may go to different warp
+//                   GROUPS so that one group's operand fetch overlaps another group's dependent part.
+//                   The upper sweep is the same code: w D^-1 is folded into the stream (k_fill_stream).
 // Parts process their rows in ascending (descending for U) global level, a topological order of the
 // whole DAG, and a level only ever waits for rows of earlier levels, so the waits cannot cycle as long
 // as every CTA is resident (grid <= SMs).
-template <bool LOWER>
-__global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
+template <bool LOWER, bool REARM, bool TRACE>
+__global__ void __launch_bounds__(896, 1) k_sweep(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     if (P.check_done && P.S->done) return;
@@ -408,20 +469,21 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
     unsigned long long* empty = full + kSweepMaxSlots;
     int* ext_ready = reinterpret_cast<int*>(sweep_smem + 128);
-    double* xwin = reinterpret_cast<double*>(sweep_smem + kSweepHeader);
+    unsigned char* xwin = sweep_smem + kSweepHeader;
     const int W = P.window, EW = P.extWindow, zrow = W + EW;
-    unsigned char* slots = reinterpret_cast<unsigned char*>(xwin + 3 * (size_t) (zrow + 2));
+    unsigned char* slots = xwin + 32 * (size_t) (zrow + 2);
     const size_t metaBytes = (size_t) P.metaCap * 4, valsBytes = (size_t) P.valsCap * 8, rhsBytes = (size_t) P.rhsCap * 24;
     const size_t slotBytes = metaBytes + valsBytes + rhsBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NW = P.nwarps, NH = P.nhalo;
     const int nslots = P.nslots;
+    constexpr int NF = LOWER ? 9 : 12;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW + 1); ext_ready[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x < 6) xwin[3 * (size_t) zrow + threadIdx.x] = 0.0;
+    if (threadIdx.x < 8) reinterpret_cast<double*>(xwin)[4 * (size_t) zrow + threadIdx.x] = 0.0;
     __syncthreads();
     const int nst = pr.stage_end - pr.stage_begin;
 
@@ -439,8 +501,8 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                 const unsigned br = (unsigned) __shfl_sync(kFull, cur.g_rows, k) * 24;
                 if (lane == 0) {
                     const int i = b0 + k, s = i % nslots;
-                    if (i >= nslots) mbar_wait(empty + s, ((i / nslots) - 1) & 1);
-                    if (P.trace && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 3] = clock64();
+                    if (i >= nslots) mbar_wait_relaxed(empty + s, ((i / nslots) - 1) & 1);
+                    if (TRACE && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 3] = clock64();
                     unsigned char* base = slots + (size_t) s * slotBytes;
                     mbar_expect_tx(full + s, bm + bv + br);
                     bulk_g2s(base, P.meta + meta_off, bm, full + s);
@@ -454,10 +516,10 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 
     if (warp > NW) {                                // ---- helpers: external rows ----
         const int h = warp - NW - 1;
-        double* ring = xwin + 3 * (size_t) W;
+        double* ring = reinterpret_cast<double*>(xwin) + 4 * (size_t) W;
         for (int i = h; i < nst; i += NH) {
             const int s = i % nslots;
-            mbar_wait(full + s, (i / nslots) & 1);
+            mbar_wait_relaxed(full + s, (i / nslots) & 1);
             const int* m = reinterpret_cast<const int*>(slots + (size_t) s * slotBytes);
             const int ngroups = m[0], ext_base = m[8];
             const int* extl = m + m[5];
@@ -485,7 +547,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
                         __nanosleep(40);
                     }
                     if (on) {
-                        double* d = ring + 3 * (size_t) ((ext_base + idx) & (EW - 1));
+                        double* d = ring + 4 * (size_t) ((ext_base + idx) & (EW - 1));
                         d[0] = x0; d[1] = x1; d[2] = x2;
                     }
                     e0 = min(e0 + 32, eend);
@@ -502,105 +564,102 @@ __global__ void __launch_bounds__(512, 1) k_sweep(const SweepArgs P)
 
     // ---- consumers ----
     const int q = lane / 3, comp = lane - 3 * q;
-    const int wmask = W - 1;
     const int nthreads = NW * 32;
-    const int rhs_lane = LOWER ? lane : comp - 3 * q;         // rhs row of this lane relative to the chunk's first row
-    const bool tracing = P.trace != nullptr && threadIdx.x == 0;
+    const int lane_row = LOWER ? lane : comp - 3 * q;          // index of this lane's entry relative to 3 * g0 (rhs and out)
+    const int lane_rhs = LOWER ? lane : -3 * q;                // first rhs entry this lane reads, relative to 3 * g0
+    double* const out_lane = P.out + lane_row;
+    double* const rearm_lane = REARM ? P.rearm + lane_row : nullptr;
+    const bool tracing = TRACE && threadIdx.x == 0;
+    const unsigned xw = smem_u32(xwin);
+    const unsigned slots32 = smem_u32(slots);
+    double carry = 0.0;
+    int s = 0;
+    unsigned parity = 0;
     for (int i = 0; i < nst; ++i) {
-        const int s = i % nslots;
         if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 0] = clock64();
-        mbar_wait(full + s, (i / nslots) & 1);
+        mbar_wait(full + s, parity);
         if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 1] = clock64();
-        const unsigned char* base = slots + (size_t) s * slotBytes;
-        const int* m = reinterpret_cast<const int*>(base);
-        const double* vv = reinterpret_cast<const double*>(base + metaBytes) + lane;
-        const int* wl = m + m[6];
-        const int4* items = reinterpret_cast<const int4*>(m + m[7]);
-        const double* rr = reinterpret_cast<const double*>(base + metaBytes + valsBytes) - 3 * m[2] + rhs_lane;
-        const int tb = wl[warp], te = wl[warp + 1], tail = wl[NW + 1 + warp];
+        const unsigned sb = slots32 + (unsigned) (s * slotBytes);
+        const int4 h0 = lds_s32x4(sb);                                 // {ngroups, nrecords, g_lo, rhs rows}
+        const int4 h1 = lds_s32x4(sb + 16);                            // {next, off_ext, off_wl, off_items}
+        const unsigned wl = sb + 4 * (unsigned) h1.z;
+        int tb, te, tail;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tb) : "r"(wl + 4 * warp));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(te) : "r"(wl + 4 * warp + 4));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(tail) : "r"(wl + 4 * (NW + 1 + warp)));
+        unsigned it_a = sb + 4 * (unsigned) h1.w + 16 * (unsigned) tb;                                  // items
+        unsigned cd_a = sb + 4 * (unsigned) (h1.w + 4 * h0.y) + 16 * lane + 512 * (unsigned) tb;         // codes
+        unsigned v_a = sb + (unsigned) metaBytes + 16 * lane + (unsigned) tb * (NF * 256);               // value pairs
+        const unsigned v8_off = 2048 + 8 * lane - 16 * lane;                                             // lower: the ninth value
+        const unsigned rr = sb + (unsigned) (metaBytes + valsBytes) + 8 * lane_rhs;
         const int tag = (i + 1) << 16;
-
-        auto fetch = [&](const int4 it) {
-            ChunkRegs c;
-            const int count = it.y & 15, nd = (it.y >> 4) & 0xfff, lanes = 3 * count;
-            const bool act = q < count;
-            const int* cp = m + (it.z & 0xffff) + q;
-            const double* vb = vv + ((unsigned) it.z >> 16);
-#pragma unroll
-            for (int j = 0; j < kSweepBatch; ++j) {
-                const bool on = j < nd;                       // warp-uniform
-                c.code[j] = (on && act) ? cp[j * count] : zrow;
-#pragma unroll
-                for (int v = 0; v < 3; ++v) c.a[j][v] = on ? vb[(j * 3 + v) * lanes] : 0.0;
+        long long tp_last = TRACE ? clock64() : 0, tp_pre = 0, tp_bar = 0, tp_post = 0;
+        for (int t = tb; t < te; ++t, it_a += 16, cd_a += 512, v_a += NF * 256) {
+            // ---- operands of record t: nothing here depends on another row
+            const int4 item = lds_s32x4(it_a);                // {rhs byte offset, first | last << 1 | count << 4 | barriers << 16, ext_need, 3 g0}
+            const int4 cd = lds_s32x4(cd_a);                  // byte offsets in xwin of the dependencies and of the result
+            const double2 a01 = lds_f64x2(v_a);
+            const double2 a23 = lds_f64x2(v_a + 512);
+            const double2 a45 = lds_f64x2(v_a + 1024);
+            const double2 a67 = lds_f64x2(v_a + 1536);
+            double a8, r0, r1 = 0.0, r2 = 0.0, i0 = 0.0, i1 = 0.0, i2 = 0.0;
+            if constexpr (LOWER) {
+                a8 = lds_f64(v_a + v8_off);
+                r0 = lds_f64(rr + item.x);
+            } else {
+                const double2 a89 = lds_f64x2(v_a + 2048);
+                const double2 aAB = lds_f64x2(v_a + 2560);
+                a8 = a89.x; i0 = a89.y; i1 = aAB.x; i2 = aAB.y;
+                r0 = lds_f64(rr + item.x); r1 = lds_f64(rr + item.x + 8); r2 = lds_f64(rr + item.x + 16);
             }
-            c.acc = act ? rr[3 * it.x] : 0.0;
-#pragma unroll
-            for (int v = 0; v < 3; ++v) c.inv[v] = LOWER ? 0.0 : vb[(nd * 3 + v) * lanes];
-            return c;
-        };
-
-        const int4 none = make_int4(0, 0, 0, 0);
-        int4 it1 = tb < te ? items[tb] : none;                // item of chunk t
-        int4 it2 = tb + 1 < te ? items[tb + 1] : none;        // item of chunk t + 1
-        ChunkRegs nx = fetch(it1);
-        for (int t = tb; t < te; ++t) {
-            const int4 it = it1;
-            const ChunkRegs c = nx;
-            it1 = it2;
-            if (t + 2 < te) it2 = items[t + 2];
-            if (t + 1 < te) nx = fetch(it1);
-            const int nbar = (it.y >> 16) & 0xffff, need = (int) ((unsigned) it.w >> 16);
-            for (int b = 0; b < nbar; ++b) named_barrier(1, nthreads);
-            if (need) {                                       // external rows of this level: parked by a helper warp
+            long long tc0 = 0, tc1 = 0;
+            if (tracing) { tc0 = clock64(); tp_pre += tc0 - tp_last; }
+            // ---- level barriers
+            if (item.y >> 16) {
+                named_barrier(1, nthreads);
+                for (int b = (item.y >> 16) - 1; b > 0; --b) named_barrier(1, nthreads);
+            }
+            if (item.z) {                                     // external rows of this level: parked by a helper warp
                 int spins = 0;
-                while (ld_volatile_s32(ext_ready + s) - (tag + need) < 0) {
+                while (ld_volatile_s32(ext_ready + s) - (tag + item.z) < 0) {
                     if ((++spins & 4095) == 0 && *((volatile int*) &P.S->trsv_timeout)) break;
                 }
                 __threadfence_block();
             }
-            // ---- exposed part: 9 reads of earlier rows, fma, publish ----
-            double acc = c.acc;
-#pragma unroll
-            for (int j = 0; j < kSweepBatch; ++j) {
-                const double* xp = xwin + 3 * c.code[j];
-                double tt = c.a[j][0] * xp[0];
-                tt = fma(c.a[j][1], xp[1], tt);
-                tt = fma(c.a[j][2], xp[2], tt);
-                acc -= tt;
+            if (tracing) { tc1 = clock64(); tp_bar += tc1 - tc0; }
+            // ---- dependent part
+            const double2 x0 = lds_f64x2(xw + cd.x);
+            const double2 x1 = lds_f64x2(xw + cd.y);
+            const double2 x2 = lds_f64x2(xw + cd.z);
+            const double x02 = lds_f64(xw + cd.x + 16);
+            const double x12 = lds_f64(xw + cd.y + 16);
+            const double x22 = lds_f64(xw + cd.z + 16);
+            double acc;
+            if constexpr (LOWER) acc = r0;
+            else acc = fma(i2, r2, fma(i1, r1, i0 * r0));
+            if (!(item.y & 1)) acc = carry;                   // continuation record of a long row
+            const double t0 = fma(a23.x, x02, fma(a01.y, x0.y, a01.x * x0.x));
+            const double t1 = fma(a45.y, x12, fma(a45.x, x1.y, a23.y * x1.x));
+            const double t2 = fma(a8, x22, fma(a67.y, x2.y, a67.x * x2.x));
+            acc = ((acc - t0) - t1) - t2;
+            carry = acc;
+            if (cd.w >= 0) {
+                sts_f64(xw + cd.w, acc);
+                st_relaxed(out_lane + item.w, acc);
+                if (REARM) rearm_lane[item.w] = sentinel();
             }
-            const int count = it.y & 15, nd = (it.y >> 4) & 0xfff;
-            const bool act = q < count;
-            if (nd > kSweepBatch) {                           // long rows (NNC, wells in the matrix): unpipelined tail
-                const int lanes = 3 * count;
-                const int* cp = m + (it.z & 0xffff) + q;
-                const double* vb = vv + ((unsigned) it.z >> 16);
-                for (int j = kSweepBatch; j < nd; ++j) {
-                    const double* xp = xwin + 3 * (act ? cp[j * count] : zrow);
-                    double tt = vb[(j * 3) * lanes] * xp[0];
-                    tt = fma(vb[(j * 3 + 1) * lanes], xp[1], tt);
-                    tt = fma(vb[(j * 3 + 2) * lanes], xp[2], tt);
-                    acc -= tt;
-                }
-            }
-            double res = acc;
-            if (!LOWER) {
-                const int b3 = act ? 3 * q : 0;
-                const double s0 = __shfl_sync(kFull, acc, b3);
-                const double s1 = __shfl_sync(kFull, acc, b3 + 1);
-                const double s2 = __shfl_sync(kFull, acc, b3 + 2);
-                res = (c.inv[0] * s0 + c.inv[1] * s1 + c.inv[2] * s2) * P.relax;
-            }
-            if (act) {
-                const int g = LOWER ? it.x + q : it.x - q;
-                xwin[3 * (((it.w & 0xffff) + q) & wmask) + comp] = res;
-                st_relaxed(P.out + 3 * (size_t) g + comp, res);
-                if (P.rearm != nullptr) P.rearm[3 * (size_t) g + comp] = sentinel();
-            }
+            if (tracing) { tp_last = clock64(); tp_post += tp_last - tc1; }
         }
         for (int b = 0; b < tail; ++b) named_barrier(1, nthreads);
         __syncwarp();
-        if (tracing && i < P.trace_cap) P.trace[((size_t) part * P.trace_cap + i) * 4 + 2] = clock64();
+        if (tracing && i < P.trace_cap) {
+            P.trace[((size_t) part * P.trace_cap + i) * 4 + 2] = clock64();
+            // second half of the trace buffer: per stage {records of warp 0, cycles before / in / after the barriers}
+            long long* t2 = P.trace + (size_t) 148 * P.trace_cap * 4 + ((size_t) part * P.trace_cap + i) * 4;
+            t2[0] = te - tb; t2[1] = tp_pre; t2[2] = tp_bar; t2[3] = tp_post;
+        }
         if (lane == 0) mbar_arrive(empty + s);
+        if (++s == nslots) { s = 0; parity ^= 1; }
     }
 }
 

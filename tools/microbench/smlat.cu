@@ -44,6 +44,36 @@ __global__ void k(int mode, int iters, double* gout, long long* cycles, double s
             while (flag[0] != -12345 && clock64() - t0 < 400000ll) { }
         }
     }
+    if (mode >= 7 && mode <= 9) {
+        __shared__ unsigned long long mbar;
+        if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(&mbar)), "r"(1) : "memory");
+        __syncthreads();
+        t0 = clock64();
+        if (warp < 8) {
+            double f[12];
+            for (int j = 0; j < 12; ++j) f[j] = 0.0;
+            for (int i = 0; i < iters; ++i) {
+                if (mode != 8 && warp == 0) {                 // "fetch" of the next record: 12 loads before the barrier
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) f[j] = sm[(i * 7 + j * 32 + lane) & 4095];
+                }
+                named_barrier(1, 256);
+                if (warp == 0) {
+                    double x0 = sm[(i * 3) & 4095], x1 = sm[(i * 3 + 1) & 4095], x2 = sm[(i * 3 + 2) & 4095];
+                    double t = f[0] * x0; t = fma(f[1], x1, t); t = fma(f[2], x2, t); a -= t;
+                    a += f[3] + f[4] + f[5] + f[6] + f[7] + f[8] + f[9] + f[10] + f[11];
+                    sm[(i * 3 + 3 + lane) & 4095] = a;
+                    st_relaxed(gout + ((i * 32 + lane) & 65535), a);
+                }
+            }
+        } else if (mode >= 8) {                               // spinning like the producer / helper warps: mbarrier.try_wait loop
+            unsigned addr = (unsigned) __cvta_generic_to_shared(&mbar);
+            unsigned ok = 0;
+            while (!ok && clock64() - t0 < 600000ll) {
+                asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(ok) : "r"(addr), "r"(0) : "memory");
+            }
+        }
+    }
     long long t1 = clock64();
     if (threadIdx.x == 0) { cycles[0] = t1 - t0; }
     if (a == 123.456 || idx == -5) gout[0] = a + idx;
@@ -54,10 +84,12 @@ int main()
     double* gout; long long* cyc;
     cudaMalloc(&gout, 65536 * 8 + 64); cudaMalloc(&cyc, 64);
     const char* names[] = {"dependent DFMA", "dependent LDS (pointer chase)", "bar.sync 8 warps, nothing else", "level step: bar + LDS + 4 DFMA + STS (warp 0 works)",
-                           "level step + st.relaxed.gpu", "level step + weak global store", "level step, 5 extra warps spinning"};
-    for (int mode = 0; mode < 7; ++mode) {
+                           "level step + st.relaxed.gpu", "level step + weak global store", "level step, 5 extra warps spinning",
+                           "level step + st.relaxed + 12 fetch loads before the barrier", "level step + st.relaxed, 5 warps spin on mbarrier.try_wait",
+                           "level step + st.relaxed + 12 fetch loads, 5 warps spin on try_wait"};
+    for (int mode = 0; mode < 10; ++mode) {
         const int iters = 2000;
-        const int threads = mode == 6 ? 416 : 256;
+        const int threads = (mode == 6 || mode >= 8) ? 416 : 256;
         for (int rep = 0; rep < 2; ++rep) k<<<1, threads>>>(mode, iters, gout, cyc, 1.5);
         cudaDeviceSynchronize();
         long long h = 0;

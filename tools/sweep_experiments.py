@@ -26,9 +26,9 @@ if which in ("all", "micro"):
     run((200, 32, 32), "4x4 pencils", parts=16)
 if which in ("all", "c3"):
     run((100, 100, 100), "c3 default", parts=148)
-    run((100, 100, 100), "c3 helpers 2", parts=148, helpers=2)
-    run((100, 100, 100), "c3 helpers 6", parts=148, helpers=6)
+    run((100, 100, 100), "c3 8 warps, 1 group", parts=148, warps=8, groups=1)
+    run((100, 100, 100), "c3 14 warps, 2 groups", parts=148, warps=14, groups=2)
+    run((100, 100, 100), "c3 24 warps, 3 groups", parts=148, warps=24, groups=3)
     run((100, 100, 100), "c3 32K/4 slots", parts=148, stage_bytes=32768, slots=4)
-    run((100, 100, 100), "c3 32K/4 slots 12 warps/3", parts=148, stage_bytes=32768, slots=4, warps=12, helpers=3)
-    run((100, 100, 100), "c3 8K/8 slots", parts=148, stage_bytes=8192, slots=8)
-    run((100, 100, 100), "c3 4 warps", parts=148, warps=4)
+    run((100, 100, 100), "c3 80K/2 slots", parts=148, stage_bytes=81920, slots=2, warps=8, groups=1)
+    run((100, 100, 100), "c3 helpers 2", parts=148, helpers=2)

@@ -14,7 +14,8 @@ be.set_option("sweep_trace", 1)
 be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
 be.ilu0_factorize()
 lo, _ = be.time_kernel("ilu_lower", 2, False)
-tr = be.sweep_trace()
+tr2 = be.sweep_trace()
+tr, det = tr2[0], tr2[1]
 print("lower %.1f us" % (lo * 1e3))
 ghz = 1.965
 for part in sorted(set([0, 1, 5, 20, 74, 147])):
@@ -29,6 +30,10 @@ for part in sorted(set([0, 1, 5, 20, 74, 147])):
     issue_to_land = (t[:, 1] - t[:, 3]) / ghz / 1e3
     print("part %3d: %4d stages, total %7.1f us | waiting for data %7.1f us (mean %.2f, max %.2f) | working %7.1f us (mean %.2f) | issue->consumed mean %.2f us"
           % (part, n, (t[-1, 2] - t0) / ghz / 1e3, wait.sum(), wait.mean(), wait.max(), work.sum(), work.mean(), issue_to_land.mean()))
+    d = det[part][:n].astype(np.float64)
+    nrec = max(d[:, 0].sum(), 1)
+    print("          warp 0: %d records; cycles per record: fetch+pre-barrier %.0f, barriers+ext wait %.0f, dependent part %.0f"
+          % (nrec, d[:, 1].sum() / nrec, d[:, 2].sum() / nrec, d[:, 3].sum() / nrec))
     if part in (0, 74):
         for i in range(min(n, 12)):
             print("   stage %3d: wait %6.2f work %6.2f us  (issued %7.2f, wait-begin %7.2f, landed %7.2f, done %7.2f)"
