@@ -375,9 +375,9 @@ class B200SolverBackend:
 
     def sweep_trace(self):
         """[148, 1024, 4] SM-clock stamps of the last traced sweep (option sweep_trace = 1)."""
-        out = np.zeros(2 * 148 * 1024 * 4, np.int64)
+        out = np.zeros(3 * 148 * 1024 * 4, np.int64)
         self._chk(lib().b200_get_sweep_trace(self._h, out, out.size))
-        return out.reshape(2, 148, 1024, 4)
+        return out.reshape(3, 148, 1024, 4)
 
     def timer_start(self) -> None:
         self._chk(lib().b200_timer_start(self._h))

@@ -143,7 +143,7 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 81920, sweep_window = 0, sweep_ext_window = 512;
+    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 81920, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 60;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -297,7 +297,7 @@ struct Solver {
         const long long nnzb_in = nnz_ / 9;
         if (rows[Nb] != nnzb_in) throw std::runtime_error("rows[Nb] != nnz / 9");
         AnalysisOptions opt;
-        opt.parts = sweep_parts > 0 ? std::min(sweep_parts, num_sms) : num_sms;      // every CTA of a sweep must be resident
+        opt.parts = sweep_parts > 0 ? std::min(sweep_parts, 8 * num_sms) : num_sms;  // every CTA of a sweep must be resident (checked below)
         opt.stageBytes = sweep_stage_bytes;
         opt.window = sweep_window;
         opt.extWindow = sweep_ext_window;
@@ -380,7 +380,6 @@ struct Solver {
         if (sweep_smem > smem_optin)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
-        if (an.nparts > num_sms) throw std::runtime_error("internal: more sweep parts than SMs");
         int occ = 8;
         const int threads = sweep_threads();
         auto prep = [&](auto kern) {
@@ -392,6 +391,9 @@ struct Solver {
         prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
         prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
         if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
+        if (an.nparts > occ * num_sms)
+            throw std::runtime_error("triangular sweeps: " + std::to_string(an.nparts) + " parts cannot all be resident (" +
+                                     std::to_string(occ) + " CTAs per SM fit); lower sweep_parts or the stage size");
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts; "
                             "L: %zu stages %lld chunks (%lld window / %lld global deps), U: %zu stages; sweep grid %d x %d, "
@@ -542,7 +544,7 @@ struct Solver {
         a.rhs = rhs; a.out = out; a.rearm = rearm; a.S = d_S.p;
         a.nparts = an.nparts; a.nslots = sweep_slots; a.window = an.window;
         a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extWindow = an.extWindow;
-        a.nwarps = sweep_warps; a.nhalo = sweep_helpers;
+        a.nwarps = sweep_warps; a.nhalo = sweep_helpers; a.helper_sleep = sweep_helper_sleep;
         a.check_done = check_done ? 1 : 0;
         a.trace = sweep_trace ? d_trace.p : nullptr;
         a.trace_cap = kTraceCap;
@@ -819,9 +821,10 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);
         else if (k == "sweep_trace") {
             s->sweep_trace = value != 0.0;
-            if (s->sweep_trace) { s->d_trace.alloc((size_t) 2 * 148 * 4 * b200::Solver::kTraceCap); CUDA_OK(cudaMemset(s->d_trace.p, 0, sizeof(long long) * s->d_trace.n)); }
+            if (s->sweep_trace) { s->d_trace.alloc((size_t) 3 * 148 * 4 * b200::Solver::kTraceCap); CUDA_OK(cudaMemset(s->d_trace.p, 0, sizeof(long long) * s->d_trace.n)); }
         }
         else if (k == "sweep_parts" || k == "sweep_warps" || k == "sweep_groups" || k == "sweep_helpers" || k == "sweep_slots" || k == "sweep_stage_bytes" || k == "sweep_window" || k == "sweep_ext_window") {
             if (s->analysed) throw std::runtime_error(k + " must be set before the first solve");

@@ -393,7 +393,7 @@ struct SweepArgs {
     double* out;
     double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
     Scalars* S;
-    int nparts, nslots, window, extWindow, metaCap, valsCap, rhsCap, nwarps, nhalo, check_done;
+    int nparts, nslots, window, extWindow, metaCap, valsCap, rhsCap, nwarps, nhalo, check_done, helper_sleep;
     long long* trace;     // debugging aid (may be null): per part and stage {wait begin, data landed, stage done, issued} in SM cycles
     int trace_cap;
 };
@@ -459,7 +459,7 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v)
 // whole DAG, and a level only ever waits for rows of earlier levels, so the waits cannot cycle as long
 // as every CTA is resident (grid <= SMs).
 template <bool LOWER, bool REARM, bool TRACE>
-__global__ void __launch_bounds__(896, 1) k_sweep(const SweepArgs P)
+__global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     if (P.check_done && P.S->done) return;
@@ -515,48 +515,76 @@ __global__ void __launch_bounds__(896, 1) k_sweep(const SweepArgs P)
     }
 
     if (warp > NW) {                                // ---- helpers: external rows ----
+        // The stage's external rows are listed in the order the levels need them.  A helper keeps a WINDOW of
+        // kHelperWindow x 32 rows in flight (one row per lane and sub-batch, three 8-byte loads each), parks every row as
+        // soon as it has arrived and publishes the length of the finished PREFIX of the list: the consumers of a level
+        // wait for `prefix >= rows needed up to this level`.  Polling one level group at a time would cap a part at one
+        // level per L2 round trip (0.6-1 us) -- slower than the part upstream produces them, so that the lag grows by a
+        // constant per level and per hop (measured: 2 us per level at the far corner of the c3 grid, profiles/).
+        constexpr int kHelperWindow = 2;
         const int h = warp - NW - 1;
         double* ring = reinterpret_cast<double*>(xwin) + 4 * (size_t) W;
         for (int i = h; i < nst; i += NH) {
             const int s = i % nslots;
             mbar_wait_relaxed(full + s, (i / nslots) & 1);
             const int* m = reinterpret_cast<const int*>(slots + (size_t) s * slotBytes);
-            const int ngroups = m[0], ext_base = m[8];
+            const int next = m[4], ext_base = m[8];
             const int* extl = m + m[5];
             const int tag = (i + 1) << 16;
-            int e0 = 0;
-            for (int gi = 0; gi < ngroups; ++gi) {
-                const int eend = m[12 + gi];
-                while (e0 < eend) {
-                    const int idx = e0 + lane;
-                    const bool on = idx < eend;
-                    const double* xp = P.out + 3 * (size_t) (on ? extl[idx] : 0);
-                    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-                    bool ok = !on;
-                    int spins = 0;
-                    while (true) {
-                        if (!ok) {
-                            x0 = ld_relaxed(xp); x1 = ld_relaxed(xp + 1); x2 = ld_relaxed(xp + 2);
-                            ok = !(is_sentinel(x0) || is_sentinel(x1) || is_sentinel(x2));
-                        }
-                        if (__all_sync(kFull, ok)) break;
-                        if ((++spins & 255) == 0 && (spins > (1 << 20) || *((volatile int*) &P.S->trsv_timeout))) {
-                            P.S->trsv_timeout = 1;
-                            break;
-                        }
-                        __nanosleep(40);
-                    }
-                    if (on) {
-                        double* d = ring + 4 * (size_t) ((ext_base + idx) & (EW - 1));
-                        d[0] = x0; d[1] = x1; d[2] = x2;
-                    }
-                    e0 = min(e0 + 32, eend);
+            int published = 0;
+            long long* t3 = TRACE && i < P.trace_cap ? P.trace + (size_t) 2 * 148 * P.trace_cap * 4 + ((size_t) part * P.trace_cap + i) * 4 : nullptr;
+            if (TRACE && t3 && lane == 0) { t3[0] = clock64(); t3[2] = next; }
+            for (int e0 = 0; e0 < next; e0 += 32 * kHelperWindow) {
+                const int wend = min(e0 + 32 * kHelperWindow, next);
+                bool done[kHelperWindow];
+                const double* xp[kHelperWindow];
+#pragma unroll
+                for (int k = 0; k < kHelperWindow; ++k) {
+                    const int idx = e0 + 32 * k + lane;
+                    done[k] = idx >= wend;
+                    xp[k] = P.out + 3 * (size_t) (done[k] ? 0 : extl[idx]);
                 }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) st_volatile_s32(ext_ready + s, tag + eend);
+                int spins = 0;
+                while (true) {
+                    double x[kHelperWindow][3];
+#pragma unroll
+                    for (int k = 0; k < kHelperWindow; ++k)
+                        if (!done[k]) { x[k][0] = ld_relaxed(xp[k]); x[k][1] = ld_relaxed(xp[k] + 1); x[k][2] = ld_relaxed(xp[k] + 2); }
+#pragma unroll
+                    for (int k = 0; k < kHelperWindow; ++k)
+                        if (!done[k] && !(is_sentinel(x[k][0]) || is_sentinel(x[k][1]) || is_sentinel(x[k][2]))) {
+                            double* d = ring + 4 * (size_t) ((ext_base + e0 + 32 * k + lane) & (EW - 1));
+                            d[0] = x[k][0]; d[1] = x[k][1]; d[2] = x[k][2];
+                            done[k] = true;
+                        }
+                    int prefix = e0;
+                    bool all = true;
+#pragma unroll
+                    for (int k = 0; k < kHelperWindow; ++k) {
+                        const unsigned bm = __ballot_sync(kFull, done[k]);
+                        if (all) {
+                            if (bm == kFull) prefix += 32;
+                            else { prefix += __ffs(~bm) - 1; all = false; }
+                        }
+                    }
+                    prefix = min(prefix, wend);
+                    if (prefix > published) {
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) st_volatile_s32(ext_ready + s, tag + prefix);
+                        published = prefix;
+                    }
+                    if (prefix >= wend) break;
+                    if ((++spins & 255) == 0 && (spins > (1 << 20) || *((volatile int*) &P.S->trsv_timeout))) {
+                        P.S->trsv_timeout = 1;
+                        if (lane == 0) st_volatile_s32(ext_ready + s, tag + next);
+                        break;
+                    }
+                    if (P.helper_sleep) __nanosleep(P.helper_sleep);
+                }
             }
             __syncwarp();
+            if (TRACE && t3 && lane == 0) t3[1] = clock64();
             if (lane == 0) mbar_arrive(empty + s);
         }
         return;

@@ -26,9 +26,9 @@ if which in ("all", "micro"):
     run((200, 32, 32), "4x4 pencils", parts=16)
 if which in ("all", "c3"):
     run((100, 100, 100), "c3 default", parts=148)
-    run((100, 100, 100), "c3 8 warps, 1 group", parts=148, warps=8, groups=1)
-    run((100, 100, 100), "c3 14 warps, 2 groups", parts=148, warps=14, groups=2)
-    run((100, 100, 100), "c3 24 warps, 3 groups", parts=148, warps=24, groups=3)
-    run((100, 100, 100), "c3 32K/4 slots", parts=148, stage_bytes=32768, slots=4)
-    run((100, 100, 100), "c3 80K/2 slots", parts=148, stage_bytes=81920, slots=2, warps=8, groups=1)
-    run((100, 100, 100), "c3 helpers 2", parts=148, helpers=2)
+    run((100, 100, 100), "c3 sleep 0", parts=148, helper_sleep=0)
+    run((100, 100, 100), "c3 sleep 20", parts=148, helper_sleep=20)
+    run((100, 100, 100), "c3 sleep 200", parts=148, helper_sleep=200)
+    run((100, 100, 100), "c3 sleep 1000", parts=148, helper_sleep=1000)
+    run((200, 32, 32), "4x4 pencils sleep 0", parts=16, helper_sleep=0)
+    run((200, 32, 32), "4x4 pencils sleep 1000", parts=16, helper_sleep=1000)

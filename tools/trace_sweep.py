@@ -15,7 +15,7 @@ be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
 be.ilu0_factorize()
 lo, _ = be.time_kernel("ilu_lower", 2, False)
 tr2 = be.sweep_trace()
-tr, det = tr2[0], tr2[1]
+tr, det, hlp = tr2[0], tr2[1], tr2[2]
 print("lower %.1f us" % (lo * 1e3))
 ghz = 1.965
 for part in sorted(set([0, 1, 5, 20, 74, 147])):
@@ -35,6 +35,8 @@ for part in sorted(set([0, 1, 5, 20, 74, 147])):
     print("          warp 0: %d records; cycles per record: fetch+pre-barrier %.0f, barriers+ext wait %.0f, dependent part %.0f"
           % (nrec, d[:, 1].sum() / nrec, d[:, 2].sum() / nrec, d[:, 3].sum() / nrec))
     if part in (0, 74):
-        for i in range(min(n, 12)):
-            print("   stage %3d: wait %6.2f work %6.2f us  (issued %7.2f, wait-begin %7.2f, landed %7.2f, done %7.2f)"
-                  % (i, wait[i], work[i], (t[i, 3] - t0) / ghz / 1e3, (t[i, 0] - t0) / ghz / 1e3, (t[i, 1] - t0) / ghz / 1e3, (t[i, 2] - t0) / ghz / 1e3))
+        hh = hlp[part][:n].astype(np.float64)
+        for i in range(min(n, 40)):
+            print("   stage %3d: wait %6.2f work %6.2f us  (issued %7.2f, wait-begin %7.2f, landed %7.2f, done %7.2f)  helper: %3d ext rows, start %7.2f done %7.2f"
+                  % (i, wait[i], work[i], (t[i, 3] - t0) / ghz / 1e3, (t[i, 0] - t0) / ghz / 1e3, (t[i, 1] - t0) / ghz / 1e3, (t[i, 2] - t0) / ghz / 1e3,
+                     hh[i, 2], (hh[i, 0] - t0) / ghz / 1e3, (hh[i, 1] - t0) / ghz / 1e3))
