@@ -188,6 +188,13 @@ struct Analysis {
     // factorisation schedule: p-space rows grouped by global level of the symmetrised pattern
     int nflev = 0;
     std::vector<int> flevPtr, flevRows;
+    // elimination plan of the factorisation (k_ilu_factor_plan): per p-space row the upstream blocks it needs, in the
+    // order the left-looking elimination uses them.  op = {p-space block, code}: code >= 0: pivot of lower entry
+    // `code & 255` of the row (offset from the row start) followed by `code >> 8` updates; code < 0: update of the row's
+    // block -(code + 1) with the current L block times this upstream U block.
+    std::vector<int> facPtr;          // Nb + 1, in ops
+    std::vector<int> facOps;          // 2 ints per op
+    int facMaxRow = 0, facMaxOps = 0;
     // triangular sweeps
     int nparts = 0, nlines = 0, window = 0, warps = 8, groups = 1, extWindow = 512;
     int nstrips = 0;
@@ -636,6 +643,28 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
     {
         std::vector<int> fill(A.flevPtr.begin(), A.flevPtr.end() - 1);
         for (int q = 0; q < Nb; ++q) A.flevRows[fill[glev[A.perm[q]]]++] = q;
+    }
+    // elimination plan: rows are final once their level has run, so every upstream block can be prefetched up front
+    A.facPtr.assign((size_t) Nb + 1, 0);
+    A.facOps.reserve((size_t) 4 * A.nnzb);
+    for (int q = 0; q < Nb; ++q) {
+        const int rs = A.prow[q], re = A.prow[q + 1], di = A.pdiag[q];
+        A.facMaxRow = std::max(A.facMaxRow, re - rs);
+        for (int kj = rs; kj < di; ++kj) {
+            const int j = A.pcol[kj];
+            const size_t head = A.facOps.size();
+            A.facOps.push_back(A.pdiag[j]);
+            A.facOps.push_back(0);
+            int nupd = 0;
+            for (int jk = A.pdiag[j] + 1; jk < A.prow[j + 1]; ++jk) {
+                const int colk = A.pcol[jk];
+                for (int ik = kj + 1; ik < re; ++ik)
+                    if (A.pcol[ik] == colk) { A.facOps.push_back(jk); A.facOps.push_back(-(ik - rs + 1)); ++nupd; break; }
+            }
+            A.facOps[head + 1] = (kj - rs) | (nupd << 8);
+        }
+        A.facPtr[q + 1] = (int) (A.facOps.size() / 2);
+        A.facMaxOps = std::max(A.facMaxOps, A.facPtr[q + 1] - A.facPtr[q]);
     }
     detail::build_sweep(A, rows, cols, glev, partOf, true, opt, A.L);
     detail::build_sweep(A, rows, cols, glev, partOf, false, opt, A.U);

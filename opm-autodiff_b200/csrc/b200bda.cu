@@ -166,7 +166,8 @@ struct Solver {
     DevBuf<int> d_send_prow, d_grow, d_gptr, d_gcol, d_gsrc;
     DevBuf<unsigned> d_push_tickets;
 
-    DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows;
+    DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows, d_facPtr, d_facOps;
+    bool fac_plan = false;
     DevBuf<StageD> d_stagesL, d_stagesU;
     DevBuf<PartD> d_partsL, d_partsU;
     DevBuf<BuildD> d_buildL, d_buildU;
@@ -351,6 +352,8 @@ struct Solver {
         };
         up(d_prow, an.prow); up(d_pcol, an.pcol); up(d_pdiag, an.pdiag); up(d_srcblk, an.srcblk); up(d_perm, an.perm);
         up(d_flevRows, an.flevRows);
+        fac_plan = an.facMaxRow <= kFacMaxRow && an.facMaxOps <= kFacMaxOps;
+        if (fac_plan) { up(d_facPtr, an.facPtr); up(d_facOps, an.facOps); }
         up(d_metaL, an.L.meta); up(d_metaU, an.U.meta); up(d_srcL, an.L.src); up(d_srcU, an.U.src);
         d_stagesL.alloc(an.L.stages.size()); d_stagesU.alloc(an.U.stages.size());
         d_partsL.alloc(an.nparts); d_partsU.alloc(an.nparts);
@@ -520,7 +523,11 @@ struct Solver {
         for (int l = 0; l < an.nflev; ++l) {
             int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
             int id = prof_begin(K_FACTOR);
-            k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
+            if (fac_plan)
+                k_ilu_factor_plan<<<(nrows + kFacWarps - 1) / kFacWarps, 32 * kFacWarps, 0, stream>>>(
+                    d_prow.p, d_pdiag.p, d_facPtr.p, reinterpret_cast<const int2*>(d_facOps.p), d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
+            else
+                k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             prof_end(id);
         }
         int id = prof_begin(K_SLICES);

@@ -275,6 +275,73 @@ __global__ void __launch_bounds__(256) k_ilu_factor_level(const int* __restrict_
     }
 }
 
+// The same factorisation with an elimination PLAN (analysis.hpp facOps): the kernel above walks the pattern with ~40
+// dependent global loads per row (15 us per level whatever its size); here a warp first fetches everything it needs in
+// two rounds -- its plan and its own row, then all upstream blocks (pivots and U blocks of earlier levels, final) -- into
+// shared memory and eliminates there: two L2/HBM round trips per level instead of forty.
+constexpr int kFacMaxRow = 16, kFacMaxOps = 48, kFacWarps = 8;
+__global__ void __launch_bounds__(32 * kFacWarps) k_ilu_factor_plan(const int* __restrict__ prow, const int* __restrict__ pdiag,
+                                                                   const int* __restrict__ facPtr, const int2* __restrict__ facOps,
+                                                                   const double* __restrict__ A, double* LU,
+                                                                   const int* __restrict__ rowlist, int nrows, Scalars* S)
+{
+    __shared__ double srow[kFacWarps][kFacMaxRow * 9];
+    __shared__ double sup[kFacWarps][kFacMaxOps * 9];
+    __shared__ int2 sop[kFacWarps][kFacMaxOps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wid = blockIdx.x * kFacWarps + w;
+    if (wid >= nrows) return;
+    const int i = rowlist[wid];
+    const int rs = prow[i], re = prow[i + 1], di = pdiag[i] - rs;
+    const int o0 = facPtr[i], nops = facPtr[i + 1] - o0;
+    double* row = srow[w];
+    double* up = sup[w];
+    for (int o = lane; o < nops; o += 32) sop[w][o] = facOps[o0 + o];
+    for (int f = lane; f < (re - rs) * 9; f += 32) row[f] = A[(size_t) rs * 9 + f];
+    __syncwarp();
+    for (int f = lane; f < nops * 9; f += 32) {
+        const int o = f / 9;
+        up[f] = LU[(size_t) sop[w][o].x * 9 + (f - 9 * o)];
+    }
+    __syncwarp();
+    const int g = lane / 9, e = lane - 9 * g, er = e / 3, ec = e - 3 * er;      // three 3x3 products side by side
+    int o = 0;
+    while (o < nops) {
+        const int code = sop[w][o].y;
+        const int toff = code & 255, nupd = code >> 8;
+        // L_ij = A_ij * inv(A_jj)
+        double lij = 0.0;
+        if (lane < 9) {
+            const double* a = row + toff * 9 + er * 3;
+            const double* d = up + o * 9 + ec;
+            lij = a[0] * d[0] + a[1] * d[3] + a[2] * d[6];
+        }
+        __syncwarp();
+        if (lane < 9) row[toff * 9 + lane] = lij;
+        __syncwarp();
+        // A_ik -= L_ij * U_jk for the blocks present in both rows: distinct targets, three at a time
+        for (int u0 = 0; u0 < nupd; u0 += 3) {
+            const int u = u0 + g;
+            if (g < 3 && u < nupd) {
+                const int tgt = -(sop[w][o + 1 + u].y + 1);
+                const double* l = row + toff * 9 + er * 3;
+                const double* uu = up + (o + 1 + u) * 9 + ec;
+                row[tgt * 9 + e] -= l[0] * uu[0] + l[1] * uu[3] + l[2] * uu[6];
+            }
+            __syncwarp();
+        }
+        o += 1 + nupd;
+    }
+    if (lane == 0) {
+        double inv[9];
+        if (!inv3(row + di * 9, inv)) S->singular = 1;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) row[di * 9 + k] = inv[k];
+    }
+    __syncwarp();
+    for (int f = lane; f < (re - rs) * 9; f += 32) LU[(size_t) rs * 9 + f] = row[f];
+}
+
 // ---- triangular solves: pencil-pipelined sweeps -----------------------------------------------------
 //
 // Device mirrors of analysis.hpp's StageRef / PartRef / BuildRef (layout checked by static_assert in
