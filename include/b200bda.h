@@ -137,7 +137,7 @@ unsigned int b200_wells_get_num_wells(const b200_wells* w);   /* getNumWells (:1
  *   - scalar products: owned entries only, summed over the ranks (Dune::OwnerOverlapCopyCommunication).
  * In this mode b200_solve_system takes N = 3 * owned rows, a pattern whose column indices run over
  * owned + n_ghost cells, and b / x of the owned rows only.  Standard wells must lie inside one rank.
- * Call order: b200_create, b200_dist_init, b200_dist_set_halo, (exchange the IPC handles),
+ * Call order: b200_create, b200_dist_init, b200_dist_set_halo, (exchange the IPC handles), b200_dist_map_rank per rank,
  * b200_dist_connect_peer per neighbour, then b200_solve_system on every rank collectively.
  */
 
@@ -152,10 +152,13 @@ b200_status b200_dist_init(b200_solver* s, int rank, int world, const unsigned c
  * Allocates the receive block and returns its CUDA IPC handle (64 bytes) for the neighbours. */
 b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const int* neigh_rank, const int* send_ptr,
                                const int* send_rows, const int* recv_ptr, unsigned char* ipc_handle64);
-/* Maps neighbour neigh_index's receive block.  peer_n_ghost: that rank's ghost count; peer_recv_offset:
- * first ghost index of MY section there (its recv_ptr[slot]); peer_slot: my index in ITS neighbour list. */
-b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, const unsigned char* peer_ipc_handle64,
-                                   int peer_n_ghost, int peer_recv_offset, int peer_slot);
+/* Maps the receive block of `rank` (its IPC handle from b200_dist_set_halo) into this process; the own rank needs no
+ * handle.  Once every rank is mapped the dot products are all-reduced through peer-memory mailboxes (one NVLink round
+ * trip per reduction, option "p2p_allreduce" = 1, default); neighbours must be mapped before b200_dist_connect_peer. */
+b200_status b200_dist_map_rank(b200_solver* s, int rank, const unsigned char* ipc_handle64);
+/* Wires the halo push to neighbour neigh_index.  peer_n_ghost: that rank's ghost count; peer_recv_offset: first ghost
+ * index of MY section there (its recv_ptr[slot]); peer_slot: my index in ITS neighbour list. */
+b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, int peer_n_ghost, int peer_recv_offset, int peer_slot);
 /* Collective y_owned = (A [x_owned; x_ghost])_owned on the uploaded system (parity tests). */
 b200_status b200_dist_spmv(b200_solver* s, const double* x_owned_host, double* y_owned_host);
 int b200_dist_rank(const b200_solver* s);

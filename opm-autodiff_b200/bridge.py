@@ -132,7 +132,8 @@ def lib():
         L.b200_dist_unique_id.argtypes = [vp]
         L.b200_dist_init.argtypes = [vp, ip, ip, vp]
         L.b200_dist_set_halo.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp]
-        L.b200_dist_connect_peer.argtypes = [vp, ip, vp, ip, ip, ip]
+        L.b200_dist_map_rank.argtypes = [vp, ip, vp]
+        L.b200_dist_connect_peer.argtypes = [vp, ip, ip, ip, ip]
         L.b200_dist_spmv.argtypes = [vp, _f64p, _f64p]
         L.b200_dist_rank.argtypes = [vp]
         L.b200_dist_world.argtypes = [vp]
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
     "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
-    "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_connect_peer", "b200_dist_spmv",
+    "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_map_rank", "b200_dist_connect_peer", "b200_dist_spmv",
     "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace",
 ]
 
@@ -364,9 +365,12 @@ class B200SolverBackend:
         self._chk(lib().b200_dist_set_halo(self._h, int(n_ghost), len(a[0]), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), out))
         return out.raw
 
-    def dist_connect_peer(self, neigh_index, peer_handle: bytes, peer_n_ghost, peer_recv_offset, peer_slot) -> None:
-        self._chk(lib().b200_dist_connect_peer(self._h, int(neigh_index), C.create_string_buffer(peer_handle, 64),
-                                                int(peer_n_ghost), int(peer_recv_offset), int(peer_slot)))
+    def dist_map_rank(self, rank: int, handle: Optional[bytes]) -> None:
+        buf = C.create_string_buffer(handle, 64) if handle is not None else None
+        self._chk(lib().b200_dist_map_rank(self._h, int(rank), buf))
+
+    def dist_connect_peer(self, neigh_index, peer_n_ghost, peer_recv_offset, peer_slot) -> None:
+        self._chk(lib().b200_dist_connect_peer(self._h, int(neigh_index), int(peer_n_ghost), int(peer_recv_offset), int(peer_slot)))
 
     def dist_spmv(self, x):
         y = np.empty(self.N)

@@ -115,7 +115,11 @@ struct Dist {
     int gnrows = 0;
     long long gnblocks = 0;
     // peers
-    std::vector<void*> peer_base;           // mapped receive block of each neighbour
+    std::vector<void*> rank_base;           // IPC-mapped block of every rank (own block: the local pointer)
+    MailD mail{};                           // mail flags / values of every rank
+    bool mail_ready = false;
+    unsigned mail_seq = 0;
+    bool use_p2p_allreduce = true;
     std::vector<HaloPeerD> peers;
     unsigned epoch = 0;
     bool peers_ready = false;
@@ -199,7 +203,7 @@ struct Solver {
 
     ~Solver()
     {
-        for (void* p : dist.peer_base) if (p) cudaIpcCloseMemHandle(p);
+        for (size_t r = 0; r < dist.rank_base.size(); ++r) if (dist.rank_base[r] && (int) r != dist.rank) cudaIpcCloseMemHandle(dist.rank_base[r]);
         if (dist.comm) g_nccl.CommDestroy(dist.comm);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_b) cudaHostUnregister((void*) reg_b);
@@ -613,6 +617,26 @@ struct Solver {
         k_finish<PHASE><<<1, 32, 0, stream>>>(d_S.p, tolerance, 2 * maxit);
         prof_end(id);
     }
+    // Sum the scalars of one Krylov phase over the ranks and run its epilogue.  PHASE as k_allreduce_p2p.
+    // Peer-memory mailboxes when every rank is mapped (default), else NCCL + k_finish.
+    template <int PHASE>
+    void reduce_phase()
+    {
+        if (!dist.enabled) return;
+        if (dist.world > 1 && dist.use_p2p_allreduce && dist.mail_ready) {
+            ++dist.mail_seq;
+            int id = prof_begin(K_ALLREDUCE);
+            k_allreduce_p2p<PHASE><<<1, 64, 0, stream>>>(dist.mail, dist.rank, dist.world, dist.mail_seq, d_S.p, tolerance, 2 * maxit);
+            prof_end(id);
+            return;
+        }
+        if (PHASE == 0) { allreduce_sum(d_S.p->red, 1); finish<0>(); }
+        if (PHASE == 1) allreduce_sum(&d_S.p->h, 1);
+        if (PHASE == 2) { allreduce_sum(d_S.p->red, 1); finish<1>(); }
+        if (PHASE == 3) allreduce_sum(&d_S.p->tr, 2);
+        if (PHASE == 4) { allreduce_sum(d_S.p->red, 2); finish<2>(); }
+        if (PHASE == 5) allreduce(&d_S.p->singular, 1, kNcclInt32, kNcclMax);
+    }
     // boundary entries of y (p-space) -> the neighbours' receive blocks; one epoch per exchange
     void halo_push(const double* y, bool check_done)
     {
@@ -630,7 +654,7 @@ struct Solver {
     }
     const double* ghost_x() const
     {
-        return reinterpret_cast<const double*>(d_halo.p + 256) + (size_t) (dist.epoch & 1u) * 3 * (size_t) dist.n_ghost;
+        return reinterpret_cast<const double*>(d_halo.p + kHaloRecvOffset) + (size_t) (dist.epoch & 1u) * 3 * (size_t) dist.n_ghost;
     }
     template <int MODE>
     void spmv_ghost(double* y, const double* d1, bool check_done)
@@ -657,24 +681,22 @@ struct Solver {
         spmv<1>(d_y.p, d_v.p, d_rt.p);
         wells_apply<1>(d_y.p, d_v.p, d_rt.p);
         spmv_ghost<1>(d_v.p, d_rt.p, true);
-        allreduce_sum(&d_S.p->h, 1);
+        reduce_phase<1>();
         id = prof_begin(K_VEC_XR1);
         k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
         prof_end(id);
-        allreduce_sum(d_S.p->red, 1);
-        finish<1>();
+        reduce_phase<2>();
         trsv_lower(d_r.p, d_w.p, true);
         trsv_upper(d_w.p, d_y.p, d_w.p, true);
         halo_push(d_y.p, true);
         spmv<2>(d_y.p, d_t.p, d_r.p);
         wells_apply<2>(d_y.p, d_t.p, d_r.p);
         spmv_ghost<2>(d_t.p, d_r.p, true);
-        allreduce_sum(&d_S.p->tr, 2);
+        reduce_phase<3>();
         id = prof_begin(K_VEC_XR2);
         k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
         prof_end(id);
-        allreduce_sum(d_S.p->red, 2);
-        finish<2>();
+        reduce_phase<4>();
     }
 
     // permutation + ILU0 + BiCGSTAB on the resident system
@@ -686,13 +708,12 @@ struct Solver {
         permute_values();
         factorize();
         CUDA_OK(cudaEventRecord(ev_b, stream));
-        allreduce(&d_S.p->singular, 1, kNcclInt32, kNcclMax);      // a failed pivot on any rank stops all of them
+        reduce_phase<5>();                                           // a failed pivot on any rank stops all of them
         int id = prof_begin(K_INIT);
         k_init<<<vec_blocks, kVecThreads, 0, stream>>>(d_bstage.p, d_perm.p, d_r.p, d_rt.p, d_x.p, d_w.p, d_y.p, N, d_S.p,
                                                         d_partials.p, d_ticket.p, tolerance, 2 * maxit, dist.enabled ? 1 : 0);
         prof_end(id);
-        allreduce_sum(d_S.p->red, 1);
-        finish<0>();
+        reduce_phase<0>();
         int enq = 0;
         while (true) {
             enqueue_iteration();
@@ -828,6 +849,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
         else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);
         else if (k == "sweep_trace") {
             s->sweep_trace = value != 0.0;
@@ -1053,15 +1075,17 @@ b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const i
             if (D.recv_ptr[n_neigh] != n_ghost) throw std::runtime_error("recv_ptr does not cover the ghost range");
         } else if (n_ghost != 0) throw std::runtime_error("ghost cells without neighbours");
         // receive block: flags + two parity buffers; zeroed so that epoch 0 never matches
-        const size_t bytes = 256 + 2 * 3 * (size_t) std::max(n_ghost, 1) * sizeof(double);
+        const size_t bytes = kHaloRecvOffset + 2 * 3 * (size_t) std::max(n_ghost, 1) * sizeof(double);
         s->d_halo.alloc(bytes);
         CUDA_OK(cudaMemset(s->d_halo.p, 0, bytes));
         s->d_push_tickets.alloc(64);
         CUDA_OK(cudaMemset(s->d_push_tickets.p, 0, 64 * sizeof(unsigned)));
-        D.peer_base.assign(n_neigh, nullptr);
+        D.rank_base.assign(D.world, nullptr);
+        D.rank_base[D.rank] = s->d_halo.p;
         D.peers.assign(n_neigh, HaloPeerD{});
         D.have_halo = true;
         D.peers_ready = (n_neigh == 0);
+        D.mail_ready = false;
         if (ipc_handle64) {
             cudaIpcMemHandle_t h;
             static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1072,28 +1096,54 @@ b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const i
     });
 }
 
-b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, const unsigned char* peer_ipc_handle64, int peer_n_ghost,
-                                   int peer_recv_offset, int peer_slot)
+b200_status b200_dist_map_rank(b200_solver* s, int rank, const unsigned char* ipc_handle64)
 {
     return guarded([&]() -> b200_status {
-        if (!s || !peer_ipc_handle64) throw std::runtime_error("null argument");
+        if (!s) throw std::runtime_error("null argument");
+        Dist& D = s->dist;
+        if (!D.have_halo) throw std::runtime_error("b200_dist_set_halo first");
+        if (rank < 0 || rank >= D.world || D.world > 64) throw std::runtime_error("bad rank");
+        CUDA_OK(cudaSetDevice(s->device));
+        if (rank != D.rank && !D.rank_base[rank]) {
+            if (!ipc_handle64) throw std::runtime_error("null IPC handle");
+            cudaIpcMemHandle_t h;
+            memcpy(&h, ipc_handle64, 64);
+            void* base = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            D.rank_base[rank] = base;
+        }
+        bool all = true;
+        for (void* p : D.rank_base) all = all && p != nullptr;
+        if (all) {
+            for (int r = 0; r < D.world; ++r) {
+                unsigned char* b = reinterpret_cast<unsigned char*>(D.rank_base[r]);
+                D.mail.flags[r] = reinterpret_cast<unsigned*>(b + 256);
+                D.mail.vals[r] = reinterpret_cast<double*>(b + 768);
+            }
+            D.mail_ready = true;
+        }
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_dist_connect_peer(b200_solver* s, int neigh_index, int peer_n_ghost, int peer_recv_offset, int peer_slot)
+{
+    return guarded([&]() -> b200_status {
+        if (!s) throw std::runtime_error("null argument");
         Dist& D = s->dist;
         if (!D.have_halo || neigh_index < 0 || neigh_index >= D.nneigh) throw std::runtime_error("bad neighbour index");
         if (peer_slot < 0 || peer_slot >= 64 || peer_recv_offset < 0 || peer_recv_offset > peer_n_ghost) throw std::runtime_error("bad peer layout");
+        void* base = D.rank_base[D.neigh_rank[neigh_index]];
+        if (!base) throw std::runtime_error("neighbour rank not mapped (b200_dist_map_rank)");
         CUDA_OK(cudaSetDevice(s->device));
-        cudaIpcMemHandle_t h;
-        memcpy(&h, peer_ipc_handle64, 64);
-        void* base = nullptr;
-        CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-        D.peer_base[neigh_index] = base;
         HaloPeerD& P = D.peers[neigh_index];
         P.flag = reinterpret_cast<unsigned*>(base) + peer_slot;
-        P.recv = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(base) + 256) + 3 * (size_t) peer_recv_offset;
+        P.recv = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(base) + kHaloRecvOffset) + 3 * (size_t) peer_recv_offset;
         P.parity_stride = 3ll * peer_n_ghost;
         P.send_begin = D.send_ptr[neigh_index];
         P.send_end = D.send_ptr[neigh_index + 1];
         bool all = true;
-        for (void* p : D.peer_base) all = all && p != nullptr;
+        for (const HaloPeerD& q : D.peers) all = all && q.recv != nullptr;
         if (all) {
             s->d_peers.alloc(D.nneigh);
             CUDA_OK(cudaMemcpy(s->d_peers.p, D.peers.data(), sizeof(HaloPeerD) * D.nneigh, cudaMemcpyHostToDevice));

@@ -247,10 +247,12 @@ class DistSolver:
         if world > 1:
             infos = _all_gather_object({"handle": handle, "n_ghost": ls.n_ghost, "neigh": list(ls.neigh_rank),
                                         "recv_ptr": [int(v) for v in ls.recv_ptr]}, group)
+            for r in range(world):                      # every rank: the dot products travel through peer-memory mailboxes
+                self.be.dist_map_rank(r, None if r == rank else infos[r]["handle"])
             for n, peer in enumerate(ls.neigh_rank):
                 pi = infos[peer]
                 slot = pi["neigh"].index(rank)
-                self.be.dist_connect_peer(n, pi["handle"], pi["n_ghost"], pi["recv_ptr"][slot], slot)
+                self.be.dist_connect_peer(n, pi["n_ghost"], pi["recv_ptr"][slot], slot)
             td.barrier(group)
         w = ls.wells
         self.wc = bridge.WellContributions("b200", False) if w is None else \
