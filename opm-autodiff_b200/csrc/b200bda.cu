@@ -347,6 +347,7 @@ struct Solver {
             CUDA_OK(cudaStreamSynchronize(stream));           // host vectors above are temporaries
         }
         nnzb = an.nnzb; nnz = 9 * nnzb;
+        static_assert(kXs == kXwinStride, "device/host value-space stride mismatch");
         static_assert(sizeof(StageD) == sizeof(StageRef) && sizeof(PartD) == sizeof(PartRef) && sizeof(BuildD) == sizeof(BuildRef),
                       "device/host sweep descriptor mismatch");
         auto up = [&](auto& dbuf, const auto& hvec) {
@@ -376,7 +377,7 @@ struct Solver {
         sweep_rhsCap = std::max(an.L.maxRhsRows, an.U.maxRhsRows);
         sweep_extCap = std::max(an.L.maxExtRows, an.U.maxExtRows);
         const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
-        const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 32 + kSweepTailPad;
+        const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 8 * kXs + kSweepTailPad;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_optin || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
@@ -646,7 +647,7 @@ struct Solver {
         if (!dist.peers_ready) throw std::runtime_error("multi-GPU solver: peers not connected (b200_dist_connect_peer)");
         int maxsend = 0;
         for (int n = 0; n < dist.nneigh; ++n) maxsend = std::max(maxsend, dist.send_ptr[n + 1] - dist.send_ptr[n]);
-        const int bx = std::max(1, std::min(32, (3 * maxsend + 2047) / 2048));
+        const int bx = std::max(1, std::min(128, (3 * maxsend + 511) / 512));
         int id = prof_begin(K_HALO_PUSH);
         k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, stream>>>(d_peers.p, d_send_prow.p, y, dist.epoch, d_push_tickets.p, d_S.p,
                                                                 check_done ? 1 : 0);

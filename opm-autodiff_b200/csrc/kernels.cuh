@@ -449,6 +449,7 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads)
 
 constexpr int kSweepMaxSlots = 8;      // ring slots (full + empty mbarriers and the ext flags fit the 256-byte header)
 constexpr int kSweepHeader = 256;
+constexpr int kXs = 4;                 // doubles per row of the shared-memory value space (== analysis.hpp kXwinStride)
 constexpr int kSweepTailPad = 512;     // lanes of a partly filled record may read (never use) a few rows past the last rhs copy
 
 struct SweepArgs {
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
     int* ext_ready = reinterpret_cast<int*>(sweep_smem + 128);
     unsigned char* xwin = sweep_smem + kSweepHeader;
     const int W = P.window, EW = P.extWindow, zrow = W + EW;
-    unsigned char* slots = xwin + 32 * (size_t) (zrow + 2);
+    unsigned char* slots = xwin + 8 * kXs * (size_t) (zrow + 2);
     const size_t metaBytes = (size_t) P.metaCap * 4, valsBytes = (size_t) P.valsCap * 8, rhsBytes = (size_t) P.rhsCap * 24;
     const size_t slotBytes = metaBytes + valsBytes + rhsBytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x < 8) reinterpret_cast<double*>(xwin)[4 * (size_t) zrow + threadIdx.x] = 0.0;
+    if (threadIdx.x < 2 * kXs) reinterpret_cast<double*>(xwin)[kXs * (size_t) zrow + threadIdx.x] = 0.0;
     __syncthreads();
     const int nst = pr.stage_end - pr.stage_begin;
 
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
         // constant per level and per hop (measured: 2 us per level at the far corner of the c3 grid, profiles/).
         constexpr int kHelperWindow = 2;
         const int h = warp - NW - 1;
-        double* ring = reinterpret_cast<double*>(xwin) + 4 * (size_t) W;
+        double* ring = reinterpret_cast<double*>(xwin) + kXs * (size_t) W;
         for (int i = h; i < nst; i += NH) {
             const int s = i % nslots;
             mbar_wait_relaxed(full + s, (i / nslots) & 1);
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
 #pragma unroll
                     for (int k = 0; k < kHelperWindow; ++k)
                         if (!done[k] && !(is_sentinel(x[k][0]) || is_sentinel(x[k][1]) || is_sentinel(x[k][2]))) {
-                            double* d = ring + 4 * (size_t) ((ext_base + e0 + 32 * k + lane) & (EW - 1));
+                            double* d = ring + kXs * (size_t) ((ext_base + e0 + 32 * k + lane) & (EW - 1));
                             d[0] = x[k][0]; d[1] = x[k][1]; d[2] = x[k][2];
                             done[k] = true;
                         }

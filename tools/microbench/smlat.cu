@@ -74,6 +74,41 @@ __global__ void k(int mode, int iters, double* gout, long long* cycles, double s
             }
         }
     }
+    if (mode >= 10 && mode <= 13) {
+        // all 8 consumer warps work: the real level step of k_sweep (6 x 16-byte operand loads, level barrier, 6 reads of
+        // earlier rows, 9 fma + 3 add, one shared + one global store); mode 11: operands loaded one record ahead;
+        // mode 12: only 4 of the 8 warps have a record; mode 13: without the global store
+        extern __shared__ double big[];
+        for (int i = threadIdx.x; i < 20000; i += blockDim.x) big[i] = seed + (i & 7);
+        __syncthreads();
+        t0 = clock64();
+        if (warp < 8) {
+            const bool has = mode != 12 || warp < 4;
+            double2 o[5]; double r = 0.0;
+            const double2* ob = reinterpret_cast<const double2*>(big) + lane + warp * 160;
+            const double* xb = big + 12000 + (lane / 3) * 4;
+            for (int j = 0; j < 5; ++j) o[j] = ob[j * 32];
+            for (int i = 0; i < iters; ++i) {
+                double2 n[5];
+                if (mode == 11 && has) for (int j = 0; j < 5; ++j) n[j] = ob[((i + 1) & 7) * 1280 + j * 32];
+                if (mode != 11 && has) { for (int j = 0; j < 5; ++j) o[j] = ob[(i & 7) * 1280 + j * 32]; r = big[11000 + ((i * 32 + lane) & 511)]; }
+                named_barrier(1, 256);
+                if (has) {
+                    const double* x0 = xb + ((i * 40) & 1023), *x1 = xb + ((i * 40 + 400) & 1023), *x2 = xb + ((i * 40 + 800) & 1023);
+                    double2 a0 = *reinterpret_cast<const double2*>(x0), a1 = *reinterpret_cast<const double2*>(x1), a2 = *reinterpret_cast<const double2*>(x2);
+                    double b0 = x0[2], b1 = x1[2], b2 = x2[2];
+                    double t0_ = fma(o[1].x, b0, fma(o[0].y, a0.y, o[0].x * a0.x));
+                    double t1_ = fma(o[2].y, b1, fma(o[2].x, a1.y, o[1].y * a1.x));
+                    double t2_ = fma(o[4].x, b2, fma(o[3].y, a2.y, o[3].x * a2.x));
+                    double acc = ((r - t0_) - t1_) - t2_;
+                    big[12000 + ((i * 40 + warp * 40 + lane) & 1023)] = acc * 1e-3;
+                    if (mode != 13) st_relaxed(gout + ((i * 256 + warp * 32 + lane) & 65535), acc);
+                    a += acc;
+                }
+                if (mode == 11 && has) for (int j = 0; j < 5; ++j) o[j] = n[j];
+            }
+        }
+    }
     long long t1 = clock64();
     if (threadIdx.x == 0) { cycles[0] = t1 - t0; }
     if (a == 123.456 || idx == -5) gout[0] = a + idx;
@@ -86,11 +121,14 @@ int main()
     const char* names[] = {"dependent DFMA", "dependent LDS (pointer chase)", "bar.sync 8 warps, nothing else", "level step: bar + LDS + 4 DFMA + STS (warp 0 works)",
                            "level step + st.relaxed.gpu", "level step + weak global store", "level step, 5 extra warps spinning",
                            "level step + st.relaxed + 12 fetch loads before the barrier", "level step + st.relaxed, 5 warps spin on mbarrier.try_wait",
-                           "level step + st.relaxed + 12 fetch loads, 5 warps spin on try_wait"};
-    for (int mode = 0; mode < 10; ++mode) {
+                           "level step + st.relaxed + 12 fetch loads, 5 warps spin on try_wait",
+                           "k_sweep level step, 8 warps x 1 record", "k_sweep level step, operands one record ahead",
+                           "k_sweep level step, 4 of 8 warps have a record", "k_sweep level step, no global store"};
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 170000);
+    for (int mode = 0; mode < 14; ++mode) {
         const int iters = 2000;
         const int threads = (mode == 6 || mode >= 8) ? 416 : 256;
-        for (int rep = 0; rep < 2; ++rep) k<<<1, threads>>>(mode, iters, gout, cyc, 1.5);
+        for (int rep = 0; rep < 2; ++rep) k<<<1, threads, 170000>>>(mode, iters, gout, cyc, 1.5);
         cudaDeviceSynchronize();
         long long h = 0;
         cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);

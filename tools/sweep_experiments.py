@@ -26,9 +26,5 @@ if which in ("all", "micro"):
     run((200, 32, 32), "4x4 pencils", parts=16)
 if which in ("all", "c3"):
     run((100, 100, 100), "c3 default", parts=148)
-    run((100, 100, 100), "c3 sleep 0", parts=148, helper_sleep=0)
-    run((100, 100, 100), "c3 sleep 20", parts=148, helper_sleep=20)
-    run((100, 100, 100), "c3 sleep 200", parts=148, helper_sleep=200)
-    run((100, 100, 100), "c3 sleep 1000", parts=148, helper_sleep=1000)
-    run((200, 32, 32), "4x4 pencils sleep 0", parts=16, helper_sleep=0)
-    run((200, 32, 32), "4x4 pencils sleep 1000", parts=16, helper_sleep=1000)
+    run((100, 100, 100), "c3 64K/3 slots", parts=148, stage_bytes=65536, slots=3)
+    run((100, 100, 100), "c3 12 warps", parts=148, warps=12)
