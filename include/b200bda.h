@@ -192,6 +192,12 @@ b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, i
 b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int stage_bytes,
                                            int window, unsigned int seed, double* max_rel_err, long long* stats);
 
+/* Host-only replay of the ILU0 elimination plan the device kernel executes (no device needed): LU in the caller's pattern
+ * with the inverse pivot in the diagonal slot, as ParallelOverlappingILU0.hpp:440-494 leaves it.  max_row / max_ops (may be
+ * NULL) return the longest block row and the longest plan; the device uses the planned kernel when they fit its buffers. */
+b200_status b200_factor_plan_check_host(int Nb, const int* rows, const int* cols, const double* vals, double* lu_out,
+                                        int* max_row, int* max_ops);
+
 /* Time `reps` back-to-back launches of one kernel with CUDA events on the solver's stream.
  * which: "spmv", "ilu_apply", "ilu_lower", "ilu_upper", "ilu_factor", "vec_p", "vec_xr1", "vec_xr2",
  * "well_apply", "permute" (b200_kernel_stats also knows "halo_push", "spmv_ghost", "allreduce", "finish").  Returns the mean milliseconds per launch and the ALGORITHMIC bytes one

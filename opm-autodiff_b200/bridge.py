@@ -128,6 +128,7 @@ def lib():
         L.b200_timer_start.argtypes = [vp]
         L.b200_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200_device_available.restype = ip
+        L.b200_factor_plan_check_host.argtypes = [ip, _i32p, _i32p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b200_get_sweep_trace.argtypes = [vp, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_longlong]
         L.b200_dist_unique_id.argtypes = [vp]
         L.b200_dist_init.argtypes = [vp, ip, ip, vp]
@@ -150,7 +151,7 @@ EXPORTED_SYMBOLS = [
     "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
     "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_map_rank", "b200_dist_connect_peer", "b200_dist_spmv",
-    "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace",
+    "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace", "b200_factor_plan_check_host",
 ]
 
 
@@ -418,6 +419,19 @@ def sweep_schedule_check_host(rows, cols, parts=0, stage_bytes=0, window=0, seed
     if lib().b200_sweep_schedule_check_host(len(rows) - 1, rows, cols, parts, stage_bytes, window, seed, C.byref(err), stats) != 0:
         raise RuntimeError(last_error())
     return err.value, dict(zip(SWEEP_STAT_NAMES, (int(v) for v in stats)))
+
+
+def factor_plan_check_host(rows, cols, vals):
+    """Host-only replay of the device's ILU0 elimination plan: returns (LU [nnzb,3,3], longest row, longest plan)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64).reshape(-1)
+    lu = np.zeros_like(vals)
+    mr, mo = C.c_int(0), C.c_int(0)
+    st = lib().b200_factor_plan_check_host(len(rows) - 1, rows, cols, vals, lu, C.byref(mr), C.byref(mo))
+    if st != 0:
+        raise RuntimeError(last_error())
+    return lu.reshape(-1, 3, 3), mr.value, mo.value
 
 
 @dataclass

@@ -1367,6 +1367,60 @@ b200_status b200_get_sweep_trace(b200_solver* s, long long* out, long long count
     });
 }
 
+// Host-only replay of the factorisation plan (no device): analyse the pattern, run the elimination plan of
+// k_ilu_factor_plan row by row in level order with the same arithmetic, return LU in the caller's pattern
+// (inverse pivot in the diagonal slot).  Lets the CPU test-suite check the plan against the oracle's ILU0.
+b200_status b200_factor_plan_check_host(int Nb, const int* rows, const int* cols, const double* vals, double* lu_out, int* max_row,
+                                        int* max_ops)
+{
+    return guarded([&]() -> b200_status {
+        if (Nb <= 0 || !rows || !cols || !vals || !lu_out) throw std::runtime_error("bad arguments");
+        Analysis A = analyse(Nb, rows, cols, AnalysisOptions());
+        const long long nnzb = rows[Nb];
+        std::vector<double> LU((size_t) nnzb * 9);
+        for (long long q = 0; q < nnzb; ++q) memcpy(LU.data() + q * 9, vals + (size_t) A.srcblk[q] * 9, 72);
+        auto inv3h = [](const double* m, double* inv) {
+            double t4 = m[0] * m[4], t6 = m[0] * m[5], t8 = m[1] * m[3], t10 = m[2] * m[3], t12 = m[1] * m[6], t14 = m[2] * m[6];
+            double det = t4 * m[8] - t6 * m[7] - t8 * m[8] + t10 * m[7] + t12 * m[5] - t14 * m[4];
+            double t17 = 1.0 / det;
+            inv[0] = (m[4] * m[8] - m[5] * m[7]) * t17; inv[1] = -(m[1] * m[8] - m[2] * m[7]) * t17; inv[2] = (m[1] * m[5] - m[2] * m[4]) * t17;
+            inv[3] = -(m[3] * m[8] - m[5] * m[6]) * t17; inv[4] = (m[0] * m[8] - t14) * t17; inv[5] = -(t6 - t10) * t17;
+            inv[6] = (m[3] * m[7] - m[4] * m[6]) * t17; inv[7] = -(m[0] * m[7] - t12) * t17; inv[8] = (t4 - t8) * t17;
+            return det != 0.0 && std::isfinite(det);
+        };
+        for (int l = 0; l < A.nflev; ++l)
+            for (int t = A.flevPtr[l]; t < A.flevPtr[l + 1]; ++t) {
+                const int i = A.flevRows[t];
+                double* row = LU.data() + (size_t) A.prow[i] * 9;
+                int o = A.facPtr[i];
+                const int oe = A.facPtr[i + 1];
+                while (o < oe) {
+                    const int code = A.facOps[2 * o + 1], toff = code & 255, nupd = code >> 8;
+                    const double* d = LU.data() + (size_t) A.facOps[2 * o] * 9;
+                    double lij[9];
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) lij[3 * r + c] = row[toff * 9 + 3 * r] * d[c] + row[toff * 9 + 3 * r + 1] * d[3 + c] + row[toff * 9 + 3 * r + 2] * d[6 + c];
+                    memcpy(row + toff * 9, lij, 72);
+                    for (int u = 0; u < nupd; ++u) {
+                        const double* uu = LU.data() + (size_t) A.facOps[2 * (o + 1 + u)] * 9;
+                        const int tgt = -(A.facOps[2 * (o + 1 + u) + 1] + 1);
+                        for (int r = 0; r < 3; ++r)
+                            for (int c = 0; c < 3; ++c) row[tgt * 9 + 3 * r + c] -= lij[3 * r] * uu[c] + lij[3 * r + 1] * uu[3 + c] + lij[3 * r + 2] * uu[6 + c];
+                    }
+                    o += 1 + nupd;
+                }
+                double inv[9];
+                double* dg = LU.data() + (size_t) A.pdiag[i] * 9;
+                if (!inv3h(dg, inv)) { g_last_error = "ILU0: singular or non-finite pivot block"; return B200_CREATE_PRECONDITIONER_FAILED; }
+                memcpy(dg, inv, 72);
+            }
+        for (long long q = 0; q < nnzb; ++q) memcpy(lu_out + (size_t) A.srcblk[q] * 9, LU.data() + q * 9, 72);
+        if (max_row) *max_row = A.facMaxRow;
+        if (max_ops) *max_ops = A.facMaxOps;
+        return B200_SUCCESS;
+    }, B200_ANALYSIS_FAILED);
+}
+
 static int kind_of(const std::string& k)
 {
     if (k == "ilu_apply") return -2;

@@ -78,3 +78,18 @@ def test_pencil_partition_of_a_structured_grid(built):
     assert st["lines"] == 24 * 24 and st["parts"] == 36
     # pencils: the bulk of the dependencies stays inside a part (shared memory)
     assert st["window_deps_L"] > 3 * st["global_deps_L"]
+
+
+@pytest.mark.parametrize("shape,faults", [((7, 6, 5), ()), ((12, 10, 8), ((6, 1),)), ((1, 1, 17), ()), ((20, 16, 3), ((7, 2), (13, 1)))])
+def test_factor_plan_replay_matches_oracle_ilu0(built, shape, faults):
+    """The elimination plan k_ilu_factor_plan executes, replayed on the host, against the oracle's left-looking
+    block ILU0 (ParallelOverlappingILU0.hpp:440-494)."""
+    from opm_autodiff_b200 import bridge, synth
+    from oracle import oracle
+    s = synth.small(*shape, faults=faults)
+    lu, max_row, max_ops = bridge.factor_plan_check_host(s.rows, s.cols, s.vals)
+    ref, diag, st = oracle.ilu0(s.rows, s.cols, s.vals)
+    assert st == 0
+    scale = np.abs(ref).max(axis=(1, 2), keepdims=True) + 1e-300
+    assert np.max(np.abs(lu - ref) / scale) < 1e-10
+    assert max_row <= 16 and max_ops <= 48          # the planned kernel's buffers hold these patterns
