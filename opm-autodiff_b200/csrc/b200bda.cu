@@ -172,6 +172,8 @@ struct Solver {
 
     DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows, d_facPtr, d_facOps;
     bool fac_plan = false;
+    cudaGraphExec_t fac_graph_exec = nullptr;
+    double fac_graph_relax = 0.0;
     DevBuf<StageD> d_stagesL, d_stagesU;
     DevBuf<PartD> d_partsL, d_partsU;
     DevBuf<BuildD> d_buildL, d_buildU;
@@ -205,6 +207,7 @@ struct Solver {
     {
         for (size_t r = 0; r < dist.rank_base.size(); ++r) if (dist.rank_base[r] && (int) r != dist.rank) cudaIpcCloseMemHandle(dist.rank_base[r]);
         if (dist.comm) g_nccl.CommDestroy(dist.comm);
+        if (fac_graph_exec) cudaGraphExecDestroy(fac_graph_exec);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_b) cudaHostUnregister((void*) reg_b);
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -522,12 +525,15 @@ struct Solver {
         prof_end(id);
     }
 
-    void factorize()
+    // ILU0 of the resident A: one kernel per level set + the two stream fills.  The launch sequence only depends on the
+    // pattern, so it is captured once into a CUDA graph and replayed per solve (298 launches for C3: the launch gaps are a
+    // third of the factorisation time); with per-kernel profiling on, the kernels are launched one by one.
+    void factorize_launches(bool count)
     {
         CUDA_OK(cudaMemsetAsync(&d_S.p->singular, 0, sizeof(int), stream));
         for (int l = 0; l < an.nflev; ++l) {
             int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
-            int id = prof_begin(K_FACTOR);
+            int id = count ? prof_begin(K_FACTOR) : -1;
             if (fac_plan)
                 k_ilu_factor_plan<<<(nrows + kFacWarps - 1) / kFacWarps, 32 * kFacWarps, 0, stream>>>(
                     d_prow.p, d_pdiag.p, d_facPtr.p, reinterpret_cast<const int2*>(d_facOps.p), d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
@@ -535,14 +541,40 @@ struct Solver {
                 k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             prof_end(id);
         }
-        int id = prof_begin(K_SLICES);
+        int id = count ? prof_begin(K_SLICES) : -1;
         k_fill_stream<true><<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
             d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p, 1.0);
         prof_end(id);
-        id = prof_begin(K_SLICES);
+        id = count ? prof_begin(K_SLICES) : -1;
         k_fill_stream<false><<<blocks_for((long long) an.U.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
             d_buildU.p, (int) an.U.build.size(), d_srcU.p, d_LU.p, d_valU.p, relaxation);
         prof_end(id);
+    }
+    void factorize()
+    {
+        if (!use_graph || profile) {
+            factorize_launches(true);
+        } else {
+            if (!fac_graph_exec || fac_graph_relax != relaxation) {
+                if (fac_graph_exec) { cudaGraphExecDestroy(fac_graph_exec); fac_graph_exec = nullptr; }
+                cudaGraph_t g = nullptr;
+                CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                try {
+                    factorize_launches(false);
+                } catch (...) {
+                    cudaStreamEndCapture(stream, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                CUDA_OK(cudaStreamEndCapture(stream, &g));
+                CUDA_OK(cudaGraphInstantiate(&fac_graph_exec, g, 0));
+                cudaGraphDestroy(g);
+                fac_graph_relax = relaxation;
+            }
+            CUDA_OK(cudaGraphLaunch(fac_graph_exec, stream));
+            stats[K_FACTOR].launches += an.nflev; stats[K_SLICES].launches += 2;
+            launch_count += an.nflev + 2;
+        }
         have_factor = true;
     }
 

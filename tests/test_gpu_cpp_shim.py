@@ -27,7 +27,8 @@ def _write_mm(path_m, path_b, rows, cols, vals, b):
                     for c in range(3):
                         f.write("%d %d %.17g\n" % (3 * i + r + 1, 3 * cols[k] + c + 1, vals[k, r, c]))
     with open(path_b, "w") as f:
-        f.write("%%MatrixMarket matrix array real general\n% ISTL_STRUCT blocked 3 1\n%d 1\n" % len(b))
+        f.write("%%MatrixMarket matrix array real general\n% ISTL_STRUCT blocked 3 1\n")
+        f.write("%d 1\n" % len(b))
         for v in b:
             f.write("%.17g\n" % v)
 
