@@ -14,7 +14,7 @@ s = synth.full_system(cfg)
 for combo in combos.split(";"):
     t = [int(v) for v in combo.split(",")]
     parts, warps, slots, sb = t[:4]
-    window = t[4] if len(t) > 4 else 2048
+    window = t[4] if len(t) > 4 else 0
     be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
     for k, v in (("sweep_parts", parts), ("sweep_warps", warps), ("sweep_slots", slots), ("sweep_stage_bytes", sb), ("sweep_window", window)):
         be.set_option(k, v)
