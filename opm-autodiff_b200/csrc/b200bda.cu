@@ -208,6 +208,7 @@ struct Solver {
         for (size_t r = 0; r < dist.rank_base.size(); ++r) if (dist.rank_base[r] && (int) r != dist.rank) cudaIpcCloseMemHandle(dist.rank_base[r]);
         if (dist.comm) g_nccl.CommDestroy(dist.comm);
         if (fac_graph_exec) cudaGraphExecDestroy(fac_graph_exec);
+        if (iter_graph_exec) cudaGraphExecDestroy(iter_graph_exec);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_b) cudaHostUnregister((void*) reg_b);
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -217,8 +218,10 @@ struct Solver {
     }
 
     // ---- launch bookkeeping ------------------------------------------------------------------
+    bool counting = true;         // false while a launch sequence is being captured into a graph (counted per replay instead)
     int prof_begin(int kind)
     {
+        if (!counting) return -1;
         stats[kind].launches++;
         launch_count++;
         if (!profile) return -1;
@@ -732,6 +735,43 @@ struct Solver {
         reduce_phase<4>();
     }
 
+    // One BiCGSTAB iteration: on a single GPU the 10-12 launches are replayed from a CUDA graph (the launch sequence
+    // depends on nothing but the pointers; the convergence logic lives on the device), otherwise launched one by one.
+    struct IterSig { const void* a[6]; int n[4]; bool operator!=(const IterSig& o) const { return memcmp(this, &o, sizeof *this) != 0; } };
+    cudaGraphExec_t iter_graph_exec = nullptr;
+    IterSig iter_sig{};
+    void run_iteration()
+    {
+        if (!use_graph || profile || dist.enabled || sweep_trace) { enqueue_iteration(); return; }
+        IterSig sig{};
+        sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
+        sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep;
+        if (!iter_graph_exec || sig != iter_sig) {
+            if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            counting = false;
+            try {
+                enqueue_iteration();
+            } catch (...) {
+                counting = true;
+                cudaStreamEndCapture(stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            counting = true;
+            CUDA_OK(cudaStreamEndCapture(stream, &g));
+            CUDA_OK(cudaGraphInstantiate(&iter_graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            iter_sig = sig;
+        }
+        CUDA_OK(cudaGraphLaunch(iter_graph_exec, stream));
+        stats[K_VEC_P].launches++; stats[K_VEC_XR1].launches++; stats[K_VEC_XR2].launches++;
+        stats[K_LOWER].launches += 2; stats[K_UPPER].launches += 2; stats[K_SPMV].launches += 2;
+        if (nwells) stats[K_WELL].launches += 2;
+        launch_count += 9 + (nwells ? 2 : 0);
+    }
+
     // permutation + ILU0 + BiCGSTAB on the resident system
     void solve_resident(b200_result* res)
     {
@@ -749,8 +789,11 @@ struct Solver {
         reduce_phase<0>();
         int enq = 0;
         while (true) {
-            enqueue_iteration();
-            ++enq;
+            // `lookahead` iterations per convergence read-back: once the device has set `done` the kernels of the
+            // remaining ones return at once
+            const int batch = std::max(1, std::min(lookahead, maxit - enq));
+            for (int b = 0; b < batch; ++b) run_iteration();
+            enq += batch;
             CUDA_OK(cudaMemcpyAsync(h_S, d_S.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
             CUDA_OK(cudaStreamSynchronize(stream));
             if (verbosity > 1)
