@@ -217,6 +217,144 @@ def slab_system(cfg, rank: int, world: int) -> LocalSystem:
     return localize(rank, ranges, s.rows, s.cols, s.vals, s.b, s.x_true, s.wells)
 
 
+# ---- 2-D block partition (y x z), x never cut -------------------------------------------------------------
+#
+# The triangular sweeps of a rank cost (levels of its sub-grid) x (time per level): a slab along z keeps nx + ny of the
+# nx + ny + nz levels whatever the rank count, a y-z block keeps nx + ny/py + nz/pz.  Lines along x (and with them the
+# horizontal wells of the synthetic configurations) stay inside one rank.  Cells are renumbered rank by rank, natural
+# (i fastest, then j, then k) inside a rank: the new numbering plays the role of Dune's owner-first local ordering, and
+# block-Jacobi ILU0 on it is what the reference's MPI run does with this partition.
+
+@dataclass
+class BlockPartition:
+    nx: int
+    ny: int
+    nz: int
+    py: int
+    pz: int
+    jcuts: List[int]
+    kcuts: List[int]
+    ranges: List[Tuple[int, int]]           # new-numbering row range of every rank (rank = bk * py + bj)
+
+    @property
+    def world(self) -> int:
+        return self.py * self.pz
+
+    def box(self, rank: int):
+        bj, bk = rank % self.py, rank // self.py
+        return self.jcuts[bj], self.jcuts[bj + 1], self.kcuts[bk], self.kcuts[bk + 1]
+
+    def new_id(self, natural: np.ndarray) -> np.ndarray:
+        """natural cell id (i + nx (j + ny k)) -> id in the rank-major numbering."""
+        c = np.asarray(natural, dtype=np.int64)
+        i = c % self.nx
+        j = (c // self.nx) % self.ny
+        k = c // (self.nx * self.ny)
+        jc, kc = np.asarray(self.jcuts), np.asarray(self.kcuts)
+        bj = np.searchsorted(jc, j, side="right") - 1
+        bk = np.searchsorted(kc, k, side="right") - 1
+        rank = bk * self.py + bj
+        j0, k0 = jc[bj], kc[bk]
+        nyr = jc[bj + 1] - j0
+        base = np.asarray([r[0] for r in self.ranges], dtype=np.int64)[rank]
+        return base + ((k - k0) * nyr + (j - j0)) * self.nx + i
+
+
+def block_partition(nx: int, ny: int, nz: int, world: int) -> BlockPartition:
+    """py x pz = world minimising the level count nx + ny/py + nz/pz of a rank's sub-grid (ties: fewer cuts in y)."""
+    best = None
+    for py in range(1, world + 1):
+        if world % py:
+            continue
+        pz = world // py
+        if py > ny or pz > nz:
+            continue
+        cost = -(-ny // py) + -(-nz // pz)
+        if best is None or cost < best[0]:
+            best = (cost, py, pz)
+    if best is None:
+        raise ValueError("more ranks than grid planes")
+    _, py, pz = best
+    jcuts = [(ny * b) // py for b in range(py + 1)]
+    kcuts = [(nz * b) // pz for b in range(pz + 1)]
+    ranges, o = [], 0
+    for bk in range(pz):
+        for bj in range(py):
+            n = nx * (jcuts[bj + 1] - jcuts[bj]) * (kcuts[bk + 1] - kcuts[bk])
+            ranges.append((o, o + n))
+            o += n
+    return BlockPartition(nx, ny, nz, py, pz, jcuts, kcuts, ranges)
+
+
+def block_system(cfg, rank: int, world: int) -> LocalSystem:
+    """This rank's y-z block of a synthetic configuration in the rank-major numbering, generated locally."""
+    from . import synth
+    import copy
+    bp = block_partition(cfg.nx, cfg.ny, cfg.nz, world)
+    j0, j1, k0, k1 = bp.box(rank)
+    s = synth.generate(cfg, k0, k1)                         # planes [k0, k1), natural global column ids, wells of these planes
+    plane = cfg.nx * cfg.ny
+    loc = np.arange(plane * (k1 - k0), dtype=np.int64)
+    jj = (loc // cfg.nx) % cfg.ny
+    mine = (jj >= j0) & (jj < j1)
+    rows_sel = np.nonzero(mine)[0]
+    cnt = np.diff(s.rows)[rows_sel]
+    rowptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    take = np.concatenate([np.arange(s.rows[r], s.rows[r + 1]) for r in rows_sel]) if len(rows_sel) else np.zeros(0, np.int64)
+    cols_new = bp.new_id(np.asarray(s.cols)[take])
+    e3 = (3 * rows_sel[:, None] + np.arange(3)[None, :]).reshape(-1)
+    wells = None
+    if s.wells is not None and s.wells.nwells > 0:
+        keep = []
+        for w in range(s.wells.nwells):
+            a, e = int(s.wells.val_pointers[w]), int(s.wells.val_pointers[w + 1])
+            cj = (np.asarray(s.wells.Bcols[a:e], dtype=np.int64) // cfg.nx) % cfg.ny
+            inside = (cj >= j0) & (cj < j1)
+            if inside.all():
+                keep.append(w)
+            elif inside.any():
+                raise ValueError("standard well %d spans two ranks" % w)
+        if keep:
+            wells = copy.copy(s.wells)
+            idx = np.concatenate([np.arange(int(s.wells.val_pointers[w]), int(s.wells.val_pointers[w + 1])) for w in keep])
+            wells.val_pointers = np.concatenate([[0], np.cumsum([int(s.wells.val_pointers[w + 1] - s.wells.val_pointers[w]) for w in keep])]).astype(np.uint32)
+            wells.Bcols = bp.new_id(np.asarray(s.wells.Bcols)[idx])
+            wells.Ccols = bp.new_id(np.asarray(s.wells.Ccols)[idx])
+            wells.B = np.asarray(s.wells.B)[idx]
+            wells.C = np.asarray(s.wells.C)[idx]
+            wells.Dinv = np.asarray(s.wells.Dinv)[keep]
+    return localize(rank, bp.ranges, rowptr, cols_new, np.asarray(s.vals)[take], s.b[e3], s.x_true[e3], wells)
+
+
+def permute_to_blocks(s, bp: BlockPartition):
+    """A whole system (natural numbering) in the rank-major numbering of `bp`: (rows, cols, vals, b, x_true, wells) --
+    the input of the partitioned oracle (contiguous parts) the multi-GPU run is compared with."""
+    import copy
+    Nb = len(s.rows) - 1
+    new_of = bp.new_id(np.arange(Nb, dtype=np.int64))
+    old_of = np.empty(Nb, dtype=np.int64)
+    old_of[new_of] = np.arange(Nb)
+    cnt = np.diff(s.rows)[old_of]
+    rows = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    cols = np.empty(int(rows[-1]), dtype=np.int32)
+    vals = np.empty((int(rows[-1]), 3, 3))
+    sv = np.asarray(s.vals).reshape(-1, 3, 3)
+    for q in range(Nb):
+        r = old_of[q]
+        a, e = int(s.rows[r]), int(s.rows[r + 1])
+        c = new_of[np.asarray(s.cols[a:e], dtype=np.int64)]
+        o = np.argsort(c, kind="stable")
+        cols[rows[q]:rows[q + 1]] = c[o]
+        vals[rows[q]:rows[q + 1]] = sv[a:e][o]
+    e3 = (3 * old_of[:, None] + np.arange(3)[None, :]).reshape(-1)
+    wells = None
+    if s.wells is not None and s.wells.nwells > 0:
+        wells = copy.copy(s.wells)
+        wells.Bcols = new_of[np.asarray(s.wells.Bcols, dtype=np.int64)].astype(np.int32)
+        wells.Ccols = new_of[np.asarray(s.wells.Ccols, dtype=np.int64)].astype(np.int32)
+    return rows, cols, vals, np.asarray(s.b)[e3], np.asarray(s.x_true)[e3], wells, new_of
+
+
 class DistSolver:
     """One rank of the multi-GPU ILU0-BiCGSTAB solve.  ``group`` is a torch.distributed process group
     (any backend) used only for the set-up exchange; the data path runs over peer memory and NCCL inside

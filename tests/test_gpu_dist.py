@@ -41,7 +41,7 @@ def _free_port():
         return sk.getsockname()[1]
 
 
-def _rank_main(rank, world, port, shape, faults, out):
+def _rank_main(rank, world, port, shape, faults, out, blocks=False):
     import torch
     import torch.distributed as td
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -51,7 +51,7 @@ def _rank_main(rank, world, port, shape, faults, out):
     try:
         from opm_autodiff_b200 import dist, synth
         cfg = synth.GridConfig("t", *shape, seed=5, faults=faults, nwells=4, nperf=3)
-        ls = dist.slab_system(cfg, rank, world)
+        ls = dist.block_system(cfg, rank, world) if blocks else dist.slab_system(cfg, rank, world)
         ds = dist.DistSolver(ls, rank, maxit=200, tolerance=1e-10)
         ds.upload()
         rng = np.random.default_rng(17)
@@ -96,3 +96,32 @@ def test_multi_gpu_solve_matches_partitioned_oracle(mods, world, shape, faults):
         x2[3 * r0:3 * r1] = xl2
     assert relerr(x, ref.x) < 1e-6 and relerr(x2, ref.x) < 1e-6
     assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells)) < 1e-8
+
+
+def test_four_gpu_block_partition_matches_partitioned_oracle(mods):
+    """2 x 2 blocks in (y, z) with the rank-major renumbering (what bench.py --gpus 4 runs)."""
+    bridge, dist, synth, oracle = mods
+    import torch
+    world, shape, faults = 4, (9, 8, 10), ((4, 1),)
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank_main, args=(world, _free_port(), shape, faults, out, True), nprocs=world, join=True)
+    cfg = synth.GridConfig("t", *shape, seed=5, faults=faults, nwells=4, nperf=3)
+    s = synth.full_system(cfg)
+    bp = dist.block_partition(cfg.nx, cfg.ny, cfg.nz, world)
+    rows, cols, vals, b, xt, wells, new_of = dist.permute_to_blocks(s, bp)
+    part_ptr = np.array([r[0] for r in bp.ranges] + [s.Nb], np.int32)
+    ref = oracle.solve(rows, cols, vals, b, oracle_wells(wells), tol=1e-10, maxit=200, part_ptr=part_ptr)
+    rng = np.random.default_rng(17)
+    xg = rng.normal(size=3 * s.Nb)                 # the ranks drew the same vector and used their [row0,row1) slice of it
+    y_ref = oracle.spmv(rows, cols, vals, xg)
+    x = np.zeros(3 * s.Nb)
+    for rank in range(world):
+        r0, r1, y, conv, it, xl, it2, xl2, launches = out[rank]
+        assert relerr(y, y_ref[3 * r0:3 * r1]) < 1e-13
+        assert conv and abs(it - ref.it) <= max(1.0, 0.1 * ref.it) and it2 == it
+        x[3 * r0:3 * r1] = xl
+    assert relerr(x, ref.x) < 1e-6
