@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--workload", default="c3", help="c2 | c3 | c4 | c5 | nx,ny,nz")
     ap.add_argument("--cpu-sample-iters", type=int, default=12, help="BiCGSTAB iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="slabs", choices=["slabs", "blocks"],
+                    help="N > 1: z-slabs (default: they cut only the weak vertical couplings) or y-z blocks (fewer levels per rank)")
     return ap.parse_args()
 
 

@@ -27,8 +27,9 @@ def run(args, metric, tol, maxit, get_cfg, ClockSampler, measured_peak):
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = get_cfg(args.workload)
     t0 = time.perf_counter()
+    blocks = getattr(args, "partition", "slabs") == "blocks"
     bp = dist.block_partition(cfg.nx, cfg.ny, cfg.nz, world)
-    ls = dist.block_system(cfg, rank, world)
+    ls = dist.block_system(cfg, rank, world) if blocks else dist.slab_system(cfg, rank, world)
     t_gen = time.perf_counter() - t0
     ds = dist.DistSolver(ls, local, maxit=maxit, tolerance=tol)
     res = bridge.BdaResult()
@@ -122,7 +123,8 @@ def run(args, metric, tol, maxit, get_cfg, ClockSampler, measured_peak):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg.name, "cells": cfg.ncells, "wells": cfg.nwells, "tolerance": tol, "relaxation": 1.0,
-                   "partition": "%d x %d blocks in (y, z), x not cut, rank-major numbering, ghosts last, block-Jacobi ILU0 per GPU" % (bp.py, bp.pz),
+                   "partition": ("%d x %d blocks in (y, z), x not cut, rank-major numbering" % (bp.py, bp.pz) if blocks
+                                 else "%d row slabs along k" % world) + ", ghosts last, block-Jacobi ILU0 per GPU",
                    "iterations": res.it, "x_error_vs_generator": float(np.sqrt(err2 / ref2)),
                    "l2": "per-GPU slab (matrix + factor) larger than L2, no flush" if ls.vals.nbytes > 1.3e8
                          else "per-GPU slab fits L2 at this rank count",
