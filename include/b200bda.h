@@ -68,11 +68,17 @@ void b200_destroy(b200_solver* s);
  *   "relaxation"  ILU0 relaxation w (setupPropertyTree.cpp:175-188; cusparse uses 1.0)  default 1.0
  *   "tolerance", "maxit", "verbosity"   override the constructor values
  *   "pin_host"    1: cudaHostRegister the caller's vals/b once and reuse   default 1
- *   "use_graph"   1: replay the BiCGSTAB iteration as a CUDA graph                        default 1
- *   "lookahead"   iterations enqueued ahead of the convergence read-back                  default 2
- *   "profile"     1: time every kernel with CUDA events (no graph), see b200_kernel_stats default 0
- *   "sweep_parts", "sweep_warps", "sweep_slots", "sweep_stage_bytes", "sweep_window"
- *                 schedule of the triangular sweeps (parts <= SMs; set before the first solve)
+ *   "use_graph"   1: replay the factorisation launches and the BiCGSTAB iteration body as CUDA graphs  default 1
+ *   "lookahead"   iterations enqueued per convergence read-back (the device stops by itself)      default 2
+ *   "profile"     1: time every kernel with CUDA events (no graphs), see b200_kernel_stats         default 0
+ *   "sweep_parts", "sweep_warps", "sweep_groups", "sweep_helpers", "sweep_slots", "sweep_stage_bytes", "sweep_window",
+ *   "sweep_ext_window"   schedule of the triangular sweeps: parts (CTAs, all resident), consumer warps per CTA and their
+ *                 level groups, helper warps, ring slots and bytes per stage, rows of the shared-memory window (0 = auto)
+ *                 and of the external-row ring; set before the first solve
+ *   "sweep_helper_sleep"  ns a helper warp sleeps between two polls of external rows                default 60
+ *   "sweep_trace" 1: record the stage timeline of the sweeps (b200_get_sweep_trace; debugging)     default 0
+ *   "spmv_blocks" upper bound of the SpMV grid                                                    default 16 per SM
+ *   "p2p_allreduce"  multi-GPU: 1 peer-memory mailboxes, 0 NCCL + finish kernel                    default 1
  * Unknown keys return B200_UNKNOWN_ERROR. */
 b200_status b200_set_option(b200_solver* s, const char* key, double value);
 
