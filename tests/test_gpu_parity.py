@@ -252,3 +252,69 @@ def test_bridge_zero_diagonal_fixup_feeds_backend(mods):
     br.get_result(x)
     assert mat.vals[d, 0, 0] == 1e-15
     assert res.converged == ref.converged and relerr(x, ref.x) <= 1e-6
+
+
+def _irregular_system(synth, shape, extra_frac, seed, drop_upper=0.0):
+    """A grid system with random long-range symmetric couplings added (NNC-like; rows get up to ~10 blocks, i.e. more than
+    the three dependency slots of a sweep record and longer elimination plans), optionally made structurally non-symmetric."""
+    s = synth.small(*shape)
+    rng = np.random.default_rng(seed)
+    Nb = s.Nb
+    nb = [dict() for _ in range(Nb)]
+    for i in range(Nb):
+        for k in range(s.rows[i], s.rows[i + 1]):
+            nb[i][int(s.cols[k])] = s.vals[k].copy()
+    for _ in range(int(extra_frac * Nb)):
+        a, b = (int(t) for t in rng.integers(0, Nb, 2))
+        if a == b or b in nb[a]:
+            continue
+        t = 0.05 * rng.random()
+        blk = -t * (np.eye(3) + 0.2 * rng.uniform(-1, 1, (3, 3))) * np.array([1e-7, 1.0, 1.0])[None, :]
+        nb[a][b] = blk
+        nb[b][a] = blk.T.copy() * np.array([1e-7, 1.0, 1.0])[None, :] / np.array([1e-7, 1.0, 1.0])[:, None]
+        for r in (a, b):
+            nb[r][r] = nb[r][r] + t * np.eye(3) * np.array([1e-7, 1.0, 1.0])[None, :]
+    if drop_upper > 0.0:
+        for i in range(Nb):
+            for c in [c for c in nb[i] if c > i + 1 and rng.random() < drop_upper]:
+                del nb[i][c]
+    rows, cols, vals = [0], [], []
+    for i in range(Nb):
+        for c in sorted(nb[i]):
+            cols.append(c); vals.append(nb[i][c])
+        rows.append(len(cols))
+    rows, cols, vals = np.array(rows, np.int32), np.array(cols, np.int32), np.array(vals)
+    return rows, cols, vals
+
+
+@pytest.mark.parametrize("shape,extra,drop,opts", [((9, 8, 7), 0.15, 0.0, {}), ((14, 9, 6), 0.3, 0.0, {"sweep_parts": 23, "sweep_stage_bytes": 4096}),
+                                                   ((10, 10, 5), 0.1, 0.3, {"sweep_parts": 7})])
+def test_irregular_patterns_vs_oracle(mods, shape, extra, drop, opts):
+    """Long rows (continuation records in the sweeps, long elimination plans), long-range dependencies (rows parked from
+    other parts or from beyond the window) and a structurally non-symmetric pattern through the real kernels."""
+    bridge, synth, oracle = mods
+    rows, cols, vals = _irregular_system(synth, shape, extra, seed=3, drop_upper=drop)
+    Nb = len(rows) - 1
+    assert np.max(np.diff(rows)) > 7
+    rng = np.random.default_rng(5)
+    xt = rng.uniform(-1, 1, 3 * Nb) * np.tile([1e5, 1.0, 1.0], Nb)
+    b = oracle.spmv(rows, cols, vals, xt)
+    be = bridge.B200SolverBackend(0, 300, 1e-10, 0)
+    for k, v in opts.items():
+        be.set_option(k, v)
+    be.upload_system(3 * Nb, 9 * len(cols), 3, vals, rows, cols, b, None)
+    assert be.ilu0_factorize() == bridge.SolverStatus.BDA_SOLVER_SUCCESS
+    LU = be.get_ilu0(len(cols))
+    LUo, diag, st = oracle.ilu0(rows, cols, vals)
+    assert st == 0
+    scale = np.abs(LUo).reshape(-1, 9).max(axis=1)[:, None, None]
+    assert np.max(np.abs(LU - LUo) / scale) < 1e-9
+    d = rng.normal(size=3 * Nb)
+    assert relerr(be.ilu0_apply(d), oracle.ilu0_apply(rows, cols, diag, LUo, d)) < 1e-9
+    assert relerr(be.spmv(d), oracle.spmv(rows, cols, vals, d)) < 1e-14
+    res = bridge.BdaResult()
+    be.solve_resident(res)
+    x = np.zeros(3 * Nb)
+    be.get_result(x)
+    ref = oracle.solve(rows, cols, vals, b, None, tol=1e-10, maxit=300)
+    assert res.converged and ref.converged and relerr(x, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
