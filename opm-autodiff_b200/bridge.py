@@ -459,6 +459,41 @@ class BsrMatrix:
 
 
 @dataclass
+class FlexibleSolverOptions:
+    """The part of a FlexibleSolver property tree this backend honours (keys and defaults as
+    FlexibleSolver_impl.hpp:147-150 and setupPropertyTree.cpp:175-188 `setupILU`): ``tol``, ``maxiter``, ``verbosity``,
+    ``solver`` (must be ``bicgstab``), ``preconditioner.type`` (``ILU0`` / ``ParOverILU0``), ``preconditioner.relaxation``,
+    ``preconditioner.ilulevel`` (must be 0).  JSON values may be strings, as in tests/options_flexiblesolver.json."""
+    tol: float = 1e-2
+    maxiter: int = 200
+    verbosity: int = 0
+    relaxation: float = 1.0
+
+    @classmethod
+    def from_tree(cls, prm: dict, strict: bool = True) -> "FlexibleSolverOptions":
+        o = cls(float(prm.get("tol", 1e-2)), int(prm.get("maxiter", 200)), int(prm.get("verbosity", 0)))
+        solver = str(prm.get("solver", "bicgstab"))
+        pre = prm.get("preconditioner", {}) or {}
+        ptype = str(pre.get("type", "ParOverILU0"))
+        if strict:
+            if solver != "bicgstab":
+                raise ValueError("the b200 backend implements solver 'bicgstab' only, got '%s'" % solver)
+            if ptype.lower() not in ("ilu0", "paroverilu0"):
+                raise ValueError("the b200 backend implements preconditioner ILU0 / ParOverILU0 only, got '%s'" % ptype)
+            if int(pre.get("ilulevel", 0)) != 0:
+                raise ValueError("the b200 backend implements fill level 0 only")
+        if ptype.lower() in ("ilu0", "paroverilu0"):
+            o.relaxation = float(pre.get("relaxation", 1.0))
+        return o
+
+    @classmethod
+    def from_json(cls, path: str, strict: bool = True) -> "FlexibleSolverOptions":
+        import json
+        with open(path) as f:
+            return cls.from_tree(json.load(f), strict)
+
+
+@dataclass
 class InverseOperatorResult:
     """Dune::InverseOperatorResult fields BdaBridge fills (BdaBridge.cpp:247-251)."""
     iterations: int = 0
@@ -494,6 +529,16 @@ class BdaBridge:
         else:
             raise ValueError("Error unknown value for parameter 'AcceleratorMode', should be passed like "
                              "'--accelerator-mode=[none|cusparse|opencl|fpga|amgcl|b200]")
+
+    @classmethod
+    def from_flexible_solver_options(cls, accelerator_mode: str, options: "FlexibleSolverOptions", deviceID: int = 0) -> "BdaBridge":
+        """Bridge configured from a FlexibleSolver property tree, the way ISTLSolverEbos passes
+        linear_solver_reduction / maxiter / verbosity to BdaBridge (ISTLSolverEbos.hpp:133-150); the ILU relaxation,
+        which the reference's GPU backends hard-wire to 1, is honoured here."""
+        br = cls(accelerator_mode, "", options.verbosity, options.maxiter, options.tol, 0, deviceID, "none")
+        if br.backend is not None:
+            br.backend.set_option("relaxation", options.relaxation)
+        return br
 
     def getUseGpu(self) -> bool:
         return self.use_gpu
