@@ -206,6 +206,47 @@ struct Analysis {
     int maxRowLen = 0;
 };
 
+// Sliced-ELL copy of the p-space matrix for the SpMV: slices of 32 consecutive rows, one LANE per row, slot k of a slice holds
+// the k-th block of each of its rows as 9 x 32 doubles ([value][lane], a warp reads 256 contiguous bytes per load) plus 32
+// column indices.  The slice width is its longest row, capped at 1.5 x its mean row length + 1: the blocks beyond the cap stay
+// in the BSR arrays and are added by the owning lane (rows much longer than their neighbours: wells folded into the matrix).
+struct SellPlan {
+    int nslices = 0;
+    std::vector<int> ptr;             // nslices + 1, in slots
+    std::vector<int> over;            // per slice: 1 if some row has blocks beyond the slice width
+    std::vector<int> col;             // 32 per slot; padding points at a valid row with zero values
+    std::vector<int> src;             // 32 per slot: source block of the caller's array (as srcblk), -1 = padding
+};
+
+inline SellPlan build_sell(int Nb, const std::vector<int>& prow, const std::vector<int>& pcol, const std::vector<int>& srcblk)
+{
+    SellPlan P;
+    P.nslices = (Nb + 31) / 32;
+    P.ptr.assign(P.nslices + 1, 0);
+    P.over.assign(P.nslices, 0);
+    for (int s = 0; s < P.nslices; ++s) {
+        const int r0 = 32 * s, r1 = std::min(Nb, r0 + 32);
+        int longest = 0;
+        for (int r = r0; r < r1; ++r) longest = std::max(longest, prow[r + 1] - prow[r]);
+        const int cap = (int) ((3LL * (prow[r1] - prow[r0]) + 2 * (r1 - r0) - 1) / (2 * (r1 - r0))) + 1;
+        const int width = std::min(longest, cap);
+        P.over[s] = longest > width;
+        P.ptr[s + 1] = P.ptr[s] + width;
+    }
+    P.col.assign((size_t) P.ptr[P.nslices] * 32, 0);
+    P.src.assign((size_t) P.ptr[P.nslices] * 32, -1);
+    for (int s = 0; s < P.nslices; ++s)
+        for (int lane = 0; lane < 32; ++lane) {
+            const int r = 32 * s + lane, width = P.ptr[s + 1] - P.ptr[s];
+            for (int k = 0; k < width; ++k) {
+                const size_t o = (size_t) (P.ptr[s] + k) * 32 + lane;
+                if (r < Nb && prow[r] + k < prow[r + 1]) { P.col[o] = pcol[prow[r] + k]; P.src[o] = srcblk[prow[r] + k]; }
+                else P.col[o] = std::min(r, Nb - 1);
+            }
+        }
+    return P;
+}
+
 struct AnalysisOptions {
     int parts = 148;            // resident CTAs of the sweep kernels
     int stageBytes = 16384;     // meta + values + rhs of one ring slot

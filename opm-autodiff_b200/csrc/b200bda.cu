@@ -172,6 +172,11 @@ struct Solver {
     DevBuf<unsigned> d_push_tickets;
 
     DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows, d_facPtr, d_facOps;
+    DevBuf<int> d_sellPtr, d_sellOver, d_sellCol, d_sellSrc;     // sliced-ELL copy of A for the SpMV (analysis.hpp SellPlan)
+    DevBuf<double> d_sellVal;
+    int sell_slices = 0;
+    long long sell_slots = 0;
+    int spmv_sell = 1;                 // option: 0 = BSR kernel (3 lanes per row)
     bool fac_plan = false;
     cudaGraphExec_t fac_graph_exec = nullptr;
     double fac_graph_relax = 0.0;
@@ -266,7 +271,7 @@ struct Solver {
             case K_VEC_XR1: return 144.0 * nb;
             case K_VEC_XR2: return 168.0 * nb;
             case K_WELL: return 272.0 * nwblocks + 128.0 * nwells;
-            case K_PERMUTE: return 148.0 * nz;
+            case K_PERMUTE: return (sell_slices ? 296.0 : 148.0) * nz;
             default: return 0.0;
         }
     }
@@ -365,6 +370,14 @@ struct Solver {
         };
         up(d_prow, an.prow); up(d_pcol, an.pcol); up(d_pdiag, an.pdiag); up(d_srcblk, an.srcblk); up(d_perm, an.perm);
         up(d_flevRows, an.flevRows);
+        sell_slices = 0; sell_slots = 0;
+        if (spmv_sell) {
+            const b200::SellPlan sp = b200::build_sell(Nb, an.prow, an.pcol, an.srcblk);
+            sell_slices = sp.nslices; sell_slots = sp.ptr[sp.nslices];
+            up(d_sellPtr, sp.ptr); up(d_sellOver, sp.over); up(d_sellCol, sp.col); up(d_sellSrc, sp.src);
+            d_sellVal.alloc((size_t) sell_slots * 288);
+            CUDA_OK(cudaStreamSynchronize(stream));            // sp is a temporary
+        }
         fac_plan = an.facMaxRow <= kFacMaxRow && an.facMaxOps <= kFacMaxOps;
         if (fac_plan) { up(d_facPtr, an.facPtr); up(d_facOps, an.facOps); }
         up(d_metaL, an.L.meta); up(d_metaU, an.U.meta); up(d_srcL, an.L.src); up(d_srcU, an.U.src);
@@ -527,6 +540,8 @@ struct Solver {
     {
         int id = prof_begin(K_PERMUTE);
         k_permute_vals<<<blocks_for(nnz, 256, num_sms * 16), 256, 0, stream>>>(d_stage.p, d_srcblk.p, d_A.p, nnz);
+        if (sell_slices)
+            k_fill_sell<<<blocks_for(sell_slots * 288, 256, num_sms * 16), 256, 0, stream>>>(d_stage.p, d_sellSrc.p, d_sellVal.p, sell_slots * 288);
         prof_end(id);
     }
 
@@ -624,8 +639,13 @@ struct Solver {
     void spmv(const double* x, double* y, const double* d1)
     {
         int id = prof_begin(K_SPMV);
-        k_spmv<MODE><<<blocks_for(N, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
-                                                                                          d_partials.p, d_ticket.p);
+        if (sell_slices)
+            k_spmv_sell<MODE><<<blocks_for(32LL * sell_slices, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(
+                d_sellPtr.p, d_sellOver.p, d_sellCol.p, d_sellVal.p, d_prow.p, d_pcol.p, d_A.p, x, y, d1, Nb, sell_slices, d_S.p,
+                d_partials.p, d_ticket.p);
+        else
+            k_spmv<MODE><<<blocks_for(N, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
+                                                                                              d_partials.p, d_ticket.p);
         prof_end(id);
     }
     template <int MODE>
@@ -927,6 +947,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
         else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);

@@ -794,6 +794,78 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv(const int* __restrict__ pr
     }
 }
 
+// The same product from the sliced-ELL copy (analysis.hpp SellPlan): one lane per block row, a warp per slice of 32 rows,
+// every value load is 256 contiguous bytes.  The BSR kernel above needs ~5 L1 wavefronts per 128 useful bytes (3 lanes per
+// row, 72-byte blocks) and is bound by the LSU data pipe (79 % busy at 72 % of the HBM peak); this layout needs one.
+// Blocks beyond the slice width (over[slice] != 0) are read from the BSR arrays by the lane that owns the row.
+template <int MODE>
+__global__ void __launch_bounds__(kVecThreads) k_spmv_sell(const int* __restrict__ sptr, const int* __restrict__ sover,
+                                                           const int* __restrict__ scol, const double* __restrict__ sval,
+                                                           const int* __restrict__ prow, const int* __restrict__ pcol,
+                                                           const double* __restrict__ A, const double* __restrict__ x,
+                                                           double* __restrict__ y, const double* __restrict__ d1, int Nb, int nslices,
+                                                           Scalars* S, double* partials, unsigned* ticket)
+{
+    if (MODE != 0 && S->done) return;
+    double acc[MODE == 2 ? 2 : 1] = {0.0};
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nslices; slice += nw) {
+        const int s0 = __ldg(sptr + slice), s1 = __ldg(sptr + slice + 1);
+        const int row = 32 * slice + lane;
+        const double* v = sval + (size_t) s0 * 288 + lane;
+        const int* c = scol + (size_t) s0 * 32 + lane;
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll 2
+        for (int k = s0; k < s1; ++k, v += 288, c += 32) {
+            const double* xx = x + 3 * (size_t) __ldg(c);
+            const double x0 = xx[0], x1 = xx[1], x2 = xx[2];
+            y0 += v[0] * x0 + v[32] * x1 + v[64] * x2;
+            y1 += v[96] * x0 + v[128] * x1 + v[160] * x2;
+            y2 += v[192] * x0 + v[224] * x1 + v[256] * x2;
+        }
+        if (__ldg(sover + slice) && row < Nb) {
+            for (int k = prow[row] + (s1 - s0), ke = prow[row + 1]; k < ke; ++k) {
+                const double* a = A + (size_t) k * 9;
+                const double* xx = x + 3 * (size_t) pcol[k];
+                const double x0 = xx[0], x1 = xx[1], x2 = xx[2];
+                y0 += a[0] * x0 + a[1] * x1 + a[2] * x2;
+                y1 += a[3] * x0 + a[4] * x1 + a[5] * x2;
+                y2 += a[6] * x0 + a[7] * x1 + a[8] * x2;
+            }
+        }
+        if (row < Nb) {
+            double* yy = y + 3 * (size_t) row;
+            yy[0] = y0; yy[1] = y1; yy[2] = y2;
+            if (MODE != 0) {
+                const double* dd = d1 + 3 * (size_t) row;
+                const double e0 = dd[0], e1 = dd[1], e2 = dd[2];
+                if (MODE == 1) acc[0] += e0 * y0 + e1 * y1 + e2 * y2;
+                if (MODE == 2) { acc[0] += y0 * e0 + y1 * e1 + y2 * e2; acc[1] += y0 * y0 + y1 * y1 + y2 * y2; }
+            }
+        }
+    }
+    if (MODE != 0) {
+        double tot[MODE == 2 ? 2 : 1];
+        if (grid_reduce<(MODE == 2 ? 2 : 1)>(acc, partials, ticket, tot)) {
+            if (MODE == 1) S->h = tot[0];
+            if (MODE == 2) { S->tr = tot[0]; S->tt = tot[1]; }
+        }
+    }
+}
+
+// sval[(slot * 9 + e) * 32 + lane] = stage[src[slot * 32 + lane] * 9 + e]   (0 for padding); one thread per output double
+__global__ void __launch_bounds__(256) k_fill_sell(const double* __restrict__ stage, const int* __restrict__ src,
+                                                   double* __restrict__ sval, long long n)
+{
+    for (long long o = (long long) blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (long long) gridDim.x * blockDim.x) {
+        const long long slot = o / 288;
+        const int rem = (int) (o - slot * 288), e = rem >> 5, lane = rem & 31;
+        const int b = __ldg(src + slot * 32 + lane);
+        sval[o] = b >= 0 ? __ldg(stage + (long long) b * 9 + e) : 0.0;
+    }
+}
+
 // ---- BiCGSTAB vector phases ------------------------------------------------------------------
 
 // p = r + beta (p - omega v), beta = (rho_new/rho)(alpha/omega); first pass: p = r.

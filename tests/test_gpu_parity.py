@@ -318,3 +318,34 @@ def test_irregular_patterns_vs_oracle(mods, shape, extra, drop, opts):
     be.get_result(x)
     ref = oracle.solve(rows, cols, vals, b, None, tol=1e-10, maxit=300)
     assert res.converged and ref.converged and relerr(x, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
+
+
+@pytest.mark.parametrize("sell", [1, 0])
+def test_spmv_layouts_with_very_long_rows(mods, sell):
+    """SpMV from the sliced-ELL copy (default) and from the BSR arrays: a few rows coupled to ~40 cells exceed the width cap of
+    their slice, so their tail comes from the BSR arrays (k_spmv_sell overflow path); Nb is not a multiple of 32."""
+    bridge, synth, oracle = mods
+    s = synth.small(11, 7, 5)
+    rng = np.random.default_rng(17)
+    Nb = s.Nb
+    nb = [dict() for _ in range(Nb)]
+    for i in range(Nb):
+        for k in range(s.rows[i], s.rows[i + 1]):
+            nb[i][int(s.cols[k])] = s.vals[k].copy()
+    for hub in (3, 200, Nb - 1):
+        for c in rng.choice(Nb, 40, replace=False):
+            if int(c) != hub:
+                nb[hub].setdefault(int(c), rng.uniform(-1, 1, (3, 3)) * 1e-3)
+    rows, cols, vals = [0], [], []
+    for i in range(Nb):
+        for c in sorted(nb[i]):
+            cols.append(c); vals.append(nb[i][c])
+        rows.append(len(cols))
+    rows, cols, vals = np.array(rows, np.int32), np.array(cols, np.int32), np.array(vals)
+    assert Nb % 32 != 0 and np.max(np.diff(rows)) > 40
+    be = bridge.B200SolverBackend(0, 10, 1e-2, 0)
+    be.set_option("spmv_sell", sell)
+    be.upload_system(3 * Nb, 9 * len(cols), 3, vals, rows, cols, np.ones(3 * Nb), None)
+    for seed in (1, 2):
+        x = np.random.default_rng(seed).normal(size=3 * Nb) * np.tile([1e5, 1.0, 1.0], Nb)
+        assert relerr(be.spmv(x), oracle.spmv(rows, cols, vals, x)) < 1e-14
