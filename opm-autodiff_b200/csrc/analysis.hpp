@@ -247,6 +247,49 @@ inline SellPlan build_sell(int Nb, const std::vector<int>& prow, const std::vect
     return P;
 }
 
+// Work units of the SpMV that runs inside the upper sweep (k_sweep<..., SPMV>): a CTA whose part is finished claims units
+// of `slicesPerUnit` SELL slices from a global counter.  A unit may start when every part that owns one of its rows or
+// columns has finished; units are listed in the order in which that is expected to happen (the upper sweep finishes the
+// parts with the HIGHEST lowest-level first).
+struct FusedPlan {
+    std::vector<int> units;           // 2 per unit: first slice, slices
+    std::vector<int> needPtr, need;   // parts a unit reads from (its own rows included)
+};
+
+inline FusedPlan build_fused(int Nb, const std::vector<int>& prow, const std::vector<int>& pcol, const std::vector<int>& partPtr,
+                             const std::vector<int>& flevPtr, const std::vector<int>& flevRows, int slicesPerUnit)
+{
+    FusedPlan F;
+    const int nparts = (int) partPtr.size() - 1, nslices = (Nb + 31) / 32;
+    std::vector<int> partOfRow(Nb), minlev(nparts, INT32_MAX);
+    for (int p = 0; p < nparts; ++p)
+        for (int r = partPtr[p]; r < partPtr[p + 1]; ++r) partOfRow[r] = p;
+    for (int l = 0; l + 1 < (int) flevPtr.size(); ++l)
+        for (int k = flevPtr[l]; k < flevPtr[l + 1]; ++k) minlev[partOfRow[flevRows[k]]] = std::min(minlev[partOfRow[flevRows[k]]], l);
+    const int nunits = (nslices + slicesPerUnit - 1) / slicesPerUnit;
+    std::vector<std::vector<int>> needOf(nunits);
+    std::vector<int> key(nunits), order(nunits), mark(nparts, -1);
+    for (int u = 0; u < nunits; ++u) {
+        const int r0 = 32 * u * slicesPerUnit, r1 = std::min(Nb, r0 + 32 * slicesPerUnit);
+        int k = INT32_MAX;
+        for (int r = r0; r < r1; ++r) {
+            auto touch = [&](int p) { if (mark[p] != u) { mark[p] = u; needOf[u].push_back(p); k = std::min(k, minlev[p]); } };
+            touch(partOfRow[r]);
+            for (int e = prow[r]; e < prow[r + 1]; ++e) touch(partOfRow[pcol[e]]);
+        }
+        key[u] = k; order[u] = u;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] > key[b]; });
+    F.needPtr.push_back(0);
+    for (int u : order) {
+        F.units.push_back(u * slicesPerUnit);
+        F.units.push_back(std::min(slicesPerUnit, nslices - u * slicesPerUnit));
+        for (int p : needOf[u]) F.need.push_back(p);
+        F.needPtr.push_back((int) F.need.size());
+    }
+    return F;
+}
+
 struct AnalysisOptions {
     int parts = 148;            // resident CTAs of the sweep kernels
     int stageBytes = 16384;     // meta + values + rhs of one ring slot

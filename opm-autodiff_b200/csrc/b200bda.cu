@@ -177,6 +177,11 @@ struct Solver {
     int sell_slices = 0;
     long long sell_slots = 0;
     int spmv_sell = 1;                 // option: 0 = BSR kernel (3 lanes per row)
+    // SpMV run by the upper sweep's CTAs as their parts finish (kernels.cuh fused_spmv_tail)
+    DevBuf<int> d_fUnits, d_fNeedPtr, d_fNeed, d_fSync;
+    DevBuf<double> d_fPartials;
+    int fused_units = 0;
+    int fuse_spmv = 1;                 // option
     bool fac_plan = false;
     cudaGraphExec_t fac_graph_exec = nullptr;
     double fac_graph_relax = 0.0;
@@ -401,12 +406,14 @@ struct Solver {
         const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 8 * kXs + kSweepTailPad;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
-        while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_optin || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
+        const bool want_fused = fuse_spmv && sell_slices && !dist.enabled && an.nparts <= kMaxSweepParts;
+        const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
+        while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_limit || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
         if ((long long) sweep_slots * sweep_extCap > an.extWindow)
             throw std::runtime_error("external-row ring of the triangular sweeps too small (" + std::to_string(sweep_extCap) + " rows per stage)");
         sweep_helpers = std::max(1, std::min({sweep_helpers, 27 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
-        if (sweep_smem > smem_optin)
+        if (sweep_smem > smem_limit)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
         int occ = 8;
@@ -419,6 +426,15 @@ struct Solver {
         };
         prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
         prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
+        fused_units = 0;
+        if (want_fused && threads <= kFusedMaxThreads) {
+            prep(k_sweep<false, true, false, 1>); prep(k_sweep<false, true, false, 2>);
+            const b200::FusedPlan fp = b200::build_fused(Nb, an.prow, an.pcol, an.partPtr, an.flevPtr, an.flevRows, 4 * (threads / 32 - 1));
+            fused_units = (int) fp.units.size() / 2;
+            up(d_fUnits, fp.units); up(d_fNeedPtr, fp.needPtr); up(d_fNeed, fp.need);
+            d_fSync.alloc(2 + an.nparts); d_fPartials.alloc((size_t) 2 * fused_units);
+            CUDA_OK(cudaStreamSynchronize(stream));            // fp is a temporary
+        }
         if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
         if (an.nparts > occ * num_sms)
             throw std::runtime_error("triangular sweeps: " + std::to_string(an.nparts) + " parts cannot all be resident (" +
@@ -600,7 +616,7 @@ struct Solver {
 
     SweepArgs sweep_args(bool lower, const double* rhs, double* out, double* rearm, bool check_done) const
     {
-        SweepArgs a;
+        SweepArgs a = {};
         a.stages = lower ? d_stagesL.p : d_stagesU.p;
         a.parts = lower ? d_partsL.p : d_partsU.p;
         a.meta = lower ? d_metaL.p : d_metaU.p;
@@ -635,6 +651,25 @@ struct Solver {
         launch_sweep<false>(sweep_args(false, rhs, out, rearm, check_done));
         prof_end(id);
     }
+    // upper sweep + the SpMV that follows it in one launch: y = A * out, dots as spmv<MODE>
+    template <int MODE>
+    void trsv_upper_spmv(const double* rhs, double* out, double* rearm, double* y, const double* d1)
+    {
+        int id = prof_begin(K_UPPER);
+        CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
+        SweepArgs a = sweep_args(false, rhs, out, rearm, true);
+        a.f.sptr = d_sellPtr.p; a.f.sover = d_sellOver.p; a.f.scol = d_sellCol.p; a.f.sval = d_sellVal.p;
+        a.f.prow = d_prow.p; a.f.pcol = d_pcol.p; a.f.A = d_A.p; a.f.y = y; a.f.d1 = d1;
+        a.f.units = reinterpret_cast<const int2*>(d_fUnits.p); a.f.need_ptr = d_fNeedPtr.p; a.f.need = d_fNeed.p;
+        a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
+        a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem;
+        if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
+        k_sweep<false, true, false, MODE><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
+        prof_end(id);
+    }
+    bool fused_now() const { return fused_units > 0 && !sweep_trace && !dist.enabled && !(profile && !fuse_in_profile); }
+    int fuse_in_profile = 0, fuse_debug = 0;
+    DevBuf<long long> d_fDbg;
     template <int MODE>
     void spmv(const double* x, double* y, const double* d1)
     {
@@ -734,9 +769,12 @@ struct Solver {
         k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
         trsv_lower(d_p.p, d_w.p, true);
-        trsv_upper(d_w.p, d_y.p, d_w.p, true);
-        halo_push(d_y.p, true);
-        spmv<1>(d_y.p, d_v.p, d_rt.p);
+        if (fused_now()) trsv_upper_spmv<1>(d_w.p, d_y.p, d_w.p, d_v.p, d_rt.p);
+        else {
+            trsv_upper(d_w.p, d_y.p, d_w.p, true);
+            halo_push(d_y.p, true);
+            spmv<1>(d_y.p, d_v.p, d_rt.p);
+        }
         wells_apply<1>(d_y.p, d_v.p, d_rt.p);
         spmv_ghost<1>(d_v.p, d_rt.p, true);
         reduce_phase<1>();
@@ -745,9 +783,12 @@ struct Solver {
         prof_end(id);
         reduce_phase<2>();
         trsv_lower(d_r.p, d_w.p, true);
-        trsv_upper(d_w.p, d_y.p, d_w.p, true);
-        halo_push(d_y.p, true);
-        spmv<2>(d_y.p, d_t.p, d_r.p);
+        if (fused_now()) trsv_upper_spmv<2>(d_w.p, d_y.p, d_w.p, d_t.p, d_r.p);
+        else {
+            trsv_upper(d_w.p, d_y.p, d_w.p, true);
+            halo_push(d_y.p, true);
+            spmv<2>(d_y.p, d_t.p, d_r.p);
+        }
         wells_apply<2>(d_y.p, d_t.p, d_r.p);
         spmv_ghost<2>(d_t.p, d_r.p, true);
         reduce_phase<3>();
@@ -767,7 +808,7 @@ struct Solver {
         if (!use_graph || profile || dist.enabled || sweep_trace) { enqueue_iteration(); return; }
         IterSig sig{};
         sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
-        sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep;
+        sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0);
         if (!iter_graph_exec || sig != iter_sig) {
             if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -948,6 +989,9 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
+        else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = value != 0.0; }
+        else if (k == "fuse_in_profile") s->fuse_in_profile = value != 0.0;
+        else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
         else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);

@@ -14,6 +14,8 @@
 //   k_wells           y -= C^T (D^-1 (B x)), full perforation loop                  wells/StandardWell_impl.hpp:1251-1277,
 //                                                                                   bda/WellContributions.cu:36-126
 #pragma once
+#include <climits>
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -452,7 +454,23 @@ constexpr int kSweepHeader = 256;
 constexpr int kXs = 4;                 // doubles per row of the shared-memory value space (== analysis.hpp kXwinStride)
 constexpr int kSweepTailPad = 512;     // lanes of a partly filled record may read (never use) a few rows past the last rhs copy
 
+// The SpMV that follows an upper sweep, run by the sweep's own CTAs as their parts finish (k_sweep<..., SPMV >= 0>)
+struct FusedSpmv {
+    const int* sptr; const int* sover; const int* scol; const double* sval;      // sliced-ELL copy of A (SellPlan)
+    const int* prow; const int* pcol; const double* A;                            // BSR arrays: rows beyond the slice width
+    double* y;                     // result of the product; the input vector is the sweep's `out`
+    const double* d1;              // dot-product partner (MODE 1: <d1, y>; MODE 2: <y, d1>, <y, y>)
+    const int2* units;             // {first slice, slices}, in expected order of readiness (FusedPlan)
+    const int* need_ptr; const int* need;
+    int* sync;                     // [0] unit counter, [1] ticket, [2 + p] part p finished; zeroed before the launch
+    double* partials;              // 2 x nunits
+    int ring_bytes;                // dynamic shared memory of the launch: ring of SELL slices once the part is swept
+    long long* dbg;                // debugging aid (may be null): per part {part done, exit, units taken, time spent waiting for parts} [ns]
+    int Nb, nunits;
+};
+
 struct SweepArgs {
+    FusedSpmv f;
     const StageD* stages;
     const PartD* parts;
     const int* meta;
@@ -526,8 +544,212 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v)
 // Parts process their rows in ascending (descending for U) global level, a topological order of the
 // whole DAG, and a level only ever waits for rows of earlier levels, so the waits cannot cycle as long
 // as every CTA is resident (grid <= SMs).
-template <bool LOWER, bool REARM, bool TRACE>
-__global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Tail of an upper-sweep CTA: its part is finished while the wavefront is still crossing the other parts (the corner part
+// is done after 50 of 240 us), so the SM would idle.  Instead it publishes "part done" and works through SpMV units (the
+// product that follows the sweep in BiCGSTAB, y = A * out) whose rows and columns all lie in finished parts.  Only CTAs
+// that have nothing left to sweep take units, so a sweeping part never shares its SM with the SpMV (a second grid on the
+// same SMs slowed the sweep by 45 %).  With 11 warps per SM plain loads cannot keep enough bytes in flight (13 GB/s per SM
+// measured), so the producer warp streams the sliced-ELL values and columns of the unit's slices with cp.async.bulk into
+// a ring over the (now free) dynamic shared memory and the other warps compute from there; only the gather of the input
+// vector (written by other SMs during this launch: ld.cg) is a register load.  Slices wider than kTailW slots take the
+// plain-load path.  Dot products: one partial per UNIT, summed in unit order by the last CTA to finish -- deterministic
+// whoever took a unit.
+constexpr int kMaxSweepParts = 1024, kTailChunk = 4, kTailBufBytes = kTailChunk * (2304 + 128), kTailMaxCons = 16;
+template <int MODE>
+__device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, unsigned char* ring)
+{
+    const FusedSpmv& F = P.f;
+    __shared__ int s_unit[2];
+    __shared__ unsigned char s_done[kMaxSweepParts];
+    __shared__ double s_red[2][32];
+    __shared__ bool s_last;
+    // every consumer warp owns two chunk buffers (kTailChunk slots of a slice each) and their barriers: a barrier is only ever
+    // waited on by one warp, phase after phase, so the parity test cannot alias
+    __shared__ __align__(8) unsigned long long s_full[kTailMaxCons][2], s_empty[kTailMaxCons][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int PW = P.nwarps;                                   // the sweep's producer warp keeps that job
+    const int NC = nwarp - 1, ci = warp < PW ? warp : warp - 1;
+    const int NR = min(min(NC, kTailMaxCons), F.ring_bytes / (2 * kTailBufBytes));   // consumers fed through the ring
+    const int NU = NR > 0 ? NR : NC;       // warps that take slices: a plain-load warp next to ring-fed ones would be the straggler
+    for (int p = threadIdx.x; p < P.nparts; p += blockDim.x) s_done[p] = 0;
+    if (threadIdx.x < 32) { s_red[0][threadIdx.x] = 0.0; s_red[1][threadIdx.x] = 0.0; }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < kTailMaxCons; ++k)
+            for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&s_full[k][b2], 1); mbar_init(&s_empty[k][b2], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                       // every row of this part is stored; the sweep's shared memory is free
+    long long t_wait = 0;
+    int n_units = 0;
+    auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (F.dbg && threadIdx.x == 0) F.dbg[4 * part] = now_ns();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_gpu_s32(F.sync + 2 + part, 1);
+        s_unit[0] = atomicAdd(F.sync, 1);
+    }
+    if (warp == PW) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const double* x = P.out;
+    int cnt = 0;                           // chunks this warp has consumed (consumer) / this lane has issued for consumer `lane` (producer)
+    for (int it = 0;; ++it) {
+        __syncthreads();
+        const int u = s_unit[it & 1];
+        if (u >= F.nunits) break;
+        const int2 un = __ldg(F.units + u);
+        if (warp == PW) {                                      // ---- producer: lane c feeds consumer c
+            if (lane < NR)
+                for (int j = lane; j < un.y; j += NU) {
+                    const int s0 = __ldg(F.sptr + un.x + j), w = __ldg(F.sptr + un.x + j + 1) - s0;
+                    for (int k0 = 0; k0 < w; k0 += kTailChunk, ++cnt) {
+                        const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                        if (cnt >= 2) mbar_wait_relaxed(&s_empty[lane][b2], ((cnt >> 1) - 1) & 1);
+                        unsigned char* buf = ring + (size_t) (2 * lane + b2) * kTailBufBytes;
+                        mbar_expect_tx(&s_full[lane][b2], (unsigned) n * (2304 + 128));
+                        bulk_g2s(buf, F.sval + (size_t) (s0 + k0) * 288, (unsigned) n * 2304, &s_full[lane][b2]);
+                        bulk_g2s(buf + kTailChunk * 2304, F.scol + (size_t) (s0 + k0) * 32, (unsigned) n * 128, &s_full[lane][b2]);
+                    }
+                }
+            continue;
+        }
+        // ---- consumers
+        if (threadIdx.x == 0) s_unit[(it + 1) & 1] = atomicAdd(F.sync, 1);     // claim ahead
+        const int n0 = __ldg(F.need_ptr + u), nn = __ldg(F.need_ptr + u + 1) - n0;
+        const long long tw0 = F.dbg && threadIdx.x == 0 ? now_ns() : 0;
+        for (int k = ci * 32 + lane; k < nn; k += NC * 32) {
+            const int p = __ldg(F.need + n0 + k);
+            if (!s_done[p]) {
+                int spins = 0;
+                while (ld_acquire_gpu_s32(F.sync + 2 + p) == 0) {
+                    __nanosleep(400);
+                    if ((++spins & 255) == 0 && (spins > (1 << 17) || *((volatile int*) &P.S->trsv_timeout))) { P.S->trsv_timeout = 1; break; }
+                }
+                s_done[p] = 1;
+            }
+        }
+        named_barrier(2, NC * 32);
+        if (F.dbg && threadIdx.x == 0) { t_wait += now_ns() - tw0; ++n_units; }
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int j = ci; j < un.y && ci < NU; j += NU) {
+            const int slice = un.x + j;
+            const int s0 = __ldg(F.sptr + slice), s1 = __ldg(F.sptr + slice + 1), w = s1 - s0;
+            const int row = 32 * slice + lane;
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+            if (ci < NR) {
+                for (int k0 = 0; k0 < w; k0 += kTailChunk, ++cnt) {
+                    const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                    mbar_wait(&s_full[ci][b2], (cnt >> 1) & 1);
+                    const unsigned char* buf = ring + (size_t) (2 * ci + b2) * kTailBufBytes;
+                    const double* vs = reinterpret_cast<const double*>(buf) + lane;
+                    const int* cs = reinterpret_cast<const int*>(buf + kTailChunk * 2304) + lane;
+                    double xr[kTailChunk][3];
+#pragma unroll
+                    for (int k = 0; k < kTailChunk; ++k)
+                        if (k < n) {
+                            const double* xx = x + 3 * (size_t) cs[32 * k];
+                            xr[k][0] = __ldcg(xx); xr[k][1] = __ldcg(xx + 1); xr[k][2] = __ldcg(xx + 2);
+                        }
+#pragma unroll
+                    for (int k = 0; k < kTailChunk; ++k)
+                        if (k < n) {
+                            const double* v = vs + 288 * k;
+                            y0 += v[0] * xr[k][0] + v[32] * xr[k][1] + v[64] * xr[k][2];
+                            y1 += v[96] * xr[k][0] + v[128] * xr[k][1] + v[160] * xr[k][2];
+                            y2 += v[192] * xr[k][0] + v[224] * xr[k][1] + v[256] * xr[k][2];
+                        }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[ci][b2]);
+                }
+            } else {
+                const double* v = F.sval + (size_t) s0 * 288 + lane;
+                const int* c = F.scol + (size_t) s0 * 32 + lane;
+#pragma unroll 2
+                for (int k = s0; k < s1; ++k, v += 288, c += 32) {
+                    const double* xx = x + 3 * (size_t) __ldg(c);
+                    const double x0 = __ldcg(xx), x1 = __ldcg(xx + 1), x2 = __ldcg(xx + 2);
+                    y0 += __ldg(v) * x0 + __ldg(v + 32) * x1 + __ldg(v + 64) * x2;
+                    y1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
+                    y2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
+                }
+            }
+            if (__ldg(F.sover + slice) && row < F.Nb) {
+                for (int k = __ldg(F.prow + row) + w, ke = __ldg(F.prow + row + 1); k < ke; ++k) {
+                    const double* a = F.A + (size_t) k * 9;
+                    const double* xx = x + 3 * (size_t) __ldg(F.pcol + k);
+                    const double x0 = __ldcg(xx), x1 = __ldcg(xx + 1), x2 = __ldcg(xx + 2);
+                    y0 += __ldg(a) * x0 + __ldg(a + 1) * x1 + __ldg(a + 2) * x2;
+                    y1 += __ldg(a + 3) * x0 + __ldg(a + 4) * x1 + __ldg(a + 5) * x2;
+                    y2 += __ldg(a + 6) * x0 + __ldg(a + 7) * x1 + __ldg(a + 8) * x2;
+                }
+            }
+            if (row < F.Nb) {
+                double* yy = F.y + 3 * (size_t) row;
+                yy[0] = y0; yy[1] = y1; yy[2] = y2;
+                const double* dd = F.d1 + 3 * (size_t) row;
+                const double e0 = __ldg(dd), e1 = __ldg(dd + 1), e2 = __ldg(dd + 2);
+                if (MODE == 1) acc0 += e0 * y0 + e1 * y1 + e2 * y2;
+                if (MODE == 2) { acc0 += y0 * e0 + y1 * e1 + y2 * e2; acc1 += y0 * y0 + y1 * y1 + y2 * y2; }
+            }
+        }
+        acc0 = warp_sum(acc0);
+        if (MODE == 2) acc1 = warp_sum(acc1);
+        if (lane == 0) { s_red[0][warp] = acc0; s_red[1][warp] = acc1; }
+        named_barrier(2, NC * 32);
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < nwarp; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+            F.partials[u] = a;
+            if (MODE == 2) F.partials[F.nunits + u] = b;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (F.dbg) { F.dbg[4 * part + 1] = now_ns(); F.dbg[4 * part + 2] = n_units; F.dbg[4 * part + 3] = t_wait; }
+        __threadfence();
+        s_last = atomicAdd(F.sync + 1, 1) == (int) gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (F.dbg && threadIdx.x == 0) {
+        long long first = LLONG_MAX, last = 0, end = 0, waited = 0, busy = 0;
+        for (int p = 0; p < P.nparts; ++p) {
+            const long long d = __ldcg(F.dbg + 4 * p), e = __ldcg(F.dbg + 4 * p + 1);
+            first = min(first, d); last = max(last, d); end = max(end, e); waited += __ldcg(F.dbg + 4 * p + 3); busy += e - d;
+        }
+        printf("fused sweep+spmv: first part done at 0, last part done +%.1f us, kernel end +%.1f us; SpMV CTA time %.1f us x CTA, of which %.1f waiting for parts\n",
+               (last - first) * 1e-3, (end - first) * 1e-3, busy * 1e-3 / P.nparts, waited * 1e-3 / P.nparts);
+        for (int p = 0; p < P.nparts; p += max(1, P.nparts / 12))
+            printf("  part %3d: done +%.1f us, exit +%.1f us, %lld units, waited %.1f us\n", p, (__ldcg(F.dbg + 4 * p) - first) * 1e-3,
+                   (__ldcg(F.dbg + 4 * p + 1) - first) * 1e-3, __ldcg(F.dbg + 4 * p + 2), __ldcg(F.dbg + 4 * p + 3) * 1e-3);
+    }
+    double a = 0.0, b = 0.0;
+    for (int u = threadIdx.x; u < F.nunits; u += blockDim.x) {
+        a += __ldcg(F.partials + u);
+        if (MODE == 2) b += __ldcg(F.partials + F.nunits + u);
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { s_red[0][warp] = a; s_red[1][warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0.0; b = 0.0;
+        for (int w = 0; w < nwarp; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+        if (MODE == 1) P.S->h = a;
+        if (MODE == 2) { P.S->tr = a; P.S->tt = b; }
+    }
+}
+
+// SPMV: -1 = sweep only; 1 / 2 = the CTA goes on with the SpMV that follows (fused_spmv_tail<SPMV>)
+constexpr int kFusedMaxThreads = 384;
+template <bool LOWER, bool REARM, bool TRACE, int SPMV = -1>
+__global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     if (P.check_done && P.S->done) return;
@@ -579,10 +801,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
                 }
             }
         }
-        return;
-    }
-
-    if (warp > NW) {                                // ---- helpers: external rows ----
+    } else if (warp > NW) {                         // ---- helpers: external rows ----
         // The stage's external rows are listed in the order the levels need them.  A helper keeps a WINDOW of
         // kHelperWindow x 32 rows in flight (one row per lane and sub-batch, three 8-byte loads each), parks every row as
         // soon as it has arrived and publishes the length of the finished PREFIX of the list: the consumers of a level
@@ -655,9 +874,7 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
             if (TRACE && t3 && lane == 0) t3[1] = clock64();
             if (lane == 0) mbar_arrive(empty + s);
         }
-        return;
-    }
-
+    } else {
     // ---- consumers ----
     const int q = lane / 3, comp = lane - 3 * q;
     const int nthreads = NW * 32;
@@ -757,6 +974,8 @@ __global__ void __launch_bounds__(896) k_sweep(const SweepArgs P)
         if (lane == 0) mbar_arrive(empty + s);
         if (++s == nslots) { s = 0; parity ^= 1; }
     }
+    }
+    if constexpr (SPMV >= 0) fused_spmv_tail<SPMV>(P, part, sweep_smem);
 }
 
 // ---- BSR SpMV with fused dot products ----------------------------------------------------------
