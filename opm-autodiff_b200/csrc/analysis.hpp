@@ -274,8 +274,11 @@ inline FusedPlan build_fused(int Nb, const std::vector<int>& prow, const std::ve
         int k = INT32_MAX;
         for (int r = r0; r < r1; ++r) {
             auto touch = [&](int p) { if (mark[p] != u) { mark[p] = u; needOf[u].push_back(p); k = std::min(k, minlev[p]); } };
+            // the vector entries are gathered through L1: every row that shares a 128-byte line with a gathered one (rows
+            // are 24 bytes) must be final too
+            auto touch_row = [&](int c) { touch(partOfRow[std::max(0, c - 6)]); touch(partOfRow[c]); touch(partOfRow[std::min(Nb - 1, c + 6)]); };
             touch(partOfRow[r]);
-            for (int e = prow[r]; e < prow[r + 1]; ++e) touch(partOfRow[pcol[e]]);
+            for (int e = prow[r]; e < prow[r + 1]; ++e) touch_row(pcol[e]);
         }
         key[u] = k; order[u] = u;
     }

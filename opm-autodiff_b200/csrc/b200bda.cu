@@ -60,10 +60,10 @@ struct DevBuf {
 };
 
 enum Kind { K_PERMUTE, K_INIT, K_FACTOR, K_SLICES, K_LOWER, K_UPPER, K_SPMV, K_WELL, K_VEC_P, K_VEC_XR1, K_VEC_XR2,
-            K_UNPERMUTE, K_MISC, K_HALO_PUSH, K_SPMV_GHOST, K_ALLREDUCE, K_FINISH, K_COUNT };
+            K_UNPERMUTE, K_MISC, K_HALO_PUSH, K_SPMV_GHOST, K_ALLREDUCE, K_FINISH, K_UPPER_SPMV, K_COUNT };
 static const char* kKindNames[K_COUNT] = {"permute", "init", "ilu_factor", "ilu_stream", "ilu_lower", "ilu_upper", "spmv",
                                           "well_apply", "vec_p", "vec_xr1", "vec_xr2", "unpermute", "misc",
-                                          "halo_push", "spmv_ghost", "allreduce", "finish"};
+                                          "halo_push", "spmv_ghost", "allreduce", "finish", "ilu_upper_spmv"};
 
 // ---- NCCL, bound at run time ------------------------------------------------------------------------
 // Only the multi-GPU entry points need NCCL, and a Python host already has torch's libnccl.so.2 mapped:
@@ -271,6 +271,7 @@ struct Solver {
             case K_SPMV: return 76.0 * nz + 52.0 * nb;
             case K_LOWER: return 76.0 * nnzL + 52.0 * nb;
             case K_UPPER: return 76.0 * (nz - nnzL) + 52.0 * nb;
+            case K_UPPER_SPMV: return 76.0 * (nz - nnzL) + 52.0 * nb + 76.0 * nz + 52.0 * nb;     // the sweep and the product it also runs
             case K_FACTOR: return 148.0 * nz + 8.0 * nb;
             case K_VEC_P: return 96.0 * nb;
             case K_VEC_XR1: return 144.0 * nb;
@@ -429,7 +430,7 @@ struct Solver {
         fused_units = 0;
         if (want_fused && threads <= kFusedMaxThreads) {
             prep(k_sweep<false, true, false, 1>); prep(k_sweep<false, true, false, 2>);
-            const b200::FusedPlan fp = b200::build_fused(Nb, an.prow, an.pcol, an.partPtr, an.flevPtr, an.flevRows, 4 * (threads / 32 - 1));
+            const b200::FusedPlan fp = b200::build_fused(Nb, an.prow, an.pcol, an.partPtr, an.flevPtr, an.flevRows, std::max(1, fuse_unit_slices) * (threads / 32 - 1));
             fused_units = (int) fp.units.size() / 2;
             up(d_fUnits, fp.units); up(d_fNeedPtr, fp.needPtr); up(d_fNeed, fp.need);
             d_fSync.alloc(2 + an.nparts); d_fPartials.alloc((size_t) 2 * fused_units);
@@ -655,7 +656,7 @@ struct Solver {
     template <int MODE>
     void trsv_upper_spmv(const double* rhs, double* out, double* rearm, double* y, const double* d1)
     {
-        int id = prof_begin(K_UPPER);
+        int id = prof_begin(K_UPPER_SPMV);
         CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
         SweepArgs a = sweep_args(false, rhs, out, rearm, true);
         a.f.sptr = d_sellPtr.p; a.f.sover = d_sellOver.p; a.f.scol = d_sellCol.p; a.f.sval = d_sellVal.p;
@@ -667,8 +668,9 @@ struct Solver {
         k_sweep<false, true, false, MODE><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
         prof_end(id);
     }
-    bool fused_now() const { return fused_units > 0 && !sweep_trace && !dist.enabled && !(profile && !fuse_in_profile); }
-    int fuse_in_profile = 0, fuse_debug = 0;
+    bool fused_now() const { return fused_units > 0 && !sweep_trace && !dist.enabled; }
+    int fuse_debug = 0;
+    int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
     DevBuf<long long> d_fDbg;
     template <int MODE>
     void spmv(const double* x, double* y, const double* d1)
@@ -830,9 +832,11 @@ struct Solver {
         }
         CUDA_OK(cudaGraphLaunch(iter_graph_exec, stream));
         stats[K_VEC_P].launches++; stats[K_VEC_XR1].launches++; stats[K_VEC_XR2].launches++;
-        stats[K_LOWER].launches += 2; stats[K_UPPER].launches += 2; stats[K_SPMV].launches += 2;
+        stats[K_LOWER].launches += 2;
+        if (fused_now()) stats[K_UPPER_SPMV].launches += 2;
+        else { stats[K_UPPER].launches += 2; stats[K_SPMV].launches += 2; }
         if (nwells) stats[K_WELL].launches += 2;
-        launch_count += 9 + (nwells ? 2 : 0);
+        launch_count += (fused_now() ? 7 : 9) + (nwells ? 2 : 0);
     }
 
     // permutation + ILU0 + BiCGSTAB on the resident system
@@ -990,8 +994,8 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "profile") s->profile = value != 0.0;
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = value != 0.0; }
-        else if (k == "fuse_in_profile") s->fuse_in_profile = value != 0.0;
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
+        else if (k == "fuse_unit_slices") s->fuse_unit_slices = (int) value;
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
         else if (k == "sweep_helper_sleep") s->sweep_helper_sleep = std::max(0, (int) value);
@@ -1592,8 +1596,9 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
         for (int it = -2; it < reps; ++it) {                      // two warm-up launches
             CUDA_OK(cudaMemcpyAsync(s->d_S.p, &hs, sizeof hs, cudaMemcpyHostToDevice, s->stream));
             if (kind == K_LOWER || kind == -2) s->fill(s->d_w.p, host_sentinel());
-            if (kind == K_UPPER || kind == -2) s->fill(s->d_y.p, host_sentinel());
-            if (kind == K_UPPER) CUDA_OK(cudaMemcpyAsync(s->d_w.p, s->d_tmp2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
+            if (kind == K_UPPER || kind == -2 || kind == K_UPPER_SPMV) s->fill(s->d_y.p, host_sentinel());
+            if (kind == K_UPPER_SPMV && !s->fused_now()) throw std::runtime_error("the fused upper sweep + SpMV is not active for this system");
+            if (kind == K_UPPER || kind == K_UPPER_SPMV) CUDA_OK(cudaMemcpyAsync(s->d_w.p, s->d_tmp2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
             if (kind == K_VEC_XR1 || kind == K_VEC_XR2 || kind == K_WELL || kind == K_SPMV)
                 CUDA_OK(cudaMemcpyAsync(s->d_y.p, s->d_tmp2.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, s->stream));
             if (flush_l2) {
@@ -1605,6 +1610,7 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
                 case K_SPMV: s->spmv<0>(s->d_y.p, s->d_t.p, nullptr); break;
                 case K_LOWER: s->trsv_lower(s->d_tmp2.p, s->d_w.p, false); break;
                 case K_UPPER: s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, false); break;
+                case K_UPPER_SPMV: s->trsv_upper_spmv<1>(s->d_w.p, s->d_y.p, s->d_w.p, s->d_t.p, s->d_tmp2.p); break;
                 case -2: s->trsv_lower(s->d_tmp2.p, s->d_w.p, false); s->trsv_upper(s->d_w.p, s->d_y.p, nullptr, false); break;
                 case K_FACTOR: s->factorize(); break;
                 case K_PERMUTE: s->permute_values(); break;

@@ -439,6 +439,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsig
     }
 }
 // 1-D bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -558,9 +569,11 @@ __device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile
 // that have nothing left to sweep take units, so a sweeping part never shares its SM with the SpMV (a second grid on the
 // same SMs slowed the sweep by 45 %).  With 11 warps per SM plain loads cannot keep enough bytes in flight (13 GB/s per SM
 // measured), so the producer warp streams the sliced-ELL values and columns of the unit's slices with cp.async.bulk into
-// a ring over the (now free) dynamic shared memory and the other warps compute from there; only the gather of the input
-// vector (written by other SMs during this launch: ld.cg) is a register load.  Slices wider than kTailW slots take the
-// plain-load path.  Dot products: one partial per UNIT, summed in unit order by the last CTA to finish -- deterministic
+// per-warp rings over the (now free) dynamic shared memory and the other warps compute from there; only the gather of
+// the input vector is a register load.  That vector was written by other SMs during this launch, but the gather may use
+// L1 (with ld.cg every 8-byte load is its own L2 request and the tail is bound by the SM's request rate): a unit's `need`
+// list names the owner of every row within 6 rows (a 128-byte line) of any row it touches, so a line fetched into L1 never
+// holds a row that is still to be written.  Dot products: one partial per UNIT, summed in unit order by the last CTA to finish -- deterministic
 // whoever took a unit.
 constexpr int kMaxSweepParts = 1024, kTailChunk = 4, kTailBufBytes = kTailChunk * (2304 + 128), kTailMaxCons = 16;
 template <int MODE>
@@ -587,8 +600,8 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();                       // every row of this part is stored; the sweep's shared memory is free
-    long long t_wait = 0;
-    int n_units = 0;
+    long long t_wait = 0, t_full = 0, t_top = 0;
+    int n_units = 0, n_chunks = 0;
     auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     if (F.dbg && threadIdx.x == 0) F.dbg[4 * part] = now_ns();
     if (threadIdx.x == 0) {
@@ -600,23 +613,39 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
     const double* x = P.out;
     int cnt = 0;                           // chunks this warp has consumed (consumer) / this lane has issued for consumer `lane` (producer)
     for (int it = 0;; ++it) {
+        const long long tt0 = F.dbg && threadIdx.x == 0 ? now_ns() : 0;
         __syncthreads();
+        if (F.dbg && threadIdx.x == 0) t_top += now_ns() - tt0;
         const int u = s_unit[it & 1];
         if (u >= F.nunits) break;
         const int2 un = __ldg(F.units + u);
         if (warp == PW) {                                      // ---- producer: lane c feeds consumer c
-            if (lane < NR)
-                for (int j = lane; j < un.y; j += NU) {
-                    const int s0 = __ldg(F.sptr + un.x + j), w = __ldg(F.sptr + un.x + j + 1) - s0;
-                    for (int k0 = 0; k0 < w; k0 += kTailChunk, ++cnt) {
-                        const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
-                        if (cnt >= 2) mbar_wait_relaxed(&s_empty[lane][b2], ((cnt >> 1) - 1) & 1);
+            // one converged loop with non-blocking barrier tests: lanes that slept in private wait loops would serialise
+            // (nine lanes x 200 ns of sleep per poll round = the whole ring starves)
+            int j = lane, k0 = 0, s0 = 0, w = 0;
+            auto next_slice = [&]() {
+                for (; j < un.y; j += NU) {
+                    s0 = __ldg(F.sptr + un.x + j); w = __ldg(F.sptr + un.x + j + 1) - s0; k0 = 0;
+                    if (w > 0) return true;
+                }
+                return false;
+            };
+            bool active = lane < NR && next_slice();
+            while (__any_sync(kFull, active)) {
+                bool issued = false;
+                if (active) {
+                    const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                    if (cnt < 2 || mbar_test(&s_empty[lane][b2], ((cnt >> 1) - 1) & 1)) {
                         unsigned char* buf = ring + (size_t) (2 * lane + b2) * kTailBufBytes;
                         mbar_expect_tx(&s_full[lane][b2], (unsigned) n * (2304 + 128));
                         bulk_g2s(buf, F.sval + (size_t) (s0 + k0) * 288, (unsigned) n * 2304, &s_full[lane][b2]);
                         bulk_g2s(buf + kTailChunk * 2304, F.scol + (size_t) (s0 + k0) * 32, (unsigned) n * 128, &s_full[lane][b2]);
+                        ++cnt; k0 += kTailChunk; issued = true;
+                        if (k0 >= w) { j += NU; active = next_slice(); }
                     }
                 }
+                if (!__any_sync(kFull, issued)) __nanosleep(64);
+            }
             continue;
         }
         // ---- consumers
@@ -645,7 +674,9 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
             if (ci < NR) {
                 for (int k0 = 0; k0 < w; k0 += kTailChunk, ++cnt) {
                     const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                    const long long tf0 = F.dbg && threadIdx.x == 0 ? now_ns() : 0;
                     mbar_wait(&s_full[ci][b2], (cnt >> 1) & 1);
+                    if (F.dbg && threadIdx.x == 0) { t_full += now_ns() - tf0; ++n_chunks; }
                     const unsigned char* buf = ring + (size_t) (2 * ci + b2) * kTailBufBytes;
                     const double* vs = reinterpret_cast<const double*>(buf) + lane;
                     const int* cs = reinterpret_cast<const int*>(buf + kTailChunk * 2304) + lane;
@@ -654,7 +685,7 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
                     for (int k = 0; k < kTailChunk; ++k)
                         if (k < n) {
                             const double* xx = x + 3 * (size_t) cs[32 * k];
-                            xr[k][0] = __ldcg(xx); xr[k][1] = __ldcg(xx + 1); xr[k][2] = __ldcg(xx + 2);
+                            xr[k][0] = xx[0]; xr[k][1] = xx[1]; xr[k][2] = xx[2];
                         }
 #pragma unroll
                     for (int k = 0; k < kTailChunk; ++k)
@@ -673,7 +704,7 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
 #pragma unroll 2
                 for (int k = s0; k < s1; ++k, v += 288, c += 32) {
                     const double* xx = x + 3 * (size_t) __ldg(c);
-                    const double x0 = __ldcg(xx), x1 = __ldcg(xx + 1), x2 = __ldcg(xx + 2);
+                    const double x0 = xx[0], x1 = xx[1], x2 = xx[2];
                     y0 += __ldg(v) * x0 + __ldg(v + 32) * x1 + __ldg(v + 64) * x2;
                     y1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
                     y2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
@@ -683,7 +714,7 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
                 for (int k = __ldg(F.prow + row) + w, ke = __ldg(F.prow + row + 1); k < ke; ++k) {
                     const double* a = F.A + (size_t) k * 9;
                     const double* xx = x + 3 * (size_t) __ldg(F.pcol + k);
-                    const double x0 = __ldcg(xx), x1 = __ldcg(xx + 1), x2 = __ldcg(xx + 2);
+                    const double x0 = xx[0], x1 = xx[1], x2 = xx[2];
                     y0 += __ldg(a) * x0 + __ldg(a + 1) * x1 + __ldg(a + 2) * x2;
                     y1 += __ldg(a + 3) * x0 + __ldg(a + 4) * x1 + __ldg(a + 5) * x2;
                     y2 += __ldg(a + 6) * x0 + __ldg(a + 7) * x1 + __ldg(a + 8) * x2;
@@ -710,7 +741,8 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
         }
     }
     if (threadIdx.x == 0) {
-        if (F.dbg) { F.dbg[4 * part + 1] = now_ns(); F.dbg[4 * part + 2] = n_units; F.dbg[4 * part + 3] = t_wait; }
+        if (F.dbg) { F.dbg[4 * part + 1] = now_ns(); F.dbg[4 * part + 2] = n_units; F.dbg[4 * part + 3] = t_wait;
+            if (part % 12 == 0) printf("    part %d warp 0: %d units, %d chunks, %.1f us waiting for chunks, %.1f us at the unit barrier, %.1f us waiting for parts, NR %d\n", part, n_units, n_chunks, t_full * 1e-3, t_top * 1e-3, t_wait * 1e-3, NR); }
         __threadfence();
         s_last = atomicAdd(F.sync + 1, 1) == (int) gridDim.x - 1;
     }

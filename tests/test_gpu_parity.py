@@ -349,3 +349,51 @@ def test_spmv_layouts_with_very_long_rows(mods, sell):
     for seed in (1, 2):
         x = np.random.default_rng(seed).normal(size=3 * Nb) * np.tile([1e5, 1.0, 1.0], Nb)
         assert relerr(be.spmv(x), oracle.spmv(rows, cols, vals, x)) < 1e-14
+
+
+@pytest.mark.parametrize("opts", [{}, {"sweep_parts": 5}, {"sweep_parts": 37, "sweep_stage_bytes": 8192, "fuse_unit_slices": 1}])
+def test_spmv_inside_the_upper_sweep_matches_separate_kernels(mods, opts):
+    """Single GPU: the upper-sweep CTAs run the following SpMV as their parts finish (fuse_spmv, default).  Same solution and
+    iteration count as with separate kernels, on a faulted grid with wells and on a pattern with rows of ~45 blocks (tail of a
+    row read from the BSR arrays inside the fused kernel)."""
+    bridge, synth, oracle = mods
+    s = synth.small(20, 16, 12, faults=((7, 2),), nwells=3, nperf=5)
+    out = {}
+    for fuse in (1, 0):
+        _, st, res, x = _solve(bridge, s, tol=1e-10, maxit=300, opts=dict(opts, fuse_spmv=fuse))
+        assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and res.converged
+        out[fuse] = (res.it, x)
+    assert out[1][0] == out[0][0] and relerr(out[1][1], out[0][1]) < 1e-9
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=300)
+    assert relerr(out[1][1], ref.x) <= 1e-6 and abs(out[1][0] - ref.it) <= max(1.0, 0.1 * ref.it)
+    # long rows
+    rows, cols, vals = _irregular_system(synth, (12, 9, 7), 0.2, seed=9)
+    Nb = len(rows) - 1
+    rng = np.random.default_rng(4)
+    nb = {}
+    hub_rows = {5: rng.choice(Nb, 40, replace=False), Nb - 3: rng.choice(Nb, 40, replace=False)}
+    r2, c2, v2 = [0], [], []
+    for i in range(Nb):
+        ent = {int(cols[k]): vals[k] for k in range(rows[i], rows[i + 1])}
+        for c in hub_rows.get(i, ()):
+            ent.setdefault(int(c), rng.uniform(-1, 1, (3, 3)) * 1e-4 * np.array([1e-7, 1.0, 1.0])[None, :])
+        for c in sorted(ent):
+            c2.append(c); v2.append(ent[c])
+        r2.append(len(c2))
+    rows, cols, vals = np.array(r2, np.int32), np.array(c2, np.int32), np.array(v2)
+    xt = rng.uniform(-1, 1, 3 * Nb) * np.tile([1e5, 1.0, 1.0], Nb)
+    b = oracle.spmv(rows, cols, vals, xt)
+    sol = {}
+    for fuse in (1, 0):
+        be = bridge.B200SolverBackend(0, 300, 1e-10, 0)
+        for k, v in dict(opts, fuse_spmv=fuse).items():
+            be.set_option(k, v)
+        be.upload_system(3 * Nb, 9 * len(cols), 3, vals, rows, cols, b, None)
+        res = bridge.BdaResult()
+        be.solve_resident(res)
+        x = np.zeros(3 * Nb); be.get_result(x)
+        assert res.converged
+        sol[fuse] = (res.it, x)
+    assert sol[1][0] == sol[0][0] and relerr(sol[1][1], sol[0][1]) < 1e-9
+    ref = oracle.solve(rows, cols, vals, b, None, tol=1e-10, maxit=300)
+    assert relerr(sol[1][1], ref.x) <= 1e-6
