@@ -407,7 +407,7 @@ struct Solver {
         const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 8 * kXs + kSweepTailPad;
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
-        const bool want_fused = fuse_spmv && sell_slices && !dist.enabled && an.nparts <= kMaxSweepParts;
+        const bool want_fused = fuse_spmv && sell_slices && an.nparts <= kMaxSweepParts;
         const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_limit || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
@@ -668,7 +668,7 @@ struct Solver {
         k_sweep<false, true, false, MODE><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
         prof_end(id);
     }
-    bool fused_now() const { return fused_units > 0 && !sweep_trace && !dist.enabled; }
+    bool fused_now() const { return fused_units > 0 && !sweep_trace; }
     int fuse_debug = 0;
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
     DevBuf<long long> d_fDbg;
@@ -771,8 +771,10 @@ struct Solver {
         k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
         trsv_lower(d_p.p, d_w.p, true);
-        if (fused_now()) trsv_upper_spmv<1>(d_w.p, d_y.p, d_w.p, d_v.p, d_rt.p);
-        else {
+        if (fused_now()) {
+            trsv_upper_spmv<1>(d_w.p, d_y.p, d_w.p, d_v.p, d_rt.p);
+            halo_push(d_y.p, true);       // multi-GPU: the neighbours' boundary rows wait for it in spmv_ghost
+        } else {
             trsv_upper(d_w.p, d_y.p, d_w.p, true);
             halo_push(d_y.p, true);
             spmv<1>(d_y.p, d_v.p, d_rt.p);
@@ -785,8 +787,10 @@ struct Solver {
         prof_end(id);
         reduce_phase<2>();
         trsv_lower(d_r.p, d_w.p, true);
-        if (fused_now()) trsv_upper_spmv<2>(d_w.p, d_y.p, d_w.p, d_t.p, d_r.p);
-        else {
+        if (fused_now()) {
+            trsv_upper_spmv<2>(d_w.p, d_y.p, d_w.p, d_t.p, d_r.p);
+            halo_push(d_y.p, true);
+        } else {
             trsv_upper(d_w.p, d_y.p, d_w.p, true);
             halo_push(d_y.p, true);
             spmv<2>(d_y.p, d_t.p, d_r.p);
