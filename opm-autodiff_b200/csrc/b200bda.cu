@@ -274,8 +274,8 @@ struct Solver {
             case K_UPPER_SPMV: return 76.0 * (nz - nnzL) + 52.0 * nb + 76.0 * nz + 52.0 * nb;     // the sweep and the product it also runs
             case K_FACTOR: return 148.0 * nz + 8.0 * nb;
             case K_VEC_P: return 96.0 * nb;
-            case K_VEC_XR1: return 144.0 * nb;
-            case K_VEC_XR2: return 168.0 * nb;
+            case K_VEC_XR1: return (defer_now() ? 72.0 : 144.0) * nb;      // deferred x update: r, v read, r written
+            case K_VEC_XR2: return (defer_now() ? 96.0 : 168.0) * nb;
             case K_WELL: return 272.0 * nwblocks + 128.0 * nwells;
             case K_PERMUTE: return (sell_slices ? 296.0 : 148.0) * nz;
             default: return 0.0;
@@ -427,6 +427,13 @@ struct Solver {
         };
         prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
         prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
+        defer_ok = false;
+        if (defer_x && threads <= kFusedMaxThreads) {
+            prep(k_sweep<true, false, false, 3>);
+            d_xSync.alloc(2);
+            CUDA_OK(cudaMemsetAsync(d_xSync.p, 0, sizeof(int) * 2, stream));
+            defer_ok = true;
+        }
         fused_units = 0;
         if (want_fused && threads <= kFusedMaxThreads) {
             prep(k_sweep<false, true, false, 1>); prep(k_sweep<false, true, false, 2>);
@@ -434,6 +441,7 @@ struct Solver {
             fused_units = (int) fp.units.size() / 2;
             up(d_fUnits, fp.units); up(d_fNeedPtr, fp.needPtr); up(d_fNeed, fp.need);
             d_fSync.alloc(2 + an.nparts); d_fPartials.alloc((size_t) 2 * fused_units);
+            CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
             CUDA_OK(cudaStreamSynchronize(stream));            // fp is a temporary
         }
         if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
@@ -640,6 +648,19 @@ struct Solver {
         if (trace) { if (rearm) go(k_sweep<LOWER, true, true>); else go(k_sweep<LOWER, false, true>); }
         else { if (rearm) go(k_sweep<LOWER, true, false>); else go(k_sweep<LOWER, false, false>); }
     }
+    // lower sweep whose CTAs then apply the pending solution update x += pend * y (kernels.cuh xupdate_tail)
+    void trsv_lower_xupdate(const double* rhs, double* out)
+    {
+        int id = prof_begin(K_LOWER);
+        SweepArgs a = sweep_args(true, rhs, out, nullptr, true);
+        a.xu.x = d_x.p; a.xu.y = d_y.p; a.xu.sync = d_xSync.p; a.xu.n = N;
+        k_sweep<true, false, false, 3><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
+        prof_end(id);
+    }
+    bool defer_now() const { return defer_x && defer_ok && !sweep_trace; }
+    int defer_x = 1;                   // option
+    bool defer_ok = false;             // the tail kernel fits (set by the analysis)
+    DevBuf<int> d_xSync;
     void trsv_lower(const double* rhs, double* out, bool check_done)
     {
         int id = prof_begin(K_LOWER);
@@ -657,7 +678,6 @@ struct Solver {
     void trsv_upper_spmv(const double* rhs, double* out, double* rearm, double* y, const double* d1)
     {
         int id = prof_begin(K_UPPER_SPMV);
-        CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
         SweepArgs a = sweep_args(false, rhs, out, rearm, true);
         a.f.sptr = d_sellPtr.p; a.f.sover = d_sellOver.p; a.f.scol = d_sellCol.p; a.f.sval = d_sellVal.p;
         a.f.prow = d_prow.p; a.f.pcol = d_pcol.p; a.f.A = d_A.p; a.f.y = y; a.f.d1 = d1;
@@ -770,7 +790,7 @@ struct Solver {
         id = prof_begin(K_VEC_P);
         k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
-        trsv_lower(d_p.p, d_w.p, true);
+        if (defer_now()) trsv_lower_xupdate(d_p.p, d_w.p); else trsv_lower(d_p.p, d_w.p, true);
         if (fused_now()) {
             trsv_upper_spmv<1>(d_w.p, d_y.p, d_w.p, d_v.p, d_rt.p);
             halo_push(d_y.p, true);       // multi-GPU: the neighbours' boundary rows wait for it in spmv_ghost
@@ -783,10 +803,10 @@ struct Solver {
         spmv_ghost<1>(d_v.p, d_rt.p, true);
         reduce_phase<1>();
         id = prof_begin(K_VEC_XR1);
-        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
+        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
         prof_end(id);
         reduce_phase<2>();
-        trsv_lower(d_r.p, d_w.p, true);
+        if (defer_now()) trsv_lower_xupdate(d_r.p, d_w.p); else trsv_lower(d_r.p, d_w.p, true);
         if (fused_now()) {
             trsv_upper_spmv<2>(d_w.p, d_y.p, d_w.p, d_t.p, d_r.p);
             halo_push(d_y.p, true);
@@ -799,7 +819,7 @@ struct Solver {
         spmv_ghost<2>(d_t.p, d_r.p, true);
         reduce_phase<3>();
         id = prof_begin(K_VEC_XR2);
-        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm);
+        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
         prof_end(id);
         reduce_phase<4>();
     }
@@ -814,7 +834,7 @@ struct Solver {
         if (!use_graph || profile || dist.enabled || sweep_trace) { enqueue_iteration(); return; }
         IterSig sig{};
         sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
-        sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0);
+        sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0) + (defer_now() ? 1 << 21 : 0);
         if (!iter_graph_exec || sig != iter_sig) {
             if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -858,6 +878,9 @@ struct Solver {
                                                         d_partials.p, d_ticket.p, tolerance, 2 * maxit, dist.enabled ? 1 : 0);
         prof_end(id);
         reduce_phase<0>();
+        // the sweep tails leave their counters and flags zeroed; once per solve in case a launch was cut short
+        if (fused_units) CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
+        if (defer_ok) CUDA_OK(cudaMemsetAsync(d_xSync.p, 0, sizeof(int) * 2, stream));
         int enq = 0;
         while (true) {
             // `lookahead` iterations per convergence read-back: once the device has set `done` the kernels of the
@@ -872,7 +895,7 @@ struct Solver {
             if (h_S->done || h_S->singular || h_S->trsv_timeout || enq >= maxit) break;
         }
         id = prof_begin(K_UNPERMUTE);
-        k_scatter_vec<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d_x.p, d_perm.p, d_xnat.p, N);
+        k_scatter_solution<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(d_x.p, d_y.p, d_perm.p, d_xnat.p, N, d_S.p);
         prof_end(id);
         CUDA_OK(cudaEventRecord(ev_c, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
@@ -999,6 +1022,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = value != 0.0; }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
+        else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = value != 0.0; }
         else if (k == "fuse_unit_slices") s->fuse_unit_slices = (int) value;
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;
@@ -1621,9 +1645,9 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
                 case K_VEC_P: s->stats[K_VEC_P].launches++; s->launch_count++;
                     k_vec_p<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_tmp2.p, s->d_p.p, s->d_v.p, N, s->d_S.p); break;
                 case K_VEC_XR1: s->stats[K_VEC_XR1].launches++; s->launch_count++;
-                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0); break;
+                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0); break;
                 case K_VEC_XR2: s->stats[K_VEC_XR2].launches++; s->launch_count++;
-                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0); break;
+                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0); break;
                 case K_WELL: s->wells_apply<0>(s->d_y.p, s->d_t.p, nullptr); break;
                 default: throw std::runtime_error(std::string("kernel '") + which + "' cannot be timed in isolation");
             }

@@ -32,6 +32,10 @@ struct Scalars {
     double rho, rho_new, alpha, omega, h, tr, tt, norm, norm0, tol;
     double red[2];      // multi-GPU: raw local sums waiting for the all-reduce (k_finish consumes them)
     int it_half, done, converged, breakdown, first, max_half, trsv_timeout, singular;
+    // deferred solution update: x += pend * y has not been applied yet (done by the idle CTAs of the next lower sweep, or
+    // folded into the final scatter when the solve ends first)
+    int pend_on, pad_;
+    double pend;
 };
 
 __device__ __forceinline__ double ld_relaxed(const double* p)
@@ -126,6 +130,18 @@ __global__ void __launch_bounds__(256) k_gather_vec(const double* __restrict__ i
         out_p[i] = in_nat[3 * perm[q] + (i - 3 * q)];
     }
 }
+// the solution, natural order, including a solution update that is still pending (Scalars::pend_on)
+__global__ void __launch_bounds__(256) k_scatter_solution(const double* __restrict__ x_p, const double* __restrict__ y_p,
+                                                          const int* __restrict__ perm, double* __restrict__ out_nat, int N,
+                                                          const Scalars* __restrict__ S)
+{
+    const bool on = S->pend_on != 0;
+    const double a = S->pend;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        int q = i / 3;
+        out_nat[3 * perm[q] + (i - 3 * q)] = on ? x_p[i] + a * y_p[i] : x_p[i];
+    }
+}
 __global__ void __launch_bounds__(256) k_scatter_vec(const double* __restrict__ in_p, const int* __restrict__ perm,
                                                      double* __restrict__ out_nat, int N)
 {
@@ -148,7 +164,7 @@ __device__ __forceinline__ void finish_init(Scalars* S, double rr, double tol, i
     S->norm0 = sqrt(rr); S->norm = S->norm0; S->rho_new = rr;
     S->rho = 1.0; S->alpha = 1.0; S->omega = 1.0; S->h = 0.0; S->tr = 0.0; S->tt = 0.0;
     S->tol = tol; S->it_half = 0; S->converged = 0; S->breakdown = 0; S->first = 1;
-    S->max_half = max_half; S->trsv_timeout = 0;
+    S->max_half = max_half; S->trsv_timeout = 0; S->pend_on = 0; S->pend = 0.0;
     // Dune: norm0 already below the absolute floor -> converged with 0 iterations
     S->done = (S->norm0 < 1e-30) ? 1 : 0;
     if (S->done) S->converged = 1;
@@ -473,15 +489,23 @@ struct FusedSpmv {
     const double* d1;              // dot-product partner (MODE 1: <d1, y>; MODE 2: <y, d1>, <y, y>)
     const int2* units;             // {first slice, slices}, in expected order of readiness (FusedPlan)
     const int* need_ptr; const int* need;
-    int* sync;                     // [0] unit counter, [1] ticket, [2 + p] part p finished; zeroed before the launch
+    int* sync;                     // [0] unit counter, [1] ticket, [2 + p] part p finished; zero at launch (the last CTA re-zeroes it)
     double* partials;              // 2 x nunits
     int ring_bytes;                // dynamic shared memory of the launch: ring of SELL slices once the part is swept
     long long* dbg;                // debugging aid (may be null): per part {part done, exit, units taken, time spent waiting for parts} [ns]
     int Nb, nunits;
 };
 
+// Deferred solution update run by idle CTAs of a lower sweep (k_sweep<true, ..., SPMV = 3>): x += pend * y, y re-armed
+struct XUpdate {
+    double* x; double* y;
+    int* sync;                     // [0] chunk counter, [1] ticket; zero at launch (the last CTA re-zeroes it)
+    int n;                         // doubles
+};
+
 struct SweepArgs {
     FusedSpmv f;
+    XUpdate xu;
     const StageD* stages;
     const PartD* parts;
     const int* meta;
@@ -776,8 +800,60 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
         if (MODE == 1) P.S->h = a;
         if (MODE == 2) { P.S->tr = a; P.S->tt = b; }
     }
+    for (int k = threadIdx.x; k < 2 + P.nparts; k += blockDim.x) F.sync[k] = 0;     // every other CTA has left: ready for the next launch
 }
 
+// Tail of a LOWER-sweep CTA: BiCGSTAB's solution updates x += alpha y / x += omega y have no consumer before the solve
+// ends, so k_vec_xr1 / k_vec_xr2 only record the coefficient (Scalars::pend) and the CTAs of the next lower sweep apply
+// it once their part is swept (and re-arm y with the sentinel for the upper sweep that follows): 96 bytes per block row
+// leave the serial part of the iteration.  The work does not depend on the sweep at all; chunks come from a counter.
+constexpr int kXUpdChunk = 8192;           // doubles per claim
+__device__ __forceinline__ void xupdate_tail(const SweepArgs& P, double pend)
+{
+    const XUpdate& X = P.xu;
+    __shared__ int s_chunk[2];
+    __shared__ bool s_lastx;
+    const int nchunks = (X.n + kXUpdChunk - 1) / kXUpdChunk;
+    const double sent = sentinel();
+    if (threadIdx.x == 0) s_chunk[0] = atomicAdd(X.sync, 1);
+    for (int it = 0;; ++it) {
+        __syncthreads();
+        const int c = s_chunk[it & 1];
+        if (c >= nchunks) break;
+        if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = atomicAdd(X.sync, 1);
+        const int i0 = c * kXUpdChunk, i1 = min(X.n, i0 + kXUpdChunk);
+        const int npair = (i1 - i0) >> 1;                      // i0 is even: 16-byte accesses
+        double2* __restrict__ x2 = reinterpret_cast<double2*>(X.x + i0);
+        double2* __restrict__ y2 = reinterpret_cast<double2*>(X.y + i0);
+        // all loads of a batch before its first store: 11 warps per SM need the bytes in flight
+        constexpr int kB = 6;
+        for (int k0 = threadIdx.x; k0 < npair; k0 += kB * blockDim.x) {
+            double2 xv[kB], yv[kB];
+#pragma unroll
+            for (int b = 0; b < kB; ++b) {
+                const int k = k0 + b * blockDim.x;
+                if (k < npair) { yv[b] = y2[k]; xv[b] = x2[k]; }
+            }
+#pragma unroll
+            for (int b = 0; b < kB; ++b) {
+                const int k = k0 + b * blockDim.x;
+                if (k < npair) {
+                    xv[b].x += pend * yv[b].x; xv[b].y += pend * yv[b].y;
+                    x2[k] = xv[b];
+                    y2[k] = make_double2(sent, sent);
+                }
+            }
+        }
+        if (threadIdx.x == 0 && ((i1 - i0) & 1)) { X.x[i1 - 1] += pend * X.y[i1 - 1]; X.y[i1 - 1] = sent; }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_lastx = atomicAdd(X.sync + 1, 1) == (int) gridDim.x - 1;
+        if (s_lastx) { P.S->pend_on = 0; X.sync[0] = 0; X.sync[1] = 0; }     // every CTA read pend_on when the kernel started
+    }
+}
+
+// SPMV: 3 = lower sweep whose CTAs then apply the pending solution update (xupdate_tail)
 // SPMV: -1 = sweep only; 1 / 2 = the CTA goes on with the SpMV that follows (fused_spmv_tail<SPMV>)
 constexpr int kFusedMaxThreads = 384;
 template <bool LOWER, bool REARM, bool TRACE, int SPMV = -1>
@@ -787,6 +863,8 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
     if (P.check_done && P.S->done) return;
     const int part = blockIdx.x;
     if (part >= P.nparts) return;
+    const bool xupd = SPMV == 3 && P.S->pend_on != 0;
+    const double xupd_coef = SPMV == 3 ? P.S->pend : 0.0;
     const PartD pr = P.parts[part];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
     unsigned long long* empty = full + kSweepMaxSlots;
@@ -1007,7 +1085,10 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
         if (++s == nslots) { s = 0; parity ^= 1; }
     }
     }
-    if constexpr (SPMV >= 0) fused_spmv_tail<SPMV>(P, part, sweep_smem);
+    if constexpr (SPMV == 1 || SPMV == 2) fused_spmv_tail<SPMV>(P, part, sweep_smem);
+    if constexpr (SPMV == 3) {
+        if (xupd) xupdate_tail(P, xupd_coef);
+    }
 }
 
 // ---- BSR SpMV with fused dot products ----------------------------------------------------------
@@ -1134,7 +1215,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_p(const double* __restrict_
 // x += alpha y; r -= alpha v; norm = ||r||; y is re-armed (its last reader).  alpha = rho_new / h.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ v, int N, Scalars* S, double* partials,
-                                                         unsigned* ticket, int dist)
+                                                         unsigned* ticket, int dist, int defer)
 {
     if (S->done) return;
     const double h = S->h;
@@ -1145,8 +1226,10 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
     const double alpha = S->rho_new / h;
     double acc[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        x[i] += alpha * y[i];
-        y[i] = sentinel();
+        if (!defer) {
+            x[i] += alpha * y[i];
+            y[i] = sentinel();
+        }
         const double rr = r[i] - alpha * v[i];
         r[i] = rr;
         acc[0] += rr * rr;
@@ -1154,6 +1237,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
     double tot[1];
     if (grid_reduce<1>(acc, partials, ticket, tot)) {
         S->alpha = alpha;
+        if (defer) { S->pend = alpha; S->pend_on = 1; }
         if (dist) S->red[0] = tot[0];
         else finish_xr1(S, tot[0]);
     }
@@ -1162,14 +1246,16 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
 // x += omega y; r -= omega t; norm = ||r||; rho <- rho_new <- <rt, r>.  omega = tr / tt.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ t, const double* __restrict__ rt, int N,
-                                                         Scalars* S, double* partials, unsigned* ticket, int dist)
+                                                         Scalars* S, double* partials, unsigned* ticket, int dist, int defer)
 {
     if (S->done) return;
     const double omega = S->tr / S->tt;
     double acc[2] = {0.0, 0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        x[i] += omega * y[i];
-        y[i] = sentinel();
+        if (!defer) {
+            x[i] += omega * y[i];
+            y[i] = sentinel();
+        }
         const double rr = r[i] - omega * t[i];
         r[i] = rr;
         acc[0] += rr * rr;
@@ -1178,6 +1264,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x,
     double tot[2];
     if (grid_reduce<2>(acc, partials, ticket, tot)) {
         S->omega = omega;
+        if (defer) { S->pend = omega; S->pend_on = 1; }
         if (dist) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
         else finish_xr2(S, tot[0], tot[1]);
     }
@@ -1200,22 +1287,41 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
 {
     if (MODE != 0 && S->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int pl = lane >> 2, r = lane & 3;
-    for (int w = warp; w < nwells; w += nwarp) {
-        double z = 0.0;
-        for (unsigned p = wptr[w] + pl; p < wptr[w + 1]; p += 8) {
-            const double* bb = B + (size_t) p * 12 + r * 3;
-            const double* xx = x + 3 * (size_t) Bcols[p];
-            z += bb[0] * xx[0] + bb[1] * xx[1] + bb[2] * xx[2];
-        }
-        z += __shfl_xor_sync(kFull, z, 4);
-        z += __shfl_xor_sync(kFull, z, 8);
-        z += __shfl_xor_sync(kFull, z, 16);                  // every lane: z1[r]
-        const double* dd = Dinv + (size_t) w * 16 + r * 4;
-        double z2 = 0.0;
+    // phase 1: one LANE per perforation (all four well equations), two wells per warp and pass so that their loads overlap:
+    // the kernel is a chain of dependent global loads (column -> x), not arithmetic
+    for (int w0 = warp; w0 < nwells; w0 += 2 * nwarp) {
+        const int w1 = w0 + nwarp;
+        const bool two = w1 < nwells;
+        const unsigned b0 = wptr[w0], e0 = wptr[w0 + 1], b1 = two ? wptr[w1] : 0u, e1 = two ? wptr[w1 + 1] : 0u;
+        double z[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+        for (unsigned off = 0; off < max(e0 - b0, e1 - b1); off += 32) {
+            const unsigned p[2] = {b0 + off + lane, b1 + off + lane};
+            const bool on[2] = {p[0] < e0, p[1] < e1};
+            double xx[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+            const double* bp[2] = {B + (size_t) p[0] * 12, B + (size_t) p[1] * 12};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) z2 += dd[c] * __shfl_sync(kFull, z, c);
-        if (lane < 4) z2g[w * 4 + r] = z2;
+            for (int h = 0; h < 2; ++h)
+                if (on[h]) {
+                    const double* xp = x + 3 * (size_t) Bcols[p[h]];
+                    xx[h][0] = xp[0]; xx[h][1] = xp[1]; xx[h][2] = xp[2];
+                }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (on[h]) z[h][r] += bp[h][3 * r] * xx[h][0] + bp[h][3 * r + 1] * xx[h][1] + bp[h][3 * r + 2] * xx[h][2];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int w = h ? w1 : w0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) z[h][r] = warp_sum(z[h][r]);
+            if (lane < 4) {
+                const double* dd = Dinv + (size_t) w * 16 + lane * 4;
+                z2g[w * 4 + lane] = dd[0] * z[h][0] + dd[1] * z[h][1] + dd[2] * z[h][2] + dd[3] * z[h][3];
+            }
+        }
     }
     __syncthreads();
     double acc[2] = {0.0, 0.0};
