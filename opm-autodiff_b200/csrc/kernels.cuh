@@ -1287,6 +1287,22 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
 {
     if (MODE != 0 && S->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // z2 of the first kWellSmem wells stays in shared memory (no global write -> read round trip between the phases)
+    constexpr int kWellSmem = 1024;
+    __shared__ double z2s[kWellSmem * 4];
+    // operands of this thread's first phase-2 item that do not depend on phase 1: issued now, they arrive while the phase-1
+    // chain (well pointer -> column -> x) runs
+    const int t0 = threadIdx.x, u0 = t0 / 3, c0 = t0 - 3 * u0;
+    const bool has0 = t0 < 3 * ncells;
+    int pe0 = 0, pe1 = 0;
+    size_t pidx = 0;
+    double pold = 0.0, pd1 = 0.0;
+    if (has0) {
+        pe0 = uptr[u0]; pe1 = uptr[u0 + 1];
+        pidx = 3 * (size_t) ucell[u0] + c0;
+        pold = y[pidx];
+        if (MODE != 0) pd1 = d1[pidx];
+    }
     // phase 1: one LANE per perforation (all four well equations), two wells per warp and pass so that their loads overlap:
     // the kernel is a chain of dependent global loads (column -> x), not arithmetic
     for (int w0 = warp; w0 < nwells; w0 += 2 * nwarp) {
@@ -1319,7 +1335,9 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
             for (int r = 0; r < 4; ++r) z[h][r] = warp_sum(z[h][r]);
             if (lane < 4) {
                 const double* dd = Dinv + (size_t) w * 16 + lane * 4;
-                z2g[w * 4 + lane] = dd[0] * z[h][0] + dd[1] * z[h][1] + dd[2] * z[h][2] + dd[3] * z[h][3];
+                const double z2 = dd[0] * z[h][0] + dd[1] * z[h][1] + dd[2] * z[h][2] + dd[3] * z[h][3];
+                if (w < kWellSmem) z2s[w * 4 + lane] = z2;
+                else z2g[w * 4 + lane] = z2;
             }
         }
     }
@@ -1328,16 +1346,19 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
     for (int t = threadIdx.x; t < 3 * ncells; t += blockDim.x) {
         const int u = t / 3, c = t - 3 * u;
         double delta = 0.0;
-        for (int e = uptr[u]; e < uptr[u + 1]; ++e) {
+        const bool pre = t == t0;
+        for (int e = pre ? pe0 : uptr[u], ee = pre ? pe1 : uptr[u + 1]; e < ee; ++e) {
             const double* cb = C + (size_t) ublock[e] * 12 + c;
-            const double* zz = z2g + 4 * uwell[e];
+            const int w = uwell[e];
+            const double* zz = w < kWellSmem ? z2s + 4 * w : z2g + 4 * w;
             delta += cb[0] * zz[0] + cb[3] * zz[1] + cb[6] * zz[2] + cb[9] * zz[3];
         }
-        const size_t idx = 3 * (size_t) ucell[u] + c;
-        const double old = y[idx], now = old - delta;
+        const size_t idx = pre ? pidx : 3 * (size_t) ucell[u] + c;
+        const double old = pre ? pold : y[idx], now = old - delta;
         y[idx] = now;
-        if (MODE == 1) acc[0] += d1[idx] * (now - old);
-        if (MODE == 2) { acc[0] += d1[idx] * (now - old); acc[1] += now * now - old * old; }
+        const double dd1 = MODE != 0 ? (pre ? pd1 : d1[idx]) : 0.0;
+        if (MODE == 1) acc[0] += dd1 * (now - old);
+        if (MODE == 2) { acc[0] += dd1 * (now - old); acc[1] += now * now - old * old; }
     }
     if (MODE != 0) {
         __shared__ double sm[2][32];
