@@ -405,12 +405,14 @@ struct Solver {
         sweep_extCap = std::max(an.L.maxExtRows, an.U.maxExtRows);
         const size_t slotBytes = (size_t) sweep_metaCap * 4 + (size_t) sweep_valsCap * 8 + (size_t) sweep_rhsCap * 24;
         const size_t fixedBytes = kSweepHeader + (size_t) (an.window + an.extWindow + 2) * 8 * kXs + kSweepTailPad;
-        sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots));
+        sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots - 1));      // nslots + 1 ready words
+        // helpers fetch one stage ahead of the ring when nslots + 1 stages of external rows fit the ring (sweep_early)
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
         const bool want_fused = fuse_spmv && sell_slices && an.nparts <= kMaxSweepParts;
         const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_limit || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
+        sweep_early = (long long) (sweep_slots + 1) * sweep_extCap <= an.extWindow;
         if ((long long) sweep_slots * sweep_extCap > an.extWindow)
             throw std::runtime_error("external-row ring of the triangular sweeps too small (" + std::to_string(sweep_extCap) + " rows per stage)");
         sweep_helpers = std::max(1, std::min({sweep_helpers, 27 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
@@ -635,6 +637,7 @@ struct Solver {
         a.metaCap = sweep_metaCap; a.valsCap = sweep_valsCap; a.rhsCap = sweep_rhsCap; a.extWindow = an.extWindow;
         a.nwarps = sweep_warps; a.nhalo = sweep_helpers; a.helper_sleep = sweep_helper_sleep;
         a.check_done = check_done ? 1 : 0;
+        a.nowait = sweep_nowait; a.early = sweep_early ? 1 : 0;
         a.trace = sweep_trace ? d_trace.p : nullptr;
         a.trace_cap = kTraceCap;
         return a;
@@ -689,7 +692,8 @@ struct Solver {
         prof_end(id);
     }
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
-    int fuse_debug = 0;
+    int fuse_debug = 0, sweep_nowait = 0;
+    bool sweep_early = false;
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
     DevBuf<long long> d_fDbg;
     template <int MODE>
@@ -1022,6 +1026,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = value != 0.0; }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
+        else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
         else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = value != 0.0; }
         else if (k == "fuse_unit_slices") s->fuse_unit_slices = (int) value;
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));

@@ -515,6 +515,8 @@ struct SweepArgs {
     double* rearm;        // may be null: vector re-armed with the sentinel row by row as it is consumed
     Scalars* S;
     int nparts, nslots, window, extWindow, metaCap, valsCap, rhsCap, nwarps, nhalo, check_done, helper_sleep;
+    int early;            // helpers start a stage's fetch when the stage before it has been issued (needs ring room for nslots + 1 stages)
+    int nowait;           // experiment: external rows are taken as they are (wrong results): what the parts could do unstarved
     long long* trace;     // debugging aid (may be null): per part and stage {wait begin, data landed, stage done, issued} in SM cycles
     int trace_cap;
 };
@@ -869,6 +871,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
     unsigned long long* full = reinterpret_cast<unsigned long long*>(sweep_smem);
     unsigned long long* empty = full + kSweepMaxSlots;
     int* ext_ready = reinterpret_cast<int*>(sweep_smem + 128);
+    int* issued = reinterpret_cast<int*>(sweep_smem + 192);         // stages the producer has issued (monotonic)
     unsigned char* xwin = sweep_smem + kSweepHeader;
     const int W = P.window, EW = P.extWindow, zrow = W + EW;
     unsigned char* slots = xwin + 8 * kXs * (size_t) (zrow + 2);
@@ -879,7 +882,9 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
     const int nslots = P.nslots;
     constexpr int NF = LOWER ? 9 : 12;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW + 1); ext_ready[s] = 0; }
+        for (int s = 0; s < nslots; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW + 1); }
+        for (int s = 0; s <= nslots; ++s) ext_ready[s] = 0;
+        *issued = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -908,6 +913,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
                     bulk_g2s(base, P.meta + meta_off, bm, full + s);
                     if (bv) bulk_g2s(base + metaBytes, P.vals + vals_off, bv, full + s);
                     bulk_g2s(base + metaBytes + valsBytes, P.rhs + 3 * (size_t) g_lo, br, full + s);
+                    st_volatile_s32(issued, i + 1);
                 }
             }
         }
@@ -921,12 +927,32 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
         constexpr int kHelperWindow = 2;
         const int h = warp - NW - 1;
         double* ring = reinterpret_cast<double*>(xwin) + kXs * (size_t) W;
+        // The list of a stage's external rows is static data: the helper reads it from the GLOBAL copy of the stage's meta
+        // block (descriptor and header one stage of its own ahead), so it can start fetching stage i as soon as stage i - 1
+        // has been ISSUED by the producer instead of when stage i has landed -- with the list read from the landed stage the rows arrived
+        // 1-2 us into the stage and every consumer of the stage's first levels waited for them (+20 % per part).
+        // Flow control: stage i - 1 issued => stage i - 1 - nslots is finished, so at most nslots + 1 stages have rows in
+        // the ring (capacity checked by the host) and the ready words are indexed modulo nslots + 1.
+        StageD sd = h < nst ? P.stages[pr.stage_begin + h] : StageD{0, 0, 0, 0, 0, 0};
         for (int i = h; i < nst; i += NH) {
-            const int s = i % nslots;
-            mbar_wait_relaxed(full + s, (i / nslots) & 1);
-            const int* m = reinterpret_cast<const int*>(slots + (size_t) s * slotBytes);
-            const int next = m[4], ext_base = m[8];
-            const int* extl = m + m[5];
+            const int s = i % nslots, rdy = i % (nslots + 1);
+            const int* m = P.meta + sd.meta_off;
+            const int next = __ldg(m + 4), ext_base = __ldg(m + 8);
+            const int* extl = m + __ldg(m + 5);
+            int first_rows[kHelperWindow];
+#pragma unroll
+            for (int k = 0; k < kHelperWindow; ++k) first_rows[k] = 32 * k + lane < next ? __ldg(extl + 32 * k + lane) : 0;
+            if (i + NH < nst) sd = P.stages[pr.stage_begin + i + NH];
+            // (a counter, not the full barrier of stage i - 1: that barrier may be two phases further when a late helper looks,
+            // and a parity wait would then never return)
+            if (!P.early) mbar_wait_relaxed(full + s, (i / nslots) & 1);
+            else {
+                int spins = 0;
+                while (ld_volatile_s32(issued) < i) {
+                    __nanosleep(100);
+                    if ((++spins & 1023) == 0 && (spins > (1 << 22) || *((volatile int*) &P.S->trsv_timeout))) { P.S->trsv_timeout = 1; break; }
+                }
+            }
             const int tag = (i + 1) << 16;
             int published = 0;
             long long* t3 = TRACE && i < P.trace_cap ? P.trace + (size_t) 2 * 148 * P.trace_cap * 4 + ((size_t) part * P.trace_cap + i) * 4 : nullptr;
@@ -939,7 +965,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
                 for (int k = 0; k < kHelperWindow; ++k) {
                     const int idx = e0 + 32 * k + lane;
                     done[k] = idx >= wend;
-                    xp[k] = P.out + 3 * (size_t) (done[k] ? 0 : extl[idx]);
+                    xp[k] = P.out + 3 * (size_t) (done[k] ? 0 : (e0 == 0 ? first_rows[k] : __ldg(extl + idx)));
                 }
                 int spins = 0;
                 while (true) {
@@ -949,7 +975,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
                         if (!done[k]) { x[k][0] = ld_relaxed(xp[k]); x[k][1] = ld_relaxed(xp[k] + 1); x[k][2] = ld_relaxed(xp[k] + 2); }
 #pragma unroll
                     for (int k = 0; k < kHelperWindow; ++k)
-                        if (!done[k] && !(is_sentinel(x[k][0]) || is_sentinel(x[k][1]) || is_sentinel(x[k][2]))) {
+                        if (!done[k] && (P.nowait || !(is_sentinel(x[k][0]) || is_sentinel(x[k][1]) || is_sentinel(x[k][2])))) {
                             double* d = ring + kXs * (size_t) ((ext_base + e0 + 32 * k + lane) & (EW - 1));
                             d[0] = x[k][0]; d[1] = x[k][1]; d[2] = x[k][2];
                             done[k] = true;
@@ -968,13 +994,13 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
                     if (prefix > published) {
                         __threadfence_block();
                         __syncwarp();
-                        if (lane == 0) st_volatile_s32(ext_ready + s, tag + prefix);
+                        if (lane == 0) st_volatile_s32(ext_ready + rdy, tag + prefix);
                         published = prefix;
                     }
                     if (prefix >= wend) break;
                     if ((++spins & 255) == 0 && (spins > (1 << 20) || *((volatile int*) &P.S->trsv_timeout))) {
                         P.S->trsv_timeout = 1;
-                        if (lane == 0) st_volatile_s32(ext_ready + s, tag + next);
+                        if (lane == 0) st_volatile_s32(ext_ready + rdy, tag + next);
                         break;
                     }
                     if (P.helper_sleep) __nanosleep(P.helper_sleep);
@@ -982,6 +1008,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
             }
             __syncwarp();
             if (TRACE && t3 && lane == 0) t3[1] = clock64();
+            mbar_wait_relaxed(full + s, (i / nslots) & 1);          // arrive in the phase of stage i
             if (lane == 0) mbar_arrive(empty + s);
         }
     } else {
@@ -1015,7 +1042,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
         unsigned v_a = sb + (unsigned) metaBytes + 16 * lane + (unsigned) tb * (NF * 256);               // value pairs
         const unsigned v8_off = 2048 + 8 * lane - 16 * lane;                                             // lower: the ninth value
         const unsigned rr = sb + (unsigned) (metaBytes + valsBytes) + 8 * lane_rhs;
-        const int tag = (i + 1) << 16;
+        const int tag = (i + 1) << 16, rdy = i % (nslots + 1);
         long long tp_last = TRACE ? clock64() : 0, tp_pre = 0, tp_bar = 0, tp_post = 0;
         for (int t = tb; t < te; ++t, it_a += 16, cd_a += 512, v_a += NF * 256) {
             // ---- operands of record t: nothing here depends on another row
@@ -1044,7 +1071,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
             }
             if (item.z) {                                     // external rows of this level: parked by a helper warp
                 int spins = 0;
-                while (ld_volatile_s32(ext_ready + s) - (tag + item.z) < 0) {
+                while (ld_volatile_s32(ext_ready + rdy) - (tag + item.z) < 0) {
                     if ((++spins & 4095) == 0 && *((volatile int*) &P.S->trsv_timeout)) break;
                 }
                 __threadfence_block();
