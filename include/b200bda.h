@@ -78,8 +78,11 @@ void b200_destroy(b200_solver* s);
  *   "sweep_helper_sleep"  ns a helper warp sleeps between two polls of external rows                default 60
  *   "sweep_trace" 1: record the stage timeline of the sweeps (b200_get_sweep_trace; debugging)     default 0
  *   "spmv_blocks" upper bound of the SpMV grid                                                    default 16 per SM
- *   "spmv_sell"   1: SpMV from a sliced-ELL copy of A (a lane per block row, coalesced value loads); 0: BSR kernel, 3 lanes
- *                 per row.  Set before the first solve                                               default 1
+ *   Size-dependent features, set before the first solve: 0 = off, 1 = automatic (on from 100 000 block rows), 2 = on     default 1
+ *   "spmv_sell"   SpMV from a sliced-ELL copy of A (a lane per block row, coalesced value loads) instead of the BSR kernel
+ *   "fuse_spmv"   the upper sweep's CTAs run the SpMV that follows it as their parts finish (needs spmv_sell)
+ *   "defer_x"     x += alpha y / omega y are applied by idle CTAs of the next lower sweep instead of the vector kernels
+ *   "sweep_early" sweep helper warps fetch a stage's external rows one stage ahead
  *   "p2p_allreduce"  multi-GPU: 1 peer-memory mailboxes, 0 NCCL + finish kernel                    default 1
  * Unknown keys return B200_UNKNOWN_ERROR. */
 b200_status b200_set_option(b200_solver* s, const char* key, double value);

@@ -176,7 +176,12 @@ struct Solver {
     DevBuf<double> d_sellVal;
     int sell_slices = 0;
     long long sell_slots = 0;
-    int spmv_sell = 1;                 // option: 0 = BSR kernel (3 lanes per row)
+    // Size-dependent features: option value 0 = off, 1 = automatic (on from kBigRows block rows: below that their fixed costs
+    // -- a second gather per solve, tail barriers and tickets, extra global reads per stage -- outweigh what they save; the
+    // Norne-size system has 44 k rows and an L2-resident matrix), 2 = on.
+    static constexpr int kBigRows = 100000;
+    bool feature_on(int opt) const { return opt == 2 || (opt == 1 && Nb >= kBigRows); }
+    int spmv_sell = 1;                 // option: SpMV from the sliced-ELL copy (else BSR kernel, 3 lanes per row)
     // SpMV run by the upper sweep's CTAs as their parts finish (kernels.cuh fused_spmv_tail)
     DevBuf<int> d_fUnits, d_fNeedPtr, d_fNeed, d_fSync;
     DevBuf<double> d_fPartials;
@@ -377,7 +382,7 @@ struct Solver {
         up(d_prow, an.prow); up(d_pcol, an.pcol); up(d_pdiag, an.pdiag); up(d_srcblk, an.srcblk); up(d_perm, an.perm);
         up(d_flevRows, an.flevRows);
         sell_slices = 0; sell_slots = 0;
-        if (spmv_sell) {
+        if (feature_on(spmv_sell)) {
             const b200::SellPlan sp = b200::build_sell(Nb, an.prow, an.pcol, an.srcblk);
             sell_slices = sp.nslices; sell_slots = sp.ptr[sp.nslices];
             up(d_sellPtr, sp.ptr); up(d_sellOver, sp.over); up(d_sellCol, sp.col); up(d_sellSrc, sp.src);
@@ -408,11 +413,11 @@ struct Solver {
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots - 1));      // nslots + 1 ready words
         // helpers fetch one stage ahead of the ring when nslots + 1 stages of external rows fit the ring (sweep_early)
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
-        const bool want_fused = fuse_spmv && sell_slices && an.nparts <= kMaxSweepParts;
+        const bool want_fused = feature_on(fuse_spmv) && sell_slices && an.nparts <= kMaxSweepParts;
         const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_limit || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
-        sweep_early = (long long) (sweep_slots + 1) * sweep_extCap <= an.extWindow;
+        sweep_early = feature_on(sweep_early_opt) && (long long) (sweep_slots + 1) * sweep_extCap <= an.extWindow;
         if ((long long) sweep_slots * sweep_extCap > an.extWindow)
             throw std::runtime_error("external-row ring of the triangular sweeps too small (" + std::to_string(sweep_extCap) + " rows per stage)");
         sweep_helpers = std::max(1, std::min({sweep_helpers, 27 - sweep_warps, sweep_slots}));   // a helper must never run a whole ring ahead
@@ -430,7 +435,7 @@ struct Solver {
         prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
         prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
         defer_ok = false;
-        if (defer_x && threads <= kFusedMaxThreads) {
+        if (feature_on(defer_x) && threads <= kFusedMaxThreads) {
             prep(k_sweep<true, false, false, 3>);
             d_xSync.alloc(2);
             CUDA_OK(cudaMemsetAsync(d_xSync.p, 0, sizeof(int) * 2, stream));
@@ -660,7 +665,7 @@ struct Solver {
         k_sweep<true, false, false, 3><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
         prof_end(id);
     }
-    bool defer_now() const { return defer_x && defer_ok && !sweep_trace; }
+    bool defer_now() const { return defer_ok && !sweep_trace; }
     int defer_x = 1;                   // option
     bool defer_ok = false;             // the tail kernel fits (set by the analysis)
     DevBuf<int> d_xSync;
@@ -694,6 +699,7 @@ struct Solver {
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
     int fuse_debug = 0, sweep_nowait = 0;
     bool sweep_early = false;
+    int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
     DevBuf<long long> d_fDbg;
     template <int MODE>
@@ -1023,11 +1029,12 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
-        else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = value != 0.0; }
-        else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = value != 0.0; }
+        else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = std::max(0, std::min(2, (int) value)); }
+        else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
-        else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = value != 0.0; }
+        else if (k == "sweep_early") { if (s->analysed) throw std::runtime_error("sweep_early must be set before the first solve"); s->sweep_early_opt = std::max(0, std::min(2, (int) value)); }
+        else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_unit_slices") s->fuse_unit_slices = (int) value;
         else if (k == "spmv_blocks") s->spmv_blocks_cap = std::max(1, std::min((int) value, kMaxPartials));
         else if (k == "p2p_allreduce") s->dist.use_p2p_allreduce = value != 0.0;

@@ -933,20 +933,24 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
         // 1-2 us into the stage and every consumer of the stage's first levels waited for them (+20 % per part).
         // Flow control: stage i - 1 issued => stage i - 1 - nslots is finished, so at most nslots + 1 stages have rows in
         // the ring (capacity checked by the host) and the ready words are indexed modulo nslots + 1.
-        StageD sd = h < nst ? P.stages[pr.stage_begin + h] : StageD{0, 0, 0, 0, 0, 0};
+        StageD sd = P.early && h < nst ? P.stages[pr.stage_begin + h] : StageD{0, 0, 0, 0, 0, 0};
         for (int i = h; i < nst; i += NH) {
             const int s = i % nslots, rdy = i % (nslots + 1);
-            const int* m = P.meta + sd.meta_off;
-            const int next = __ldg(m + 4), ext_base = __ldg(m + 8);
-            const int* extl = m + __ldg(m + 5);
+            const int* m;
+            if (P.early) m = P.meta + sd.meta_off;
+            else {                                         // small rings: the list of the landed stage, as before
+                mbar_wait_relaxed(full + s, (i / nslots) & 1);
+                m = reinterpret_cast<const int*>(slots + (size_t) s * slotBytes);
+            }
+            const int next = m[4], ext_base = m[8];
+            const int* extl = m + m[5];
             int first_rows[kHelperWindow];
 #pragma unroll
-            for (int k = 0; k < kHelperWindow; ++k) first_rows[k] = 32 * k + lane < next ? __ldg(extl + 32 * k + lane) : 0;
-            if (i + NH < nst) sd = P.stages[pr.stage_begin + i + NH];
-            // (a counter, not the full barrier of stage i - 1: that barrier may be two phases further when a late helper looks,
-            // and a parity wait would then never return)
-            if (!P.early) mbar_wait_relaxed(full + s, (i / nslots) & 1);
-            else {
+            for (int k = 0; k < kHelperWindow; ++k) first_rows[k] = 32 * k + lane < next ? extl[32 * k + lane] : 0;
+            if (P.early) {
+                if (i + NH < nst) sd = P.stages[pr.stage_begin + i + NH];
+                // (a counter, not the full barrier of stage i - 1: that barrier may be two phases further when a late helper
+                // looks, and a parity wait would then never return)
                 int spins = 0;
                 while (ld_volatile_s32(issued) < i) {
                     __nanosleep(100);
@@ -965,7 +969,7 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
                 for (int k = 0; k < kHelperWindow; ++k) {
                     const int idx = e0 + 32 * k + lane;
                     done[k] = idx >= wend;
-                    xp[k] = P.out + 3 * (size_t) (done[k] ? 0 : (e0 == 0 ? first_rows[k] : __ldg(extl + idx)));
+                    xp[k] = P.out + 3 * (size_t) (done[k] ? 0 : (e0 == 0 ? first_rows[k] : extl[idx]));
                 }
                 int spins = 0;
                 while (true) {

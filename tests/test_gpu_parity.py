@@ -86,12 +86,16 @@ def test_kernels_vs_oracle(mods, shape, faults):
 
 @pytest.mark.parametrize("shape,faults,nwells,nperf", [((12, 10, 8), ((6, 1),), 3, 4), ((24, 20, 16), (), 0, 0),
                                                         ((30, 24, 20), ((10, 1), (20, 2)), 6, 15)])
-def test_solve_parity_small(mods, shape, faults, nwells, nperf):
-    """north_star parity: ||x - x_ref|| / ||x_ref|| <= 1e-6 at 1e-10 relative residual, iterations +-10%."""
+@pytest.mark.parametrize("big", [0, 2])
+def test_solve_parity_small(mods, shape, faults, nwells, nperf, big):
+    """north_star parity: ||x - x_ref|| / ||x_ref|| <= 1e-6 at 1e-10 relative residual, iterations +-10%.
+    big = 2 forces the features that are automatic from 100 000 rows (SELL SpMV, SpMV inside the upper sweep, deferred solution
+    update, early helpers); big = 0 switches them off."""
     bridge, synth, oracle = mods
     s = synth.small(*shape, faults=faults, nwells=nwells, nperf=nperf)
     ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200)
-    be, st, res, x = _solve(bridge, s)
+    feats = {k: big for k in ("spmv_sell", "fuse_spmv", "defer_x", "sweep_early")}
+    be, st, res, x = _solve(bridge, s, opts=feats)
     assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and res.converged and ref.converged
     assert relerr(x, ref.x) <= 1e-6
     assert abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
@@ -100,7 +104,7 @@ def test_solve_parity_small(mods, shape, faults, nwells, nperf):
     assert res.iterations == int(res.it)                              # cusparseSolverBackend.cu:172
     # relaxation 0.9 (Flow's CPU default, FlowLinearSolverParameters.hpp:146-150): same solution
     ref9 = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200, relaxation=0.9)
-    _, _, res9, x9 = _solve(bridge, s, relaxation=0.9)
+    _, _, res9, x9 = _solve(bridge, s, relaxation=0.9, opts=feats)
     assert res9.converged and relerr(x9, ref9.x) <= 1e-6 and abs(res9.it - ref9.it) <= max(1.0, 0.1 * ref9.it)
 
 
@@ -320,7 +324,7 @@ def test_irregular_patterns_vs_oracle(mods, shape, extra, drop, opts):
     assert res.converged and ref.converged and relerr(x, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
 
 
-@pytest.mark.parametrize("sell", [1, 0])
+@pytest.mark.parametrize("sell", [2, 0])
 def test_spmv_layouts_with_very_long_rows(mods, sell):
     """SpMV from the sliced-ELL copy (default) and from the BSR arrays: a few rows coupled to ~40 cells exceed the width cap of
     their slice, so their tail comes from the BSR arrays (k_spmv_sell overflow path); Nb is not a multiple of 32."""
@@ -353,19 +357,21 @@ def test_spmv_layouts_with_very_long_rows(mods, sell):
 
 @pytest.mark.parametrize("opts", [{}, {"sweep_parts": 5}, {"sweep_parts": 37, "sweep_stage_bytes": 8192, "fuse_unit_slices": 1}])
 def test_spmv_inside_the_upper_sweep_matches_separate_kernels(mods, opts):
-    """Single GPU: the upper-sweep CTAs run the following SpMV as their parts finish (fuse_spmv, default).  Same solution and
+    """The upper-sweep CTAs run the following SpMV as their parts finish, the lower-sweep CTAs apply the deferred solution
+    update, helpers fetch a stage ahead (all on by default from 100 000 rows, forced here).  Same solution and
     iteration count as with separate kernels, on a faulted grid with wells and on a pattern with rows of ~45 blocks (tail of a
     row read from the BSR arrays inside the fused kernel)."""
     bridge, synth, oracle = mods
     s = synth.small(20, 16, 12, faults=((7, 2),), nwells=3, nperf=5)
     out = {}
-    for fuse in (1, 0):
-        _, st, res, x = _solve(bridge, s, tol=1e-10, maxit=300, opts=dict(opts, fuse_spmv=fuse))
+    FORCE = {"spmv_sell": 2, "defer_x": 2, "sweep_early": 2}        # small systems: the automatic setting would switch them off
+    for fuse in (2, 0):
+        _, st, res, x = _solve(bridge, s, tol=1e-10, maxit=300, opts=dict(opts, fuse_spmv=fuse, **(FORCE if fuse else {})))
         assert st == bridge.SolverStatus.BDA_SOLVER_SUCCESS and res.converged
         out[fuse] = (res.it, x)
-    assert out[1][0] == out[0][0] and relerr(out[1][1], out[0][1]) < 1e-9
+    assert out[2][0] == out[0][0] and relerr(out[2][1], out[0][1]) < 1e-9
     ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=300)
-    assert relerr(out[1][1], ref.x) <= 1e-6 and abs(out[1][0] - ref.it) <= max(1.0, 0.1 * ref.it)
+    assert relerr(out[2][1], ref.x) <= 1e-6 and abs(out[2][0] - ref.it) <= max(1.0, 0.1 * ref.it)
     # long rows
     rows, cols, vals = _irregular_system(synth, (12, 9, 7), 0.2, seed=9)
     Nb = len(rows) - 1
@@ -384,9 +390,9 @@ def test_spmv_inside_the_upper_sweep_matches_separate_kernels(mods, opts):
     xt = rng.uniform(-1, 1, 3 * Nb) * np.tile([1e5, 1.0, 1.0], Nb)
     b = oracle.spmv(rows, cols, vals, xt)
     sol = {}
-    for fuse in (1, 0):
+    for fuse in (2, 0):
         be = bridge.B200SolverBackend(0, 300, 1e-10, 0)
-        for k, v in dict(opts, fuse_spmv=fuse).items():
+        for k, v in dict(opts, fuse_spmv=fuse, **(FORCE if fuse else {})).items():
             be.set_option(k, v)
         be.upload_system(3 * Nb, 9 * len(cols), 3, vals, rows, cols, b, None)
         res = bridge.BdaResult()
@@ -394,6 +400,6 @@ def test_spmv_inside_the_upper_sweep_matches_separate_kernels(mods, opts):
         x = np.zeros(3 * Nb); be.get_result(x)
         assert res.converged
         sol[fuse] = (res.it, x)
-    assert sol[1][0] == sol[0][0] and relerr(sol[1][1], sol[0][1]) < 1e-9
+    assert sol[2][0] == sol[0][0] and relerr(sol[2][1], sol[0][1]) < 1e-9
     ref = oracle.solve(rows, cols, vals, b, None, tol=1e-10, maxit=300)
-    assert relerr(sol[1][1], ref.x) <= 1e-6
+    assert relerr(sol[2][1], ref.x) <= 1e-6
