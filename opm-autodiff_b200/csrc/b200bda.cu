@@ -586,7 +586,18 @@ struct Solver {
         for (int l = 0; l < an.nflev; ++l) {
             int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
             int id = count ? prof_begin(K_FACTOR) : -1;
-            if (fac_plan)
+            if (fac_plan && fac_pdl && l > 0) {
+                // programmatic dependent launch on the previous level: the launch gap and the prologue hide behind it
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((nrows + kFacWarps - 1) / kFacWarps); cfg.blockDim = dim3(32 * kFacWarps); cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                CUDA_OK(cudaLaunchKernelEx(&cfg, k_ilu_factor_plan, (const int*) d_prow.p, (const int*) d_pdiag.p, (const int*) d_facPtr.p,
+                                           reinterpret_cast<const int2*>(d_facOps.p), (const double*) d_A.p, d_LU.p,
+                                           (const int*) (d_flevRows.p + row0), nrows, d_S.p));
+            } else if (fac_plan)
                 k_ilu_factor_plan<<<(nrows + kFacWarps - 1) / kFacWarps, 32 * kFacWarps, 0, stream>>>(
                     d_prow.p, d_pdiag.p, d_facPtr.p, reinterpret_cast<const int2*>(d_facOps.p), d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             else
@@ -698,6 +709,7 @@ struct Solver {
     }
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
     int fuse_debug = 0, sweep_nowait = 0;
+    int fac_pdl = 0;                   // option: factorisation levels chained by programmatic dependent launch
     bool sweep_early = false;
     int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
@@ -1033,6 +1045,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
+        else if (k == "fac_pdl") { s->fac_pdl = value != 0.0; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
         else if (k == "sweep_early") { if (s->analysed) throw std::runtime_error("sweep_early must be set before the first solve"); s->sweep_early_opt = std::max(0, std::min(2, (int) value)); }
         else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_unit_slices") s->fuse_unit_slices = (int) value;

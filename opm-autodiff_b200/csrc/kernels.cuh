@@ -308,6 +308,11 @@ __global__ void __launch_bounds__(32 * kFacWarps) k_ilu_factor_plan(const int* _
     __shared__ int2 sop[kFacWarps][kFacMaxOps];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int wid = blockIdx.x * kFacWarps + w;
+    // Programmatic dependent launch: the next level's grid may be scheduled as soon as every CTA of this one has got here,
+    // and runs its prologue (plan and own row of A, which no level writes) while this level still eliminates; it touches LU
+    // only after griddepcontrol.wait, i.e. after this grid has completed and its stores are visible.  Launched without the
+    // attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (wid >= nrows) return;
     const int i = rowlist[wid];
     const int rs = prow[i], re = prow[i + 1], di = pdiag[i] - rs;
@@ -317,6 +322,7 @@ __global__ void __launch_bounds__(32 * kFacWarps) k_ilu_factor_plan(const int* _
     for (int o = lane; o < nops; o += 32) sop[w][o] = facOps[o0 + o];
     for (int f = lane; f < (re - rs) * 9; f += 32) row[f] = A[(size_t) rs * 9 + f];
     __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int f = lane; f < nops * 9; f += 32) {
         const int o = f / 9;
         up[f] = LU[(size_t) sop[w][o].x * 9 + (f - 9 * o)];

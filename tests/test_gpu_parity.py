@@ -403,3 +403,30 @@ def test_spmv_inside_the_upper_sweep_matches_separate_kernels(mods, opts):
     assert sol[2][0] == sol[0][0] and relerr(sol[2][1], sol[0][1]) < 1e-9
     ref = oracle.solve(rows, cols, vals, b, None, tol=1e-10, maxit=300)
     assert relerr(sol[2][1], ref.x) <= 1e-6
+
+
+def test_repeated_solves_reproduce_bit_for_bit(mods):
+    """Race hunting without a sanitizer: repeated solves with every size-dependent feature forced on (dataflow sweeps, SpMV and
+    solution updates in the sweep tails, per-unit dot partials) must reproduce the first solution bit for bit.
+    tools/stress_determinism.py is the long version."""
+    bridge, synth, oracle = mods
+    for shape, nw, opts in (((33, 17, 29), 0, {"sweep_parts": 37}), ((25, 25, 25), 5, {"sweep_parts": 9, "fuse_unit_slices": 1})):
+        s = synth.small(*shape, nwells=nw, nperf=6)
+        be = bridge.B200SolverBackend(0, 300, 1e-10, 0)
+        for k in ("spmv_sell", "fuse_spmv", "defer_x", "sweep_early"):
+            be.set_option(k, 2)
+        for k, v in opts.items():
+            be.set_option(k, v)
+        be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(s.wells))
+        res = bridge.BdaResult()
+        first = None
+        for rep in range(8):
+            be.solve_resident(res)
+            x = np.zeros(3 * s.Nb)
+            be.get_result(x)
+            assert res.converged
+            if first is None:
+                first, it0 = x.copy(), res.it
+            else:
+                assert np.array_equal(x, first) and res.it == it0
+        assert relerr(first, s.x_true) < 1e-5
