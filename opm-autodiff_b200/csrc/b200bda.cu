@@ -709,7 +709,7 @@ struct Solver {
     }
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
     int fuse_debug = 0, sweep_nowait = 0;
-    int fac_pdl = 0;                   // option: factorisation levels chained by programmatic dependent launch
+    int fac_pdl = 1;                   // option: factorisation levels chained by programmatic dependent launch
     bool sweep_early = false;
     int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
