@@ -659,11 +659,25 @@ struct Solver {
         return a;
     }
     int sweep_threads() const { return (sweep_warps + 1 + sweep_helpers) * 32; }
+    // Launch of a kernel of the BiCGSTAB iteration (all of them start with pdl_enter()): with iter_pdl the launch carries the
+    // programmatic-stream-serialization attribute, so its CTAs are scheduled while the previous kernel drains.
+    int iter_pdl = 0;                  // option (measured: slower)
+    template <class... KArgs, class... Args>
+    void launch_iter(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = iter_pdl ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_OK(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+    }
     template <bool LOWER>
     void launch_sweep(const SweepArgs& a)
     {
         const bool rearm = a.rearm != nullptr, trace = a.trace != nullptr;
-        auto go = [&](auto kern) { kern<<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a); };
+        auto go = [&](auto kern) { launch_iter(kern, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a); };
         if (trace) { if (rearm) go(k_sweep<LOWER, true, true>); else go(k_sweep<LOWER, false, true>); }
         else { if (rearm) go(k_sweep<LOWER, true, false>); else go(k_sweep<LOWER, false, false>); }
     }
@@ -673,7 +687,7 @@ struct Solver {
         int id = prof_begin(K_LOWER);
         SweepArgs a = sweep_args(true, rhs, out, nullptr, true);
         a.xu.x = d_x.p; a.xu.y = d_y.p; a.xu.sync = d_xSync.p; a.xu.n = N;
-        k_sweep<true, false, false, 3><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
+        launch_iter(k_sweep<true, false, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
     bool defer_now() const { return defer_ok && !sweep_trace; }
@@ -704,7 +718,7 @@ struct Solver {
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
         a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
-        k_sweep<false, true, false, MODE><<<an.nparts, sweep_threads(), sweep_smem, stream>>>(a);
+        launch_iter(k_sweep<false, true, false, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
@@ -719,12 +733,12 @@ struct Solver {
     {
         int id = prof_begin(K_SPMV);
         if (sell_slices)
-            k_spmv_sell<MODE><<<blocks_for(32LL * sell_slices, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(
-                d_sellPtr.p, d_sellOver.p, d_sellCol.p, d_sellVal.p, d_prow.p, d_pcol.p, d_A.p, x, y, d1, Nb, sell_slices, d_S.p,
-                d_partials.p, d_ticket.p);
+            launch_iter(k_spmv_sell<MODE>, dim3(blocks_for(32LL * sell_slices, kVecThreads, spmv_blocks_cap)), dim3(kVecThreads), 0,
+                        d_sellPtr.p, d_sellOver.p, d_sellCol.p, d_sellVal.p, d_prow.p, d_pcol.p, d_A.p, x, y, d1, Nb, sell_slices, d_S.p,
+                        d_partials.p, d_ticket.p);
         else
-            k_spmv<MODE><<<blocks_for(N, kVecThreads, spmv_blocks_cap), kVecThreads, 0, stream>>>(d_prow.p, d_pcol.p, d_A.p, x, y, d1, N, d_S.p,
-                                                                                              d_partials.p, d_ticket.p);
+            launch_iter(k_spmv<MODE>, dim3(blocks_for(N, kVecThreads, spmv_blocks_cap)), dim3(kVecThreads), 0, d_prow.p, d_pcol.p, d_A.p, x, y,
+                        d1, N, d_S.p, d_partials.p, d_ticket.p);
         prof_end(id);
     }
     template <int MODE>
@@ -732,7 +746,7 @@ struct Solver {
     {
         if (nwells == 0) return;
         int id = prof_begin(K_WELL);
-        k_wells<MODE><<<1, 1024, 0, stream>>>(nwells, d_wptr.p, d_Bcols.p, d_B.p, d_C.p, d_Dinv.p, nucells, d_ucell.p, d_uptr.p,
+        launch_iter(k_wells<MODE>, dim3(1), dim3(1024), 0, nwells, d_wptr.p, d_Bcols.p, d_B.p, d_C.p, d_Dinv.p, nucells, d_ucell.p, d_uptr.p,
                                               d_ublock.p, d_uwell.p, d_z2.p, x, y, d1, d_S.p);
         prof_end(id);
     }
@@ -810,7 +824,7 @@ struct Solver {
         const int dm = dist.enabled ? 1 : 0;
         int id;
         id = prof_begin(K_VEC_P);
-        k_vec_p<<<vec_blocks, kVecThreads, 0, stream>>>(d_r.p, d_p.p, d_v.p, N, d_S.p);
+        launch_iter(k_vec_p, dim3(vec_blocks), dim3(kVecThreads), 0, d_r.p, d_p.p, d_v.p, N, d_S.p);
         prof_end(id);
         if (defer_now()) trsv_lower_xupdate(d_p.p, d_w.p); else trsv_lower(d_p.p, d_w.p, true);
         if (fused_now()) {
@@ -825,7 +839,7 @@ struct Solver {
         spmv_ghost<1>(d_v.p, d_rt.p, true);
         reduce_phase<1>();
         id = prof_begin(K_VEC_XR1);
-        k_vec_xr1<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
+        launch_iter(k_vec_xr1, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
         prof_end(id);
         reduce_phase<2>();
         if (defer_now()) trsv_lower_xupdate(d_r.p, d_w.p); else trsv_lower(d_r.p, d_w.p, true);
@@ -841,7 +855,7 @@ struct Solver {
         spmv_ghost<2>(d_t.p, d_r.p, true);
         reduce_phase<3>();
         id = prof_begin(K_VEC_XR2);
-        k_vec_xr2<<<vec_blocks, kVecThreads, 0, stream>>>(d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
+        launch_iter(k_vec_xr2, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
         prof_end(id);
         reduce_phase<4>();
     }
@@ -1045,6 +1059,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
+        else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "fac_pdl") { s->fac_pdl = value != 0.0; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
         else if (k == "sweep_early") { if (s->analysed) throw std::runtime_error("sweep_early must be set before the first solve"); s->sweep_early_opt = std::max(0, std::min(2, (int) value)); }
         else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = std::max(0, std::min(2, (int) value)); }

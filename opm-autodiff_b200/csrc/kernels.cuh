@@ -51,6 +51,15 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
 __device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long) __double_as_longlong(v) == kSentinel; }
 __device__ __forceinline__ double sentinel() { return __longlong_as_double((long long) kSentinel); }
 
+// Programmatic dependent launch (kernels of the BiCGSTAB iteration): let the next kernel of the stream be scheduled while this
+// one runs, and wait for the previous one to complete (its stores visible) before touching anything it wrote.  Both are
+// no-ops in a launch without the attribute.  A kernel launched WITH the attribute must call this before its first access.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -868,6 +877,7 @@ template <bool LOWER, bool REARM, bool TRACE, int SPMV = -1>
 __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
+    pdl_enter();
     if (P.check_done && P.S->done) return;
     const int part = blockIdx.x;
     if (part >= P.nparts) return;
@@ -1139,6 +1149,7 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv(const int* __restrict__ pr
                                                       double* __restrict__ y, const double* __restrict__ d1, int N,
                                                       Scalars* S, double* partials, unsigned* ticket)
 {
+    pdl_enter();
     if (MODE != 0 && S->done) return;
     double acc[MODE == 2 ? 2 : 1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
@@ -1175,6 +1186,7 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_sell(const int* __restrict
                                                            double* __restrict__ y, const double* __restrict__ d1, int Nb, int nslices,
                                                            Scalars* S, double* partials, unsigned* ticket)
 {
+    pdl_enter();
     if (MODE != 0 && S->done) return;
     double acc[MODE == 2 ? 2 : 1] = {0.0};
     const int lane = threadIdx.x & 31;
@@ -1241,6 +1253,7 @@ __global__ void __launch_bounds__(256) k_fill_sell(const double* __restrict__ st
 __global__ void __launch_bounds__(kVecThreads) k_vec_p(const double* __restrict__ r, double* __restrict__ p,
                                                        const double* __restrict__ v, int N, Scalars* S)
 {
+    pdl_enter();
     if (S->done) return;
     const bool first = S->first != 0;
     const double omega = S->omega;
@@ -1254,6 +1267,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
                                                          const double* __restrict__ v, int N, Scalars* S, double* partials,
                                                          unsigned* ticket, int dist, int defer)
 {
+    pdl_enter();
     if (S->done) return;
     const double h = S->h;
     if (fabs(h) < 1e-80) {        // Dune: SolverAbort "abs(h) < EPSILON"
@@ -1285,6 +1299,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x,
                                                          const double* __restrict__ t, const double* __restrict__ rt, int N,
                                                          Scalars* S, double* partials, unsigned* ticket, int dist, int defer)
 {
+    pdl_enter();
     if (S->done) return;
     const double omega = S->tr / S->tt;
     double acc[2] = {0.0, 0.0};
@@ -1322,6 +1337,7 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
                                                 const int* __restrict__ uwell, double* z2g, const double* __restrict__ x,
                                                 double* y, const double* __restrict__ d1, Scalars* S)
 {
+    pdl_enter();
     if (MODE != 0 && S->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     // z2 of the first kWellSmem wells stays in shared memory (no global write -> read round trip between the phases)
