@@ -274,6 +274,7 @@ class B200SolverBackend:
 
     def get_result(self, x: np.ndarray) -> None:
         assert x.dtype == np.float64 and x.flags.c_contiguous and x.size >= self.N
+        self._keep_x = x                         # page-locked by the library until the next call
         if lib().b200_get_result(self._h, _ptr(x)) != 0:
             raise RuntimeError(last_error())
 

@@ -212,6 +212,7 @@ struct Solver {
     // pinned-host registration of the caller's arrays
     const void* reg_vals = nullptr; size_t reg_vals_bytes = 0;
     const void* reg_b = nullptr; size_t reg_b_bytes = 0;
+    const void* reg_x = nullptr; size_t reg_x_bytes = 0;      // the caller's solution vector (get_result)
 
     KStat stats[K_COUNT];
     long long launch_count = 0;
@@ -226,6 +227,7 @@ struct Solver {
         if (fac_graph_exec) cudaGraphExecDestroy(fac_graph_exec);
         if (iter_graph_exec) cudaGraphExecDestroy(iter_graph_exec);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
+        if (reg_x) cudaHostUnregister((void*) reg_x);
         if (reg_b) cudaHostUnregister((void*) reg_b);
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (cudaEvent_t e : {ev_a, ev_b, ev_c, ev_d, ev_t0, ev_t1}) if (e) cudaEventDestroy(e);
@@ -479,7 +481,7 @@ struct Solver {
     {
         if (!pin_host) return;
         if (reg == ptr && reg_bytes == bytes) return;
-        if (reg) { cudaHostUnregister((void*) reg); reg = nullptr; reg_bytes = 0; }
+        if (reg) { cudaHostUnregister((void*) reg); cudaGetLastError(); reg = nullptr; reg_bytes = 0; }
         cudaError_t e = cudaHostRegister((void*) ptr, bytes, cudaHostRegisterDefault);
         if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
         if (e != cudaSuccess) { cudaGetLastError(); return; }   // pageable copy still works
@@ -1147,6 +1149,7 @@ b200_status b200_get_result(b200_solver* s, double* x)
     return guarded([&]() -> b200_status {
         if (!s->analysed) throw std::runtime_error("get_result before any solve");
         CUDA_OK(cudaSetDevice(s->device));
+        s->maybe_register(s->reg_x, s->reg_x_bytes, x, sizeof(double) * s->N);     // pageable D2H of 24 B per row costs 2 ms on C3
         CUDA_OK(cudaMemcpyAsync(x, s->d_xnat.p, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
         CUDA_OK(cudaStreamSynchronize(s->stream));
         return B200_SUCCESS;
