@@ -40,7 +40,7 @@ MAXIT = 2000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", help="c2 | c3 | c4 | c5 | nx,ny,nz")
@@ -83,47 +83,94 @@ def get_cfg(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md's clocks
+    line).  NVML is polled from a thread of this process every 5 ms, so that even a timed region of a few tens of
+    milliseconds gets samples; `nvidia-smi -lms` (which needs ~0.3 s to produce its first line) is only the fallback when
+    the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bit masks (nvml.h)
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index=0, period_s=0.005):
+        self.rows, self.proc, self.idx, self.period = [], None, gpu_index, period_s
+        self.nvml, self.handle, self.thread, self.stop_flag, self.source = None, None, None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis:
+                ids = [t.strip() for t in vis.split(",")]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        nv, h = self.nvml, self.handle
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                mask = int(get_reasons(h))
+                self.rows.append((sm, self.sm_max, pw, mask))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        if self.nvml is not None:
+            self.source = "nvml, %g ms period" % (1e3 * self.period)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.source = "nvidia-smi -lms 20"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+            r = [t.strip() for t in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                mask = 0
+                for (name, bit), v in zip(self.REASONS, r[5:9]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]), mask))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML binding and no nvidia-smi"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        self.thread.join(timeout=2)
+        rows = list(self.rows)
+        sm = [r[0] for r in rows]
+        power = [r[2] for r in rows if r[2] == r[2]]
+        reasons = sorted(name for name, bit in self.REASONS if any(r[3] & bit for r in rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "source": self.source, "reasons": reasons}
 
 
 def measured_peak():

@@ -115,7 +115,7 @@ b200_status b200_solve_resident(b200_solver* s, b200_result* res);
 
 const char* b200_last_error(void);
 
-/* ---- standard wells: replaces Opm::WellContributions (WellContributions.hpp:60-214) -------- */
+/* ---- wells (standard and multisegment): replaces Opm::WellContributions (WellContributions.hpp:60-214) -------- */
 
 typedef enum { B200_WELL_C = 0, B200_WELL_D = 1, B200_WELL_B = 2 } b200_well_matrix; /* MatrixType, :69-73 */
 
@@ -132,7 +132,22 @@ b200_status b200_wells_alloc(b200_wells* w);
 /* addMatrix (:152-213): per well C, then D, then B; fails before alloc.  col_indices ignored for D. */
 b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const int* col_indices,
                                   const double* values, unsigned int val_size);
-unsigned int b200_wells_get_num_wells(const b200_wells* w);   /* getNumWells (:152-154 of the .hpp) */
+unsigned int b200_wells_get_num_wells(const b200_wells* w);   /* getNumWells: standard + multisegment (WellContributions.hpp:164-166) */
+
+/* WellContributions::addMultisegmentWellContribution (WellContributions.hpp:195-213, .cpp:261-271) and the constructor of
+ * MultisegmentWellContribution (MultisegmentWellContribution.cpp:32-58): B and C in blocked CSR (Mb block rows = segments,
+ * dim_wells x dim blocks, row-major [well eq][cell eq], C on B's pattern), D as the scalar CSC matrix handed to UMFPACK
+ * (DcolPointers[dim_wells * Mb + 1], DrowIndices / Dvalues [DnumBlocks * dim_wells^2]).  May be called at any time before
+ * the solve, independently of the standard wells' three phases.  Where the reference factorises D with UMFPACK on the host
+ * and then solves on the host inside every operator apply (x D2H, y H2D: WellContributions.cu:167-187), this library
+ * inverts D here (dense, partial pivoting) and applies y -= C^T (D^-1 (B x)) on the device.  Fails unless dim == 3 and
+ * dim_wells == 4, or if D is singular.  Not supported on several ranks yet. */
+b200_status b200_wells_add_multisegment(b200_wells* w, unsigned int dim, unsigned int dim_wells, unsigned int Mb,
+                                        const double* Bvalues, const unsigned int* BcolIndices, const unsigned int* BrowPointers,
+                                        unsigned int DnumBlocks, const double* Dvalues, const int* DcolPointers,
+                                        const int* DrowIndices, const double* Cvalues);
+/* Test hook (host only): the dense row-major (4 Mb)^2 inverse of D held for multisegment well `index`. */
+b200_status b200_wells_get_multisegment_inverse(const b200_wells* w, unsigned int index, double* Dinv_out);
 
 /* ---- multi-GPU: row slabs, halo exchange over NVLink peer memory, NCCL all-reduce ------------ */
 /*

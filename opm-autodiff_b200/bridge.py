@@ -110,6 +110,8 @@ def lib():
         L.b200_wells_add_matrix.argtypes = [vp, ip, vp, vp, C.c_uint]
         L.b200_wells_get_num_wells.argtypes = [vp]
         L.b200_wells_get_num_wells.restype = C.c_uint
+        L.b200_wells_add_multisegment.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, C.c_uint, vp, vp, vp, vp]
+        L.b200_wells_get_multisegment_inverse.argtypes = [vp, C.c_uint, vp]
         L.b200_spmv.argtypes = [vp, _f64p, _f64p]
         L.b200_well_apply.argtypes = [vp, _f64p, _f64p]
         L.b200_ilu0_factorize.argtypes = [vp]
@@ -146,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "b200_create", "b200_destroy", "b200_set_option", "b200_solve_system", "b200_get_result",
     "b200_upload_system", "b200_solve_resident", "b200_last_error", "b200_wells_create",
     "b200_wells_destroy", "b200_wells_set_block_size", "b200_wells_add_num_blocks", "b200_wells_alloc",
-    "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_spmv", "b200_well_apply",
+    "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_wells_add_multisegment", "b200_wells_get_multisegment_inverse", "b200_spmv", "b200_well_apply",
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
     "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
@@ -168,9 +170,10 @@ def _ptr(a):
 
 
 class WellContributions:
-    """Opm::WellContributions (standard wells only).  Three phases, as the reference:
+    """Opm::WellContributions.  Standard wells in three phases, as the reference:
     setBlockSize + addNumBlocks per well, alloc, then per well addMatrix C, D, B
-    (bda/WellContributions.cpp:152-259; fill order wells/StandardWellEval.cpp:1202-1251)."""
+    (bda/WellContributions.cpp:152-259; fill order wells/StandardWellEval.cpp:1202-1251);
+    multisegment wells one call each (addMultisegmentWellContribution, .cpp:261-271)."""
 
     class MatrixType(enum.IntEnum):
         C = 0
@@ -207,6 +210,28 @@ class WellContributions:
 
     def getNumWells(self) -> int:
         return int(lib().b200_wells_get_num_wells(self._h))
+
+    def addMultisegmentWellContribution(self, dim, dim_wells, Mb, Bvalues, BcolIndices, BrowPointers, DnumBlocks, Dvalues,
+                                        DcolPointers, DrowIndices, Cvalues) -> None:
+        """bda/WellContributions.hpp:195-213: B, C blocked CSR (dim_wells x dim blocks), D scalar CSC (UMFPACK layout)."""
+        Bv = np.ascontiguousarray(Bvalues, dtype=np.float64)
+        Bc = np.ascontiguousarray(BcolIndices, dtype=np.uint32)
+        Br = np.ascontiguousarray(BrowPointers, dtype=np.uint32)
+        Dv = np.ascontiguousarray(Dvalues, dtype=np.float64)
+        Dc = np.ascontiguousarray(DcolPointers, dtype=np.int32)
+        Dr = np.ascontiguousarray(DrowIndices, dtype=np.int32)
+        Cv = np.ascontiguousarray(Cvalues, dtype=np.float64)
+        if (dim, dim_wells) == (3, 4) and (len(Br) != Mb + 1 or len(Bc) < Br[-1] or Bv.size < 12 * Br[-1] or Cv.size < 12 * Br[-1] or len(Dc) != dim_wells * Mb + 1 \
+                or len(Dr) < Dc[-1] or Dv.size < Dc[-1]):
+            raise ValueError("addMultisegmentWellContribution: array sizes do not match Mb / the row and column pointers")
+        self._check(lib().b200_wells_add_multisegment(self._h, int(dim), int(dim_wells), int(Mb), _ptr(Bv), _ptr(Bc), _ptr(Br),
+                                                      int(DnumBlocks), _ptr(Dv), _ptr(Dc), _ptr(Dr), _ptr(Cv)))
+
+    def multisegment_inverse(self, index: int, M: int) -> np.ndarray:
+        """Test hook: the dense M x M inverse of D the library holds for multisegment well `index`."""
+        out = np.empty((M, M))
+        self._check(lib().b200_wells_get_multisegment_inverse(self._h, int(index), _ptr(out)))
+        return out
 
     @classmethod
     def from_arrays(cls, val_pointers, Bcols, Ccols, B, C, Dinv, accelerator_mode="b200"):

@@ -139,7 +139,58 @@ struct Wells {
     std::vector<unsigned> val_pointers;
     std::vector<int> Ccols, Bcols;
     std::vector<double> Cnnzs, Dnnzs, Bnnzs;
+    // multisegment wells (bda/WellContributions.hpp:85,92): one entry per addMultisegmentWellContribution
+    struct MsWell {
+        unsigned Mb = 0;                       // segments = block rows of B, C and D
+        std::vector<unsigned> Brows, Bcols;    // blocked CSR pattern shared by B and C
+        std::vector<double> B, C;              // 4x3 blocks, row-major [well eq][cell eq]
+        std::vector<double> Dinv;              // dense (4 Mb) x (4 Mb), row-major
+    };
+    std::vector<MsWell> ms;
 };
+
+// Dense inverse of the scalar CSC matrix D of a multisegment well (Gauss-Jordan with partial pivoting on the host).  The
+// reference factorises D with UMFPACK at the same point (MultisegmentWellContribution.cpp:56-57) and solves on the host in
+// every operator apply; with the explicit inverse the apply is a dense mat-vec on the device.
+static void invert_csc(int M, const int* colptr, const int* rowidx, const double* vals, std::vector<double>& inv)
+{
+    std::vector<double> A((size_t) M * M, 0.0);
+    for (int c = 0; c < M; ++c) {
+        if (colptr[c + 1] < colptr[c]) throw std::runtime_error("multisegment well: D column pointers must ascend");
+        for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
+            if (rowidx[q] < 0 || rowidx[q] >= M) throw std::runtime_error("multisegment well: D row index out of range");
+            A[(size_t) rowidx[q] * M + c] += vals[q];
+        }
+    }
+    inv.assign((size_t) M * M, 0.0);
+    for (int i = 0; i < M; ++i) inv[(size_t) i * M + i] = 1.0;
+    for (int k = 0; k < M; ++k) {
+        int pr = k;
+        double best = std::fabs(A[(size_t) k * M + k]);
+        for (int i = k + 1; i < M; ++i) {
+            const double a = std::fabs(A[(size_t) i * M + k]);
+            if (a > best) { best = a; pr = i; }
+        }
+        if (!(best > 0.0)) throw std::runtime_error("multisegment well: matrix D is singular");
+        if (pr != k)
+            for (int c = 0; c < M; ++c) {
+                std::swap(A[(size_t) k * M + c], A[(size_t) pr * M + c]);
+                std::swap(inv[(size_t) k * M + c], inv[(size_t) pr * M + c]);
+            }
+        const double piv = 1.0 / A[(size_t) k * M + k];
+        double* ak = &A[(size_t) k * M];
+        double* ik = &inv[(size_t) k * M];
+        for (int c = 0; c < M; ++c) { ak[c] *= piv; ik[c] *= piv; }
+        for (int i = 0; i < M; ++i) {
+            if (i == k) continue;
+            const double f = A[(size_t) i * M + k];
+            if (f == 0.0) continue;
+            double* ai = &A[(size_t) i * M];
+            double* ii = &inv[(size_t) i * M];
+            for (int c = 0; c < M; ++c) { ai[c] -= f * ak[c]; ii[c] -= f * ik[c]; }
+        }
+    }
+}
 
 struct Solver {
     int verbosity = 0, maxit = 200, device = 0;
@@ -208,6 +259,13 @@ struct Solver {
     DevBuf<unsigned> d_wptr;
     DevBuf<int> d_Bcols, d_ucell, d_uptr, d_ublock, d_uwell;
     DevBuf<double> d_B, d_C, d_Dinv, d_z2;
+    // multisegment wells (device, p-space columns); ms_epoch changes whenever they are uploaded (graph signature)
+    int nms = 0, ms_blocks = 0, ms_rows = 0, ms_ncells = 0, ms_epoch = 0;
+    long long ms_dinv_entries = 0;
+    DevBuf<int> d_msZoff, d_msRowoff, d_msRowptr, d_msBcol, d_msUcell, d_msUptr, d_msUblock, d_msUz;
+    DevBuf<long long> d_msDoff;
+    DevBuf<double> d_msB, d_msC, d_msDinv, d_msZ1, d_msZ2;
+    MsWellsD msD{};
 
     // pinned-host registration of the caller's arrays
     const void* reg_vals = nullptr; size_t reg_vals_bytes = 0;
@@ -283,7 +341,7 @@ struct Solver {
             case K_VEC_P: return 96.0 * nb;
             case K_VEC_XR1: return (defer_now() ? 72.0 : 144.0) * nb;      // deferred x update: r, v read, r written
             case K_VEC_XR2: return (defer_now() ? 96.0 : 168.0) * nb;
-            case K_WELL: return 272.0 * nwblocks + 128.0 * nwells;
+            case K_WELL: return 272.0 * nwblocks + 128.0 * nwells + 272.0 * ms_blocks + 8.0 * (double) ms_dinv_entries;
             case K_PERMUTE: return (sell_slices ? 296.0 : 148.0) * nz;
             default: return 0.0;
         }
@@ -488,8 +546,75 @@ struct Solver {
         reg = ptr; reg_bytes = bytes;
     }
 
+    // Multisegment wells: everything the two apply kernels need, in one piece (persistent device buffers).
+    void upload_mswells(const Wells* w)
+    {
+        const bool had = nms > 0;
+        nms = 0; ms_blocks = 0; ms_rows = 0; ms_ncells = 0; ms_dinv_entries = 0;
+        if (had) ++ms_epoch;
+        if (!w || w->ms.empty()) return;
+        if (dist.enabled && dist.world > 1)
+            throw std::runtime_error("multisegment wells are not supported on several ranks yet");
+        ++ms_epoch;
+        nms = (int) w->ms.size();
+        std::vector<int> zoff(nms + 1, 0), rowoff(nms + 1, 0), rowptr(1, 0), bcol, uz_of_block;
+        std::vector<long long> doff(nms, 0);
+        std::vector<double> B, Cv, Dinv;
+        for (int i = 0; i < nms; ++i) {
+            const Wells::MsWell& m = w->ms[i];
+            zoff[i + 1] = zoff[i] + 4 * (int) m.Mb;
+            rowoff[i + 1] = rowoff[i] + (int) m.Mb;
+            doff[i] = (long long) Dinv.size();
+            Dinv.insert(Dinv.end(), m.Dinv.begin(), m.Dinv.end());
+            const int base = (int) bcol.size();
+            for (unsigned r = 0; r < m.Mb; ++r) {
+                for (unsigned q = m.Brows[r]; q < m.Brows[r + 1]; ++q) {
+                    if (m.Bcols[q] >= (unsigned) Nb) throw std::runtime_error("multisegment well column index out of range");
+                    bcol.push_back(an.iperm[m.Bcols[q]]);
+                    uz_of_block.push_back(zoff[i] + 4 * (int) r);
+                }
+                rowptr.push_back(base + (int) m.Brows[r + 1]);
+            }
+            B.insert(B.end(), m.B.begin(), m.B.end());
+            Cv.insert(Cv.end(), m.C.begin(), m.C.end());
+        }
+        ms_blocks = (int) bcol.size(); ms_rows = rowoff[nms]; ms_dinv_entries = (long long) Dinv.size();
+        std::vector<int> order(ms_blocks), ucell, uptr, ublock(ms_blocks), uz(ms_blocks);
+        for (int p = 0; p < ms_blocks; ++p) order[p] = p;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bcol[a] < bcol[b]; });
+        for (int e = 0; e < ms_blocks; ++e) {
+            const int p = order[e];
+            if (e == 0 || bcol[p] != ucell.back()) { ucell.push_back(bcol[p]); uptr.push_back(e); }
+            ublock[e] = p; uz[e] = uz_of_block[p];
+        }
+        uptr.push_back(ms_blocks);
+        ms_ncells = (int) ucell.size();
+        d_msZoff.alloc(nms + 1); d_msRowoff.alloc(nms + 1); d_msDoff.alloc(nms); d_msRowptr.alloc(ms_rows + 1);
+        d_msBcol.alloc(ms_blocks); d_msUcell.alloc(ms_ncells); d_msUptr.alloc(ms_ncells + 1); d_msUblock.alloc(ms_blocks);
+        d_msUz.alloc(ms_blocks); d_msB.alloc((size_t) ms_blocks * 12); d_msC.alloc((size_t) ms_blocks * 12);
+        d_msDinv.alloc(Dinv.size()); d_msZ1.alloc(zoff[nms]); d_msZ2.alloc(zoff[nms]);
+        auto H2D = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
+        H2D(d_msZoff.p, zoff.data(), sizeof(int) * (nms + 1));
+        H2D(d_msRowoff.p, rowoff.data(), sizeof(int) * (nms + 1));
+        H2D(d_msDoff.p, doff.data(), sizeof(long long) * nms);
+        H2D(d_msRowptr.p, rowptr.data(), sizeof(int) * (ms_rows + 1));
+        H2D(d_msBcol.p, bcol.data(), sizeof(int) * ms_blocks);
+        H2D(d_msUcell.p, ucell.data(), sizeof(int) * ms_ncells);
+        H2D(d_msUptr.p, uptr.data(), sizeof(int) * (ms_ncells + 1));
+        H2D(d_msUblock.p, ublock.data(), sizeof(int) * ms_blocks);
+        H2D(d_msUz.p, uz.data(), sizeof(int) * ms_blocks);
+        H2D(d_msB.p, B.data(), sizeof(double) * B.size());
+        H2D(d_msC.p, Cv.data(), sizeof(double) * Cv.size());
+        H2D(d_msDinv.p, Dinv.data(), sizeof(double) * Dinv.size());
+        CUDA_OK(cudaStreamSynchronize(stream));   // the host vectors above are temporaries
+        msD.nwells = nms; msD.zoff = d_msZoff.p; msD.rowoff = d_msRowoff.p; msD.doff = d_msDoff.p; msD.rowptr = d_msRowptr.p;
+        msD.bcol = d_msBcol.p; msD.B = d_msB.p; msD.C = d_msC.p; msD.Dinv = d_msDinv.p; msD.z1 = d_msZ1.p; msD.z2 = d_msZ2.p;
+        msD.ncells = ms_ncells; msD.ucell = d_msUcell.p; msD.uptr = d_msUptr.p; msD.ublock = d_msUblock.p; msD.uz = d_msUz.p;
+    }
+
     void upload_wells(const Wells* w)
     {
+        upload_mswells(w);
         nwells = 0; nwblocks = 0; nucells = 0;
         if (!w || w->num_std_wells == 0) return;
         if (w->num_std_wells_so_far != w->num_std_wells || w->num_blocks_so_far != w->num_blocks)
@@ -743,9 +868,20 @@ struct Solver {
                         d1, N, d_S.p, d_partials.p, d_ticket.p);
         prof_end(id);
     }
+    // multisegment wells first, then the standard wells: the order of WellContributions::apply (WellContributions.cu:167-193)
+    template <int MODE>
+    void mswells_apply(const double* x, double* y, const double* d1)
+    {
+        if (nms == 0) return;
+        int id = prof_begin(K_WELL);
+        launch_iter(k_mswell_z, dim3(nms), dim3(256), 0, msD, x, d_S.p, MODE != 0 ? 1 : 0);
+        launch_iter(k_mswell_y<MODE>, dim3(1), dim3(1024), 0, msD, y, d1, d_S.p);
+        prof_end(id);
+    }
     template <int MODE>
     void wells_apply(const double* x, double* y, const double* d1)
     {
+        mswells_apply<MODE>(x, y, d1);
         if (nwells == 0) return;
         int id = prof_begin(K_WELL);
         launch_iter(k_wells<MODE>, dim3(1), dim3(1024), 0, nwells, d_wptr.p, d_Bcols.p, d_B.p, d_C.p, d_Dinv.p, nucells, d_ucell.p, d_uptr.p,
@@ -864,7 +1000,7 @@ struct Solver {
 
     // One BiCGSTAB iteration: on a single GPU the 10-12 launches are replayed from a CUDA graph (the launch sequence
     // depends on nothing but the pointers; the convergence logic lives on the device), otherwise launched one by one.
-    struct IterSig { const void* a[6]; int n[4]; bool operator!=(const IterSig& o) const { return memcmp(this, &o, sizeof *this) != 0; } };
+    struct IterSig { const void* a[6]; int n[6]; bool operator!=(const IterSig& o) const { return memcmp(this, &o, sizeof *this) != 0; } };
     cudaGraphExec_t iter_graph_exec = nullptr;
     IterSig iter_sig{};
     void run_iteration()
@@ -873,6 +1009,7 @@ struct Solver {
         IterSig sig{};
         sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
         sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0) + (defer_now() ? 1 << 21 : 0);
+        sig.n[4] = nms; sig.n[5] = ms_epoch;
         if (!iter_graph_exec || sig != iter_sig) {
             if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -898,7 +1035,8 @@ struct Solver {
         if (fused_now()) stats[K_UPPER_SPMV].launches += 2;
         else { stats[K_UPPER].launches += 2; stats[K_SPMV].launches += 2; }
         if (nwells) stats[K_WELL].launches += 2;
-        launch_count += (fused_now() ? 7 : 9) + (nwells ? 2 : 0);
+        if (nms) stats[K_WELL].launches += 4;
+        launch_count += (fused_now() ? 7 : 9) + (nwells ? 2 : 0) + (nms ? 4 : 0);
     }
 
     // permutation + ILU0 + BiCGSTAB on the resident system
@@ -1240,7 +1378,47 @@ b200_status b200_wells_add_matrix(b200_wells* w, b200_well_matrix type, const in
         return B200_SUCCESS;
     });
 }
-unsigned int b200_wells_get_num_wells(const b200_wells* w) { return w ? w->num_std_wells : 0; }
+unsigned int b200_wells_get_num_wells(const b200_wells* w) { return w ? w->num_std_wells + (unsigned) w->ms.size() : 0; }
+
+b200_status b200_wells_get_multisegment_inverse(const b200_wells* w, unsigned int index, double* Dinv_out)
+{
+    return guarded([&]() -> b200_status {
+        if (!w || !Dinv_out) throw std::runtime_error("null argument");
+        if (index >= w->ms.size()) throw std::runtime_error("multisegment well index out of range");
+        memcpy(Dinv_out, w->ms[index].Dinv.data(), sizeof(double) * w->ms[index].Dinv.size());
+        return B200_SUCCESS;
+    });
+}
+
+b200_status b200_wells_add_multisegment(b200_wells* w, unsigned int dim, unsigned int dim_wells, unsigned int Mb,
+                                        const double* Bvalues, const unsigned int* BcolIndices, const unsigned int* BrowPointers,
+                                        unsigned int DnumBlocks, const double* Dvalues, const int* DcolPointers,
+                                        const int* DrowIndices, const double* Cvalues)
+{
+    return guarded([&]() -> b200_status {
+        if (!w) throw std::runtime_error("null wells");
+        if (dim != 3 || dim_wells != 4)
+            throw std::runtime_error("WellContributions::addMultisegmentWellContribution error: dim and dim_wells must be equal to 3 and 4");
+        if (Mb == 0 || !Bvalues || !BcolIndices || !BrowPointers || !Dvalues || !DcolPointers || !DrowIndices || !Cvalues)
+            throw std::runtime_error("addMultisegmentWellContribution: null argument or no segments");
+        const unsigned M = Mb * dim_wells;
+        if (BrowPointers[0] != 0) throw std::runtime_error("addMultisegmentWellContribution: BrowPointers must start at 0");
+        for (unsigned r = 0; r < Mb; ++r)
+            if (BrowPointers[r + 1] < BrowPointers[r]) throw std::runtime_error("addMultisegmentWellContribution: BrowPointers must ascend");
+        if ((size_t) DcolPointers[M] != (size_t) DnumBlocks * dim_wells * dim_wells)
+            throw std::runtime_error("addMultisegmentWellContribution: DcolPointers[M] must equal DnumBlocks * dim_wells^2");
+        b200::Wells::MsWell m;
+        m.Mb = Mb;
+        const unsigned nB = BrowPointers[Mb];
+        m.Brows.assign(BrowPointers, BrowPointers + Mb + 1);
+        m.Bcols.assign(BcolIndices, BcolIndices + nB);
+        m.B.assign(Bvalues, Bvalues + (size_t) nB * 12);
+        m.C.assign(Cvalues, Cvalues + (size_t) nB * 12);
+        b200::invert_csc((int) M, DcolPointers, DrowIndices, Dvalues, m.Dinv);
+        w->ms.push_back(std::move(m));
+        return B200_SUCCESS;
+    });
+}
 
 // ---- multi-GPU: one process (and one b200_solver) per GPU ---------------------------------------------
 

@@ -1432,6 +1432,108 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
     }
 }
 
+// ---- multisegment wells ---------------------------------------------------------------------------
+//
+// y -= C^T (D^-1 (B x)) for multisegment wells (bda/MultisegmentWellContribution.cpp:70-110).  The reference copies x and y
+// to the host in every operator apply, runs an UMFPACK solve per well and copies y back (bda/WellContributions.cu:167-187).
+// Here D^-1 is formed ONCE per solve on the host (where the reference runs umfpack_di_numeric) as a dense M x M matrix
+// (M = 4 segments), so the apply is two small launches on the solver's stream and the vectors never leave the device.
+//
+// k_mswell_z: one CTA per well.  z1 = B x (a thread per well equation of a segment), then z2 = D^-1 z1 (a warp per row of
+// D^-1, lanes stride the row: coalesced, fixed summation order).
+struct MsWellsD {
+    int nwells;
+    const int* zoff;          // [nwells + 1] first entry of a well in z1 / z2 (4 per segment)
+    const int* rowoff;        // [nwells + 1] first segment (block row) of a well
+    const long long* doff;    // [nwells] first entry of a well's dense D^-1 (row-major M x M)
+    const int* rowptr;        // [segments + 1] blocks of a segment
+    const int* bcol;          // [blocks] perforated cell (p-space)
+    const double* B;          // [blocks][4][3]
+    const double* C;          // [blocks][4][3]
+    const double* Dinv;
+    double* z1;
+    double* z2;
+    // gather lists of phase 2: unique perforated cells, their blocks and the z2 offset of each block's segment
+    int ncells;
+    const int* ucell;
+    const int* uptr;
+    const int* ublock;
+    const int* uz;
+};
+
+__global__ void __launch_bounds__(256) k_mswell_z(MsWellsD W, const double* __restrict__ x, const Scalars* S, int check_done)
+{
+    pdl_enter();
+    if (check_done && S->done) return;
+    const int w = blockIdx.x;
+    const int z0 = W.zoff[w], M = W.zoff[w + 1] - z0, r0 = W.rowoff[w];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const int row = r0 + (i >> 2), j = i & 3;
+        double acc = 0.0;
+        for (int blk = W.rowptr[row], be = W.rowptr[row + 1]; blk < be; ++blk) {
+            const double* bb = W.B + (size_t) blk * 12 + j * 3;
+            const double* xx = x + 3 * (size_t) W.bcol[blk];
+            acc += bb[0] * xx[0] + bb[1] * xx[1] + bb[2] * xx[2];
+        }
+        W.z1[z0 + i] = acc;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double* D = W.Dinv + W.doff[w];
+    const double* z1 = W.z1 + z0;
+    for (int i = warp; i < M; i += nwarp) {
+        const double* dr = D + (size_t) i * M;
+        double acc = 0.0;
+        for (int k = lane; k < M; k += 32) acc += dr[k] * z1[k];
+        acc = warp_sum(acc);
+        if (lane == 0) W.z2[z0 + i] = acc;
+    }
+}
+
+// k_mswell_y: one CTA; a thread per (unique perforated cell, component) gathers every contribution to that cell (no
+// atomics, deterministic; wells may share a cell) and patches the dot products the SpMV epilogue took before the wells
+// were applied, exactly as phase 2 of k_wells.
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_mswell_y(MsWellsD W, double* y, const double* __restrict__ d1, Scalars* S)
+{
+    pdl_enter();
+    if (MODE != 0 && S->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double acc[2] = {0.0, 0.0};
+    for (int t = threadIdx.x; t < 3 * W.ncells; t += blockDim.x) {
+        const int u = t / 3, c = t - 3 * u;
+        double delta = 0.0;
+        for (int e = W.uptr[u], ee = W.uptr[u + 1]; e < ee; ++e) {
+            const double* cb = W.C + (size_t) W.ublock[e] * 12 + c;
+            const double* zz = W.z2 + W.uz[e];
+            delta += cb[0] * zz[0] + cb[3] * zz[1] + cb[6] * zz[2] + cb[9] * zz[3];
+        }
+        const size_t idx = 3 * (size_t) W.ucell[u] + c;
+        const double old = y[idx], now = old - delta;
+        y[idx] = now;
+        const double dd1 = MODE != 0 ? d1[idx] : 0.0;
+        if (MODE == 1) acc[0] += dd1 * (now - old);
+        if (MODE == 2) { acc[0] += dd1 * (now - old); acc[1] += now * now - old * old; }
+    }
+    if (MODE != 0) {
+        __shared__ double sm[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double v = warp_sum(acc[i]);
+            if (lane == 0) sm[i][warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double a = lane < nwarp ? sm[0][lane] : 0.0, b = lane < nwarp ? sm[1][lane] : 0.0;
+            a = warp_sum(a); b = warp_sum(b);
+            if (lane == 0) {
+                if (MODE == 1) S->h += a;
+                if (MODE == 2) { S->tr += a; S->tt += b; }
+            }
+        }
+    }
+}
+
 // ---- multi-GPU: halo exchange over NVLink peer memory -----------------------------------------------
 //
 // Row-slab partition, ghosts numbered last (ISTLSolverEbos.hpp:171-180, findOverlapRowsAndColumns.hpp:119-139).

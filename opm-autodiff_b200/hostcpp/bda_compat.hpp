@@ -14,6 +14,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/b200bda.h"
 
@@ -55,6 +56,15 @@ public:
     void addMatrix(MatrixType type, int* colIndices, double* values, unsigned int val_size)
     {
         check(b200_wells_add_matrix(h_, static_cast<b200_well_matrix>(static_cast<int>(type)), colIndices, values, val_size));
+    }
+    // WellContributions.hpp:195-213 (UMFPackIndex is int for Dune >= 2.7)
+    void addMultisegmentWellContribution(unsigned int dim, unsigned int dim_wells, unsigned int Mb, std::vector<double>& Bvalues,
+                                         std::vector<unsigned int>& BcolIndices, std::vector<unsigned int>& BrowPointers,
+                                         unsigned int DnumBlocks, double* Dvalues, int* DcolPointers, int* DrowIndices,
+                                         std::vector<double>& Cvalues)
+    {
+        check(b200_wells_add_multisegment(h_, dim, dim_wells, Mb, Bvalues.data(), BcolIndices.data(), BrowPointers.data(),
+                                          DnumBlocks, Dvalues, DcolPointers, DrowIndices, Cvalues.data()));
     }
     b200_wells* handle() { return h_; }
 

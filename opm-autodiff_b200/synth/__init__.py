@@ -239,3 +239,105 @@ def small(nx, ny, nz, seed=7, sigma=1.0, faults=(), nwells=0, nperf=4, kvkh=0.1,
     return full_system(GridConfig("small-%dx%dx%d" % (nx, ny, nz), nx, ny, nz, sigma=sigma, seed=seed,
                                   faults=tuple(faults), nwells=nwells, nperf=nperf, kvkh=kvkh,
                                   acc_frac=acc_frac))
+
+
+@dataclass
+class MSWellData:
+    """One multisegment well in the layout of WellContributions::addMultisegmentWellContribution
+    (bda/WellContributions.hpp:195-213): B, C blocked CSR with 4x3 blocks on one pattern, D scalar CSC."""
+    Mb: int
+    Bvalues: np.ndarray        # [nblocks,4,3]
+    BcolIndices: np.ndarray    # uint32 [nblocks]
+    BrowPointers: np.ndarray   # uint32 [Mb+1]
+    DnumBlocks: int
+    Dvalues: np.ndarray        # [16 DnumBlocks]
+    DcolPointers: np.ndarray   # int32 [4 Mb + 1]
+    DrowIndices: np.ndarray    # int32 [16 DnumBlocks]
+    Cvalues: np.ndarray        # [nblocks,4,3]
+
+    def dense_D(self) -> np.ndarray:
+        M = 4 * self.Mb
+        D = np.zeros((M, M))
+        for c in range(M):
+            for q in range(self.DcolPointers[c], self.DcolPointers[c + 1]):
+                D[self.DrowIndices[q], c] += self.Dvalues[q]
+        return D
+
+
+def add_mswells(system: System, nwells: int, nseg: int, seed: int = 4242, share_cells: bool = True):
+    """Synthetic multisegment wells on a whole system (single-GPU use), in place: every well is a tree of `nseg` segments
+    (segment s > 0 drains into a random earlier one; D couples a segment with its outlet, 4x4 blocks, as
+    MultisegmentWell_impl.hpp:636-643 describes), segment 0 is the top segment without perforations (unless it is the only one), the others perforate
+    0-2 cells (one segment per cell inside a well; with share_cells two wells may meet in a cell).  The perforation
+    conductance goes on A's diagonal and b is updated so that x_true stays the solution:
+    b += A_add x_true - sum_w C^T D^-1 B x_true.  Returns the list of MSWellData."""
+    rng = np.random.default_rng(seed)
+    Nb = system.Nb
+    cs = np.array([1e-7, 1.0, 1.0])
+    E = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0.3, 0.3, 0.3]], dtype=np.float64)
+    wr = 0.25
+    xt = system.x_true.reshape(-1, 3)
+    bb = system.b.reshape(-1, 3)
+    rows, cols = system.rows, system.cols
+    vals = system.vals.reshape(-1, 3, 3)
+    out = []
+    prev_cells = np.zeros(0, np.int64)
+    for w in range(nwells):
+        nperf_seg = rng.integers(0, 3, size=nseg)
+        nperf_seg[0] = 0 if nseg > 1 else 2
+        if nseg > 1 and nperf_seg.sum() == 0:
+            nperf_seg[-1] = 1
+        nblk = int(nperf_seg.sum())
+        cells = rng.choice(Nb, size=nblk, replace=False).astype(np.int64)
+        if share_cells and w > 0 and nblk > 0 and len(prev_cells) > 0:
+            cells[0] = prev_cells[0]                    # two wells meet in one cell
+            if len(set(cells.tolist())) != nblk:
+                cells = rng.choice(Nb, size=nblk, replace=False).astype(np.int64)
+        prev_cells = cells
+        Brow = np.concatenate([[0], np.cumsum(nperf_seg)]).astype(np.uint32)
+        T = 0.5 + 1.5 * rng.random(nblk)
+        B = -T[:, None, None] * (E[None] + wr * (2 * rng.random((nblk, 4, 3)) - 1)) * cs[None, None, :]
+        Cm = -T[:, None, None] * (E[None] + wr * (2 * rng.random((nblk, 4, 3)) - 1))
+        # D: block tree
+        parent = np.array([-1] + [int(rng.integers(0, s)) for s in range(1, nseg)])
+        flow = 0.5 + 1.5 * rng.random(nseg)
+        blocks = {}
+        segT = np.array([T[Brow[s]:Brow[s + 1]].sum() for s in range(nseg)])
+        for s_ in range(nseg):
+            blocks[(s_, s_)] = (segT[s_] + 1.0) * np.diag([1.0, 1.0, 1.0, 1.9]) + wr * (2 * rng.random((4, 4)) - 1)
+        for s_ in range(1, nseg):
+            q = parent[s_]
+            blocks[(s_, q)] = -flow[s_] * (np.eye(4) + wr * (2 * rng.random((4, 4)) - 1))
+            blocks[(q, s_)] = -flow[s_] * (np.eye(4) + wr * (2 * rng.random((4, 4)) - 1))
+            blocks[(s_, s_)] += flow[s_] * np.diag([1.0, 1.0, 1.0, 1.9])
+            blocks[(q, q)] += flow[s_] * np.diag([1.0, 1.0, 1.0, 1.9])
+        M = 4 * nseg
+        # scalar CSC with the block pattern (every entry of a block stored, zeros included, as UMFPACK gets it from Dune)
+        colptr, rowidx, dvals = [0], [], []
+        for c in range(M):
+            bc, cc = divmod(c, 4)
+            for br in sorted(r for (r, c2) in blocks if c2 == bc):
+                for rr in range(4):
+                    rowidx.append(4 * br + rr)
+                    dvals.append(blocks[(br, bc)][rr, cc])
+            colptr.append(len(rowidx))
+        ms = MSWellData(nseg, B, cells.astype(np.uint32), Brow, len(blocks), np.array(dvals), np.array(colptr, np.int32),
+                        np.array(rowidx, np.int32), Cm)
+        out.append(ms)
+        # A's diagonal and the right-hand side
+        dblk = T[:, None, None] * (np.eye(3)[None] + wr * (2 * rng.random((nblk, 3, 3)) - 1)) * cs[None, None, :]
+        for p_, cell in enumerate(cells):
+            lo, hi = rows[cell], rows[cell + 1]
+            d = lo + int(np.searchsorted(cols[lo:hi], cell))
+            assert cols[d] == cell
+            vals[d] += dblk[p_]
+            bb[cell] += dblk[p_] @ xt[cell]
+        z1 = np.zeros(M)
+        for s_ in range(nseg):
+            for blk in range(Brow[s_], Brow[s_ + 1]):
+                z1[4 * s_:4 * s_ + 4] += B[blk] @ xt[cells[blk]]
+        z2 = np.linalg.solve(ms.dense_D(), z1)
+        for s_ in range(nseg):
+            for blk in range(Brow[s_], Brow[s_ + 1]):
+                bb[cells[blk]] -= Cm[blk].T @ z2[4 * s_:4 * s_ + 4]
+    return out

@@ -68,6 +68,13 @@ def lib():
                                 _f64p, C.POINTER(_OrcResult), C.c_void_p, C.c_int]
         L.orc_solve.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        L.orc_ms_create.restype = C.c_void_p
+        L.orc_ms_destroy.argtypes = [C.c_void_p]
+        L.orc_ms_add.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, _f64p, _u32p, _u32p, C.c_uint, _f64p,
+                                 _i32p, _i32p, _f64p]
+        L.orc_ms_add.restype = C.c_int
+        L.orc_ms_apply.argtypes = [C.c_void_p, _f64p, _f64p]
+        L.orc_attach_mswells.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
@@ -106,6 +113,47 @@ class Wells:
     @property
     def nwells(self) -> int:
         return len(self.val_pointers) - 1
+
+
+@dataclass
+class MultisegmentWell:
+    """One multisegment well in the layout MultisegmentWellContribution's constructor takes
+    (bda/MultisegmentWellContribution.cpp:32-37): B, C blocked CSR with 4x3 blocks, D scalar CSC."""
+    Mb: int
+    Bvalues: np.ndarray        # float64 [nblocks, 4, 3]
+    BcolIndices: np.ndarray    # uint32 [nblocks]
+    BrowPointers: np.ndarray   # uint32 [Mb+1]
+    DnumBlocks: int
+    Dvalues: np.ndarray        # float64 [16 DnumBlocks]
+    DcolPointers: np.ndarray   # int32 [4 Mb + 1]
+    DrowIndices: np.ndarray    # int32 [16 DnumBlocks]
+    Cvalues: np.ndarray        # float64 [nblocks, 4, 3]
+
+
+class MSWells:
+    """The `multisegments` vector of a WellContributions object (bda/WellContributions.hpp:92)."""
+
+    def __init__(self, wells):
+        self.wells = list(wells)
+        self._h = lib().orc_ms_create()
+        for w in self.wells:
+            st = lib().orc_ms_add(self._h, 3, 4, int(w.Mb), _c(w.Bvalues, np.float64).reshape(-1),
+                                  _c(w.BcolIndices, np.uint32), _c(w.BrowPointers, np.uint32), int(w.DnumBlocks),
+                                  _c(w.Dvalues, np.float64).reshape(-1), _c(w.DcolPointers, np.int32),
+                                  _c(w.DrowIndices, np.int32), _c(w.Cvalues, np.float64).reshape(-1))
+            if st != 0:
+                raise RuntimeError("multisegment well: singular D" if st == 2 else "multisegment well: bad block sizes")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.orc_ms_destroy(h)
+
+    def apply(self, x, y):
+        """y -= C^T D^-1 B x over all wells (on a copy, returned).  MultisegmentWellContribution.cpp:70-110."""
+        y = np.array(y, dtype=np.float64).reshape(-1)
+        lib().orc_ms_apply(self._h, _c(x, np.float64).reshape(-1), y)
+        return y
 
 
 def _c(a, dt):
@@ -199,7 +247,7 @@ class OracleResult:
 
 
 def solve(rows, cols, vals, b, wells: Optional[Wells] = None, tol=1e-10, maxit=200, relaxation=1.0,
-          part_ptr=None, threads: Optional[int] = None) -> OracleResult:
+          part_ptr=None, threads: Optional[int] = None, mswells: Optional["MSWells"] = None) -> OracleResult:
     """The whole reference CPU path: ILU0 (per partition) + Dune BiCGSTAB (+ wells)."""
     L = lib()
     if threads is not None:
@@ -221,9 +269,13 @@ def solve(rows, cols, vals, b, wells: Optional[Wells] = None, tol=1e-10, maxit=2
     else:
         wargs = [0, None, None, None, None, None, None]
     pp = None if part_ptr is None else _c(part_ptr, np.int32)
-    st = L.orc_solve(Nb, rows, cols, vals, b, *wargs, float(tol), int(maxit), float(relaxation),
-                     0 if pp is None else len(pp) - 1, _ptr(pp), x, C.byref(res),
-                     _ptr(hist), len(hist))
+    L.orc_attach_mswells(mswells._h if mswells is not None else None)
+    try:
+        st = L.orc_solve(Nb, rows, cols, vals, b, *wargs, float(tol), int(maxit), float(relaxation),
+                         0 if pp is None else len(pp) - 1, _ptr(pp), x, C.byref(res),
+                         _ptr(hist), len(hist))
+    finally:
+        L.orc_attach_mswells(None)
     if st != 0:
         raise RuntimeError({1: "diagonal entry missing", 2: "ILU failed to invert matrix block",
                             3: "bad partition"}.get(st, "oracle error %d" % st))
@@ -233,8 +285,10 @@ def solve(rows, cols, vals, b, wells: Optional[Wells] = None, tol=1e-10, maxit=2
                         hist[:max(nh, 1)].copy())
 
 
-def true_residual(rows, cols, vals, b, x, wells: Optional[Wells] = None) -> float:
+def true_residual(rows, cols, vals, b, x, wells: Optional[Wells] = None, mswells: Optional["MSWells"] = None) -> float:
     y = spmv(rows, cols, vals, x)
+    if mswells is not None:
+        y = mswells.apply(x, y)
     if wells is not None and wells.nwells > 0:
         y = well_apply(wells, x, y)
     b = np.asarray(b, dtype=np.float64).reshape(-1)

@@ -169,6 +169,127 @@ void orc_well_apply(int nwells, const unsigned *wptr, const int *Bcols, const in
     }
 }
 
+/* ---- multisegment-well apply --------------------------------------------- */
+
+/* One multisegment well: B and C are Mb x Nb block matrices in blocked CSR with 4x3 blocks
+ * (row-major [well eq][cell eq]; C shares B's pattern), D is the (4 Mb) x (4 Mb) scalar matrix in
+ * CSC as handed to UMFPACK.  opm/simulators/linalg/bda/MultisegmentWellContribution.cpp:32-58.
+ * UMFPACK (SuiteSparse) is absent here; the reference uses it as an exact sparse LU
+ * (umfpack_di_numeric at :56-57, umfpack_di_solve at :92), so this restatement factorises D as a
+ * dense LU with partial pivoting -- the same solve up to rounding. */
+typedef struct {
+    int Mb, M, nB;
+    unsigned *Brows, *Bcols;
+    double *Bvals, *Cvals;
+    double *LU;      /* M x M row-major, L unit lower + U */
+    int *piv;
+    double *z1, *z2;
+} orc_msw;
+
+typedef struct { int n, cap; orc_msw *w; } orc_mswells;
+
+orc_mswells *orc_ms_create(void) { return (orc_mswells *) calloc(1, sizeof(orc_mswells)); }
+
+void orc_ms_destroy(orc_mswells *h)
+{
+    if (!h) return;
+    for (int i = 0; i < h->n; ++i) {
+        orc_msw *w = &h->w[i];
+        free(w->Brows); free(w->Bcols); free(w->Bvals); free(w->Cvals); free(w->LU); free(w->piv); free(w->z1); free(w->z2);
+    }
+    free(h->w); free(h);
+}
+
+/* Arguments as MultisegmentWellContribution's constructor (:32-37).  Returns 0, or 2 if D is singular. */
+int orc_ms_add(orc_mswells *h, unsigned dim, unsigned dim_wells, unsigned Mb, const double *Bvalues,
+               const unsigned *BcolIndices, const unsigned *BrowPointers, unsigned DnumBlocks, const double *Dvalues,
+               const int *DcolPointers, const int *DrowIndices, const double *Cvalues)
+{
+    if (dim != BS || dim_wells != 4) return 1;
+    if (h->n == h->cap) { h->cap = h->cap ? 2 * h->cap : 4; h->w = (orc_msw *) realloc(h->w, (size_t) h->cap * sizeof(orc_msw)); }
+    orc_msw *w = &h->w[h->n];
+    memset(w, 0, sizeof *w);
+    w->Mb = (int) Mb; w->M = (int) (Mb * dim_wells); w->nB = (int) BrowPointers[Mb];
+    size_t nv = (size_t) w->nB * dim * dim_wells;
+    w->Brows = (unsigned *) malloc((Mb + 1) * sizeof(unsigned)); memcpy(w->Brows, BrowPointers, (Mb + 1) * sizeof(unsigned));
+    w->Bcols = (unsigned *) malloc((size_t) (w->nB + 1) * sizeof(unsigned)); memcpy(w->Bcols, BcolIndices, (size_t) w->nB * sizeof(unsigned));
+    w->Bvals = (double *) malloc((nv + 1) * sizeof(double)); memcpy(w->Bvals, Bvalues, nv * sizeof(double));
+    w->Cvals = (double *) malloc((nv + 1) * sizeof(double)); memcpy(w->Cvals, Cvalues, nv * sizeof(double));
+    int M = w->M;
+    w->LU = (double *) calloc((size_t) M * M, sizeof(double));
+    w->piv = (int *) malloc((size_t) M * sizeof(int));
+    w->z1 = (double *) malloc((size_t) M * sizeof(double));
+    w->z2 = (double *) malloc((size_t) M * sizeof(double));
+    ++h->n;
+    /* CSC -> dense (duplicates add, as UMFPACK sums them) */
+    (void) DnumBlocks;
+    for (int c = 0; c < M; ++c)
+        for (int q = DcolPointers[c]; q < DcolPointers[c + 1]; ++q) w->LU[(size_t) DrowIndices[q] * M + c] += Dvalues[q];
+    for (int k = 0; k < M; ++k) {
+        int pr = k; double best = fabs(w->LU[(size_t) k * M + k]);
+        for (int i = k + 1; i < M; ++i) { double a = fabs(w->LU[(size_t) i * M + k]); if (a > best) { best = a; pr = i; } }
+        if (best == 0.0) return 2;
+        w->piv[k] = pr;
+        if (pr != k)
+            for (int c = 0; c < M; ++c) { double t = w->LU[(size_t) k * M + c]; w->LU[(size_t) k * M + c] = w->LU[(size_t) pr * M + c]; w->LU[(size_t) pr * M + c] = t; }
+        double inv = 1.0 / w->LU[(size_t) k * M + k];
+        for (int i = k + 1; i < M; ++i) {
+            double l = w->LU[(size_t) i * M + k] * inv;
+            w->LU[(size_t) i * M + k] = l;
+            if (l != 0.0)
+                for (int c = k + 1; c < M; ++c) w->LU[(size_t) i * M + c] -= l * w->LU[(size_t) k * M + c];
+        }
+    }
+    return 0;
+}
+
+int orc_ms_num(const orc_mswells *h) { return h ? h->n : 0; }
+
+/* y -= C^T (D^-1 (B x)) for every multisegment well, host vectors:
+ * opm/simulators/linalg/bda/MultisegmentWellContribution.cpp:70-110 (z1 = B x at :77-89, z2 = D^-1 z1 at :92,
+ * y -= C^T z2 at :96-109; C block entry [j + k * dim] multiplies z2[k]). */
+void orc_ms_apply(const orc_mswells *h, const double *x, double *y)
+{
+    if (!h) return;
+    for (int wi = 0; wi < h->n; ++wi) {
+        const orc_msw *w = &h->w[wi];
+        int M = w->M;
+        for (int i = 0; i < M; ++i) { w->z1[i] = 0.0; w->z2[i] = 0.0; }
+        for (int row = 0; row < w->Mb; ++row)
+            for (unsigned blk = w->Brows[row]; blk < w->Brows[row + 1]; ++blk) {
+                const double *xx = x + (size_t) w->Bcols[blk] * BS;
+                for (int j = 0; j < 4; ++j) {
+                    double t = 0.0;
+                    for (int k = 0; k < BS; ++k) t += w->Bvals[(size_t) blk * 12 + j * BS + k] * xx[k];
+                    w->z1[row * 4 + j] += t;
+                }
+            }
+        /* P z1, forward (unit L), backward (U) */
+        for (int i = 0; i < M; ++i) w->z2[i] = w->z1[i];
+        for (int k = 0; k < M; ++k) { int pr = w->piv[k]; if (pr != k) { double t = w->z2[k]; w->z2[k] = w->z2[pr]; w->z2[pr] = t; } }
+        for (int i = 1; i < M; ++i) { double s = w->z2[i]; for (int c = 0; c < i; ++c) s -= w->LU[(size_t) i * M + c] * w->z2[c]; w->z2[i] = s; }
+        for (int i = M - 1; i >= 0; --i) {
+            double s = w->z2[i];
+            for (int c = i + 1; c < M; ++c) s -= w->LU[(size_t) i * M + c] * w->z2[c];
+            w->z2[i] = s / w->LU[(size_t) i * M + i];
+        }
+        for (int row = 0; row < w->Mb; ++row)
+            for (unsigned blk = w->Brows[row]; blk < w->Brows[row + 1]; ++blk) {
+                double *yy = y + (size_t) w->Bcols[blk] * BS;
+                for (int j = 0; j < BS; ++j) {
+                    double t = 0.0;
+                    for (int k = 0; k < 4; ++k) t += w->Cvals[(size_t) blk * 12 + j + k * BS] * w->z2[row * 4 + k];
+                    yy[j] -= t;
+                }
+            }
+    }
+}
+
+/* The multisegment wells the operator of orc_solve / orc_true_residual applies (NULL: none).  Applied before the standard
+ * wells, as WellContributions::apply does (opm/simulators/linalg/bda/WellContributions.cu:167-193). */
+static const orc_mswells *g_mswells = NULL;
+void orc_attach_mswells(const orc_mswells *h) { g_mswells = h; }
+
 /* ---- block ILU0 ---------------------------------------------------------- */
 
 /* In-place left-looking block ILU0 with stored inverse diagonal, restricted to
@@ -358,6 +479,7 @@ typedef struct {
 static void op_apply(const orc_sys *S, const double *x, double *y)
 {
     orc_spmv(S->Nb, S->rows, S->cols, S->vals, x, y);
+    if (g_mswells) orc_ms_apply(g_mswells, x, y);
     if (S->nwells > 0)
         orc_well_apply(S->nwells, S->wptr, S->Bcols, S->Ccols, S->B, S->C, S->Dinv, x, y);
 }

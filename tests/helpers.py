@@ -16,6 +16,38 @@ def bridge_wells(w, mode="b200"):
     return bridge.WellContributions.from_arrays(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv, mode)
 
 
+def oracle_mswells(ms):
+    from oracle import oracle
+    if not ms:
+        return None
+    return oracle.MSWells([oracle.MultisegmentWell(m.Mb, m.Bvalues, m.BcolIndices, m.BrowPointers, m.DnumBlocks, m.Dvalues,
+                                                   m.DcolPointers, m.DrowIndices, m.Cvalues) for m in ms])
+
+
+def add_bridge_mswells(wc, ms):
+    """Append multisegment wells to a bridge.WellContributions (addMultisegmentWellContribution per well)."""
+    for m in ms or ():
+        wc.addMultisegmentWellContribution(3, 4, m.Mb, m.Bvalues, m.BcolIndices, m.BrowPointers, m.DnumBlocks, m.Dvalues,
+                                           m.DcolPointers, m.DrowIndices, m.Cvalues)
+    return wc
+
+
+def dense_mswell_operator(ms, Nb):
+    """sum over multisegment wells of C^T D^-1 B as a dense (3Nb x 3Nb) matrix."""
+    Mop = np.zeros((3 * Nb, 3 * Nb))
+    for m in ms or ():
+        M = 4 * m.Mb
+        Bd = np.zeros((M, 3 * Nb))
+        Cd = np.zeros((M, 3 * Nb))
+        for r in range(m.Mb):
+            for blk in range(int(m.BrowPointers[r]), int(m.BrowPointers[r + 1])):
+                c = int(m.BcolIndices[blk])
+                Bd[4 * r:4 * r + 4, 3 * c:3 * c + 3] += np.asarray(m.Bvalues[blk]).reshape(4, 3)
+                Cd[4 * r:4 * r + 4, 3 * c:3 * c + 3] += np.asarray(m.Cvalues[blk]).reshape(4, 3)
+        Mop += Cd.T @ np.linalg.solve(m.dense_D(), Bd)
+    return Mop
+
+
 def dense_from_bsr(rows, cols, vals):
     Nb = len(rows) - 1
     A = np.zeros((3 * Nb, 3 * Nb))

@@ -77,6 +77,42 @@ def test_well_contributions_error_behaviour(built):
     assert empty.getNumWells() == 0
 
 
+def test_multisegment_well_container(built):
+    """addMultisegmentWellContribution (WellContributions.hpp:195-213, .cpp:261-271): host-side behaviour -- counts, block-size
+    check, and the dense inverse of the CSC matrix D that stands in for the reference's UMFPACK factorisation
+    (MultisegmentWellContribution.cpp:56-57)."""
+    from opm_autodiff_b200 import synth
+    from opm_autodiff_b200.bridge import WellContributions as WC
+    from tests.helpers import add_bridge_mswells
+    s = synth.small(6, 5, 4)
+    ms = synth.add_mswells(s, 3, 7, seed=11)
+    w = add_bridge_mswells(WC("b200", False), ms)
+    assert w.getNumWells() == 3                      # num_std_wells + num_ms_wells (WellContributions.hpp:164-166)
+    for i, m in enumerate(ms):
+        D = m.dense_D()
+        inv = w.multisegment_inverse(i, 4 * m.Mb)
+        assert np.abs(inv @ D - np.eye(4 * m.Mb)).max() < 1e-12
+    m = ms[0]
+    with pytest.raises(ValueError, match="must be equal to 3 and 4"):
+        w.addMultisegmentWellContribution(3, 3, m.Mb, m.Bvalues, m.BcolIndices, m.BrowPointers, m.DnumBlocks, m.Dvalues,
+                                          m.DcolPointers, m.DrowIndices, m.Cvalues)
+    with pytest.raises(ValueError, match="singular"):
+        w.addMultisegmentWellContribution(3, 4, m.Mb, m.Bvalues, m.BcolIndices, m.BrowPointers, m.DnumBlocks,
+                                          np.zeros_like(m.Dvalues), m.DcolPointers, m.DrowIndices, m.Cvalues)
+    with pytest.raises(ValueError, match="array sizes"):
+        w.addMultisegmentWellContribution(3, 4, m.Mb + 1, m.Bvalues, m.BcolIndices, m.BrowPointers, m.DnumBlocks, m.Dvalues,
+                                          m.DcolPointers, m.DrowIndices, m.Cvalues)
+    assert w.getNumWells() == 3
+    # a pivoting case: D with a zero on the diagonal is still inverted
+    P = WC("b200", False)
+    Dd = np.array([[0.0, 2.0, 0, 0], [1.0, 0.0, 0, 0], [0, 0, 0.0, 4.0], [0, 0, 3.0, 1.0]])
+    colptr = np.arange(0, 17, 4, dtype=np.int32)
+    rowidx = np.tile(np.arange(4, dtype=np.int32), 4)
+    P.addMultisegmentWellContribution(3, 4, 1, np.zeros(12), np.zeros(1, np.uint32), np.array([0, 1], np.uint32), 1,
+                                      Dd.T.reshape(-1).copy(), colptr, rowidx, np.zeros(12))
+    assert np.abs(P.multisegment_inverse(0, 4) @ Dd - np.eye(4)).max() < 1e-14
+
+
 def test_bridge_mode_strings_and_zero_diagonal(built):
     from opm_autodiff_b200 import bridge
     with pytest.raises(ValueError, match="AcceleratorMode"):

@@ -204,3 +204,28 @@ def test_level_schedule_vs_live_reference(built):
         assert np.array_equal(to, rto) and np.array_equal(fr, rfr) and np.array_equal(lp, rlp)
         if nnc == 0:
             assert len(lp) - 1 == nx + ny + nz - 2
+
+
+def test_multisegment_well_apply_against_dense_algebra():
+    """The oracle's restatement of MultisegmentWellContribution::apply (bda/MultisegmentWellContribution.cpp:70-110, dense
+    LU with partial pivoting in place of UMFPACK) against C^T D^-1 B built densely with numpy; and the operator of the
+    oracle's solve applies multisegment wells before the standard ones (bda/WellContributions.cu:167-193).
+    Parity unpinned by the reference: no reference test builds a MultisegmentWellContribution."""
+    from opm_autodiff_b200 import synth
+    from tests.helpers import dense_mswell_operator, dense_well_operator, dense_from_bsr, oracle_mswells, oracle_wells, relerr
+    s = synth.small(7, 6, 5, nwells=2, nperf=3)
+    ms = synth.add_mswells(s, 3, 6, seed=5)
+    assert any(len(set(a.BcolIndices.tolist()) & set(b.BcolIndices.tolist())) for a in ms for b in ms if a is not b)
+    om = oracle_mswells(ms)
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal(3 * s.Nb), rng.standard_normal(3 * s.Nb)
+    Mop = dense_mswell_operator(ms, s.Nb)
+    assert relerr(om.apply(x, y), y - Mop @ x) < 1e-14
+    # the generator keeps x_true the solution of (A - std wells - ms wells) x = b
+    A = dense_from_bsr(s.rows, s.cols, s.vals) - dense_well_operator(s.wells, s.Nb) - Mop
+    assert relerr(A @ s.x_true, s.b) < 1e-12
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, s.x_true, oracle_wells(s.wells), om) < 1e-13
+    r = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200, mswells=om)
+    assert r.converged and relerr(r.x, s.x_true) < 1e-5
+    r0 = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200)
+    assert relerr(r0.x, s.x_true) > 1e-3            # the wells matter
