@@ -19,6 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle_bda.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libref_reorder.so")
+_REF_CUSPARSE_PATH = os.path.join(_HERE, "_ref", "libref_cusparse.so")   # incumbent GPU backend (tools/incumbent_cusparse.py)
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -37,7 +38,7 @@ def build(force: bool = False) -> None:
     if force or not os.path.exists(_LIB_PATH) or \
             os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "oracle_bda.c")):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_bda.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/opm") and (force or not os.path.exists(_REF_PATH)):
+    if os.path.isdir("/root/reference/opm") and (force or not os.path.exists(_REF_PATH) or not os.path.exists(_REF_CUSPARSE_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
