@@ -40,7 +40,11 @@ def run_incumbent(L, s, wells, tol, maxit, nsolves):
     N, nnz = 3 * s.Nb, 9 * s.nnzb
     vals = np.ascontiguousarray(s.vals, np.float64).reshape(-1).copy()
     rows = np.ascontiguousarray(s.rows, np.int32)
-    cols = np.ascontiguousarray(s.cols, np.int32)
+    # the reference copies nnz (not nnzb) column indices to the device (cusparseSolverBackend.cu:295): it reads 8/9 of that
+    # range past the end of the caller's array, which faults for a 1 M-cell system; the harness therefore hands it a
+    # column array padded to nnz ints (the reference itself stays unmodified)
+    cols = np.zeros(nnz, np.int32)
+    cols[:s.nnzb] = s.cols
     b = np.ascontiguousarray(s.b, np.float64).copy()
     x = np.zeros(N)
     wall = np.zeros(nsolves)
