@@ -271,6 +271,7 @@ struct Solver {
     const void* reg_vals = nullptr; size_t reg_vals_bytes = 0;
     const void* reg_b = nullptr; size_t reg_b_bytes = 0;
     const void* reg_x = nullptr; size_t reg_x_bytes = 0;      // the caller's solution vector (get_result)
+    const void* cand_vals = nullptr; const void* cand_b = nullptr; const void* cand_x = nullptr;   // seen once, not yet pinned
 
     KStat stats[K_COUNT];
     long long launch_count = 0;
@@ -535,11 +536,15 @@ struct Solver {
         analysed = true;
     }
 
-    void maybe_register(const void*& reg, size_t& reg_bytes, const void* ptr, size_t bytes)
+    // Page-locks a caller's array once it has been handed in on two consecutive calls (Flow's matrix, rhs and solution
+    // storage persists over the Newton steps).  A caller that passes a fresh buffer every time never pays for the
+    // registration -- pinning and unpinning a new 12 MB vector per call cost more than the pageable copy it replaces.
+    void maybe_register(const void*& reg, size_t& reg_bytes, const void*& cand, const void* ptr, size_t bytes)
     {
         if (!pin_host) return;
         if (reg == ptr && reg_bytes == bytes) return;
         if (reg) { cudaHostUnregister((void*) reg); cudaGetLastError(); reg = nullptr; reg_bytes = 0; }
+        if (cand != ptr) { cand = ptr; return; }     // first sighting: pageable copy this time
         cudaError_t e = cudaHostRegister((void*) ptr, bytes, cudaHostRegisterDefault);
         if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
         if (e != cudaSuccess) { cudaGetLastError(); return; }   // pageable copy still works
@@ -674,8 +679,8 @@ struct Solver {
         } else if (N_ != N || nnz_ != nnz_stage) {
             throw std::runtime_error("sparsity pattern changed after the first call (fixed, cusparseSolverBackend.cu:312)");
         }
-        maybe_register(reg_vals, reg_vals_bytes, vals, sizeof(double) * nnz_stage);
-        maybe_register(reg_b, reg_b_bytes, b, sizeof(double) * N);
+        maybe_register(reg_vals, reg_vals_bytes, cand_vals, vals, sizeof(double) * nnz_stage);
+        maybe_register(reg_b, reg_b_bytes, cand_b, b, sizeof(double) * N);
         CUDA_OK(cudaEventRecord(ev_a, stream));
         CUDA_OK(cudaMemcpyAsync(d_stage.p, vals, sizeof(double) * nnz_stage, cudaMemcpyHostToDevice, stream));
         CUDA_OK(cudaMemcpyAsync(d_bstage.p, b, sizeof(double) * N, cudaMemcpyHostToDevice, stream));
@@ -1287,7 +1292,7 @@ b200_status b200_get_result(b200_solver* s, double* x)
     return guarded([&]() -> b200_status {
         if (!s->analysed) throw std::runtime_error("get_result before any solve");
         CUDA_OK(cudaSetDevice(s->device));
-        s->maybe_register(s->reg_x, s->reg_x_bytes, x, sizeof(double) * s->N);     // pageable D2H of 24 B per row costs 2 ms on C3
+        s->maybe_register(s->reg_x, s->reg_x_bytes, s->cand_x, x, sizeof(double) * s->N);     // pageable D2H of 24 B per row costs 2 ms on C3
         CUDA_OK(cudaMemcpyAsync(x, s->d_xnat.p, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
         CUDA_OK(cudaStreamSynchronize(s->stream));
         return B200_SUCCESS;

@@ -411,8 +411,10 @@ class DistSolver:
         self.be.solve_resident(res)
         return res
 
-    def get_result(self) -> np.ndarray:
-        x = np.zeros(self.N)
+    def get_result(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Owned part of the solution; `out` lets a caller keep ONE solution vector over the solves, as Flow does (the
+        library page-locks a vector it sees on consecutive calls)."""
+        x = np.zeros(self.N) if out is None else out
         self.be.get_result(x)
         return x
 

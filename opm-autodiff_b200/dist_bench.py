@@ -49,16 +49,17 @@ def run(args, metric, tol, maxit, get_cfg, ClockSampler, measured_peak):
         return float(t[0])
 
     # ---- e2e: host buffers, H2D of values + rhs and D2H of x inside the timed region --------------------
+    x = np.zeros(ds.N)
     for _ in range(args.warmup):
         ds.solve_system(res)
-        x = ds.get_result()
+        ds.get_result(x)
     assert res.converged, "solve did not converge"
     t_analysis = res.t_analysis
     sync()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ds.solve_system(res)
-        x = ds.get_result()
+        ds.get_result(x)
     sync()
     e2e_s = maxf((time.perf_counter() - t0) / args.steps)
     err2 = sumf(float(np.sum((x - ls.x_true) ** 2)))
