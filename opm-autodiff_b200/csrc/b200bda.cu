@@ -149,46 +149,71 @@ struct Wells {
     std::vector<MsWell> ms;
 };
 
-// Dense inverse of the scalar CSC matrix D of a multisegment well (Gauss-Jordan with partial pivoting on the host).  The
+// Inverse of the scalar CSC matrix D of a multisegment well as a dense row-major M x M matrix, on the host: LU with partial
+// pivoting that skips structural zeros through per-row column extents (D is a block tree, mostly a chain of segments: the
+// factors stay banded, O(M bw^2)), then one forward / backward substitution per column of the identity (O(M^2 bw)).  The
 // reference factorises D with UMFPACK at the same point (MultisegmentWellContribution.cpp:56-57) and solves on the host in
 // every operator apply; with the explicit inverse the apply is a dense mat-vec on the device.
 static void invert_csc(int M, const int* colptr, const int* rowidx, const double* vals, std::vector<double>& inv)
 {
     std::vector<double> A((size_t) M * M, 0.0);
+    std::vector<int> lo(M, M), hi(M, -1), perm(M);
     for (int c = 0; c < M; ++c) {
         if (colptr[c + 1] < colptr[c]) throw std::runtime_error("multisegment well: D column pointers must ascend");
         for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
-            if (rowidx[q] < 0 || rowidx[q] >= M) throw std::runtime_error("multisegment well: D row index out of range");
-            A[(size_t) rowidx[q] * M + c] += vals[q];
+            const int r = rowidx[q];
+            if (r < 0 || r >= M) throw std::runtime_error("multisegment well: D row index out of range");
+            A[(size_t) r * M + c] += vals[q];
+            lo[r] = std::min(lo[r], c); hi[r] = std::max(hi[r], c);
         }
     }
-    inv.assign((size_t) M * M, 0.0);
-    for (int i = 0; i < M; ++i) inv[(size_t) i * M + i] = 1.0;
+    for (int i = 0; i < M; ++i) perm[i] = i;
     for (int k = 0; k < M; ++k) {
-        int pr = k;
-        double best = std::fabs(A[(size_t) k * M + k]);
-        for (int i = k + 1; i < M; ++i) {
+        int pr = -1;
+        double best = 0.0;
+        for (int i = k; i < M; ++i) {
+            if (lo[i] > k) continue;
             const double a = std::fabs(A[(size_t) i * M + k]);
             if (a > best) { best = a; pr = i; }
         }
-        if (!(best > 0.0)) throw std::runtime_error("multisegment well: matrix D is singular");
-        if (pr != k)
-            for (int c = 0; c < M; ++c) {
-                std::swap(A[(size_t) k * M + c], A[(size_t) pr * M + c]);
-                std::swap(inv[(size_t) k * M + c], inv[(size_t) pr * M + c]);
-            }
-        const double piv = 1.0 / A[(size_t) k * M + k];
-        double* ak = &A[(size_t) k * M];
-        double* ik = &inv[(size_t) k * M];
-        for (int c = 0; c < M; ++c) { ak[c] *= piv; ik[c] *= piv; }
-        for (int i = 0; i < M; ++i) {
-            if (i == k) continue;
-            const double f = A[(size_t) i * M + k];
-            if (f == 0.0) continue;
-            double* ai = &A[(size_t) i * M];
-            double* ii = &inv[(size_t) i * M];
-            for (int c = 0; c < M; ++c) { ai[c] -= f * ak[c]; ii[c] -= f * ik[c]; }
+        if (pr < 0) throw std::runtime_error("multisegment well: matrix D is singular");
+        if (pr != k) {
+            std::swap_ranges(A.begin() + (size_t) k * M, A.begin() + (size_t) (k + 1) * M, A.begin() + (size_t) pr * M);
+            std::swap(lo[k], lo[pr]); std::swap(hi[k], hi[pr]); std::swap(perm[k], perm[pr]);
         }
+        const double* ak = &A[(size_t) k * M];
+        const double piv = 1.0 / ak[k];
+        const int hk = hi[k];
+        for (int i = k + 1; i < M; ++i) {
+            if (lo[i] > k) continue;
+            double* ai = &A[(size_t) i * M];
+            if (ai[k] == 0.0) continue;
+            const double f = ai[k] * piv;
+            ai[k] = f;
+            for (int c = k + 1; c <= hk; ++c) ai[c] -= f * ak[c];
+            hi[i] = std::max(hi[i], hk);
+        }
+    }
+    // columns of the inverse: L U x = P e_j
+    inv.assign((size_t) M * M, 0.0);
+    std::vector<double> y(M);
+    for (int q = 0; q < M; ++q) {
+        const int j = perm[q];                 // (P e_j) is the unit vector e_q
+        for (int i = 0; i < q; ++i) y[i] = 0.0;
+        y[q] = 1.0;
+        for (int i = q + 1; i < M; ++i) {
+            const double* ai = &A[(size_t) i * M];
+            double sacc = 0.0;
+            for (int c = std::max(lo[i], q); c < i; ++c) sacc += ai[c] * y[c];
+            y[i] = -sacc;
+        }
+        for (int i = M - 1; i >= 0; --i) {
+            const double* ai = &A[(size_t) i * M];
+            double sacc = y[i];
+            for (int c = i + 1; c <= hi[i]; ++c) sacc -= ai[c] * y[c];
+            y[i] = sacc / ai[i];
+        }
+        for (int i = 0; i < M; ++i) inv[(size_t) i * M + j] = y[i];
     }
 }
 
