@@ -68,6 +68,8 @@ void b200_destroy(b200_solver* s);
  *   "relaxation"  ILU0 relaxation w (setupPropertyTree.cpp:175-188; cusparse uses 1.0)  default 1.0
  *   "tolerance", "maxit", "verbosity"   override the constructor values
  *   "pin_host"    1: cudaHostRegister the caller's vals / b / x once they are seen on two consecutive calls   default 1
+ *   "wells_flat"  1: standard wells that fit one CTA (<= 1024 perforations, <= 128 wells) use the apply kernel with
+ *                 host-resolved index chains (k_wells_flat); 0: always the general kernel                 default 1
  *   "use_graph"   1: replay the factorisation launches and the BiCGSTAB iteration body as CUDA graphs  default 1
  *   "lookahead"   iterations enqueued per convergence read-back (the device stops by itself)      default 2
  *   "profile"     1: time every kernel with CUDA events (no graphs), see b200_kernel_stats         default 0

@@ -284,6 +284,12 @@ struct Solver {
     DevBuf<unsigned> d_wptr;
     DevBuf<int> d_Bcols, d_ucell, d_uptr, d_ublock, d_uwell;
     DevBuf<double> d_B, d_C, d_Dinv, d_z2;
+    // standard wells, index chains resolved on the host (k_wells_flat): used when the wells fit one CTA
+    int wells_flat = 1;                // option: 0 never, 1 when they fit
+    bool flat_ok = false;
+    DevBuf<int4> d_item;
+    DevBuf<double> d_itemC;
+    WellsFlatD flatD{};
     // multisegment wells (device, p-space columns); ms_epoch changes whenever they are uploaded (graph signature)
     int nms = 0, ms_blocks = 0, ms_rows = 0, ms_ncells = 0, ms_epoch = 0;
     long long ms_dinv_entries = 0;
@@ -685,6 +691,26 @@ struct Solver {
         H2D(d_B.p, w->Bnnzs.data(), sizeof(double) * nwblocks * 12);
         H2D(d_C.p, w->Cnnzs.data(), sizeof(double) * nwblocks * 12);
         H2D(d_Dinv.p, w->Dnnzs.data(), sizeof(double) * nwells * 16);
+        // k_wells_flat: one int4 + four C entries per (unique cell, component), in thread order
+        const int nitems = 3 * nucells;
+        flat_ok = nwblocks <= 1024 && nitems <= 3072 && nwells <= 128 && 3ll * Nb < (1ll << 31);
+        std::vector<int4> item;
+        std::vector<double> itemC;
+        if (flat_ok) {
+            item.resize(nitems); itemC.resize((size_t) nitems * 4);
+            for (int u = 0; u < nucells; ++u)
+                for (int c = 0; c < 3; ++c) {
+                    const int t = 3 * u + c, e0 = uptr[u];
+                    item[t] = make_int4(3 * ucell[u] + c, uptr[u + 1] - uptr[u], e0, 4 * uwell[e0]);
+                    for (int k = 0; k < 4; ++k) itemC[(size_t) t * 4 + k] = w->Cnnzs[(size_t) ublock[e0] * 12 + 3 * k + c];
+                }
+            d_item.alloc(nitems); d_itemC.alloc((size_t) nitems * 4);
+            H2D(d_item.p, item.data(), sizeof(int4) * nitems);
+            H2D(d_itemC.p, itemC.data(), sizeof(double) * nitems * 4);
+            flatD.nwells = nwells; flatD.nblocks = nwblocks; flatD.nitems = nitems; flatD.wptr = d_wptr.p; flatD.bcol = d_Bcols.p;
+            flatD.B = d_B.p; flatD.Dinv = d_Dinv.p; flatD.item = d_item.p; flatD.itemC = d_itemC.p; flatD.C = d_C.p;
+            flatD.ublock = d_ublock.p; flatD.uwell = d_uwell.p;
+        }
         CUDA_OK(cudaStreamSynchronize(stream));   // the host vectors above are temporaries
     }
 
@@ -914,6 +940,11 @@ struct Solver {
         mswells_apply<MODE>(x, y, d1);
         if (nwells == 0) return;
         int id = prof_begin(K_WELL);
+        if (flat_ok && wells_flat) {
+            launch_iter(k_wells_flat<MODE>, dim3(1), dim3(1024), 0, flatD, x, y, d1, d_S.p);
+            prof_end(id);
+            return;
+        }
         launch_iter(k_wells<MODE>, dim3(1), dim3(1024), 0, nwells, d_wptr.p, d_Bcols.p, d_B.p, d_C.p, d_Dinv.p, nucells, d_ucell.p, d_uptr.p,
                                               d_ublock.p, d_uwell.p, d_z2.p, x, y, d1, d_S.p);
         prof_end(id);
@@ -1030,7 +1061,7 @@ struct Solver {
 
     // One BiCGSTAB iteration: on a single GPU the 10-12 launches are replayed from a CUDA graph (the launch sequence
     // depends on nothing but the pointers; the convergence logic lives on the device), otherwise launched one by one.
-    struct IterSig { const void* a[6]; int n[6]; bool operator!=(const IterSig& o) const { return memcmp(this, &o, sizeof *this) != 0; } };
+    struct IterSig { const void* a[8]; int n[6]; bool operator!=(const IterSig& o) const { return memcmp(this, &o, sizeof *this) != 0; } };
     cudaGraphExec_t iter_graph_exec = nullptr;
     IterSig iter_sig{};
     void run_iteration()
@@ -1040,6 +1071,8 @@ struct Solver {
         sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
         sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0) + (defer_now() ? 1 << 21 : 0);
         sig.n[4] = nms; sig.n[5] = ms_epoch;
+        sig.a[6] = d_item.p; sig.a[7] = d_itemC.p;
+        sig.n[3] += (flat_ok && wells_flat) ? 1 << 22 : 0;
         if (!iter_graph_exec || sig != iter_sig) {
             if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -1225,6 +1258,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "use_graph") s->use_graph = value != 0.0;
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
+        else if (k == "wells_flat") s->wells_flat = value != 0.0 ? 1 : 0;
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;

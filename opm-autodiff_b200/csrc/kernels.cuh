@@ -1432,6 +1432,142 @@ __global__ void __launch_bounds__(1024) k_wells(int nwells, const unsigned* __re
     }
 }
 
+// The same apply with every index chain resolved on the host (the wells are re-uploaded for every solve anyway): used when
+// the wells fit one CTA's registers and shared memory (<= 1024 perforations, <= 3072 (cell, component) items, <= 128 wells;
+// C3: 1000 / 3000 / 50), k_wells otherwise.  k_wells is a chain of dependent global loads (well pointer -> column -> x, then
+// list pointer -> block -> C); here a thread owns ONE perforation in phase 1 and up to three (cell, component) items in
+// phase 2, and everything that does not depend on x or z2 -- column, B block, D^-1 row, the item's y index, its four C
+// entries, its well -- is loaded at the top of the kernel from arrays laid out in thread order.  What is left on the
+// critical path: one gather of x, two shared-memory steps, the y update and the block reduction.
+//   phase 1: part[p][r] = (B_p x_p)[r]; thread (w, r) adds the parts of well w in perforation order (deterministic, the
+//            oracle's order) and applies D^-1.
+//   phase 2: item t = (unique cell u, component c): y -= sum_e C_e[:, c] . z2[well(e)]; the first contribution comes from
+//            the pre-gathered itemC, further ones (two wells in one cell) walk the generic lists.
+struct WellsFlatD {
+    int nwells, nblocks, nitems;
+    const unsigned* wptr;     // [nwells + 1]
+    const int* bcol;          // [nblocks] p-space column of B_p
+    const double* B;          // [nblocks][4][3]
+    const double* Dinv;       // [nwells][4][4]
+    const int4* item;         // [nitems] {3 * cell + c, contributions, first list entry, 4 * well of the first contribution}
+    const double* itemC;      // [nitems][4] C entries of the first contribution: C[k][c], k = 0..3
+    // generic lists for items with more than one contribution
+    const double* C;
+    const int* ublock;
+    const int* uwell;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_wells_flat(WellsFlatD W, const double* __restrict__ x, double* y,
+                                                     const double* __restrict__ d1, Scalars* S)
+{
+    pdl_enter();
+    constexpr int kMaxWells = 128, kItems = 3;
+    __shared__ double part[1024 * 4];
+    __shared__ double z1s[kMaxWells * 4];
+    __shared__ double z2s[kMaxWells * 4];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
+    // ---- loads that depend on nothing computed here
+    const bool hasp = t < W.nblocks;
+    int col = 0;
+    double b[12];
+    if (hasp) {
+        col = W.bcol[t];
+        const double2* bp = reinterpret_cast<const double2*>(W.B + (size_t) t * 12);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double2 v = bp[i]; b[2 * i] = v.x; b[2 * i + 1] = v.y; }
+    }
+    const bool hasw = t < 4 * W.nwells;
+    double dinv[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned wb = 0, we = 0;
+    if (hasw) {
+        const int w = t >> 2;
+        wb = W.wptr[w]; we = W.wptr[w + 1];
+        const double2* dp = reinterpret_cast<const double2*>(W.Dinv + (size_t) t * 4);
+        const double2 v0 = dp[0], v1 = dp[1];
+        dinv[0] = v0.x; dinv[1] = v0.y; dinv[2] = v1.x; dinv[3] = v1.y;
+    }
+    int4 it[kItems];
+    double ic[kItems][4], yold[kItems], dd1[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        const int q = t + k * 1024;
+        it[k] = make_int4(0, 0, 0, 0);
+        yold[k] = 0.0; dd1[k] = 0.0;
+        if (q < W.nitems) {
+            it[k] = W.item[q];
+            const double2* cp = reinterpret_cast<const double2*>(W.itemC + (size_t) q * 4);
+            const double2 v0 = cp[0], v1 = cp[1];
+            ic[k][0] = v0.x; ic[k][1] = v0.y; ic[k][2] = v1.x; ic[k][3] = v1.y;
+        }
+    }
+    const int done = MODE != 0 ? S->done : 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+        if (t + k * 1024 < W.nitems) {
+            yold[k] = y[it[k].x];
+            if (MODE != 0) dd1[k] = d1[it[k].x];
+        }
+    if (done) return;
+    // ---- phase 1
+    if (hasp) {
+        const double* xp = x + 3 * (size_t) col;
+        const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) part[t * 4 + r] = b[3 * r] * x0 + b[3 * r + 1] * x1 + b[3 * r + 2] * x2;
+    }
+    __syncthreads();
+    if (hasw) {
+        const int r = t & 3;
+        double z = 0.0;
+        for (unsigned p = wb; p < we; ++p) z += part[p * 4 + r];
+        z1s[t] = z;
+    }
+    __syncthreads();
+    if (hasw) {
+        const double* zz = z1s + (t & ~3);
+        z2s[t] = dinv[0] * zz[0] + dinv[1] * zz[1] + dinv[2] * zz[2] + dinv[3] * zz[3];
+    }
+    __syncthreads();
+    // ---- phase 2
+    double acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        if (t + k * 1024 >= W.nitems) continue;
+        const double* zz = z2s + it[k].w;
+        double delta = ic[k][0] * zz[0] + ic[k][1] * zz[1] + ic[k][2] * zz[2] + ic[k][3] * zz[3];
+        if (it[k].y > 1) {
+            const int c = it[k].x % 3;
+            for (int e = it[k].z + 1, ee = it[k].z + it[k].y; e < ee; ++e) {
+                const double* cb = W.C + (size_t) W.ublock[e] * 12 + c;
+                const double* z2 = z2s + 4 * W.uwell[e];
+                delta += cb[0] * z2[0] + cb[3] * z2[1] + cb[6] * z2[2] + cb[9] * z2[3];
+            }
+        }
+        const double now = yold[k] - delta;
+        y[it[k].x] = now;
+        if (MODE == 1) acc[0] += dd1[k] * (now - yold[k]);
+        if (MODE == 2) { acc[0] += dd1[k] * (now - yold[k]); acc[1] += now * now - yold[k] * yold[k]; }
+    }
+    if (MODE != 0) {
+        __shared__ double sm[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double v = warp_sum(acc[i]);
+            if (lane == 0) sm[i][warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double a = lane < nwarp ? sm[0][lane] : 0.0, bsum = lane < nwarp ? sm[1][lane] : 0.0;
+            a = warp_sum(a); bsum = warp_sum(bsum);
+            if (lane == 0) {
+                if (MODE == 1) S->h += a;
+                if (MODE == 2) { S->tr += a; S->tt += bsum; }
+            }
+        }
+    }
+}
+
 // ---- multisegment wells ---------------------------------------------------------------------------
 //
 // y -= C^T (D^-1 (B x)) for multisegment wells (bda/MultisegmentWellContribution.cpp:70-110).  The reference copies x and y

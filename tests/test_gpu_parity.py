@@ -430,3 +430,57 @@ def test_repeated_solves_reproduce_bit_for_bit(mods):
             else:
                 assert np.array_equal(x, first) and res.it == it0
         assert relerr(first, s.x_true) < 1e-5
+
+
+def test_wells_flat_and_general_kernels_agree(mods):
+    """Standard wells run through k_wells_flat when they fit one CTA (<= 1024 perforations, <= 128 wells) and through
+    k_wells otherwise (option wells_flat = 0 forces the general kernel): both against the oracle, on wells that share
+    cells and whose B and C columns differ, in the apply alone and inside a solve; and a container beyond the flat
+    limits (1500 perforations) still takes the general kernel."""
+    bridge, synth, oracle = mods
+    from opm_autodiff_b200.synth import WellData
+    s = synth.small(14, 12, 10)
+    rng = np.random.default_rng(21)
+    cs = np.array([1e-7, 1.0, 1.0])
+
+    def wells(nw, nperf, shared):
+        ptr, cb, cc = [0], [], []
+        for w in range(nw):
+            c = rng.permutation(s.Nb)[:nperf].astype(np.int32)
+            if shared and w > 0:
+                c[:3] = cb[-1][:3]                               # three cells shared with the previous well
+            cb.append(c)
+            cc.append(c[::-1].copy() if w % 2 else c.copy())     # C columns differ from B columns on odd wells
+            ptr.append(ptr[-1] + nperf)
+        n = ptr[-1]
+        return WellData(np.array(ptr, np.uint32), np.concatenate(cb), np.concatenate(cc), 0.05 * rng.normal(size=(n, 4, 3)) * cs,
+                        0.05 * rng.normal(size=(n, 4, 3)), np.stack([np.eye(4) + 0.1 * rng.normal(size=(4, 4)) for _ in range(nw)]))
+
+    x = rng.normal(size=3 * s.Nb)
+    y0 = rng.normal(size=3 * s.Nb)
+    for nw, nperf, shared in ((1, 1, False), (7, 37, True), (40, 25, True), (3, 500, False), (130, 2, False)):
+        w = wells(nw, nperf, shared)
+        ref = oracle.well_apply(oracle_wells(w), x, y0)
+        got = {}
+        for flat in (1, 0):
+            be = bridge.B200SolverBackend(0, 200, 1e-10, 0)
+            be.set_option("wells_flat", flat)
+            be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(w))
+            got[flat] = be.well_apply(x, y0)
+            assert relerr(got[flat] - y0, ref - y0) < 1e-12, (nw, nperf, flat)
+            assert np.array_equal(be.well_apply(x, y0), got[flat])
+        assert relerr(got[1], got[0]) < 1e-13
+    # inside a solve: same iterates within rounding, same iteration count
+    w = wells(6, 30, True)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(w), tol=1e-10, maxit=300)
+    its = []
+    for flat in (1, 0):
+        be = bridge.B200SolverBackend(0, 300, 1e-10, 0)
+        be.set_option("wells_flat", flat)
+        res = bridge.BdaResult()
+        be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(w), res)
+        xs = np.zeros(3 * s.Nb)
+        be.get_result(xs)
+        assert res.converged and relerr(xs, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
+        its.append(res.it)
+    assert its[0] == its[1]
