@@ -14,6 +14,7 @@ Jacobian.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every
   roofline  dominant kernel of the step: algorithmic bytes / mean launch duration (CUDA events around
           every launch in a separate profiled solve) against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the CPU oracle (port of the reference's ISTL path) on this box's host cores, bounded sample
+  also    (default workload only) a short measurement of BASELINE.json's other single-GPU configuration, C2
 
 --impl reference times the reference's own CPU algorithm (the oracle port: the Dune/ISTL path does
 not compile in this image) with all host threads, one block-Jacobi ILU0 partition per
