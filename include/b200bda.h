@@ -75,7 +75,8 @@ void b200_destroy(b200_solver* s);
  *   "profile"     1: time every kernel with CUDA events (no graphs), see b200_kernel_stats         default 0
  *   "sweep_parts", "sweep_warps", "sweep_groups", "sweep_helpers", "sweep_slots", "sweep_stage_bytes", "sweep_window",
  *   "sweep_ext_window"   schedule of the triangular sweeps: parts (CTAs, all resident), consumer warps per CTA and their
- *                 level groups, helper warps, ring slots and bytes per stage, rows of the shared-memory window (0 = auto)
+ *                 level groups, helper warps, ring slots and bytes per stage (0 = auto: a quarter of a part's factor bytes,
+ *                 16 KB .. 80 KB), rows of the shared-memory window (0 = auto)
  *                 and of the external-row ring; set before the first solve
  *   "sweep_helper_sleep"  ns a helper warp sleeps between two polls of external rows                default 60
  *   "sweep_trace" 1: record the stage timeline of the sweeps (b200_get_sweep_trace; debugging)     default 0

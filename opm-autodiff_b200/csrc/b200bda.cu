@@ -223,7 +223,7 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 81920, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 60;
+    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 60;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -290,6 +290,10 @@ struct Solver {
     DevBuf<int4> d_item;
     DevBuf<double> d_itemC;
     WellsFlatD flatD{};
+    // host copy of the last uploaded well structure (see upload_wells)
+    bool wells_structure_valid = false;
+    std::vector<unsigned> h_wptr;
+    std::vector<int> h_wBcols, h_wCcols, h_ucell, h_uptr, h_ublock, h_uwell;
     // multisegment wells (device, p-space columns); ms_epoch changes whenever they are uploaded (graph signature)
     int nms = 0, ms_blocks = 0, ms_rows = 0, ms_ncells = 0, ms_epoch = 0;
     long long ms_dinv_entries = 0;
@@ -419,7 +423,18 @@ struct Solver {
         if (rows[Nb] != nnzb_in) throw std::runtime_error("rows[Nb] != nnz / 9");
         AnalysisOptions opt;
         opt.parts = sweep_parts > 0 ? std::min(sweep_parts, 8 * num_sms) : num_sms;  // every CTA of a sweep must be resident (checked below)
-        opt.stageBytes = sweep_stage_bytes;
+        // Stage size of the sweeps' TMA ring.  A part's consumers start when its first stage has landed, so a part that is
+        // only one or two stages long (Norne size: 80 KB of factor per part) neither overlaps load and compute nor hands its
+        // face rows over early; large parts (C3: 2 MB) want the largest stage that fits (per-stage hand-shakes amortised).
+        // Measured on B200: C2 10.95 ms per solve at 80 KB, 10.42 at 24 KB, 10.51 at 16 KB, 12.2 at 8 KB; C3 35.8 ms at 80 KB,
+        // 37.0 at 64 KB, 41.5 at 48 KB.  Automatic (option value 0): a quarter of the lower sweep's bytes per part.
+        int stage_bytes = sweep_stage_bytes;
+        if (stage_bytes <= 0) {
+            const double nnzL = 0.5 * (double) (nnzb_in - Nb);
+            const double part_bytes = (76.0 * nnzL + 52.0 * (double) Nb) / std::max(1, opt.parts);
+            stage_bytes = (int) std::min(81920.0, std::max(16384.0, 4096.0 * std::ceil(part_bytes / 4.0 / 4096.0)));
+        }
+        opt.stageBytes = stage_bytes;
         opt.window = sweep_window;
         opt.extWindow = sweep_ext_window;
         opt.warps = sweep_warps;
@@ -656,38 +671,48 @@ struct Solver {
         if (w->num_std_wells_so_far != w->num_std_wells || w->num_blocks_so_far != w->num_blocks)
             throw std::runtime_error("WellContributions incomplete: every well needs addMatrix C, D and B");
         nwells = (int) w->num_std_wells; nwblocks = (int) w->num_blocks;
-        std::vector<int> bc(nwblocks), cc(nwblocks);
-        for (int p = 0; p < nwblocks; ++p) {
-            if (w->Bcols[p] < 0 || w->Bcols[p] >= Nb || w->Ccols[p] < 0 || w->Ccols[p] >= Nb)
-                throw std::runtime_error("well column index out of range");
-            bc[p] = an.iperm[w->Bcols[p]];
-            cc[p] = an.iperm[w->Ccols[p]];
+        auto H2D = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
+        // The perforation pattern rarely changes between Newton steps: the index side (p-space columns, per-cell gather
+        // lists, item table) is rebuilt and uploaded only when val_pointers / Bcols / Ccols differ from the last call
+        // (the well container's structure stays on the device, the values are refreshed in one piece).
+        const bool same = wells_structure_valid && w->val_pointers == h_wptr && w->Bcols == h_wBcols && w->Ccols == h_wCcols;
+        if (!same) {
+            std::vector<int> bc(nwblocks), cc(nwblocks);
+            for (int p = 0; p < nwblocks; ++p) {
+                if (w->Bcols[p] < 0 || w->Bcols[p] >= Nb || w->Ccols[p] < 0 || w->Ccols[p] >= Nb)
+                    throw std::runtime_error("well column index out of range");
+                bc[p] = an.iperm[w->Bcols[p]];
+                cc[p] = an.iperm[w->Ccols[p]];
+            }
+            // unique perforated cells (by C column) with their contribution lists
+            std::vector<int> order(nwblocks), well_of(nwblocks);
+            for (int wi = 0; wi < nwells; ++wi)
+                for (unsigned p = w->val_pointers[wi]; p < w->val_pointers[wi + 1]; ++p) well_of[p] = wi;
+            for (int p = 0; p < nwblocks; ++p) order[p] = p;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cc[a] < cc[b]; });
+            h_ucell.clear(); h_uptr.clear(); h_ublock.assign(nwblocks, 0); h_uwell.assign(nwblocks, 0);
+            for (int e = 0; e < nwblocks; ++e) {
+                int p = order[e];
+                if (e == 0 || cc[p] != h_ucell.back()) { h_ucell.push_back(cc[p]); h_uptr.push_back(e); }
+                h_ublock[e] = p; h_uwell[e] = well_of[p];
+            }
+            h_uptr.push_back(nwblocks);
+            wells_structure_valid = false;
+            h_wptr = w->val_pointers; h_wBcols = w->Bcols; h_wCcols = w->Ccols;
+            nucells = (int) h_ucell.size();
+            d_wptr.alloc(nwells + 1); d_Bcols.alloc(nwblocks); d_ucell.alloc(nucells); d_uptr.alloc(nucells + 1);
+            d_ublock.alloc(nwblocks); d_uwell.alloc(nwblocks);
+            d_B.alloc((size_t) nwblocks * 12); d_C.alloc((size_t) nwblocks * 12); d_Dinv.alloc((size_t) nwells * 16);
+            d_z2.alloc((size_t) nwells * 4);
+            H2D(d_wptr.p, w->val_pointers.data(), sizeof(unsigned) * (nwells + 1));
+            H2D(d_Bcols.p, bc.data(), sizeof(int) * nwblocks);
+            H2D(d_ucell.p, h_ucell.data(), sizeof(int) * nucells);
+            H2D(d_uptr.p, h_uptr.data(), sizeof(int) * (nucells + 1));
+            H2D(d_ublock.p, h_ublock.data(), sizeof(int) * nwblocks);
+            H2D(d_uwell.p, h_uwell.data(), sizeof(int) * nwblocks);
+            CUDA_OK(cudaStreamSynchronize(stream));   // bc is a temporary
         }
-        // unique perforated cells (by C column) with their contribution lists
-        std::vector<int> order(nwblocks), well_of(nwblocks);
-        for (int wi = 0; wi < nwells; ++wi)
-            for (unsigned p = w->val_pointers[wi]; p < w->val_pointers[wi + 1]; ++p) well_of[p] = wi;
-        for (int p = 0; p < nwblocks; ++p) order[p] = p;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cc[a] < cc[b]; });
-        std::vector<int> ucell, uptr, ublock(nwblocks), uwell(nwblocks);
-        for (int e = 0; e < nwblocks; ++e) {
-            int p = order[e];
-            if (e == 0 || cc[p] != ucell.back()) { ucell.push_back(cc[p]); uptr.push_back(e); }
-            ublock[e] = p; uwell[e] = well_of[p];
-        }
-        uptr.push_back(nwblocks);
-        nucells = (int) ucell.size();
-        d_wptr.alloc(nwells + 1); d_Bcols.alloc(nwblocks); d_ucell.alloc(nucells); d_uptr.alloc(nucells + 1);
-        d_ublock.alloc(nwblocks); d_uwell.alloc(nwblocks);
-        d_B.alloc((size_t) nwblocks * 12); d_C.alloc((size_t) nwblocks * 12); d_Dinv.alloc((size_t) nwells * 16);
-        d_z2.alloc((size_t) nwells * 4);
-        auto H2D = [&](void* d, const void* h, size_t bytes) { CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
-        H2D(d_wptr.p, w->val_pointers.data(), sizeof(unsigned) * (nwells + 1));
-        H2D(d_Bcols.p, bc.data(), sizeof(int) * nwblocks);
-        H2D(d_ucell.p, ucell.data(), sizeof(int) * nucells);
-        H2D(d_uptr.p, uptr.data(), sizeof(int) * (nucells + 1));
-        H2D(d_ublock.p, ublock.data(), sizeof(int) * nwblocks);
-        H2D(d_uwell.p, uwell.data(), sizeof(int) * nwblocks);
+        nucells = (int) h_ucell.size();
         H2D(d_B.p, w->Bnnzs.data(), sizeof(double) * nwblocks * 12);
         H2D(d_C.p, w->Cnnzs.data(), sizeof(double) * nwblocks * 12);
         H2D(d_Dinv.p, w->Dnnzs.data(), sizeof(double) * nwells * 16);
@@ -697,21 +722,23 @@ struct Solver {
         std::vector<int4> item;
         std::vector<double> itemC;
         if (flat_ok) {
-            item.resize(nitems); itemC.resize((size_t) nitems * 4);
+            itemC.resize((size_t) nitems * 4);
+            if (!same) item.resize(nitems);
             for (int u = 0; u < nucells; ++u)
                 for (int c = 0; c < 3; ++c) {
-                    const int t = 3 * u + c, e0 = uptr[u];
-                    item[t] = make_int4(3 * ucell[u] + c, uptr[u + 1] - uptr[u], e0, 4 * uwell[e0]);
-                    for (int k = 0; k < 4; ++k) itemC[(size_t) t * 4 + k] = w->Cnnzs[(size_t) ublock[e0] * 12 + 3 * k + c];
+                    const int t = 3 * u + c, e0 = h_uptr[u];
+                    if (!same) item[t] = make_int4(3 * h_ucell[u] + c, h_uptr[u + 1] - h_uptr[u], e0, 4 * h_uwell[e0]);
+                    for (int k = 0; k < 4; ++k) itemC[(size_t) t * 4 + k] = w->Cnnzs[(size_t) h_ublock[e0] * 12 + 3 * k + c];
                 }
             d_item.alloc(nitems); d_itemC.alloc((size_t) nitems * 4);
-            H2D(d_item.p, item.data(), sizeof(int4) * nitems);
+            if (!same) H2D(d_item.p, item.data(), sizeof(int4) * nitems);
             H2D(d_itemC.p, itemC.data(), sizeof(double) * nitems * 4);
             flatD.nwells = nwells; flatD.nblocks = nwblocks; flatD.nitems = nitems; flatD.wptr = d_wptr.p; flatD.bcol = d_Bcols.p;
             flatD.B = d_B.p; flatD.Dinv = d_Dinv.p; flatD.item = d_item.p; flatD.itemC = d_itemC.p; flatD.C = d_C.p;
             flatD.ublock = d_ublock.p; flatD.uwell = d_uwell.p;
         }
         CUDA_OK(cudaStreamSynchronize(stream));   // the host vectors above are temporaries
+        wells_structure_valid = true;
     }
 
     // H2D of values + rhs (+ pattern and analysis on the first call)
@@ -1283,7 +1310,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
             else if (k == "sweep_groups") s->sweep_groups = std::max(1, v);
             else if (k == "sweep_helpers") s->sweep_helpers = std::min(8, std::max(1, v));
             else if (k == "sweep_slots") s->sweep_slots = std::min(kSweepMaxSlots, std::max(2, v));
-            else if (k == "sweep_stage_bytes") s->sweep_stage_bytes = std::max(1024, v);
+            else if (k == "sweep_stage_bytes") s->sweep_stage_bytes = v <= 0 ? 0 : std::max(1024, v);
             else if (k == "sweep_ext_window") s->sweep_ext_window = v;
             else s->sweep_window = v;
         }

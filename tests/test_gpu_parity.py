@@ -484,3 +484,37 @@ def test_wells_flat_and_general_kernels_agree(mods):
         assert res.converged and relerr(xs, ref.x) <= 1e-6 and abs(res.it - ref.it) <= max(1.0, 0.1 * ref.it)
         its.append(res.it)
     assert its[0] == its[1]
+
+
+def test_well_values_change_under_a_cached_structure(mods):
+    """WellContributions is rebuilt by the caller for every solve (ISTLSolverEbos.hpp:265-272) with new values on, usually,
+    the same perforation pattern: the library keeps the index side on the device and refreshes the values only.  Same
+    pattern / new values, then a new pattern, then the first one again, each against the oracle; both well kernels."""
+    bridge, synth, oracle = mods
+    import copy
+    s = synth.small(12, 10, 8, nwells=4, nperf=5)
+    rng = np.random.default_rng(77)
+    x = rng.normal(size=3 * s.Nb)
+    y0 = rng.normal(size=3 * s.Nb)
+    w1 = s.wells
+    w2 = copy.copy(w1)                                       # same pattern, other values
+    w2.B = w1.B * (1.0 + 0.3 * rng.normal(size=w1.B.shape))
+    w2.C = w1.C * (1.0 + 0.3 * rng.normal(size=w1.C.shape))
+    w2.Dinv = w1.Dinv * (1.0 + 0.1 * rng.normal(size=w1.Dinv.shape))
+    w3 = copy.copy(w2)                                       # other pattern (columns reversed per container), same sizes
+    w3.Bcols = w2.Bcols[::-1].copy()
+    w3.Ccols = w2.Ccols[::-1].copy()
+    for flat in (1, 0):
+        be = bridge.B200SolverBackend(0, 200, 1e-10, 0)
+        be.set_option("wells_flat", flat)
+        for w in (w1, w2, w3, w1, w2):
+            be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(w))
+            ref = oracle.well_apply(oracle_wells(w), x, y0)
+            assert relerr(be.well_apply(x, y0) - y0, ref - y0) < 1e-12
+        res = bridge.BdaResult()
+        for w in (w2, w3):
+            be.solve_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(w), res)
+            xs = np.zeros(3 * s.Nb)
+            be.get_result(xs)
+            ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(w), tol=1e-10, maxit=200)
+            assert res.converged == ref.converged and relerr(xs, ref.x) <= 1e-6

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sweep ONE solver option over several values on one configuration (GPU box tool):
-  python tools/ab_values.py c2 sweep_parts 0 32 48 64 96
+  python tools/ab_values.py c2 sweep_parts 0 32 48 64 96      (or a grid: 64,64,48[,nwells])
 Prints device ms per resident solve (mean of 8 after 2 warm-up solves, second of two passes) and the iteration count."""
 import os
 import sys
@@ -8,7 +8,12 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from opm_autodiff_b200 import bridge, synth
 
-s = synth.full_system(sys.argv[1])
+name = sys.argv[1]
+if "," in name:                                   # nx,ny,nz[,nwells]
+    t = [int(v) for v in name.split(",")]
+    s = synth.full_system(synth.GridConfig("custom-%dx%dx%d" % tuple(t[:3]), t[0], t[1], t[2], nwells=t[3] if len(t) > 3 else 0, nperf=8))
+else:
+    s = synth.full_system(name)
 key = sys.argv[2]
 values = [float(t) for t in sys.argv[3:]]
 w = s.wells
