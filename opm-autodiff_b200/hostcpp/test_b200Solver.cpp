@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <vector>
 
 #include "b200SolverBackend.hpp"
 #include "istl_mm.hpp"
@@ -44,6 +45,15 @@ int main(int argc, char** argv)
             return 77;
         }
         Opm::WellContributions wellContribs("b200", false);
+        if (std::getenv("B200_TEST_MSWELL")) {
+            // one multisegment well with a single segment perforating cell 0, B = 0 (so it changes nothing): exercises
+            // WellContributions::addMultisegmentWellContribution (WellContributions.hpp:195-213) through the C++ surface
+            std::vector<double> Bv(12, 0.0), Cv(12, 1.0), Dv = {2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2};
+            std::vector<unsigned int> Bc = {0u}, Br = {0u, 1u};
+            std::vector<int> Dcol = {0, 4, 8, 12, 16}, Drow = {0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3};
+            wellContribs.addMultisegmentWellContribution(3, 4, 1, Bv, Bc, Br, 1, Dv.data(), Dcol.data(), Drow.data(), Cv);
+            if (wellContribs.getNumWells() != 1) { std::fprintf(stderr, "getNumWells() != 1\n"); return 4; }
+        }
         bda::BdaResult result;
         const int N = A.Nb * 3, nnz = (int) A.cols.size() * 9;
         bda::SolverStatus st = backend->solve_system(N, nnz, 3, A.vals.data(), A.rows.data(), A.cols.data(), rhs.data(), wellContribs, result);

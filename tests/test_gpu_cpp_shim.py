@@ -33,12 +33,13 @@ def _write_mm(path_m, path_b, rows, cols, vals, b):
             f.write("%.17g\n" % v)
 
 
-def _run(tmp_path, rows, cols, vals, b, tol, maxit):
+def _run(tmp_path, rows, cols, vals, b, tol, maxit, env=None):
     if not os.path.exists(BIN):
         pytest.fail("C++ shim test binary not built (run __graft_entry__.build())")
     pm, pb = str(tmp_path / "m.mm"), str(tmp_path / "b.mm")
     _write_mm(pm, pb, rows, cols, vals, b)
-    out = subprocess.run([BIN, pm, pb, repr(tol), str(maxit)], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([BIN, pm, pb, repr(tol), str(maxit)], capture_output=True, text=True, timeout=120,
+                         env=dict(os.environ, **(env or {})))
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().splitlines()
     return lines[0], np.array([float(t) for t in lines[1:]])
@@ -56,6 +57,18 @@ def test_grid_system_through_the_cpp_backend(built, tmp_path):
     from oracle import oracle
     s = synth.small(9, 7, 5, faults=((4, 1),))
     head, x = _run(tmp_path, s.rows, s.cols, s.vals, s.b, 1e-10, 200)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, None, tol=1e-10, maxit=200)
+    assert "converged 1" in head
+    assert np.linalg.norm(x - ref.x) / np.linalg.norm(ref.x) < 1e-6
+
+
+def test_multisegment_well_through_the_cpp_surface(built, tmp_path):
+    """Opm::WellContributions::addMultisegmentWellContribution of the C++ stand-in (bda_compat.hpp) reaches the device path:
+    a one-segment well with B = 0 leaves the solution unchanged."""
+    from opm_autodiff_b200 import synth
+    from oracle import oracle
+    s = synth.small(9, 7, 5)
+    head, x = _run(tmp_path, s.rows, s.cols, s.vals, s.b, 1e-10, 200, env={"B200_TEST_MSWELL": "1"})
     ref = oracle.solve(s.rows, s.cols, s.vals, s.b, None, tol=1e-10, maxit=200)
     assert "converged 1" in head
     assert np.linalg.norm(x - ref.x) / np.linalg.norm(ref.x) < 1e-6
