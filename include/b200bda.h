@@ -78,7 +78,8 @@ void b200_destroy(b200_solver* s);
  *                 level groups, helper warps, ring slots and bytes per stage (0 = auto: a quarter of a part's factor bytes,
  *                 16 KB .. 80 KB), rows of the shared-memory window (0 = auto)
  *                 and of the external-row ring; set before the first solve
- *   "sweep_helper_sleep"  ns a helper warp sleeps between two polls of external rows                default 60
+ *   "sweep_helper_sleep"  ns a helper warp sleeps between two polls of external rows (measured: 0 is 2.5 % faster than 60
+ *                 on 44 k and 110 k rows and no slower on 1 M)                                       default 0
  *   "sweep_trace" 1: record the stage timeline of the sweeps (b200_get_sweep_trace; debugging)     default 0
  *   "spmv_blocks" upper bound of the SpMV grid                                                    default 16 per SM
  *   Size-dependent features, set before the first solve: 0 = off, 1 = automatic (on from 100 000 block rows), 2 = on     default 1

@@ -223,7 +223,7 @@ struct Solver {
     bool pin_host = true, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 60;
+    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 0;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
