@@ -86,6 +86,7 @@ void b200_destroy(b200_solver* s);
  *   "spmv_sell"   SpMV from a sliced-ELL copy of A (a lane per block row, coalesced value loads) instead of the BSR kernel
  *   "fuse_spmv"   the upper sweep's CTAs run the SpMV that follows it as their parts finish (needs spmv_sell)
  *   "defer_x"     x += alpha y / omega y are applied by idle CTAs of the next lower sweep instead of the vector kernels
+ *                 (automatic = on at every size)
  *   "sweep_early" sweep helper warps fetch a stage's external rows one stage ahead
  *   "p2p_allreduce"  multi-GPU: 1 peer-memory mailboxes, 0 NCCL + finish kernel                    default 1
  * Unknown keys return B200_UNKNOWN_ERROR. */
