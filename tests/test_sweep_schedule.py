@@ -21,6 +21,10 @@ from tests.patterns import grid_pattern
     ((20, 18, 16), 37, 4096, 256),
     ((30, 30, 1), 16, 0, 64),
     ((1, 25, 25), 148, 0, 0),
+    # the stage sizes the automatic rule picks (a quarter of a part's factor bytes, 16-80 KB): Norne size and 110 k rows
+    ((36, 56, 22), 148, 16384, 0),
+    ((36, 56, 22), 148, 20480, 0),
+    ((48, 48, 48), 148, 57344, 0),
 ])
 def test_emulated_sweeps_match_sequential_substitution(built, shape, parts, stage_bytes, window):
     from opm_autodiff_b200 import bridge
