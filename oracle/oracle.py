@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle_bda.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libref_reorder.so")
-_REF_CUSPARSE_PATH = os.path.join(_HERE, "_ref", "libref_cusparse.so")   # incumbent GPU backend (tools/incumbent_cusparse.py)
+_REF_CUSPARSE_PATH = os.path.join(_HERE, "_ref", "libref_cusparse.so")   # incumbent GPU backend (tests/incumbent_cusparse.py)
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")

@@ -4,7 +4,10 @@ UNMODIFIED from /root/reference into oracle/_ref/libref_cusparse.so, see oracle/
 same box, the same system and the same call: solve_system + get_result with host buffers (SURVEY 8d "incumbent GPU
 number").  Reported only; the product never loads that library.
 
-  python tools/incumbent_cusparse.py [--workload c3] [--solves 4] [--out gpurun_out/incumbent.json]
+  python tests/incumbent_cusparse.py [--workload c3] [--solves 4] [--out gpurun_out/incumbent.json]
+
+Lives under tests/ because it loads oracle/_ref and the oracle (test infrastructure); tests/test_gpu_incumbent.py uses
+run_incumbent() to pin small solves -- wells included -- against the reference's own GPU kernels.
 
 Two legs: without wells (both backends solve the identical system; the solutions are cross-checked) and with the
 workload's standard wells (the reference's well kernel is launched with 32 threads and only applies the first 10
