@@ -11,9 +11,14 @@
  * (tests/test_flexiblesolver.cpp:114-116, matr33.txt + rhs3.txt; see
  * tests/golden/make_golden.py), for the ILU0 factor property by the restated
  * tests/test_milu.cpp:42-99 checks, and for the level sets by the compiled
- * reference function (oracle/_ref, bda/Reorder.cpp:266-318).  UNPINNED for the
- * standard-well apply and for iteration counts (the reference holds no vector
- * for either); the Krylov loop is restated from upstream
+ * reference function (oracle/_ref, bda/Reorder.cpp:266-318).  The reference's
+ * tests hold no vector for the standard-well apply or for iteration counts
+ * (SURVEY.md 8c); both are pinned against the reference ITSELF on the GPU box:
+ * tests/test_gpu_incumbent.py runs the unmodified cusparseSolverBackend<3> +
+ * WellContributions (oracle/_ref/libref_cusparse.so) and compares its solution
+ * and iteration count with this oracle's (wells of <= 10 perforations, which its
+ * kernel covers).  UNPINNED: the multisegment-well apply (no reference test, and
+ * UMFPACK is absent; checked against dense algebra).  The Krylov loop is restated from upstream
  * dune-istl (dune/istl/solvers.hh, BiCGSTABSolver::apply, >= 2.6, not vendored
  * in /root/reference) whose control flow the reference mirrors at
  * opm/simulators/linalg/bda/cusparseSolverBackend.cu:60-184.
