@@ -19,6 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle_bda.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libref_reorder.so")
+_REF_MSWELL_PATH = os.path.join(_HERE, "_ref", "libref_mswell.so")       # reference MultisegmentWellContribution (UMFPACK shimmed)
 _REF_CUSPARSE_PATH = os.path.join(_HERE, "_ref", "libref_cusparse.so")   # incumbent GPU backend (tests/incumbent_cusparse.py)
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -38,7 +39,8 @@ def build(force: bool = False) -> None:
     if force or not os.path.exists(_LIB_PATH) or \
             os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "oracle_bda.c")):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_bda.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/opm") and (force or not os.path.exists(_REF_PATH) or not os.path.exists(_REF_CUSPARSE_PATH)):
+    if os.path.isdir("/root/reference/opm") and (force or not os.path.exists(_REF_PATH) or not os.path.exists(_REF_CUSPARSE_PATH)
+                                                 or not os.path.exists(_REF_MSWELL_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -99,6 +101,29 @@ def ref_lib():
         R.ref_block_mult_sub.argtypes = [_f64p, _f64p, _f64p]
         _ref = R
     return _ref
+
+
+_ref_ms = None
+
+
+def ref_mswell_apply(w: "MultisegmentWell", x, y):
+    """y -= C^T D^-1 B x by the reference's OWN Opm::MultisegmentWellContribution (constructor + apply, compiled unmodified
+    into oracle/_ref/libref_mswell.so; UMFPACK's entry points are a dense-LU stand-in, oracle/ref_mswell_glue.cpp).
+    Returns None when that library was never built."""
+    global _ref_ms
+    if _ref_ms is None:
+        build()
+        if not os.path.exists(_REF_MSWELL_PATH):
+            return None
+        _ref_ms = C.CDLL(_REF_MSWELL_PATH)
+        _ref_ms.ref_mswell_apply.argtypes = [C.c_uint, C.c_uint, C.c_uint, _f64p, _u32p, _u32p, C.c_uint, _f64p, _i32p, _i32p,
+                                             _f64p, _f64p, _f64p]
+    y = np.array(y, dtype=np.float64).reshape(-1)
+    _ref_ms.ref_mswell_apply(3, 4, int(w.Mb), _c(w.Bvalues, np.float64).reshape(-1), _c(w.BcolIndices, np.uint32),
+                             _c(w.BrowPointers, np.uint32), int(w.DnumBlocks), _c(w.Dvalues, np.float64).reshape(-1).copy(),
+                             _c(w.DcolPointers, np.int32).copy(), _c(w.DrowIndices, np.int32).copy(),
+                             _c(w.Cvalues, np.float64).reshape(-1), _c(x, np.float64).reshape(-1).copy(), y)
+    return y
 
 
 @dataclass

@@ -17,8 +17,9 @@
  * tests/test_gpu_incumbent.py runs the unmodified cusparseSolverBackend<3> +
  * WellContributions (oracle/_ref/libref_cusparse.so) and compares its solution
  * and iteration count with this oracle's (wells of <= 10 perforations, which its
- * kernel covers).  UNPINNED: the multisegment-well apply (no reference test, and
- * UMFPACK is absent; checked against dense algebra).  The Krylov loop is restated from upstream
+ * kernel covers).  The multisegment-well apply is pinned against the reference's
+ * own class compiled with a stand-in for UMFPACK's five entry points
+ * (oracle/_ref/libref_mswell.so, tests/test_oracle.py).  The Krylov loop is restated from upstream
  * dune-istl (dune/istl/solvers.hh, BiCGSTABSolver::apply, >= 2.6, not vendored
  * in /root/reference) whose control flow the reference mirrors at
  * opm/simulators/linalg/bda/cusparseSolverBackend.cu:60-184.

@@ -1,7 +1,7 @@
 """GPU parity tests of the multisegment-well apply: the CUDA path through the C ABI vs the CPU oracle's
 restatement of MultisegmentWellContribution::apply (bda/MultisegmentWellContribution.cpp:70-110).
-Parity unpinned by the reference (no reference test builds a MultisegmentWellContribution); the oracle itself is checked
-against dense algebra in tests/test_oracle.py."""
+No reference test builds a MultisegmentWellContribution; the oracle itself is pinned against the reference's own class
+(compiled with a stand-in for UMFPACK) and against dense algebra in tests/test_oracle.py."""
 import numpy as np
 import pytest
 

@@ -210,7 +210,7 @@ def test_multisegment_well_apply_against_dense_algebra():
     """The oracle's restatement of MultisegmentWellContribution::apply (bda/MultisegmentWellContribution.cpp:70-110, dense
     LU with partial pivoting in place of UMFPACK) against C^T D^-1 B built densely with numpy; and the operator of the
     oracle's solve applies multisegment wells before the standard ones (bda/WellContributions.cu:167-193).
-    Parity unpinned by the reference: no reference test builds a MultisegmentWellContribution."""
+    No reference test builds a MultisegmentWellContribution; the next test pins the restatement against the class itself."""
     from opm_autodiff_b200 import synth
     from tests.helpers import dense_mswell_operator, dense_well_operator, dense_from_bsr, oracle_mswells, oracle_wells, relerr
     s = synth.small(7, 6, 5, nwells=2, nperf=3)
@@ -229,3 +229,24 @@ def test_multisegment_well_apply_against_dense_algebra():
     assert r.converged and relerr(r.x, s.x_true) < 1e-5
     r0 = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200)
     assert relerr(r0.x, s.x_true) > 1e-3            # the wells matter
+
+
+def test_multisegment_well_apply_against_the_reference_class():
+    """Pins orc_ms_apply against the reference's own Opm::MultisegmentWellContribution::apply
+    (bda/MultisegmentWellContribution.cpp:32-110), compiled unmodified into oracle/_ref/libref_mswell.so; only UMFPACK's five
+    entry points are replaced (dense LU), so the block layouts and loops are the reference's."""
+    from opm_autodiff_b200 import synth
+    from tests.helpers import oracle_mswells, relerr
+    s = synth.small(9, 8, 7)
+    ms = synth.add_mswells(s, 4, 9, seed=17)
+    rng = np.random.default_rng(4)
+    x, y = rng.standard_normal(3 * s.Nb), rng.standard_normal(3 * s.Nb)
+    om = oracle_mswells(ms)
+    ref = y.copy()
+    for w in om.wells:
+        ref = oracle.ref_mswell_apply(w, x, ref)
+        if ref is None:
+            pytest.skip("oracle/_ref/libref_mswell.so was not built (needs /root/reference at build time)")
+    got = om.apply(x, y)
+    assert np.linalg.norm(ref - y) > 1e-3
+    assert relerr(got - y, ref - y) < 1e-12
