@@ -1,6 +1,6 @@
 /*
  * b200bda.h -- C ABI of libb200bda.so, the B200-native (sm_100a) ILU0-BiCGSTAB backend for
- * OPM Flow's per-Newton-step linear solve (3x3-block BSR, fp64) plus the standard-well apply.
+ * OPM Flow's per-Newton-step linear solve (3x3-block BSR, fp64) plus the standard- and multisegment-well apply.
  *
  * Drop-in boundary.  The entry points below are exactly what a `bda::BdaSolver<3>` subclass and
  * an `Opm::WellContributions`-compatible container need; each one names the reference interface

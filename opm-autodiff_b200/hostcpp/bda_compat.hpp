@@ -3,7 +3,7 @@
 // OpenCL headers that are not in this image).  Inside opm-simulators define B200_IN_OPM_TREE and the
 // real headers are used instead; names, signatures and member meaning are identical:
 //   bda::BdaResult, bda::SolverStatus, bda::BdaSolver<block_size>   bda/BdaResult.hpp:28-40, bda/BdaSolver.hpp:32-90
-//   Opm::WellContributions (standard-well part of the public API)  bda/WellContributions.hpp:60-214
+//   Opm::WellContributions (standard wells and addMultisegmentWellContribution)  bda/WellContributions.hpp:60-214
 #pragma once
 
 #ifdef B200_IN_OPM_TREE
