@@ -185,3 +185,56 @@ def test_synth_slabs_equal_full_system(built):
     assert c3.ncells == 1_000_000 and c3.nwells == 50
     c2 = synth.generate(synth.CONFIGS["c2"])
     assert c2.Nb == 44352 and c2.nnzb >= 302384        # + NNC blocks
+
+
+def test_multisegment_inverse_on_hard_patterns(built):
+    """invert_csc (extent-aware LU with partial pivoting) against numpy on matrices that need pivoting and whose pattern is
+    not banded: a segment tree with shuffled numbering, weak diagonals, an arrow matrix, duplicates in the CSC input
+    (UMFPACK sums them)."""
+    from opm_autodiff_b200.bridge import WellContributions as WC
+    rng = np.random.default_rng(123)
+
+    def check(D, dup=False):
+        M = D.shape[0]
+        assert M % 4 == 0
+        colptr, rowidx, vals = [0], [], []
+        for c in range(M):
+            nz = np.nonzero(D[:, c])[0]
+            for r in nz:
+                if dup:                                   # split the entry in two
+                    rowidx += [int(r), int(r)]; vals += [0.25 * D[r, c], 0.75 * D[r, c]]
+                else:
+                    rowidx.append(int(r)); vals.append(D[r, c])
+            colptr.append(len(rowidx))
+        while len(vals) % 16:                             # DnumBlocks * 16 entries: pad with explicit zeros in the last column
+            rowidx.append(M - 1); vals.append(0.0); colptr[-1] += 1
+        w = WC("b200", False)
+        Mb = M // 4
+        w.addMultisegmentWellContribution(3, 4, Mb, np.zeros(12), np.zeros(1, np.uint32), np.array([0] + [1] * Mb, np.uint32),
+                                          len(vals) // 16, np.array(vals), np.array(colptr, np.int32), np.array(rowidx, np.int32),
+                                          np.zeros(12))
+        inv = w.multisegment_inverse(0, M)
+        ref = np.linalg.inv(D)
+        assert np.abs(inv - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+
+    # tree with shuffled segment numbering, weak (sometimes zero) diagonal entries
+    nseg = 12
+    order = rng.permutation(nseg)
+    D = np.zeros((4 * nseg, 4 * nseg))
+    for s_ in range(nseg):
+        a = order[s_]
+        D[4 * a:4 * a + 4, 4 * a:4 * a + 4] = rng.normal(size=(4, 4))
+        D[4 * a, 4 * a] = 0.0                              # forces row exchanges
+        if s_ > 0:
+            q = order[rng.integers(0, s_)]
+            D[4 * a:4 * a + 4, 4 * q:4 * q + 4] = rng.normal(size=(4, 4))
+            D[4 * q:4 * q + 4, 4 * a:4 * a + 4] = rng.normal(size=(4, 4))
+    check(D)
+    check(D, dup=True)
+    # arrow: dense first block row and column
+    M = 32
+    A = np.diag(2.0 + rng.random(M))
+    A[:4, :] = rng.normal(size=(4, M)); A[:, :4] = rng.normal(size=(M, 4))
+    check(A)
+    # fully dense 8 x 8
+    check(rng.normal(size=(8, 8)))
