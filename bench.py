@@ -298,7 +298,8 @@ def run_b200_single(args):
     x = np.zeros(N)
 
     # ---- e2e: the call a BdaBridge makes, host buffers, copies inside the timed region -----------------
-    for _ in range(args.warmup):
+    # at least two untimed calls: the library page-locks the caller's arrays when it sees them the second time
+    for _ in range(max(args.warmup, 2)):
         be.solve_system(N, nnz, 3, system.vals, system.rows, system.cols, system.b, wc, res)
         be.get_result(x)
     assert res.converged, "solve did not converge"

@@ -50,7 +50,7 @@ def run(args, metric, tol, maxit, get_cfg, ClockSampler, measured_peak):
 
     # ---- e2e: host buffers, H2D of values + rhs and D2H of x inside the timed region --------------------
     x = np.zeros(ds.N)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 2)):      # the library page-locks the caller's arrays on their second sighting
         ds.solve_system(res)
         ds.get_result(x)
     assert res.converged, "solve did not converge"
