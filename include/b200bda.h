@@ -9,8 +9,8 @@
  * string-chain patches a maintainer adds to the reference are shown in INTEGRATION.md.
  *
  * Conventions: plain pointers and sizes, no CUDA / torch types.  All `*_host` pointers are host
- * memory owned by the caller and not retained after the call returns (except for an optional
- * cudaHostRegister pin of `vals`/`b`, released in b200_destroy).  Functions return a
+ * memory owned by the caller and not retained after the call returns (page-locking of `vals`/`b`/`x`
+ * happens only on request: b200_host_register, or the "pin_host" option).  Functions return a
  * b200_status; on anything but B200_SUCCESS b200_last_error() describes the failure.  There is
  * no CPU fallback anywhere in the library: without a usable sm_100 device every entry point that
  * computes fails loudly.
@@ -67,7 +67,10 @@ void b200_destroy(b200_solver* s);
 /* Options the reference fixes at compile time or takes from the FlexibleSolver JSON tree:
  *   "relaxation"  ILU0 relaxation w (setupPropertyTree.cpp:175-188; cusparse uses 1.0)  default 1.0
  *   "tolerance", "maxit", "verbosity"   override the constructor values
- *   "pin_host"    1: cudaHostRegister the caller's vals / b / x once they are seen on two consecutive calls   default 1
+ *   "pin_host"    1: cudaHostRegister the caller's vals / b / x once they are seen on two consecutive calls.
+ *                 Contract: a buffer handed in stays allocated until another one replaces it, b200_host_unregister releases
+ *                 it, or the solver is destroyed (Flow's matrix, rhs and solution storage live as long as the simulator).
+ *                 Off by default -- the library does not own that memory; see also b200_host_register.            default 0
  *   "wells_flat"  1: standard wells that fit one CTA (<= 1024 perforations, <= 128 wells) use the apply kernel with
  *                 host-resolved index chains (k_wells_flat); 0: always the general kernel                 default 1
  *   "use_graph"   1: replay the factorisation launches and the BiCGSTAB iteration body as CUDA graphs  default 1
@@ -109,6 +112,13 @@ b200_status b200_solve_system(b200_solver* s, int N, int nnz, int dim,
 /* BdaSolver<3>::get_result (BdaSolver.hpp:90; cusparseSolverBackend.cu:464-475): N doubles D2H.
  * Always safe to call after a solve (the reference tests call it unconditionally). */
 b200_status b200_get_result(b200_solver* s, double* x_host);
+
+/* Page-lock (cudaHostRegister) a caller-owned host buffer -- the matrix values, the right-hand side, the solution vector --
+ * so that the copies of b200_solve_system / b200_get_result run at PCIe speed (55 GB/s instead of ~10 GB/s pageable).  The
+ * caller, who knows the buffer's lifetime, must call b200_host_unregister before freeing it (b200_destroy releases what is
+ * left).  No reference counterpart: the reference copies from pageable memory (cusparseSolverBackend.cu:286-299). */
+b200_status b200_host_register(b200_solver* s, void* ptr, size_t bytes);
+b200_status b200_host_unregister(b200_solver* s, void* ptr);
 
 /* Same solve with the system already resident in HBM (uploaded by the last b200_solve_system or
  * b200_upload_system): repeats permutation + ILU0 + BiCGSTAB without any host<->device copy of
@@ -222,6 +232,15 @@ b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, i
  * max rhs rows, reference levels.  Fails with B200_ANALYSIS_FAILED if the schedule could deadlock. */
 b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int stage_bytes,
                                            int window, unsigned int seed, double* max_rel_err, long long* stats);
+
+/* The same check for the round-2 sweep schedule (groups of consumer warps that stream their own records; csrc/sweep2.hpp,
+ * k_sweep2): host emulation of the kernel with random factor values against the sequential natural-order substitution, the
+ * upper sweep with relaxation `relax` (x = relax * U^-1 L^-1 rhs, ParallelOverlappingILU0.hpp:897-901).  Arguments <= 0 select
+ * the defaults.  stats (12 values, may be NULL): parts, lines, strips, records L, records U, empty records L, shared-memory
+ * deps L, external deps L, external rows L, helper blocks L, max groups, max warps per group. */
+b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int window, int ext_window,
+                                            int consumer_warps, int helpers, int groups, int wg, unsigned int seed, double relax,
+                                            double* max_rel_err, long long* stats);
 
 /* Host-only replay of the ILU0 elimination plan the device kernel executes (no device needed): LU in the caller's pattern
  * with the inverse pivot in the diagonal slot, as ParallelOverlappingILU0.hpp:440-494 leaves it.  max_row / max_ops (may be

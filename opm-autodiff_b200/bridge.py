@@ -121,6 +121,10 @@ def lib():
         L.b200_level_schedule_host.argtypes = [ip, _i32p, _i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
         L.b200_sweep_schedule_check_host.argtypes = [ip, _i32p, _i32p, ip, ip, ip, C.c_uint, C.POINTER(C.c_double),
                                                      np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+        L.b200_sweep2_schedule_check_host.argtypes = [ip, _i32p, _i32p, ip, ip, ip, ip, ip, ip, ip, C.c_uint, C.c_double,
+                                                      C.POINTER(C.c_double), np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+        L.b200_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.b200_host_unregister.argtypes = [vp, vp]
         L.b200_time_kernel.argtypes = [vp, C.c_char_p, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200_kernel_stats.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]
@@ -150,7 +154,7 @@ EXPORTED_SYMBOLS = [
     "b200_wells_destroy", "b200_wells_set_block_size", "b200_wells_add_num_blocks", "b200_wells_alloc",
     "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_wells_add_multisegment", "b200_wells_get_multisegment_inverse", "b200_spmv", "b200_well_apply",
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
-    "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
+    "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_sweep2_schedule_check_host", "b200_host_register", "b200_host_unregister", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
     "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_map_rank", "b200_dist_connect_peer", "b200_dist_spmv",
     "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace", "b200_factor_plan_check_host",
@@ -445,6 +449,24 @@ def sweep_schedule_check_host(rows, cols, parts=0, stage_bytes=0, window=0, seed
     if lib().b200_sweep_schedule_check_host(len(rows) - 1, rows, cols, parts, stage_bytes, window, seed, C.byref(err), stats) != 0:
         raise RuntimeError(last_error())
     return err.value, dict(zip(SWEEP_STAT_NAMES, (int(v) for v in stats)))
+
+
+SWEEP2_STAT_NAMES = ("parts", "lines", "strips", "records_L", "records_U", "multi_record_warp_steps_L", "window_deps_L", "external_deps_L",
+                     "external_rows_L", "reserved", "max_chunks_per_step", "consumer_warps")
+
+
+def sweep2_schedule_check_host(rows, cols, parts=0, window=0, ext_window=0, consumer_warps=0, helpers=0, groups=0, wg=0, seed=1,
+                               relax=1.0):
+    """Host-only emulation of the round-2 sweep schedule (groups of consumer warps streaming their own records): returns the
+    largest error against the sequential natural-order substitution (relative to max|x|) and the schedule statistics."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    err = C.c_double(0)
+    stats = np.zeros(12, np.int64)
+    if lib().b200_sweep2_schedule_check_host(len(rows) - 1, rows, cols, parts, window, ext_window, consumer_warps, helpers, groups, wg,
+                                             seed, relax, C.byref(err), stats) != 0:
+        raise RuntimeError(last_error())
+    return err.value, dict(zip(SWEEP2_STAT_NAMES, (int(v) for v in stats)))
 
 
 def factor_plan_check_host(rows, cols, vals):

@@ -142,9 +142,9 @@ inline LevelSchedule level_schedule(int Nb, const int* rows, const int* cols)
 //               {32 * xwin row of dependency 0, 1, 2, byte offset of the lane's result in xwin or -1 (no store)}
 //   vals blob (doubles): per record NF x 32 doubles, field f of lane l at sweep_vidx(f, l).
 //     lower sweep, NF = 9 : field 3 j + v = L[block j of row q][comp][v]
-//     upper sweep, NF = 12: field 3 j + v = (w D^-1 U)[block j of row q][comp][v], field 9 + v = (w D^-1)[comp][v]
+//     upper sweep, NF = 12: field 3 j + v = (D^-1 U)[block j of row q][comp][v], field 9 + v = (w D^-1)[comp][v]
 //     (the inverse pivot and the relaxation factor w are folded into the stream when it is filled, so that the
-//     dependent part of a row is the same 9 fma for both sweeps: x = (w D^-1) y - sum (w D^-1 U) x)
+//     dependent part of a row is the same 9 fma for both sweeps: x = (w D^-1) y - sum (D^-1 U) x, with x = w U^-1 y)
 // position of field f of lane l inside a record of the value stream: doubles are paired so that a lane fetches two with
 // one 16-byte load (lower: 4 pairs + the ninth value alone; upper: 6 pairs)
 inline int sweep_vidx(bool lower, int f, int l) { return (lower && f == 8) ? 256 + l : (f >> 1) * 64 + 2 * l + (f & 1); }
@@ -302,6 +302,7 @@ struct AnalysisOptions {
     int groups = 1;             // consecutive levels go to different warp groups (warps / groups warps each): while one group
                                 // runs the dependent part of level l, the next ones already hold the operands of l+1, l+2
     int extWindow = 512;        // rows of the external-row ring (power of two); bounds ring slots x external rows per stage
+    bool buildStreams = true;   // false: the round-2 schedule (sweep2.hpp) is built instead of the packed round-1 streams
 };
 
 namespace detail {
@@ -754,8 +755,10 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
         A.facPtr[q + 1] = (int) (A.facOps.size() / 2);
         A.facMaxOps = std::max(A.facMaxOps, A.facPtr[q + 1] - A.facPtr[q]);
     }
-    detail::build_sweep(A, rows, cols, glev, partOf, true, opt, A.L);
-    detail::build_sweep(A, rows, cols, glev, partOf, false, opt, A.U);
+    if (opt.buildStreams) {
+        detail::build_sweep(A, rows, cols, glev, partOf, true, opt, A.L);
+        detail::build_sweep(A, rows, cols, glev, partOf, false, opt, A.U);
+    }
     return A;
 }
 
@@ -775,8 +778,8 @@ inline void fill_stream_host(const SweepPlan& S, bool lower, const double* LU, d
             double inv[3] = {0.0, 0.0, 0.0};
             if (!lower) {
                 const int kp = S.src[B.src_off + 3 * B.count + q];
-                for (int e = 0; e < 3; ++e) inv[e] = relax * LU[(size_t) kp * 9 + comp * 3 + e];
-                if (B.first) for (int v = 0; v < 3; ++v) vals[B.vals_off + sweep_vidx(false, 9 + v, l)] = inv[v];
+                for (int e = 0; e < 3; ++e) inv[e] = LU[(size_t) kp * 9 + comp * 3 + e];
+                if (B.first) for (int v = 0; v < 3; ++v) vals[B.vals_off + sweep_vidx(false, 9 + v, l)] = relax * inv[v];
             }
             for (int j = 0; j < 3; ++j) {
                 const int k = S.src[B.src_off + j * B.count + q];

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "analysis.hpp"
+#include "sweep2.hpp"
 #include "kernels.cuh"
 
 namespace b200 {
@@ -220,10 +221,14 @@ static void invert_csc(int M, const int* colptr, const int* rowidx, const double
 struct Solver {
     int verbosity = 0, maxit = 200, device = 0;
     double tolerance = 1e-2, relaxation = 1.0;
-    bool pin_host = true, use_graph = true, profile = false;
+    bool pin_host = false, use_graph = true, profile = false;
     int lookahead = 2;
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
-    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 512, sweep_helper_sleep = 0;
+    int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 0, sweep_helper_sleep = 0;
+    // round-2 sweeps (k_sweep2): consumer warps (G x WG per part), helper warps, forced group count / group width (0 = automatic)
+    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_kmin = 3, s2_kmax = 6;
+    bool v2 = false;
+    Sweep2Plan L2, U2;
 
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -271,6 +276,10 @@ struct Solver {
     DevBuf<BuildD> d_buildL, d_buildU;
     DevBuf<int> d_metaL, d_metaU, d_srcL, d_srcU;
     DevBuf<double> d_valL, d_valU;
+    DevBuf<S2PartD> d_s2partsL, d_s2partsU;
+    DevBuf<S2StreamD> d_s2streamsL, d_s2streamsU;
+    DevBuf<S2BuildD> d_s2buildL, d_s2buildU;
+    DevBuf<int> d_s2hdrsL, d_s2hdrsU, d_s2codesL, d_s2codesU, d_s2extL, d_s2extU, d_s2srcL, d_s2srcU;
     DevBuf<double> d_stage, d_bstage, d_A, d_LU;
     DevBuf<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_w, d_xnat, d_tmp1, d_tmp2;
     DevBuf<double> d_partials;
@@ -307,6 +316,7 @@ struct Solver {
     const void* reg_b = nullptr; size_t reg_b_bytes = 0;
     const void* reg_x = nullptr; size_t reg_x_bytes = 0;      // the caller's solution vector (get_result)
     const void* cand_vals = nullptr; const void* cand_b = nullptr; const void* cand_x = nullptr;   // seen once, not yet pinned
+    std::vector<std::pair<void*, size_t>> host_regs;          // b200_host_register: page-locked on the caller's explicit request
 
     KStat stats[K_COUNT];
     long long launch_count = 0;
@@ -320,6 +330,7 @@ struct Solver {
         if (dist.comm) g_nccl.CommDestroy(dist.comm);
         if (fac_graph_exec) cudaGraphExecDestroy(fac_graph_exec);
         if (iter_graph_exec) cudaGraphExecDestroy(iter_graph_exec);
+        for (auto& r : host_regs) cudaHostUnregister(r.first);
         if (reg_vals) cudaHostUnregister((void*) reg_vals);
         if (reg_x) cudaHostUnregister((void*) reg_x);
         if (reg_b) cudaHostUnregister((void*) reg_b);
@@ -436,11 +447,23 @@ struct Solver {
         }
         opt.stageBytes = stage_bytes;
         opt.window = sweep_window;
-        opt.extWindow = sweep_ext_window;
+        v2 = sweep_v2 != 0;
+        opt.extWindow = sweep_ext_window > 0 ? sweep_ext_window : (v2 ? 2048 : 512);
+        opt.buildStreams = !v2;
         opt.warps = sweep_warps;
         opt.groups = sweep_groups;
+        auto build_v2 = [&](const int* r_, const int* c_) {
+            Sweep2Options o2;
+            s2_helpers = std::max(1, std::min(s2_helpers, kS2MaxHelpers));
+            s2_cw = std::max(1, std::min(s2_cw, kS2Threads / 32 - s2_helpers));
+            s2_cw = std::min(s2_cw, kS2MaxWarps);
+            o2.consumerWarps = s2_cw;
+            L2 = Sweep2Plan(); U2 = Sweep2Plan();
+            build_sweep2_plans(an, r_, c_, o2, L2, U2);
+        };
         if (!dist.enabled) {
             an = b200::analyse(Nb, rows, cols, opt);
+            if (v2) build_v2(rows, cols);
         } else {
             // Row slab of a partitioned matrix: columns >= Nb are ghosts (numbered last).  The preconditioner is
             // block-Jacobi ILU0 on the owned x owned block, exactly what the reference's parallel ILU0 does
@@ -461,6 +484,7 @@ struct Solver {
                 if (any) { grow_nat.push_back(r); gptr.push_back((int) gcol.size()); }
             }
             an = b200::analyse(Nb, sq_rows.data(), sq_cols.data(), opt);
+            if (v2) build_v2(sq_rows.data(), sq_cols.data());
             for (auto& b : an.srcblk) b = sq_src[b];            // p-space block -> block of the caller's array
             dist.gnrows = (int) grow_nat.size();
             dist.gnblocks = (long long) gcol.size();
@@ -498,11 +522,72 @@ struct Solver {
         }
         fac_plan = an.facMaxRow <= kFacMaxRow && an.facMaxOps <= kFacMaxOps;
         if (fac_plan) { up(d_facPtr, an.facPtr); up(d_facOps, an.facOps); }
+        auto upraw = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
+        const bool want_fused = feature_on(fuse_spmv) && sell_slices && an.nparts <= kMaxSweepParts;
+        const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
+        int occ = 8;
+        int threads = 0;
+        auto prep = [&](auto kern) {
+            CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
+            int o = 0;
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, sweep_smem));
+            occ = std::min(occ, o);
+        };
+        if (v2) {
+            static_assert(sizeof(S2PartD) == sizeof(S2Part) && sizeof(S2StreamD) == sizeof(S2Stream) &&
+                          sizeof(S2BuildD) == sizeof(S2Build), "device/host round-2 sweep descriptor mismatch");
+            auto up2 = [&](Sweep2Plan& P2, DevBuf<S2PartD>& dp, DevBuf<S2StreamD>& ds, DevBuf<S2BuildD>& dbu, DevBuf<int>& dh,
+                           DevBuf<int>& dc, DevBuf<int>& de, DevBuf<int>& dsr, DevBuf<double>& dv) {
+                dp.alloc(P2.parts.size()); ds.alloc(P2.streams.size()); dbu.alloc(std::max<size_t>(1, P2.build.size()));
+                upraw(dp.p, P2.parts.data(), sizeof(S2Part) * P2.parts.size());
+                upraw(ds.p, P2.streams.data(), sizeof(S2Stream) * P2.streams.size());
+                upraw(dbu.p, P2.build.data(), sizeof(S2Build) * P2.build.size());
+                dh.alloc(P2.hdrs.size() + 4 * 64); dc.alloc(P2.codes.size() + 2); de.alloc(P2.ext.size() + 1); dsr.alloc(P2.src.size() + 1);
+                upraw(dh.p, P2.hdrs.data(), sizeof(int) * P2.hdrs.size());
+                upraw(dc.p, P2.codes.data(), sizeof(int) * P2.codes.size());
+                upraw(de.p, P2.ext.data(), sizeof(int) * P2.ext.size());
+                upraw(dsr.p, P2.src.data(), sizeof(int) * P2.src.size());
+                dv.alloc((size_t) P2.nvals + 2);
+            };
+            up2(L2, d_s2partsL, d_s2streamsL, d_s2buildL, d_s2hdrsL, d_s2codesL, d_s2extL, d_s2srcL, d_valL);
+            up2(U2, d_s2partsU, d_s2streamsU, d_s2buildU, d_s2hdrsU, d_s2codesU, d_s2extU, d_s2srcU, d_valU);
+            CUDA_OK(cudaStreamSynchronize(stream));
+            // the schedule stays on the host only as long as the analysis needs it (the build lists are large)
+            for (Sweep2Plan* P2 : {&L2, &U2}) { std::vector<int>().swap(P2->src); std::vector<int>().swap(P2->codes); std::vector<int>().swap(P2->hdrs); std::vector<int>().swap(P2->stepChunks); }
+            threads = sweep_threads();
+            const size_t need = kS2Header + 24 * (size_t) (an.window + an.extWindow + 1);
+            // the SpMV tail streams SELL slices through the same dynamic shared memory: two chunk buffers per ring-fed consumer warp
+            const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * kTailBufBytes * std::min(kTailMaxCons, threads / 32 - 1)) : 0;
+            sweep_smem = std::max(need, tail);
+            if (sweep_smem > smem_limit) throw std::runtime_error("value space of the triangular sweeps does not fit the shared memory");
+            prep(k_sweep2<true, false>); prep(k_sweep2<true, true>); prep(k_sweep2<false, false>); prep(k_sweep2<false, true>);
+            defer_ok = false;
+            if (defer_x != 0) {
+                prep(k_sweep2<true, false, 3>);
+                d_xSync.alloc(2);
+                CUDA_OK(cudaMemsetAsync(d_xSync.p, 0, sizeof(int) * 2, stream));
+                defer_ok = true;
+            }
+            fused_units = 0;
+            if (want_fused) {
+                prep(k_sweep2<false, true, 1>); prep(k_sweep2<false, true, 2>);
+                const b200::FusedPlan fp = b200::build_fused(Nb, an.prow, an.pcol, an.partPtr, an.flevPtr, an.flevRows, std::max(1, fuse_unit_slices) * (threads / 32 - 1));
+                fused_units = (int) fp.units.size() / 2;
+                up(d_fUnits, fp.units); up(d_fNeedPtr, fp.needPtr); up(d_fNeed, fp.need);
+                d_fSync.alloc(2 + an.nparts); d_fPartials.alloc((size_t) 2 * fused_units);
+                CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
+                CUDA_OK(cudaStreamSynchronize(stream));            // fp is a temporary
+            }
+            if (verbosity > 0)
+                fprintf(stderr, "[b200bda] round-2 sweeps: %d parts, %d consumer warps + %d helper(s), %d threads, %zu B smem (window %d + ring %d rows); "
+                                "L: %lld records (up to %d chunks per step, %lld warp-steps with several records), %lld external rows, %.1f MB; U: %lld records, %.1f MB\n",
+                        an.nparts, s2_cw, s2_helpers, threads, sweep_smem, an.window, an.extWindow, L2.nrecords, L2.maxChunks, L2.nmulti, L2.nExtRows,
+                        L2.nvals * 8e-6, U2.nrecords, U2.nvals * 8e-6);
+        } else {
         up(d_metaL, an.L.meta); up(d_metaU, an.U.meta); up(d_srcL, an.L.src); up(d_srcU, an.U.src);
         d_stagesL.alloc(an.L.stages.size()); d_stagesU.alloc(an.U.stages.size());
         d_partsL.alloc(an.nparts); d_partsU.alloc(an.nparts);
         d_buildL.alloc(an.L.build.size()); d_buildU.alloc(an.U.build.size());
-        auto upraw = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
         upraw(d_stagesL.p, an.L.stages.data(), sizeof(StageRef) * an.L.stages.size());
         upraw(d_stagesU.p, an.U.stages.data(), sizeof(StageRef) * an.U.stages.size());
         upraw(d_partsL.p, an.L.parts.data(), sizeof(PartRef) * an.nparts);
@@ -520,8 +605,6 @@ struct Solver {
         sweep_slots = std::max(2, std::min(sweep_slots, kSweepMaxSlots - 1));      // nslots + 1 ready words
         // helpers fetch one stage ahead of the ring when nslots + 1 stages of external rows fit the ring (sweep_early)
         // the stages in flight must fit the shared memory of an SM and their external rows the external ring
-        const bool want_fused = feature_on(fuse_spmv) && sell_slices && an.nparts <= kMaxSweepParts;
-        const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
         while (sweep_slots > 2 && (fixedBytes + sweep_slots * slotBytes > smem_limit || (long long) sweep_slots * sweep_extCap > an.extWindow)) --sweep_slots;
         sweep_smem = fixedBytes + sweep_slots * slotBytes;
         sweep_early = feature_on(sweep_early_opt) && (long long) (sweep_slots + 1) * sweep_extCap <= an.extWindow;
@@ -531,14 +614,7 @@ struct Solver {
         if (sweep_smem > smem_limit)
             throw std::runtime_error("a block row is too long for the shared-memory ring of the triangular sweeps (" +
                                      std::to_string(slotBytes) + " B per stage)");
-        int occ = 8;
-        const int threads = sweep_threads();
-        auto prep = [&](auto kern) {
-            CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem));
-            int o = 0;
-            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, sweep_smem));
-            occ = std::min(occ, o);
-        };
+        threads = sweep_threads();
         prep(k_sweep<true, false, false>); prep(k_sweep<true, true, false>); prep(k_sweep<false, false, false>); prep(k_sweep<false, true, false>);
         prep(k_sweep<true, false, true>); prep(k_sweep<true, true, true>); prep(k_sweep<false, false, true>); prep(k_sweep<false, true, true>);
         defer_ok = false;
@@ -559,17 +635,20 @@ struct Solver {
             CUDA_OK(cudaMemsetAsync(d_fSync.p, 0, sizeof(int) * (2 + an.nparts), stream));
             CUDA_OK(cudaStreamSynchronize(stream));            // fp is a temporary
         }
+        }
         if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
         if (an.nparts > occ * num_sms)
             throw std::runtime_error("triangular sweeps: " + std::to_string(an.nparts) + " parts cannot all be resident (" +
                                      std::to_string(occ) + " CTAs per SM fit); lower sweep_parts or the stage size");
-        if (verbosity > 0)
+        if (verbosity > 0 && !v2)
             fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts; "
                             "L: %zu stages %lld chunks (%lld window / %lld global deps), U: %zu stages; sweep grid %d x %d, "
-                            "%d slots x %zu B + window %d rows = %zu B smem; %lld external rows L (max %d per stage)\n",
+                            "%d slots + window %d rows = %zu B smem; %lld external rows L (max %d per stage)\n",
                     Nb, (long long) nnzb, an.nlev, an.nlines, an.nstrips, an.nparts, an.L.stages.size(), an.L.nchunks, an.L.nWindow,
-                    an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, slotBytes, sweep_window, sweep_smem,
+                    an.L.nExternal, an.U.stages.size(), an.nparts, threads, sweep_slots, sweep_window, sweep_smem,
                     an.L.nExtRows, sweep_extCap);
+        if (verbosity > 0 && v2)
+            fprintf(stderr, "[b200bda] analysis: Nb %d nnzb %lld, %d reference levels, %d lines, %d strips, %d parts\n", Nb, (long long) nnzb, an.nlev, an.nlines, an.nstrips, an.nparts);
         d_stage.alloc(nnz_stage); d_bstage.alloc(N); d_A.alloc(nnz); d_LU.alloc(nnz);
         // + 8 doubles: the sweeps' 16-byte aligned rhs copies may read one row past the end
         for (DevBuf<double>* v : {&d_x, &d_r, &d_rt, &d_p, &d_v, &d_t, &d_y, &d_w, &d_xnat, &d_tmp1, &d_tmp2}) {
@@ -583,9 +662,12 @@ struct Solver {
         analysed = true;
     }
 
-    // Page-locks a caller's array once it has been handed in on two consecutive calls (Flow's matrix, rhs and solution
-    // storage persists over the Newton steps).  A caller that passes a fresh buffer every time never pays for the
-    // registration -- pinning and unpinning a new 12 MB vector per call cost more than the pageable copy it replaces.
+    // Option pin_host = 1 (off by default: the library does not own the caller's memory): page-locks a caller's array once it
+    // has been handed in on two consecutive calls (Flow's matrix, rhs and solution storage persists over the Newton steps).
+    // A caller that passes a fresh buffer every time never pays for the registration -- pinning and unpinning a new 12 MB
+    // vector per call cost more than the pageable copy it replaces.  Contract of the option: a buffer handed in stays
+    // allocated until it is replaced by another one, released with b200_host_unregister, or the solver is destroyed.  The
+    // explicit route (no heuristics) is b200_host_register / b200_host_unregister.
     void maybe_register(const void*& reg, size_t& reg_bytes, const void*& cand, const void* ptr, size_t bytes)
     {
         if (!pin_host) return;
@@ -815,6 +897,19 @@ struct Solver {
                 k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             prof_end(id);
         }
+        if (v2) {
+            int id2 = count ? prof_begin(K_SLICES) : -1;
+            if (!L2.build.empty())
+                k_fill_stream2<true><<<blocks_for((long long) L2.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+                    d_s2buildL.p, (int) L2.build.size(), d_s2srcL.p, d_LU.p, d_valL.p, 1.0);
+            prof_end(id2);
+            id2 = count ? prof_begin(K_SLICES) : -1;
+            if (!U2.build.empty())
+                k_fill_stream2<false><<<blocks_for((long long) U2.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
+                    d_s2buildU.p, (int) U2.build.size(), d_s2srcU.p, d_LU.p, d_valU.p, relaxation);
+            prof_end(id2);
+            return;
+        }
         int id = count ? prof_begin(K_SLICES) : -1;
         k_fill_stream<true><<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
             d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p, 1.0);
@@ -867,9 +962,20 @@ struct Solver {
         a.nowait = sweep_nowait; a.early = sweep_early ? 1 : 0;
         a.trace = sweep_trace ? d_trace.p : nullptr;
         a.trace_cap = kTraceCap;
+        if (v2) {
+            a.v2.parts = lower ? d_s2partsL.p : d_s2partsU.p;
+            a.v2.streams = lower ? d_s2streamsL.p : d_s2streamsU.p;
+            a.v2.hdrs = reinterpret_cast<const int4*>(lower ? d_s2hdrsL.p : d_s2hdrsU.p);
+            a.v2.codes = reinterpret_cast<const int2*>(lower ? d_s2codesL.p : d_s2codesU.p);
+            a.v2.ext = lower ? d_s2extL.p : d_s2extU.p;
+            a.v2.vals = lower ? d_valL.p : d_valU.p;
+            a.v2.window = an.window; a.v2.extWindow = an.extWindow; a.v2.ncw = s2_cw; a.v2.nh = s2_helpers; a.v2.kmin = s2_kmin; a.v2.kmax = s2_kmax;
+            a.nwarps = s2_cw;              // the SpMV tail's producer warp = the first helper warp
+            a.trace = nullptr;
+        }
         return a;
     }
-    int sweep_threads() const { return (sweep_warps + 1 + sweep_helpers) * 32; }
+    int sweep_threads() const { return v2 ? (s2_cw + s2_helpers) * 32 : (sweep_warps + 1 + sweep_helpers) * 32; }
     // Launch of a kernel of the BiCGSTAB iteration (all of them start with pdl_enter()): with iter_pdl the launch carries the
     // programmatic-stream-serialization attribute, so its CTAs are scheduled while the previous kernel drains.
     int iter_pdl = 0;                  // option (measured: slower)
@@ -889,6 +995,7 @@ struct Solver {
     {
         const bool rearm = a.rearm != nullptr, trace = a.trace != nullptr;
         auto go = [&](auto kern) { launch_iter(kern, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a); };
+        if (v2) { if (rearm) go(k_sweep2<LOWER, true>); else go(k_sweep2<LOWER, false>); return; }
         if (trace) { if (rearm) go(k_sweep<LOWER, true, true>); else go(k_sweep<LOWER, false, true>); }
         else { if (rearm) go(k_sweep<LOWER, true, false>); else go(k_sweep<LOWER, false, false>); }
     }
@@ -898,7 +1005,8 @@ struct Solver {
         int id = prof_begin(K_LOWER);
         SweepArgs a = sweep_args(true, rhs, out, nullptr, true);
         a.xu.x = d_x.p; a.xu.y = d_y.p; a.xu.sync = d_xSync.p; a.xu.n = N;
-        launch_iter(k_sweep<true, false, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2) launch_iter(k_sweep2<true, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        else launch_iter(k_sweep<true, false, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
     bool defer_now() const { return defer_ok && !sweep_trace; }
@@ -929,7 +1037,8 @@ struct Solver {
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
         a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
-        launch_iter(k_sweep<false, true, false, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        else launch_iter(k_sweep<false, true, false, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
     bool fused_now() const { return fused_units > 0 && !sweep_trace; }
@@ -1291,6 +1400,15 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
+        else if (k == "s2_kmin") s->s2_kmin = (int) value;
+        else if (k == "s2_kmax") s->s2_kmax = (int) value;
+        else if (k == "sweep_v2" || k == "s2_cw" || k == "s2_helpers") {
+            if (s->analysed) throw std::runtime_error("the sweep schedule must be set before the first solve");
+            const int v = (int) value;
+            if (k == "sweep_v2") s->sweep_v2 = v != 0;
+            else if (k == "s2_cw") s->s2_cw = std::max(1, v);
+            else s->s2_helpers = std::max(1, v);
+        }
         else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "fac_pdl") { s->fac_pdl = value != 0.0; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
         else if (k == "sweep_early") { if (s->analysed) throw std::runtime_error("sweep_early must be set before the first solve"); s->sweep_early_opt = std::max(0, std::min(2, (int) value)); }
@@ -1370,6 +1488,40 @@ b200_status b200_solve_resident(b200_solver* s, b200_result* res)
     return guarded([&]() -> b200_status {
         CUDA_OK(cudaSetDevice(s->device));
         return solve_common(s, res, 0.0, 0.0);
+    });
+}
+
+// Explicit page-locking of caller-owned buffers (the caller knows their lifetime; the library does not).
+b200_status b200_host_register(b200_solver* s, void* ptr, size_t bytes)
+{
+    if (!s || !ptr || !bytes) { g_last_error = "null argument"; return B200_UNKNOWN_ERROR; }
+    return guarded([&]() -> b200_status {
+        CUDA_OK(cudaSetDevice(s->device));
+        for (auto& r : s->host_regs) if (r.first == ptr) { if (r.second == bytes) return B200_SUCCESS; throw std::runtime_error("b200_host_register: pointer already registered with another size"); }
+        cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+        if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200_SUCCESS; }      // pinned by someone else: nothing to own
+        if (e != cudaSuccess) { cudaGetLastError(); throw CudaError(std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+        s->host_regs.emplace_back(ptr, bytes);
+        return B200_SUCCESS;
+    });
+}
+b200_status b200_host_unregister(b200_solver* s, void* ptr)
+{
+    if (!s || !ptr) { g_last_error = "null argument"; return B200_UNKNOWN_ERROR; }
+    return guarded([&]() -> b200_status {
+        CUDA_OK(cudaSetDevice(s->device));
+        CUDA_OK(cudaStreamSynchronize(s->stream));
+        for (size_t i = 0; i < s->host_regs.size(); ++i)
+            if (s->host_regs[i].first == ptr) {
+                cudaHostUnregister(ptr); cudaGetLastError();
+                s->host_regs.erase(s->host_regs.begin() + i);
+                return B200_SUCCESS;
+            }
+        // buffers the pin_host heuristic registered
+        for (const void** r : {&s->reg_vals, &s->reg_b, &s->reg_x})
+            if (*r == ptr) { cudaHostUnregister(ptr); cudaGetLastError(); *r = nullptr; return B200_SUCCESS; }
+        for (const void** c : {&s->cand_vals, &s->cand_b, &s->cand_x}) if (*c == ptr) *c = nullptr;
+        return B200_SUCCESS;     // not registered by this solver: nothing to do
     });
 }
 
@@ -1782,6 +1934,41 @@ b200_status b200_level_schedule_host(int Nb, const int* rows, const int* cols, i
 // values, run the packed streams through the chunk-by-chunk emulator and compare with the sequential
 // natural-order substitution.  stats: [nparts, nlines, nstrips, stagesL, stagesU, chunksL, windowDepsL, globalDepsL,
 // maxMetaInts, maxValsDoubles, maxRhsRows, levels].
+// pseudo-random factor in the permuted pattern (small off-diagonal blocks, well-conditioned "inverse pivots"), a right-hand side
+// and the sequential natural-order solves y = L^-1 rhs, x = U^-1 y on p-space storage: the reference the host emulations of the
+// sweep kernels are compared with
+static void sweep_check_reference(const Analysis& A, unsigned seed, std::vector<double>& LU, std::vector<double>& rhs, std::vector<double>& yr,
+                                  std::vector<double>& xr)
+{
+    const int Nb = A.Nb;
+    LU.assign((size_t) A.nnzb * 9, 0.0);
+    unsigned long long st = seed * 2654435761ull + 88172645463325252ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double) (st >> 11) / 9007199254740992.0 - 0.5; };
+    for (int q = 0; q < Nb; ++q)
+        for (int k = A.prow[q]; k < A.prow[q + 1]; ++k)
+            for (int e = 0; e < 9; ++e)
+                LU[(size_t) k * 9 + e] = (k == A.pdiag[q] ? (e % 4 == 0 ? 1.0 : 0.0) : 0.0) + 0.3 * rnd();
+    rhs.assign((size_t) 3 * Nb + 8, 0.0); yr.assign((size_t) 3 * Nb, 0.0); xr.assign((size_t) 3 * Nb, 0.0);
+    for (int i = 0; i < 3 * Nb; ++i) rhs[i] = rnd();
+    for (int r = 0; r < Nb; ++r) {
+        const int q = A.iperm[r];
+        double acc[3] = {rhs[3 * q], rhs[3 * q + 1], rhs[3 * q + 2]};
+        for (int k = A.prow[q]; k < A.pdiag[q]; ++k)
+            for (int c = 0; c < 3; ++c)
+                for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * yr[3 * (size_t) A.pcol[k] + e];
+        for (int c = 0; c < 3; ++c) yr[3 * (size_t) q + c] = acc[c];
+    }
+    for (int r = Nb - 1; r >= 0; --r) {
+        const int q = A.iperm[r];
+        double acc[3] = {yr[3 * q], yr[3 * q + 1], yr[3 * q + 2]};
+        for (int k = A.pdiag[q] + 1; k < A.prow[q + 1]; ++k)
+            for (int c = 0; c < 3; ++c)
+                for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * xr[3 * (size_t) A.pcol[k] + e];
+        const double* d = LU.data() + (size_t) A.pdiag[q] * 9;
+        for (int c = 0; c < 3; ++c) xr[3 * (size_t) q + c] = d[c * 3] * acc[0] + d[c * 3 + 1] * acc[1] + d[c * 3 + 2] * acc[2];
+    }
+}
+
 b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int stage_bytes, int window,
                                            unsigned seed, double* max_rel_err, long long* stats)
 {
@@ -1792,35 +1979,8 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
         if (stage_bytes > 0) opt.stageBytes = stage_bytes;
         if (window > 0) opt.window = window;
         Analysis A = analyse(Nb, rows, cols, opt);
-        const long long nnzb = rows[Nb];
-        // pseudo-random factor in the permuted pattern: small off-diagonal blocks, well-conditioned "inverse pivots"
-        std::vector<double> LU((size_t) nnzb * 9);
-        unsigned long long st = seed * 2654435761ull + 88172645463325252ull;
-        auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double) (st >> 11) / 9007199254740992.0 - 0.5; };
-        for (int q = 0; q < Nb; ++q)
-            for (int k = A.prow[q]; k < A.prow[q + 1]; ++k)
-                for (int e = 0; e < 9; ++e)
-                    LU[(size_t) k * 9 + e] = (k == A.pdiag[q] ? (e % 4 == 0 ? 1.0 : 0.0) : 0.0) + 0.3 * rnd();
-        std::vector<double> rhs((size_t) 3 * Nb + 8), y((size_t) 3 * Nb + 8), x((size_t) 3 * Nb + 8), yr((size_t) 3 * Nb), xr((size_t) 3 * Nb);
-        for (int i = 0; i < 3 * Nb; ++i) rhs[i] = rnd();
-        // sequential reference in NATURAL order on p-space storage
-        for (int r = 0; r < Nb; ++r) {
-            const int q = A.iperm[r];
-            double acc[3] = {rhs[3 * q], rhs[3 * q + 1], rhs[3 * q + 2]};
-            for (int k = A.prow[q]; k < A.pdiag[q]; ++k)
-                for (int c = 0; c < 3; ++c)
-                    for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * yr[3 * (size_t) A.pcol[k] + e];
-            for (int c = 0; c < 3; ++c) yr[3 * (size_t) q + c] = acc[c];
-        }
-        for (int r = Nb - 1; r >= 0; --r) {
-            const int q = A.iperm[r];
-            double acc[3] = {yr[3 * q], yr[3 * q + 1], yr[3 * q + 2]};
-            for (int k = A.pdiag[q] + 1; k < A.prow[q + 1]; ++k)
-                for (int c = 0; c < 3; ++c)
-                    for (int e = 0; e < 3; ++e) acc[c] -= LU[(size_t) k * 9 + c * 3 + e] * xr[3 * (size_t) A.pcol[k] + e];
-            const double* d = LU.data() + (size_t) A.pdiag[q] * 9;
-            for (int c = 0; c < 3; ++c) xr[3 * (size_t) q + c] = d[c * 3] * acc[0] + d[c * 3 + 1] * acc[1] + d[c * 3 + 2] * acc[2];
-        }
+        std::vector<double> LU, rhs, yr, xr, y((size_t) 3 * Nb + 8), x((size_t) 3 * Nb + 8);
+        sweep_check_reference(A, seed, LU, rhs, yr, xr);
         std::vector<double> vL, vU;
         fill_stream_host(A.L, true, LU.data(), 1.0, vL);
         fill_stream_host(A.U, false, LU.data(), 1.0, vU);
@@ -1836,6 +1996,51 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
             const long long v[12] = {A.nparts, A.nlines, A.nstrips, (long long) A.L.stages.size(), (long long) A.U.stages.size(), A.L.nchunks,
                                      A.L.nWindow, A.L.nExternal, std::max(A.L.maxMetaInts, A.U.maxMetaInts),
                                      std::max(A.L.maxValsDoubles, A.U.maxValsDoubles), std::max(A.L.maxRhsRows, A.U.maxRhsRows), A.nlev};
+            memcpy(stats, v, sizeof v);
+        }
+        return B200_SUCCESS;
+    }, B200_ANALYSIS_FAILED);
+}
+
+// The same check for the round-2 schedule (sweep2.hpp): builds the record streams for `parts` parts, `consumer_warps` consumer
+// warps (groups x group width per part; 0 = the library's defaults), `helpers` helper warps, fills them from a pseudo-random
+// factor and runs the host emulation of k_sweep2 against the sequential natural-order solves.
+// stats (12): parts, lines, strips, records L, records U, empty records L, window deps L, external deps L, external rows L,
+// helper blocks L, max groups, max group width.
+b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int window, int ext_window,
+                                            int consumer_warps, int helpers, int groups, int wg, unsigned seed, double relax,
+                                            double* max_rel_err, long long* stats)
+{
+    return guarded([&]() -> b200_status {
+        if (Nb <= 0 || !rows || !cols) throw std::runtime_error("bad arguments");
+        AnalysisOptions opt;
+        if (parts > 0) opt.parts = parts;
+        if (window > 0) opt.window = window;
+        opt.extWindow = ext_window > 0 ? ext_window : 2048;
+        opt.buildStreams = false;
+        Analysis A = analyse(Nb, rows, cols, opt);
+        Sweep2Options o2;
+        if (consumer_warps > 0) o2.consumerWarps = consumer_warps;
+        (void) helpers;
+        (void) groups; (void) wg;
+        Sweep2Plan L, U;
+        build_sweep2_plans(A, rows, cols, o2, L, U);
+        std::vector<double> LU, rhs, yr, xr, y((size_t) 3 * Nb + 8), x((size_t) 3 * Nb + 8);
+        sweep_check_reference(A, seed, LU, rhs, yr, xr);
+        std::vector<double> vL, vU;
+        fill_stream2_host(L, true, LU.data(), 1.0, vL);
+        fill_stream2_host(U, false, LU.data(), relax, vU);
+        if (!emulate_sweep2(A, L, true, vL, rhs.data(), y.data())) throw std::runtime_error("lower sweep schedule deadlocks");
+        if (!emulate_sweep2(A, U, false, vU, y.data(), x.data())) throw std::runtime_error("upper sweep schedule deadlocks");
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < 3 * Nb; ++i) {
+            num = std::max(num, std::fabs(x[i] - relax * xr[i]) + std::fabs(y[i] - yr[i]));
+            den = std::max(den, std::fabs(xr[i]));
+        }
+        if (max_rel_err) *max_rel_err = den > 0.0 ? num / den : num;
+        if (stats) {
+            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, L.nExtRows,
+                                     0, L.maxChunks, o2.consumerWarps};
             memcpy(stats, v, sizeof v);
         }
         return B200_SUCCESS;

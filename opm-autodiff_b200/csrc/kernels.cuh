@@ -390,7 +390,7 @@ __device__ __forceinline__ int vidx(int f, int lane) { return (LOWER && f == 8) 
 // Scatter the BSR factor (p-space) into the record stream of one sweep (analysis.hpp): one warp per record, one
 // lane per (row q, component comp) of the record.
 //   lower: field 3 j + v = L[block j][comp][v]
-//   upper: field 3 j + v = (w D^-1 U)[block j][comp][v], field 9 + v = (w D^-1)[comp][v]  (first record of a row only)
+//   upper: field 3 j + v = (D^-1 U)[block j][comp][v], field 9 + v = (w D^-1)[comp][v]  (first record of a row only)
 template <bool LOWER>
 __global__ void __launch_bounds__(256) k_fill_stream(const BuildD* __restrict__ build, int nrec, const int* __restrict__ src,
                                                      const double* __restrict__ LU, double* __restrict__ vals, double relax)
@@ -405,10 +405,12 @@ __global__ void __launch_bounds__(256) k_fill_stream(const BuildD* __restrict__ 
         if (!LOWER) {
             if (act) {
                 const double* d = LU + (size_t) src[b.src_off + 3 * b.count + q] * 9 + comp * 3;
-                inv[0] = relax * d[0]; inv[1] = relax * d[1]; inv[2] = relax * d[2];
+                inv[0] = d[0]; inv[1] = d[1]; inv[2] = d[2];
             }
+            // z = w U^-1 y (ParallelOverlappingILU0.hpp:897-901: the back-substitution, then `v *= w`): with z' = w z the recurrence
+            // is z'_i = (w D^-1) y_i - (D^-1 U_ij) z'_j, so only the pivot field carries the relaxation factor
 #pragma unroll
-            for (int v = 0; v < 3; ++v) out[vidx<LOWER>(9 + v, lane)] = b.first ? inv[v] : 0.0;
+            for (int v = 0; v < 3; ++v) out[vidx<LOWER>(9 + v, lane)] = b.first ? relax * inv[v] : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -518,9 +520,14 @@ struct XUpdate {
     int n;                         // doubles
 };
 
+}  // namespace b200
+#include "sweep2.cuh"
+namespace b200 {
+
 struct SweepArgs {
     FusedSpmv f;
     XUpdate xu;
+    Sweep2Args v2;        // round-2 schedule (k_sweep2)
     const StageD* stages;
     const PartD* parts;
     const int* meta;
@@ -1131,6 +1138,206 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
         if (lane == 0) mbar_arrive(empty + s);
         if (++s == nslots) { s = 0; parity ^= 1; }
     }
+    }
+    if constexpr (SPMV == 1 || SPMV == 2) fused_spmv_tail<SPMV>(P, part, sweep_smem);
+    if constexpr (SPMV == 3) {
+        if (xupd) xupdate_tail(P, xupd_coef);
+    }
+}
+
+// ---- round-2 sweep kernel (schedule and rationale: sweep2.hpp, sweep2.cuh) ---------------------------------------------------
+// SPMV as k_sweep: -1 sweep only, 1 / 2 go on with the SpMV that follows (fused_spmv_tail), 3 lower sweep + pending x update.
+constexpr int kS2Threads = 512;
+template <bool LOWER, bool REARM, int SPMV = -1>
+__global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
+{
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
+    pdl_enter();
+    if (P.check_done && P.S->done) return;
+    const int part = blockIdx.x;
+    if (part >= P.nparts) return;
+    const bool xupd = SPMV == 3 && P.S->pend_on != 0;
+    const double xupd_coef = SPMV == 3 ? P.S->pend : 0.0;
+    const Sweep2Args& V = P.v2;
+    const S2PartD pr = V.parts[part];
+    int* hp = reinterpret_cast<int*>(sweep_smem);
+    const int W = V.window, EW = V.extWindow, zslot = W + EW;
+    double* xyp = reinterpret_cast<double*>(sweep_smem + kS2Header);      // value space, components 0 and 1: 16 bytes per slot
+    double* zp = xyp + 2 * (size_t) (zslot + 1);                            // component 2: 8 bytes per slot
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 16) hp[threadIdx.x] = 0;
+    if (threadIdx.x == 32) { xyp[2 * (size_t) zslot] = 0.0; xyp[2 * (size_t) zslot + 1] = 0.0; zp[zslot] = 0.0; }
+    __syncthreads();
+    constexpr int NP = LOWER ? 14 : 18;
+
+    if (warp < pr.ncw) {
+        // ---- consumers: warp w walks stream w of the part
+        const S2StreamD sd = V.streams[pr.stream0 + warp];
+        const int nrec = sd.nrec;
+        const int4* __restrict__ hdrs = V.hdrs + sd.hdr_off;
+        const double* vp = V.vals + sd.vals_off;
+        const int2* cp = V.codes + sd.code_off;
+        const unsigned xy = smem_u32(xyp), z = smem_u32(zp);
+        const int zcode = 8 * zslot;
+        const int4 hzero = make_int4(0, 0, 0, 0);
+        int4 hb = lane < nrec ? __ldg(hdrs + lane) : hzero;                // headers of the records 32 b + lane
+        int4 hbn = 32 + lane < nrec ? __ldg(hdrs + 32 + lane) : hzero;
+        auto header = [&](int j) {
+            return make_int4(__shfl_sync(kFull, hb.x, j), __shfl_sync(kFull, hb.y, j), __shfl_sync(kFull, hb.z, j), __shfl_sync(kFull, hb.w, j));
+        };
+        S2Ops<LOWER> o;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) o.v[k] = make_double2(0.0, 0.0);
+        o.r0 = o.r1 = o.r2 = 0.0;
+        // issue the loads of the record described by hd (nothing waits for them here) and advance the stream
+        auto fetch = [&](const int4& hd) {
+            const int cnt = hd.y & 255;
+            if (lane < cnt) {
+                const double* v = vp + 2 * lane;
+#pragma unroll
+                for (int k = 0; k < NP; ++k) o.v[k] = ldg_stream_f64x2(v + 2 * (size_t) k * cnt);
+                o.cd = ldg_stream_s32x2(cp + lane);
+                if (hd.y & (S2D_FIRST << 8)) {
+                    const double* r = P.rhs + 3 * (size_t) (LOWER ? hd.x + lane : hd.x - lane);
+                    o.r0 = r[0]; o.r1 = r[1]; o.r2 = r[2];
+                }
+            } else o.cd = make_int2(zcode | (zcode << 16), zcode);
+            vp += 2 * (size_t) NP * cnt;
+            cp += cnt;
+        };
+        int4 h = header(0);
+        if (nrec > 0) fetch(h);
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        long long t_start = 0;
+        for (int i = 0; i < nrec; ++i) {
+            const int cnt = h.y & 255, flags = (h.y >> 8) & 255;
+            const unsigned d0 = (unsigned) o.cd.x & 0xffffu, d1 = (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & 0xffffu, oc = (unsigned) o.cd.y >> 16;
+            const double* v = reinterpret_cast<const double*>(o.v);
+            // start value: nothing here depends on another row
+            if (flags & S2D_FIRST) {
+                if constexpr (LOWER) { y0 = o.r0; y1 = o.r1; y2 = o.r2; }
+                else {
+                    y0 = fma(v[29], o.r2, fma(v[28], o.r1, v[27] * o.r0));
+                    y1 = fma(v[32], o.r2, fma(v[31], o.r1, v[30] * o.r0));
+                    y2 = fma(v[35], o.r2, fma(v[34], o.r1, v[33] * o.r0));
+                }
+            }
+            if (flags & S2D_SYNC) {
+                bar_sync_n((h.y >> 16) & 15, 32 * (int) ((unsigned) h.z >> 24));       // the previous step is complete
+                if ((flags & S2D_LEAD) && lane == 0) st_volatile_s32(hp + 8, h.w & 0xffffff);   // external rows nobody reads any more: ring slots free
+            }
+            const int need = h.z & 0xffffff;
+            if (need && P.nowait < 2) {                                                      // external rows of this step: parked by the helper warp
+                int spins = 0;
+                while (ld_volatile_s32(hp) < need) {
+                    if ((++spins & 1023) == 0) {
+                        if (t_start == 0) t_start = globaltimer_ns();
+                        if (ld_volatile_s32(hp + 9) || globaltimer_ns() - t_start > kS2TimeoutNs) { P.S->trsv_timeout = 1; st_volatile_s32(hp + 9, 1); break; }
+                    }
+                }
+            }
+            // ---- dependent part
+            const double2 a0 = lds_f64x2(xy + 2 * d0), a1 = lds_f64x2(xy + 2 * d1), a2 = lds_f64x2(xy + 2 * d2);
+            const double b0 = lds_f64(z + d0), b1 = lds_f64(z + d1), b2 = lds_f64(z + d2);
+            const double p0 = fma(v[2], b0, fma(v[1], a0.y, v[0] * a0.x));
+            const double p1 = fma(v[5], b0, fma(v[4], a0.y, v[3] * a0.x));
+            const double p2 = fma(v[8], b0, fma(v[7], a0.y, v[6] * a0.x));
+            const double q0 = fma(v[11], b1, fma(v[10], a1.y, v[9] * a1.x));
+            const double q1 = fma(v[14], b1, fma(v[13], a1.y, v[12] * a1.x));
+            const double q2 = fma(v[17], b1, fma(v[16], a1.y, v[15] * a1.x));
+            const double s0 = fma(v[20], b2, fma(v[19], a2.y, v[18] * a2.x));
+            const double s1 = fma(v[23], b2, fma(v[22], a2.y, v[21] * a2.x));
+            const double s2 = fma(v[26], b2, fma(v[25], a2.y, v[24] * a2.x));
+            y0 = ((y0 - p0) - q0) - s0; y1 = ((y1 - p1) - q1) - s1; y2 = ((y2 - p2) - q2) - s2;
+            const bool store = (flags & S2D_LAST) && lane < cnt;
+            if (store) { sts_f64x2(xy + 2 * oc, y0, y1); sts_f64(z + oc, y2); }
+            if (flags & S2D_ARRIVE) bar_arrive_n((h.y >> 20) & 15, 32 * (int) ((unsigned) h.w >> 24));   // this warp's share of the step is in shared memory
+            if (store) {
+                const size_t gi = 3 * (size_t) (LOWER ? h.x + lane : h.x - lane);
+                st_relaxed(P.out + gi, y0); st_relaxed(P.out + gi + 1, y1); st_relaxed(P.out + gi + 2, y2);
+                if (REARM) { P.rearm[gi] = sentinel(); P.rearm[gi + 1] = sentinel(); P.rearm[gi + 2] = sentinel(); }
+            }
+            // ---- operands of the next record of this warp: G steps ahead of their use
+            if (i + 1 < nrec) {
+                const int j = (i + 1) & 31;
+                if (j == 0) { hb = hbn; hbn = i + 33 + lane < nrec ? __ldg(hdrs + i + 33 + lane) : hzero; }
+                h = header(j);
+                fetch(h);
+            }
+        }
+    } else if (warp == V.ncw && P.nowait < 3) {
+        // ---- helper: external rows in list order, a lane per (row, component)
+        constexpr int KMAX = 8;
+        const int kmin = max(1, min(V.kmin, KMAX)), kmax = max(kmin, min(V.kmax, KMAX));
+        const int* __restrict__ extl = V.ext + pr.ext0;
+        double* rxy = xyp + 2 * (size_t) W;
+        double* rz = zp + W;
+        const int nelem = 3 * pr.next;
+        int base = 0;                      // elements [0, base) are parked
+        int K = kmin;                      // windows polled per round
+        long long t_start = 0;
+        int idle = 0;
+        while (base < nelem) {
+            const int limit = min(nelem, 3 * (ld_volatile_s32(hp + 8) + EW));     // ring slots of rows that are still read must not be overwritten
+            if (base >= limit) {
+                __nanosleep(100);
+                if ((++idle & 1023) == 0) {
+                    if (t_start == 0) t_start = globaltimer_ns();
+                    if (ld_volatile_s32(hp + 9) || globaltimer_ns() - t_start > kS2TimeoutNs) { P.S->trsv_timeout = 1; if (lane == 0) { st_volatile_s32(hp + 9, 1); st_volatile_s32(hp, 0x7fffffff); } break; }
+                }
+                continue;
+            }
+            double val[KMAX];
+            bool act[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const int e = base + 32 * k + lane;
+                act[k] = k < K && e < limit;
+                if (act[k]) {
+                    const int r = e / 3;
+                    val[k] = ld_relaxed(P.out + 3 * (size_t) __ldg(extl + r) + (e - 3 * r));
+                }
+            }
+            int adv = 0;
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const bool ok = act[k] && (P.nowait || !is_sentinel(val[k]));
+                if (ok) {
+                    const int e = base + 32 * k + lane, r = e / 3, c = e - 3 * r, slot = r & (EW - 1);
+                    if (c == 2) rz[slot] = val[k]; else rxy[2 * slot + c] = val[k];
+                }
+                const unsigned bm = __ballot_sync(kFull, ok);
+                if (all) {
+                    if (bm == kFull) adv += 32;
+                    else { adv += __ffs(~bm) - 1; all = false; }
+                }
+            }
+            if (adv > 0) {
+                const int nb = base + adv;
+                if (nb / 3 > base / 3) {
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) st_volatile_s32(hp, nb / 3);
+                }
+                base = nb;
+                idle = 0;
+            }
+            // everything polled has arrived: the producers are ahead, widen; the first window is still armed: poll only that one
+            if (adv >= 32 * K) K = min(kmax, 2 * K);
+            else if (adv < 32) K = kmin;
+            if (adv == 0) {
+                if ((++idle & 255) == 0) {
+                    if (t_start == 0) t_start = globaltimer_ns();
+                    if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || globaltimer_ns() - t_start > kS2TimeoutNs) {
+                        P.S->trsv_timeout = 1;
+                        if (lane == 0) { st_volatile_s32(hp + 9, 1); st_volatile_s32(hp, 0x7fffffff); }
+                        break;
+                    }
+                }
+                if (P.helper_sleep) __nanosleep(P.helper_sleep);
+            }
+        }
     }
     if constexpr (SPMV == 1 || SPMV == 2) fused_spmv_tail<SPMV>(P, part, sweep_smem);
     if constexpr (SPMV == 3) {

@@ -78,6 +78,13 @@ def test_kernels_vs_oracle(mods, shape, faults):
     v = be.ilu0_apply(d)
     vo = oracle.ilu0_apply(s.rows, s.cols, diag, LUo, d)
     assert relerr(v, vo) < 1e-9
+    # relaxed apply v = w (LU)^-1 d: the back-substitution runs unrelaxed, then `v *= w` (ParallelOverlappingILU0.hpp:897-901)
+    be.set_option("relaxation", 0.9)
+    assert be.ilu0_factorize() == bridge.SolverStatus.BDA_SOLVER_SUCCESS
+    v9 = be.ilu0_apply(d)
+    assert relerr(v9, oracle.ilu0_apply(s.rows, s.cols, diag, LUo, d, w=0.9)) < 1e-9
+    assert relerr(v9, 0.9 * vo) < 1e-9
+    be.set_option("relaxation", 1.0)
     # level schedule of the uploaded pattern == oracle restatement of Reorder.cpp:266-318
     to, fr, rpl = be.get_level_schedule()
     oto, ofr, olp = oracle.level_schedule(s.rows, s.cols)
