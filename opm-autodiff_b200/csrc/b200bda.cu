@@ -226,7 +226,7 @@ struct Solver {
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
     int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 0, sweep_helper_sleep = 0;
     // round-2 sweeps (k_sweep2): consumer warps (G x WG per part), helper warps, forced group count / group width (0 = automatic)
-    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_kmin = 3, s2_kmax = 6;
+    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_kmin = 2, s2_kmax = 6;
     bool v2 = false;
     Sweep2Plan L2, U2;
 
@@ -448,7 +448,7 @@ struct Solver {
         opt.stageBytes = stage_bytes;
         opt.window = sweep_window;
         v2 = sweep_v2 != 0;
-        opt.extWindow = sweep_ext_window > 0 ? sweep_ext_window : (v2 ? 2048 : 512);
+        opt.extWindow = sweep_ext_window > 0 ? (v2 ? std::max(512, sweep_ext_window) : sweep_ext_window) : (v2 ? 2048 : 512);     // v2: the helper stages 512 row indices ahead
         opt.buildStreams = !v2;
         opt.warps = sweep_warps;
         opt.groups = sweep_groups;
@@ -555,7 +555,7 @@ struct Solver {
             // the schedule stays on the host only as long as the analysis needs it (the build lists are large)
             for (Sweep2Plan* P2 : {&L2, &U2}) { std::vector<int>().swap(P2->src); std::vector<int>().swap(P2->codes); std::vector<int>().swap(P2->hdrs); std::vector<int>().swap(P2->stepChunks); }
             threads = sweep_threads();
-            const size_t need = kS2Header + 24 * (size_t) (an.window + an.extWindow + 1);
+            const size_t need = kS2Header + 24 * (size_t) (an.window + an.extWindow + 1) + 4 * (size_t) an.extWindow;      // value space + row indices of the ring
             // the SpMV tail streams SELL slices through the same dynamic shared memory: two chunk buffers per ring-fed consumer warp
             const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * kTailBufBytes * std::min(kTailMaxCons, threads / 32 - 1)) : 0;
             sweep_smem = std::max(need, tail);
@@ -971,7 +971,6 @@ struct Solver {
             a.v2.vals = lower ? d_valL.p : d_valU.p;
             a.v2.window = an.window; a.v2.extWindow = an.extWindow; a.v2.ncw = s2_cw; a.v2.nh = s2_helpers; a.v2.kmin = s2_kmin; a.v2.kmax = s2_kmax;
             a.nwarps = s2_cw;              // the SpMV tail's producer warp = the first helper warp
-            a.trace = nullptr;
         }
         return a;
     }

@@ -1166,6 +1166,7 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
     double* zp = xyp + 2 * (size_t) (zslot + 1);                            // component 2: 8 bytes per slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 16) hp[threadIdx.x] = 0;
+    if (P.trace && threadIdx.x == 0) { P.trace[8 * part] = globaltimer_ns(); for (int k = 1; k < 8; ++k) P.trace[8 * part + k] = 0; }
     if (threadIdx.x == 32) { xyp[2 * (size_t) zslot] = 0.0; xyp[2 * (size_t) zslot + 1] = 0.0; zp[zslot] = 0.0; }
     __syncthreads();
     constexpr int NP = LOWER ? 14 : 18;
@@ -1209,6 +1210,9 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
         if (nrec > 0) fetch(h);
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
         long long t_start = 0;
+        // debugging aid: where the cycles of this warp go (parts 0 and 1 + nparts / 2 of a traced launch)
+        const bool prof = P.trace != nullptr && (part == 0 || part == P.nparts / 2);
+        long long pc[6] = {0, 0, 0, 0, 0, 0}, c0 = prof ? clock64() : 0;
         for (int i = 0; i < nrec; ++i) {
             const int cnt = h.y & 255, flags = (h.y >> 8) & 255;
             const unsigned d0 = (unsigned) o.cd.x & 0xffffu, d1 = (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & 0xffffu, oc = (unsigned) o.cd.y >> 16;
@@ -1222,11 +1226,15 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                     y2 = fma(v[35], o.r2, fma(v[34], o.r1, v[33] * o.r0));
                 }
             }
+            if (prof) { const long long c = clock64(); pc[0] += c - c0; c0 = c; }      // fetch issue, header, start value
             if (flags & S2D_SYNC) {
                 bar_sync_n((h.y >> 16) & 15, 32 * (int) ((unsigned) h.z >> 24));       // the previous step is complete
                 if ((flags & S2D_LEAD) && lane == 0) st_volatile_s32(hp + 8, h.w & 0xffffff);   // external rows nobody reads any more: ring slots free
             }
+            if (prof) { const long long c = clock64(); pc[1] += c - c0; c0 = c; }      // waiting for the previous step
             const int need = h.z & 0xffffff;
+            const bool tr = P.trace != nullptr && (flags & S2D_LEAD) && lane == 0;      // debugging aid: timeline of the part's steps
+            const long long tw0 = tr ? globaltimer_ns() : 0;
             if (need && P.nowait < 2) {                                                      // external rows of this step: parked by the helper warp
                 int spins = 0;
                 while (ld_volatile_s32(hp) < need) {
@@ -1236,6 +1244,14 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                     }
                 }
             }
+            if (tr) {                                                     // stores only: nothing here waits for global memory
+                const long long t = globaltimer_ns();
+                const int st = ld_volatile_s32(hp + 10);                  // LEAD records of a part are its steps in order (one warp at a time)
+                st_volatile_s32(hp + 10, st + 1);
+                P.trace[8 * part + 5] = st + 1;
+                if (st < 256) { P.trace[8192 + 2 * (256 * part + st)] = t; P.trace[8192 + 2 * (256 * part + st) + 1] = t - tw0; }
+            }
+            if (prof) { const long long c = clock64(); pc[2] += c - c0; c0 = c; }      // waiting for external rows
             // ---- dependent part
             const double2 a0 = lds_f64x2(xy + 2 * d0), a1 = lds_f64x2(xy + 2 * d1), a2 = lds_f64x2(xy + 2 * d2);
             const double b0 = lds_f64(z + d0), b1 = lds_f64(z + d1), b2 = lds_f64(z + d2);
@@ -1250,6 +1266,7 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             const double s2 = fma(v[26], b2, fma(v[25], a2.y, v[24] * a2.x));
             y0 = ((y0 - p0) - q0) - s0; y1 = ((y1 - p1) - q1) - s1; y2 = ((y2 - p2) - q2) - s2;
             const bool store = (flags & S2D_LAST) && lane < cnt;
+            if (prof) { if (__double_as_longlong(y0) == 0x7ff123456789abcdLL) pc[5]++; const long long c = clock64(); pc[3] += c - c0; c0 = c; }   // dependencies + operands landed + fma
             if (store) { sts_f64x2(xy + 2 * oc, y0, y1); sts_f64(z + oc, y2); }
             if (flags & S2D_ARRIVE) bar_arrive_n((h.y >> 20) & 15, 32 * (int) ((unsigned) h.w >> 24));   // this warp's share of the step is in shared memory
             if (store) {
@@ -1257,7 +1274,8 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 st_relaxed(P.out + gi, y0); st_relaxed(P.out + gi + 1, y1); st_relaxed(P.out + gi + 2, y2);
                 if (REARM) { P.rearm[gi] = sentinel(); P.rearm[gi + 1] = sentinel(); P.rearm[gi + 2] = sentinel(); }
             }
-            // ---- operands of the next record of this warp: G steps ahead of their use
+            if (prof) { const long long c = clock64(); pc[4] += c - c0; c0 = c; }      // stores, arrive
+            // ---- operands of the next record of this warp: several steps ahead of their use
             if (i + 1 < nrec) {
                 const int j = (i + 1) & 31;
                 if (j == 0) { hb = hbn; hbn = i + 33 + lane < nrec ? __ldg(hdrs + i + 33 + lane) : hzero; }
@@ -1265,20 +1283,50 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 fetch(h);
             }
         }
+        if (prof && lane == 0) {
+            long long* o2 = P.trace + 8192 + 2 * 256 * 1024 + (part == 0 ? 0 : 256) + 8 * warp;
+            for (int k = 0; k < 6; ++k) o2[k] = pc[k];
+            o2[6] = nrec; o2[7] = clock64() - c0;
+        }
     } else if (warp == V.ncw && P.nowait < 3) {
-        // ---- helper: external rows in list order, a lane per (row, component)
-        constexpr int KMAX = 8;
+        // ---- helper: external rows in list order.  Windows of 10 rows, lane = 3 x row + component (lanes 30 and 31 idle); the
+        // round is kept SHORT (a lone warp issues an instruction every 4-5 cycles: the first version, with a division per
+        // element and eight unrolled windows, needed 450 cycles to issue its polls and 1000 to park and publish what had
+        // arrived, on top of the 600 cycles of the L2 round trip)
+        constexpr int KMAX = 6;
         const int kmin = max(1, min(V.kmin, KMAX)), kmax = max(kmin, min(V.kmax, KMAX));
         const int* __restrict__ extl = V.ext + pr.ext0;
-        double* rxy = xyp + 2 * (size_t) W;
-        double* rz = zp + W;
-        const int nelem = 3 * pr.next;
-        int base = 0;                      // elements [0, base) are parked
+        const int lr = lane / 3, lc = lane - 3 * lr;
+        const bool lane_on = lane < 30;
+        int* rrow = reinterpret_cast<int*>(zp + zslot + 1);            // p-space row of the list entry that owns a ring slot (staged ahead)
+        // byte address (shared window) of this lane's component of ring slot 0, and the stride between slots
+        const unsigned park0 = lc == 2 ? smem_u32(zp + W) : smem_u32(xyp + 2 * (size_t) W) + 8 * lc;
+        const unsigned park_stride = lc == 2 ? 8u : 16u;
+        const unsigned rrow0 = smem_u32(rrow);
+        const double* outc = P.out + lc;
+        const int next = pr.next;
+        int base = 0;                      // rows [0, base) of the list are parked
         int K = kmin;                      // windows polled per round
+        int staged = 0;                    // list entries [0, staged) have their row index in shared memory
+        int pend_row = 0, pend_at = -1;    // index load in flight: entry pend_at + lane
         long long t_start = 0;
         int idle = 0;
-        while (base < nelem) {
-            const int limit = min(nelem, 3 * (ld_volatile_s32(hp + 8) + EW));     // ring slots of rows that are still read must not be overwritten
+        long long hs[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // debugging aid: rounds, windows polled, rounds without progress, rows, cycles: issue / wait for the polls / park + publish, -
+        for (; staged < min(next, 512); staged += 32)
+            if (staged + lane < next) rrow[(staged + lane) & (EW - 1)] = __ldg(extl + staged + lane);
+        __syncwarp();
+        while (base < next) {
+            // stage the row indices of the list ahead of the polls: the load issued in the previous round lands now
+            if (pend_at >= 0) {
+                if (pend_at + lane < next) rrow[(pend_at + lane) & (EW - 1)] = pend_row;
+                staged = pend_at + 32; pend_at = -1;
+                __syncwarp();
+            }
+            if (staged < next && staged < base + 256) {
+                pend_at = staged;
+                if (staged + lane < next) pend_row = __ldg(extl + staged + lane);
+            }
+            const int limit = min(min(next, staged), ld_volatile_s32(hp + 8) + EW);   // ring slots still read must not be overwritten
             if (base >= limit) {
                 __nanosleep(100);
                 if ((++idle & 1023) == 0) {
@@ -1287,45 +1335,54 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 }
                 continue;
             }
+            const long long hc0 = P.trace ? clock64() : 0;
             double val[KMAX];
+            unsigned slot[KMAX];
             bool act[KMAX];
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const int e = base + 32 * k + lane;
-                act[k] = k < K && e < limit;
+                const int r = base + 10 * k + lr;
+                act[k] = lane_on && k < K && r < limit;
+                slot[k] = (unsigned) r & (unsigned) (EW - 1);
                 if (act[k]) {
-                    const int r = e / 3;
-                    val[k] = ld_relaxed(P.out + 3 * (size_t) __ldg(extl + r) + (e - 3 * r));
+                    int row;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(rrow0 + 4 * slot[k]));
+                    val[k] = ld_relaxed(outc + 3 * (size_t) row);
                 }
+            }
+            long long hc1 = 0, hc2 = 0;
+            if (P.trace) {
+                hs[0]++; hs[1] += K;
+                hc1 = clock64();
+                if (act[0] && __double_as_longlong(val[0]) == 0x7ff123456789abcdLL) hs[7]++;       // waits for the first poll
+                hc2 = clock64();
             }
             int adv = 0;
             bool all = true;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const bool ok = act[k] && (P.nowait || !is_sentinel(val[k]));
-                if (ok) {
-                    const int e = base + 32 * k + lane, r = e / 3, c = e - 3 * r, slot = r & (EW - 1);
-                    if (c == 2) rz[slot] = val[k]; else rxy[2 * slot + c] = val[k];
-                }
-                const unsigned bm = __ballot_sync(kFull, ok);
-                if (all) {
-                    if (bm == kFull) adv += 32;
-                    else { adv += __ffs(~bm) - 1; all = false; }
+                if (k < K) {
+                    const bool ok = act[k] && (P.nowait || !is_sentinel(val[k]));
+                    if (ok) sts_f64(park0 + park_stride * slot[k], val[k]);
+                    const unsigned bm = __ballot_sync(kFull, ok);
+                    if (all) {
+                        const unsigned miss = ~(bm & (bm >> 1) & (bm >> 2)) & 0x09249249u;      // bit 3 q: row q of the window is incomplete
+                        const int n = miss ? (__ffs(miss) - 1) / 3 : 10;
+                        adv += n;
+                        all = n == 10;
+                    }
                 }
             }
             if (adv > 0) {
-                const int nb = base + adv;
-                if (nb / 3 > base / 3) {
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) st_volatile_s32(hp, nb / 3);
-                }
-                base = nb;
+                base += adv;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) st_volatile_s32(hp, base);
                 idle = 0;
             }
-            // everything polled has arrived: the producers are ahead, widen; the first window is still armed: poll only that one
-            if (adv >= 32 * K) K = min(kmax, 2 * K);
-            else if (adv < 32) K = kmin;
+            if (P.trace) { hs[2] += adv == 0; hs[3] += adv; hs[4] += hc1 - hc0; hs[5] += hc2 - hc1; hs[6] += clock64() - hc2; }
+            // poll one window more than what arrived in this round (the producers' rate), at least kmin
+            K = max(kmin, min(kmax, (adv + 9) / 10 + 1));
             if (adv == 0) {
                 if ((++idle & 255) == 0) {
                     if (t_start == 0) t_start = globaltimer_ns();
@@ -1338,6 +1395,7 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 if (P.helper_sleep) __nanosleep(P.helper_sleep);
             }
         }
+        if (P.trace && lane == 0) { long long* o3 = P.trace + 8192 + 2 * 256 * 1024 + 512 + 8 * part; for (int k = 0; k < 8; ++k) o3[k] = hs[k]; }
     }
     if constexpr (SPMV == 1 || SPMV == 2) fused_spmv_tail<SPMV>(P, part, sweep_smem);
     if constexpr (SPMV == 3) {
