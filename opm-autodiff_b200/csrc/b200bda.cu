@@ -226,7 +226,7 @@ struct Solver {
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
     int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 0, sweep_helper_sleep = 0;
     // round-2 sweeps (k_sweep2): consumer warps (G x WG per part), helper warps, forced group count / group width (0 = automatic)
-    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_kmin = 2, s2_kmax = 6;
+    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1;      // s2_helpers: warps beyond the consumers (they only work in the tails)
     bool v2 = false;
     Sweep2Plan L2, U2;
 
@@ -279,7 +279,7 @@ struct Solver {
     DevBuf<S2PartD> d_s2partsL, d_s2partsU;
     DevBuf<S2StreamD> d_s2streamsL, d_s2streamsU;
     DevBuf<S2BuildD> d_s2buildL, d_s2buildU;
-    DevBuf<int> d_s2hdrsL, d_s2hdrsU, d_s2codesL, d_s2codesU, d_s2extL, d_s2extU, d_s2srcL, d_s2srcU;
+    DevBuf<int> d_s2hdrsL, d_s2hdrsU, d_s2codesL, d_s2codesU, d_s2srcL, d_s2srcU;
     DevBuf<double> d_stage, d_bstage, d_A, d_LU;
     DevBuf<double> d_x, d_r, d_rt, d_p, d_v, d_t, d_y, d_w, d_xnat, d_tmp1, d_tmp2;
     DevBuf<double> d_partials;
@@ -448,14 +448,14 @@ struct Solver {
         opt.stageBytes = stage_bytes;
         opt.window = sweep_window;
         v2 = sweep_v2 != 0;
-        opt.extWindow = sweep_ext_window > 0 ? (v2 ? std::max(512, sweep_ext_window) : sweep_ext_window) : (v2 ? 2048 : 512);     // v2: the helper stages 512 row indices ahead
+        opt.extWindow = sweep_ext_window > 0 ? sweep_ext_window : 512;
         opt.buildStreams = !v2;
         opt.warps = sweep_warps;
         opt.groups = sweep_groups;
         auto build_v2 = [&](const int* r_, const int* c_) {
             Sweep2Options o2;
-            s2_helpers = std::max(1, std::min(s2_helpers, kS2MaxHelpers));
-            s2_cw = std::max(1, std::min(s2_cw, kS2Threads / 32 - s2_helpers));
+            s2_helpers = std::max(1, std::min(s2_helpers, 8));
+            s2_cw = std::max(1, std::min(s2_cw, kS2Threads / 32 - 1));
             s2_cw = std::min(s2_cw, kS2MaxWarps);
             o2.consumerWarps = s2_cw;
             L2 = Sweep2Plan(); U2 = Sweep2Plan();
@@ -537,30 +537,32 @@ struct Solver {
             static_assert(sizeof(S2PartD) == sizeof(S2Part) && sizeof(S2StreamD) == sizeof(S2Stream) &&
                           sizeof(S2BuildD) == sizeof(S2Build), "device/host round-2 sweep descriptor mismatch");
             auto up2 = [&](Sweep2Plan& P2, DevBuf<S2PartD>& dp, DevBuf<S2StreamD>& ds, DevBuf<S2BuildD>& dbu, DevBuf<int>& dh,
-                           DevBuf<int>& dc, DevBuf<int>& de, DevBuf<int>& dsr, DevBuf<double>& dv) {
+                           DevBuf<int>& dc, DevBuf<int>& dsr, DevBuf<double>& dv) {
                 dp.alloc(P2.parts.size()); ds.alloc(P2.streams.size()); dbu.alloc(std::max<size_t>(1, P2.build.size()));
                 upraw(dp.p, P2.parts.data(), sizeof(S2Part) * P2.parts.size());
                 upraw(ds.p, P2.streams.data(), sizeof(S2Stream) * P2.streams.size());
                 upraw(dbu.p, P2.build.data(), sizeof(S2Build) * P2.build.size());
-                dh.alloc(P2.hdrs.size() + 4 * 64); dc.alloc(P2.codes.size() + 2); de.alloc(P2.ext.size() + 1); dsr.alloc(P2.src.size() + 1);
+                dh.alloc(P2.hdrs.size() + 4 * 64); dc.alloc(P2.codes.size() + 4); dsr.alloc(P2.src.size() + 1);
                 upraw(dh.p, P2.hdrs.data(), sizeof(int) * P2.hdrs.size());
                 upraw(dc.p, P2.codes.data(), sizeof(int) * P2.codes.size());
-                upraw(de.p, P2.ext.data(), sizeof(int) * P2.ext.size());
                 upraw(dsr.p, P2.src.data(), sizeof(int) * P2.src.size());
                 dv.alloc((size_t) P2.nvals + 2);
             };
-            up2(L2, d_s2partsL, d_s2streamsL, d_s2buildL, d_s2hdrsL, d_s2codesL, d_s2extL, d_s2srcL, d_valL);
-            up2(U2, d_s2partsU, d_s2streamsU, d_s2buildU, d_s2hdrsU, d_s2codesU, d_s2extU, d_s2srcU, d_valU);
+            up2(L2, d_s2partsL, d_s2streamsL, d_s2buildL, d_s2hdrsL, d_s2codesL, d_s2srcL, d_valL);
+            up2(U2, d_s2partsU, d_s2streamsU, d_s2buildU, d_s2hdrsU, d_s2codesU, d_s2srcU, d_valU);
             CUDA_OK(cudaStreamSynchronize(stream));
             // the schedule stays on the host only as long as the analysis needs it (the build lists are large)
             for (Sweep2Plan* P2 : {&L2, &U2}) { std::vector<int>().swap(P2->src); std::vector<int>().swap(P2->codes); std::vector<int>().swap(P2->hdrs); std::vector<int>().swap(P2->stepChunks); }
             threads = sweep_threads();
-            const size_t need = kS2Header + 24 * (size_t) (an.window + an.extWindow + 1) + 4 * (size_t) an.extWindow;      // value space + row indices of the ring
+            const size_t need = kS2Header + 24 * (size_t) (an.window + 1);        // window of recent rows + the zero row
             // the SpMV tail streams SELL slices through the same dynamic shared memory: two chunk buffers per ring-fed consumer warp
-            const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * kTailBufBytes * std::min(kTailMaxCons, threads / 32 - 1)) : 0;
+            // (the shared-memory carve-out is taken from the L1: with the whole 227 KB handed to the tail's ring the sweeps ran 40 % slower --
+            // their strided rhs loads and record headers live in L1 -- so only `fuse_ring_warps` consumers are ring-fed)
+            const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * kTailBufBytes * std::min({kTailMaxCons, threads / 32 - 1, std::max(1, fuse_ring_warps)})) : 0;
             sweep_smem = std::max(need, tail);
             if (sweep_smem > smem_limit) throw std::runtime_error("value space of the triangular sweeps does not fit the shared memory");
             prep(k_sweep2<true, false>); prep(k_sweep2<true, true>); prep(k_sweep2<false, false>); prep(k_sweep2<false, true>);
+            prep(k_sweep2<true, false, -1, true>); prep(k_sweep2<true, true, -1, true>); prep(k_sweep2<false, false, -1, true>); prep(k_sweep2<false, true, -1, true>);
             defer_ok = false;
             if (defer_x != 0) {
                 prep(k_sweep2<true, false, 3>);
@@ -579,9 +581,9 @@ struct Solver {
                 CUDA_OK(cudaStreamSynchronize(stream));            // fp is a temporary
             }
             if (verbosity > 0)
-                fprintf(stderr, "[b200bda] round-2 sweeps: %d parts, %d consumer warps + %d helper(s), %d threads, %zu B smem (window %d + ring %d rows); "
-                                "L: %lld records (up to %d chunks per step, %lld warp-steps with several records), %lld external rows, %.1f MB; U: %lld records, %.1f MB\n",
-                        an.nparts, s2_cw, s2_helpers, threads, sweep_smem, an.window, an.extWindow, L2.nrecords, L2.maxChunks, L2.nmulti, L2.nExtRows,
+                fprintf(stderr, "[b200bda] round-2 sweeps: %d parts, %d consumer warps, %d threads, %zu B smem (window %d rows); "
+                                "L: %lld records (up to %d chunks per step, %lld warp-steps with several records), %lld external dependencies, %.1f MB; U: %lld records, %.1f MB\n",
+                        an.nparts, s2_cw, threads, sweep_smem, an.window, L2.nrecords, L2.maxChunks, L2.nmulti, L2.nExternal,
                         L2.nvals * 8e-6, U2.nrecords, U2.nvals * 8e-6);
         } else {
         up(d_metaL, an.L.meta); up(d_metaU, an.U.meta); up(d_srcL, an.L.src); up(d_srcU, an.U.src);
@@ -965,16 +967,15 @@ struct Solver {
         if (v2) {
             a.v2.parts = lower ? d_s2partsL.p : d_s2partsU.p;
             a.v2.streams = lower ? d_s2streamsL.p : d_s2streamsU.p;
-            a.v2.hdrs = reinterpret_cast<const int4*>(lower ? d_s2hdrsL.p : d_s2hdrsU.p);
-            a.v2.codes = reinterpret_cast<const int2*>(lower ? d_s2codesL.p : d_s2codesU.p);
-            a.v2.ext = lower ? d_s2extL.p : d_s2extU.p;
+            a.v2.hdrs = reinterpret_cast<const int2*>(lower ? d_s2hdrsL.p : d_s2hdrsU.p);
+            a.v2.codes = reinterpret_cast<const int4*>(lower ? d_s2codesL.p : d_s2codesU.p);
             a.v2.vals = lower ? d_valL.p : d_valU.p;
-            a.v2.window = an.window; a.v2.extWindow = an.extWindow; a.v2.ncw = s2_cw; a.v2.nh = s2_helpers; a.v2.kmin = s2_kmin; a.v2.kmax = s2_kmax;
-            a.nwarps = s2_cw;              // the SpMV tail's producer warp = the first helper warp
+            a.v2.window = an.window; a.v2.ncw = s2_cw;
+            a.nwarps = s2_cw;              // the SpMV tail's producer warp = the warp after the consumers
         }
         return a;
     }
-    int sweep_threads() const { return v2 ? (s2_cw + s2_helpers) * 32 : (sweep_warps + 1 + sweep_helpers) * 32; }
+    int sweep_threads() const { return v2 ? std::min(kS2Threads, (s2_cw + s2_helpers) * 32) : (sweep_warps + 1 + sweep_helpers) * 32; }
     // Launch of a kernel of the BiCGSTAB iteration (all of them start with pdl_enter()): with iter_pdl the launch carries the
     // programmatic-stream-serialization attribute, so its CTAs are scheduled while the previous kernel drains.
     int iter_pdl = 0;                  // option (measured: slower)
@@ -994,7 +995,11 @@ struct Solver {
     {
         const bool rearm = a.rearm != nullptr, trace = a.trace != nullptr;
         auto go = [&](auto kern) { launch_iter(kern, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a); };
-        if (v2) { if (rearm) go(k_sweep2<LOWER, true>); else go(k_sweep2<LOWER, false>); return; }
+        if (v2) {
+            if (trace) { if (rearm) go(k_sweep2<LOWER, true, -1, true>); else go(k_sweep2<LOWER, false, -1, true>); }
+            else { if (rearm) go(k_sweep2<LOWER, true>); else go(k_sweep2<LOWER, false>); }
+            return;
+        }
         if (trace) { if (rearm) go(k_sweep<LOWER, true, true>); else go(k_sweep<LOWER, false, true>); }
         else { if (rearm) go(k_sweep<LOWER, true, false>); else go(k_sweep<LOWER, false, false>); }
     }
@@ -1046,6 +1051,7 @@ struct Solver {
     bool sweep_early = false;
     int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
+    int fuse_ring_warps = 8;           // option (round-2 sweeps): warps of the SpMV tail fed through the shared-memory ring (19 KB each)
     DevBuf<long long> d_fDbg;
     template <int MODE>
     void spmv(const double* x, double* y, const double* d1)
@@ -1399,8 +1405,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
-        else if (k == "s2_kmin") s->s2_kmin = (int) value;
-        else if (k == "s2_kmax") s->s2_kmax = (int) value;
+        else if (k == "fuse_ring_warps") { if (s->analysed) throw std::runtime_error("fuse_ring_warps must be set before the first solve"); s->fuse_ring_warps = std::max(1, (int) value); }
         else if (k == "sweep_v2" || k == "s2_cw" || k == "s2_helpers") {
             if (s->analysed) throw std::runtime_error("the sweep schedule must be set before the first solve");
             const int v = (int) value;
@@ -2015,7 +2020,7 @@ b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* 
         AnalysisOptions opt;
         if (parts > 0) opt.parts = parts;
         if (window > 0) opt.window = window;
-        opt.extWindow = ext_window > 0 ? ext_window : 2048;
+        (void) ext_window;
         opt.buildStreams = false;
         Analysis A = analyse(Nb, rows, cols, opt);
         Sweep2Options o2;
@@ -2038,7 +2043,7 @@ b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* 
         }
         if (max_rel_err) *max_rel_err = den > 0.0 ? num / den : num;
         if (stats) {
-            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, L.nExtRows,
+            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, 0,
                                      0, L.maxChunks, o2.consumerWarps};
             memcpy(stats, v, sizeof v);
         }

@@ -1147,8 +1147,9 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
 
 // ---- round-2 sweep kernel (schedule and rationale: sweep2.hpp, sweep2.cuh) ---------------------------------------------------
 // SPMV as k_sweep: -1 sweep only, 1 / 2 go on with the SpMV that follows (fused_spmv_tail), 3 lower sweep + pending x update.
-constexpr int kS2Threads = 512;
-template <bool LOWER, bool REARM, int SPMV = -1>
+constexpr int kS2Threads = 512;        // 15 consumer warps + an idle one (tails only) at 128 registers: the register file is handed out in
+                                       // units that make 136 and 144 registers x 15 / 14 warps not fit (occupancy query: 0)
+template <bool LOWER, bool REARM, int SPMV = -1, bool TRACE = false>
 __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
@@ -1161,13 +1162,13 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
     const Sweep2Args& V = P.v2;
     const S2PartD pr = V.parts[part];
     int* hp = reinterpret_cast<int*>(sweep_smem);
-    const int W = V.window, EW = V.extWindow, zslot = W + EW;
-    double* xyp = reinterpret_cast<double*>(sweep_smem + kS2Header);      // value space, components 0 and 1: 16 bytes per slot
-    double* zp = xyp + 2 * (size_t) (zslot + 1);                            // component 2: 8 bytes per slot
+    const int W = V.window;
+    double* xyp = reinterpret_cast<double*>(sweep_smem + kS2Header);      // window of recent rows, components 0 and 1: 16 bytes per slot
+    double* zp = xyp + 2 * (size_t) (W + 1);                                // component 2: 8 bytes per slot; slot W is the all-zero row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 16) hp[threadIdx.x] = 0;
-    if (P.trace && threadIdx.x == 0) { P.trace[8 * part] = globaltimer_ns(); for (int k = 1; k < 8; ++k) P.trace[8 * part + k] = 0; }
-    if (threadIdx.x == 32) { xyp[2 * (size_t) zslot] = 0.0; xyp[2 * (size_t) zslot + 1] = 0.0; zp[zslot] = 0.0; }
+    if (TRACE && threadIdx.x == 0) { P.trace[8 * part] = globaltimer_ns(); for (int k = 1; k < 8; ++k) P.trace[8 * part + k] = 0; }
+    if (threadIdx.x == 32) { xyp[2 * (size_t) W] = 0.0; xyp[2 * (size_t) W + 1] = 0.0; zp[W] = 0.0; }
     __syncthreads();
     constexpr int NP = LOWER ? 14 : 18;
 
@@ -1175,49 +1176,66 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
         // ---- consumers: warp w walks stream w of the part
         const S2StreamD sd = V.streams[pr.stream0 + warp];
         const int nrec = sd.nrec;
-        const int4* __restrict__ hdrs = V.hdrs + sd.hdr_off;
-        const double* vp = V.vals + sd.vals_off;
-        const int2* cp = V.codes + sd.code_off;
+        const int2* __restrict__ hdrs = V.hdrs + sd.hdr_off;
+        const double* vp = V.vals + sd.vals_off + 2 * lane;
+        const int4* cp = V.codes + sd.code_off + lane;
         const unsigned xy = smem_u32(xyp), z = smem_u32(zp);
-        const int zcode = 8 * zslot;
-        const int4 hzero = make_int4(0, 0, 0, 0);
-        int4 hb = lane < nrec ? __ldg(hdrs + lane) : hzero;                // headers of the records 32 b + lane
-        int4 hbn = 32 + lane < nrec ? __ldg(hdrs + 32 + lane) : hzero;
-        auto header = [&](int j) {
-            return make_int4(__shfl_sync(kFull, hb.x, j), __shfl_sync(kFull, hb.y, j), __shfl_sync(kFull, hb.z, j), __shfl_sync(kFull, hb.w, j));
-        };
+        const int zcode = 8 * W;
+        const int2 hzero = make_int2(0, 0);
+        int2 hb = lane < nrec ? __ldg(hdrs + lane) : hzero;                // headers of the records 32 b + lane
+        int2 hbn = 32 + lane < nrec ? __ldg(hdrs + 32 + lane) : hzero;
+        auto header = [&](int j) { return make_int2(__shfl_sync(kFull, hb.x, j), __shfl_sync(kFull, hb.y, j)); };
         S2Ops<LOWER> o;
 #pragma unroll
         for (int k = 0; k < NP; ++k) o.v[k] = make_double2(0.0, 0.0);
         o.r0 = o.r1 = o.r2 = 0.0;
+        o.xa0 = o.xa1 = o.xa2 = o.xb0 = o.xb1 = o.xb2 = 0.0;
         // issue the loads of the record described by hd (nothing waits for them here) and advance the stream
-        auto fetch = [&](const int4& hd) {
-            const int cnt = hd.y & 255;
+        auto fetch = [&](const int2& hd) {
+            const int cnt = hd.y & 63;
             if (lane < cnt) {
-                const double* v = vp + 2 * lane;
+                const double* v = vp;
+                const size_t stride = 2 * (size_t) cnt;
 #pragma unroll
-                for (int k = 0; k < NP; ++k) o.v[k] = ldg_stream_f64x2(v + 2 * (size_t) k * cnt);
-                o.cd = ldg_stream_s32x2(cp + lane);
-                if (hd.y & (S2D_FIRST << 8)) {
+                for (int k = 0; k < NP; ++k, v += stride)
+                    if (!TRACE || !(P.nowait & 8)) o.v[k] = ldg_stream_f64x2(v);
+                o.cd = ldg_stream_s32x4(cp);
+                if ((hd.y & (S2D_FIRST << 6)) && (!TRACE || !(P.nowait & 16))) {
                     const double* r = P.rhs + 3 * (size_t) (LOWER ? hd.x + lane : hd.x - lane);
                     o.r0 = r[0]; o.r1 = r[1]; o.r2 = r[2];
                 }
-            } else o.cd = make_int2(zcode | (zcode << 16), zcode);
-            vp += 2 * (size_t) NP * cnt;
+                if (hd.y & (S2D_EXT << 6)) {                              // first poll of the row's external dependencies
+                    if (o.cd.z >= 0) { const double* x = P.out + 3 * (size_t) o.cd.z; o.xa0 = ld_relaxed(x); o.xa1 = ld_relaxed(x + 1); o.xa2 = ld_relaxed(x + 2); }
+                    if (o.cd.w >= 0) { const double* x = P.out + 3 * (size_t) o.cd.w; o.xb0 = ld_relaxed(x); o.xb1 = ld_relaxed(x + 1); o.xb2 = ld_relaxed(x + 2); }
+                }
+            } else o.cd = make_int4(zcode | (zcode << 16), zcode, -1, -1);
+            vp += (size_t) (2 * NP) * cnt;
             cp += cnt;
         };
-        int4 h = header(0);
-        if (nrec > 0) fetch(h);
+        // The loads of a record are issued when the warp has finished its previous one, (warps / chunks per step) steps ahead of
+        // their use -- with 15 warps and 3 chunks per step that is 5 step times, and a warp needs HBM latency + its own work
+        // (~1500 + 700 cycles) per record, i.e. >= 440 cycles per step.  So the bytes of the record AFTER the next one are
+        // pulled into L2 at the same time (no registers needed): the loads that follow find them there.
+        const unsigned char* pf = reinterpret_cast<const unsigned char*>(V.vals + sd.vals_off);      // start of the record after the next
+        auto prefetch_l2 = [&](int idx) {
+            if (idx >= nrec) return;
+            const int j = idx & 31;
+            const int y = __shfl_sync(kFull, (idx >> 5) == ((idx - 1) >> 5) || idx == 0 ? hb.y : hbn.y, j);      // header batch of idx
+            const unsigned bytes = 16u * NP * (unsigned) (y & 63);
+            if (lane == 0 && bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(bytes) : "memory");
+            pf += bytes;
+        };
+        int2 h = header(0);
+        if (nrec > 0) { prefetch_l2(0); fetch(h); prefetch_l2(1); }
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-        long long t_start = 0;
-        // debugging aid: where the cycles of this warp go (parts 0 and 1 + nparts / 2 of a traced launch)
-        const bool prof = P.trace != nullptr && (part == 0 || part == P.nparts / 2);
+        // debugging aid: where the cycles of this warp go (parts 0 and nparts / 2 of a traced launch)
+        const bool prof = TRACE && P.trace_cap < 0 && (part == 0 || part == P.nparts / 2);      // trace_cap < 0: per-warp cycle accounting as well (spills: slow)
         long long pc[6] = {0, 0, 0, 0, 0, 0}, c0 = prof ? clock64() : 0;
         for (int i = 0; i < nrec; ++i) {
-            const int cnt = h.y & 255, flags = (h.y >> 8) & 255;
+            const int cnt = h.y & 63, flags = (h.y >> 6) & 63;
             const unsigned d0 = (unsigned) o.cd.x & 0xffffu, d1 = (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & 0xffffu, oc = (unsigned) o.cd.y >> 16;
             const double* v = reinterpret_cast<const double*>(o.v);
-            // start value: nothing here depends on another row
+            // start value: nothing here depends on another row of the part
             if (flags & S2D_FIRST) {
                 if constexpr (LOWER) { y0 = o.r0; y1 = o.r1; y2 = o.r2; }
                 else {
@@ -1227,34 +1245,57 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 }
             }
             if (prof) { const long long c = clock64(); pc[0] += c - c0; c0 = c; }      // fetch issue, header, start value
-            if (flags & S2D_SYNC) {
-                bar_sync_n((h.y >> 16) & 15, 32 * (int) ((unsigned) h.z >> 24));       // the previous step is complete
-                if ((flags & S2D_LEAD) && lane == 0) st_volatile_s32(hp + 8, h.w & 0xffffff);   // external rows nobody reads any more: ring slots free
-            }
-            if (prof) { const long long c = clock64(); pc[1] += c - c0; c0 = c; }      // waiting for the previous step
-            const int need = h.z & 0xffffff;
-            const bool tr = P.trace != nullptr && (flags & S2D_LEAD) && lane == 0;      // debugging aid: timeline of the part's steps
-            const long long tw0 = tr ? globaltimer_ns() : 0;
-            if (need && P.nowait < 2) {                                                      // external rows of this step: parked by the helper warp
-                int spins = 0;
-                while (ld_volatile_s32(hp) < need) {
-                    if ((++spins & 1023) == 0) {
-                        if (t_start == 0) t_start = globaltimer_ns();
-                        if (ld_volatile_s32(hp + 9) || globaltimer_ns() - t_start > kS2TimeoutNs) { P.S->trsv_timeout = 1; st_volatile_s32(hp + 9, 1); break; }
+            if (flags & S2D_EXT) {
+                // external dependencies (rows of other parts: the value is its own ready flag): polled with the operands; poll
+                // again while the sentinel is still there; then fold their contribution into the start value
+                if (P.nowait < 2) {
+                    int spins = 0;
+                    while (true) {
+                        const bool wa = o.cd.z >= 0 && (is_sentinel(o.xa0) || is_sentinel(o.xa1) || is_sentinel(o.xa2));
+                        const bool wb = o.cd.w >= 0 && (is_sentinel(o.xb0) || is_sentinel(o.xb1) || is_sentinel(o.xb2));
+                        if (!__any_sync(kFull, wa || wb)) break;
+                        if (wa) { const double* x = P.out + 3 * (size_t) o.cd.z; o.xa0 = ld_relaxed(x); o.xa1 = ld_relaxed(x + 1); o.xa2 = ld_relaxed(x + 2); }
+                        if (wb) { const double* x = P.out + 3 * (size_t) o.cd.w; o.xb0 = ld_relaxed(x); o.xb1 = ld_relaxed(x + 1); o.xb2 = ld_relaxed(x + 2); }
+                        if ((++spins & 255) == 0) {
+                            // (~0.3 us per poll round: 2^24 rounds are seconds -- a deadlock, not a slow neighbour)
+                            if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || spins > (1 << 24)) {
+                                P.S->trsv_timeout = 1; st_volatile_s32(hp + 9, 1);
+                                break;
+                            }
+                        }
                     }
                 }
+                if (o.cd.z >= 0) {
+                    y0 -= fma(v[20], o.xa2, fma(v[19], o.xa1, v[18] * o.xa0));
+                    y1 -= fma(v[23], o.xa2, fma(v[22], o.xa1, v[21] * o.xa0));
+                    y2 -= fma(v[26], o.xa2, fma(v[25], o.xa1, v[24] * o.xa0));
+                }
+                if (o.cd.w >= 0) {
+                    y0 -= fma(v[11], o.xb2, fma(v[10], o.xb1, v[9] * o.xb0));
+                    y1 -= fma(v[14], o.xb2, fma(v[13], o.xb1, v[12] * o.xb0));
+                    y2 -= fma(v[17], o.xb2, fma(v[16], o.xb1, v[15] * o.xb0));
+                }
+            }
+            if (prof) { const long long c = clock64(); pc[2] += c - c0; c0 = c; }      // external rows
+            const bool tr = TRACE && (flags & S2D_LEAD) && lane == 0;      // debugging aid: timeline of the part's steps
+            if (flags & S2D_SYNC) bar_sync_n((h.y >> 12) & 15, 32 * ((h.y >> 20) & 31));    // the previous step is complete
+            if (prof) {      // (bar.sync does not block at issue: a shared load behind it does)
+                if (ld_volatile_s32(hp + 9) == 12345) pc[5]++;
+                const long long c = clock64(); pc[1] += c - c0; c0 = c;                // waiting for the previous step
             }
             if (tr) {                                                     // stores only: nothing here waits for global memory
-                const long long t = globaltimer_ns();
                 const int st = ld_volatile_s32(hp + 10);                  // LEAD records of a part are its steps in order (one warp at a time)
                 st_volatile_s32(hp + 10, st + 1);
                 P.trace[8 * part + 5] = st + 1;
-                if (st < 256) { P.trace[8192 + 2 * (256 * part + st)] = t; P.trace[8192 + 2 * (256 * part + st) + 1] = t - tw0; }
+                if (st < 256) P.trace[8192 + 2 * (256 * part + st)] = globaltimer_ns();
             }
-            if (prof) { const long long c = clock64(); pc[2] += c - c0; c0 = c; }      // waiting for external rows
             // ---- dependent part
             const double2 a0 = lds_f64x2(xy + 2 * d0), a1 = lds_f64x2(xy + 2 * d1), a2 = lds_f64x2(xy + 2 * d2);
             const double b0 = lds_f64(z + d0), b1 = lds_f64(z + d1), b2 = lds_f64(z + d2);
+            if (prof) {      // the shared loads have landed
+                if (__double_as_longlong(a0.x + a1.x + a2.x + b0 + b1 + b2) == 0x7ff123456789abcdLL) pc[5]++;
+                const long long c = clock64(); pc[5] += c - c0; c0 = c;
+            }
             const double p0 = fma(v[2], b0, fma(v[1], a0.y, v[0] * a0.x));
             const double p1 = fma(v[5], b0, fma(v[4], a0.y, v[3] * a0.x));
             const double p2 = fma(v[8], b0, fma(v[7], a0.y, v[6] * a0.x));
@@ -1266,10 +1307,10 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             const double s2 = fma(v[26], b2, fma(v[25], a2.y, v[24] * a2.x));
             y0 = ((y0 - p0) - q0) - s0; y1 = ((y1 - p1) - q1) - s1; y2 = ((y2 - p2) - q2) - s2;
             const bool store = (flags & S2D_LAST) && lane < cnt;
-            if (prof) { if (__double_as_longlong(y0) == 0x7ff123456789abcdLL) pc[5]++; const long long c = clock64(); pc[3] += c - c0; c0 = c; }   // dependencies + operands landed + fma
+            if (prof) { if (__double_as_longlong(y0) == 0x7ff123456789abcdLL) pc[5]++; const long long c = clock64(); pc[3] += c - c0; c0 = c; }   // dependencies + fma
             if (store) { sts_f64x2(xy + 2 * oc, y0, y1); sts_f64(z + oc, y2); }
-            if (flags & S2D_ARRIVE) bar_arrive_n((h.y >> 20) & 15, 32 * (int) ((unsigned) h.w >> 24));   // this warp's share of the step is in shared memory
-            if (store) {
+            if (flags & S2D_ARRIVE) bar_arrive_n((h.y >> 16) & 15, 32 * ((h.y >> 25) & 31));   // this warp's share of the step is in shared memory
+            if (store && (!TRACE || !(P.nowait & 4))) {
                 const size_t gi = 3 * (size_t) (LOWER ? h.x + lane : h.x - lane);
                 st_relaxed(P.out + gi, y0); st_relaxed(P.out + gi + 1, y1); st_relaxed(P.out + gi + 2, y2);
                 if (REARM) { P.rearm[gi] = sentinel(); P.rearm[gi + 1] = sentinel(); P.rearm[gi + 2] = sentinel(); }
@@ -1281,6 +1322,7 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 if (j == 0) { hb = hbn; hbn = i + 33 + lane < nrec ? __ldg(hdrs + i + 33 + lane) : hzero; }
                 h = header(j);
                 fetch(h);
+                prefetch_l2(i + 2);
             }
         }
         if (prof && lane == 0) {
@@ -1288,114 +1330,6 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             for (int k = 0; k < 6; ++k) o2[k] = pc[k];
             o2[6] = nrec; o2[7] = clock64() - c0;
         }
-    } else if (warp == V.ncw && P.nowait < 3) {
-        // ---- helper: external rows in list order.  Windows of 10 rows, lane = 3 x row + component (lanes 30 and 31 idle); the
-        // round is kept SHORT (a lone warp issues an instruction every 4-5 cycles: the first version, with a division per
-        // element and eight unrolled windows, needed 450 cycles to issue its polls and 1000 to park and publish what had
-        // arrived, on top of the 600 cycles of the L2 round trip)
-        constexpr int KMAX = 6;
-        const int kmin = max(1, min(V.kmin, KMAX)), kmax = max(kmin, min(V.kmax, KMAX));
-        const int* __restrict__ extl = V.ext + pr.ext0;
-        const int lr = lane / 3, lc = lane - 3 * lr;
-        const bool lane_on = lane < 30;
-        int* rrow = reinterpret_cast<int*>(zp + zslot + 1);            // p-space row of the list entry that owns a ring slot (staged ahead)
-        // byte address (shared window) of this lane's component of ring slot 0, and the stride between slots
-        const unsigned park0 = lc == 2 ? smem_u32(zp + W) : smem_u32(xyp + 2 * (size_t) W) + 8 * lc;
-        const unsigned park_stride = lc == 2 ? 8u : 16u;
-        const unsigned rrow0 = smem_u32(rrow);
-        const double* outc = P.out + lc;
-        const int next = pr.next;
-        int base = 0;                      // rows [0, base) of the list are parked
-        int K = kmin;                      // windows polled per round
-        int staged = 0;                    // list entries [0, staged) have their row index in shared memory
-        int pend_row = 0, pend_at = -1;    // index load in flight: entry pend_at + lane
-        long long t_start = 0;
-        int idle = 0;
-        long long hs[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // debugging aid: rounds, windows polled, rounds without progress, rows, cycles: issue / wait for the polls / park + publish, -
-        for (; staged < min(next, 512); staged += 32)
-            if (staged + lane < next) rrow[(staged + lane) & (EW - 1)] = __ldg(extl + staged + lane);
-        __syncwarp();
-        while (base < next) {
-            // stage the row indices of the list ahead of the polls: the load issued in the previous round lands now
-            if (pend_at >= 0) {
-                if (pend_at + lane < next) rrow[(pend_at + lane) & (EW - 1)] = pend_row;
-                staged = pend_at + 32; pend_at = -1;
-                __syncwarp();
-            }
-            if (staged < next && staged < base + 256) {
-                pend_at = staged;
-                if (staged + lane < next) pend_row = __ldg(extl + staged + lane);
-            }
-            const int limit = min(min(next, staged), ld_volatile_s32(hp + 8) + EW);   // ring slots still read must not be overwritten
-            if (base >= limit) {
-                __nanosleep(100);
-                if ((++idle & 1023) == 0) {
-                    if (t_start == 0) t_start = globaltimer_ns();
-                    if (ld_volatile_s32(hp + 9) || globaltimer_ns() - t_start > kS2TimeoutNs) { P.S->trsv_timeout = 1; if (lane == 0) { st_volatile_s32(hp + 9, 1); st_volatile_s32(hp, 0x7fffffff); } break; }
-                }
-                continue;
-            }
-            const long long hc0 = P.trace ? clock64() : 0;
-            double val[KMAX];
-            unsigned slot[KMAX];
-            bool act[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                const int r = base + 10 * k + lr;
-                act[k] = lane_on && k < K && r < limit;
-                slot[k] = (unsigned) r & (unsigned) (EW - 1);
-                if (act[k]) {
-                    int row;
-                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(row) : "r"(rrow0 + 4 * slot[k]));
-                    val[k] = ld_relaxed(outc + 3 * (size_t) row);
-                }
-            }
-            long long hc1 = 0, hc2 = 0;
-            if (P.trace) {
-                hs[0]++; hs[1] += K;
-                hc1 = clock64();
-                if (act[0] && __double_as_longlong(val[0]) == 0x7ff123456789abcdLL) hs[7]++;       // waits for the first poll
-                hc2 = clock64();
-            }
-            int adv = 0;
-            bool all = true;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    const bool ok = act[k] && (P.nowait || !is_sentinel(val[k]));
-                    if (ok) sts_f64(park0 + park_stride * slot[k], val[k]);
-                    const unsigned bm = __ballot_sync(kFull, ok);
-                    if (all) {
-                        const unsigned miss = ~(bm & (bm >> 1) & (bm >> 2)) & 0x09249249u;      // bit 3 q: row q of the window is incomplete
-                        const int n = miss ? (__ffs(miss) - 1) / 3 : 10;
-                        adv += n;
-                        all = n == 10;
-                    }
-                }
-            }
-            if (adv > 0) {
-                base += adv;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) st_volatile_s32(hp, base);
-                idle = 0;
-            }
-            if (P.trace) { hs[2] += adv == 0; hs[3] += adv; hs[4] += hc1 - hc0; hs[5] += hc2 - hc1; hs[6] += clock64() - hc2; }
-            // poll one window more than what arrived in this round (the producers' rate), at least kmin
-            K = max(kmin, min(kmax, (adv + 9) / 10 + 1));
-            if (adv == 0) {
-                if ((++idle & 255) == 0) {
-                    if (t_start == 0) t_start = globaltimer_ns();
-                    if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || globaltimer_ns() - t_start > kS2TimeoutNs) {
-                        P.S->trsv_timeout = 1;
-                        if (lane == 0) { st_volatile_s32(hp + 9, 1); st_volatile_s32(hp, 0x7fffffff); }
-                        break;
-                    }
-                }
-                if (P.helper_sleep) __nanosleep(P.helper_sleep);
-            }
-        }
-        if (P.trace && lane == 0) { long long* o3 = P.trace + 8192 + 2 * 256 * 1024 + 512 + 8 * part; for (int k = 0; k < 8; ++k) o3[k] = hs[k]; }
     }
     if constexpr (SPMV == 1 || SPMV == 2) fused_spmv_tail<SPMV>(P, part, sweep_smem);
     if constexpr (SPMV == 3) {

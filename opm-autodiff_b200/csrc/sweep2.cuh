@@ -1,22 +1,20 @@
-// sweep2.cuh -- round-2 triangular sweeps (included by kernels.cuh; schedule: sweep2.hpp).
+// sweep2.cuh -- round-2 triangular sweeps: device-side descriptors and the stream fill kernel (the sweep kernel itself, k_sweep2,
+// is in kernels.cuh next to the tails it shares with the round-1 kernel; schedule and rationale: sweep2.hpp).
 //
 // One persistent CTA per PART (pencil of grid lines), all resident, as in round 1; inside the CTA
 //   consumer warps : the steps (level sets) of the part are cut into chunks of <= 32 rows (a lane per row) and the chunks of
 //                    consecutive steps go round robin to the consumer warps.  A warp walks ITS OWN record stream: values (27 or 36
-//                    doubles per block row), 8 bytes of codes per row, both fetched from global memory straight into registers
+//                    doubles per block row), 16 bytes of codes per row, both fetched from global memory straight into registers
 //                    right after the warp has finished its previous chunk, i.e. several step times before they are used -- the
 //                    HBM latency hides behind the other warps' steps and nothing but the dependencies passes through shared
 //                    memory.  What is left between two steps of a part is the dependent chain only: bar.sync (step l - 1
 //                    complete) -> 6 shared loads of earlier rows -> 27 fma -> 2 shared stores -> bar.arrive.  The global stores
 //                    of the result and the next fetch come after the arrive.
-//   helper warp    : rows owned by other parts travel through L2 (the result vector is armed with a NaN sentinel, the value is
-//                    its own ready flag, as in round 1).  The part's external rows are listed in the order the steps need them.
-//                    One warp walks the list, a lane per (row, component): it keeps a few 32-element windows in flight, parks
-//                    what has arrived in the external ring of the shared value space and publishes the length of the finished
-//                    prefix; a consumer compares it with the count in its record header.  Polling is FRUGAL: while the first
-//                    window is still armed only that window is polled (32 requests per L2 round trip and SM).  With 4 helper
-//                    warps x 64 rows x 3 loads in flight the polls alone took half of the L2 request rate (the sweep ran at
-//                    109 us with the waits switched off, against 55 us in the stand-alone prototype).
+//   external rows  : rows owned by other parts travel through L2 (the result vector is armed with a NaN sentinel, the value is
+//                    its own ready flag, as in round 1).  The lane that needs one polls it itself: the loads are issued with the
+//                    operand fetch, checked -- and repeated while the sentinel is still there -- before the warp waits for the
+//                    previous step, and their contribution is folded into the row's start value there, outside the dependent
+//                    chain.  No helper warps, no parking ring, no published counters.
 // Measured building blocks on B200 (tools/microbench/fp64lat.cu, sweep2_proto.cu): DFMA 8 cycles dependent / 2.3 issue, shared
 // load 30, bar.sync 26-40, STS -> bar -> LDS -> DFMA 65-90; a 64-row step takes 310 cycles with 8 groups x 2 warps against 510
 // with one group and 850 in the round-1 kernel; 148 CTAs stream at 6.3 TB/s (96 % of the measured copy bandwidth).
@@ -24,23 +22,20 @@
 
 namespace b200 {
 
-struct S2PartD { int ncw, nsteps, row0, nrows, stream0, ext0, next, pad; };
+struct S2PartD { int ncw, nsteps, row0, nrows, stream0, pad0, pad1, pad2; };
 struct S2StreamD { long long vals_off, code_off; int hdr_off, nrec; };
 struct S2BuildD { long long vals_off; int src_off, cnt, first, pad; };
-enum : int { S2D_FIRST = 1, S2D_LAST = 2, S2D_SYNC = 4, S2D_ARRIVE = 8, S2D_LEAD = 16 };
+enum : int { S2D_FIRST = 1, S2D_LAST = 2, S2D_SYNC = 4, S2D_ARRIVE = 8, S2D_EXT = 16, S2D_LEAD = 32 };
 
-constexpr int kS2Header = 128;         // shared: [0] external rows parked (prefix of the part's list), [8] external rows free for reuse, [9] timeout seen
-constexpr int kS2MaxHelpers = 8;
+constexpr int kS2Header = 128;         // shared: [9] timeout seen, [10] steps traced
 
 struct Sweep2Args {
     const S2PartD* parts;
     const S2StreamD* streams;
-    const int4* hdrs;
-    const int2* codes;
-    const int* ext;
+    const int2* hdrs;
+    const int4* codes;
     const double* vals;
-    int window, extWindow, ncw, nh;    // consumer warps, helper warps (the first one polls, all of them work in the tails)
-    int kmin, kmax;                    // 32-element windows of external rows the helper polls per round: while it waits / while rows arrive
+    int window, ncw;                   // rows of the shared-memory window, consumer warps
 };
 
 __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p)
@@ -49,10 +44,10 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ int2 ldg_stream_s32x2(const int2* p)
+__device__ __forceinline__ int4 ldg_stream_s32x4(const int4* p)
 {
-    int2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -108,7 +103,8 @@ template <bool LOWER>
 struct S2Ops {
     double2 v[LOWER ? 14 : 18];
     double r0, r1, r2;
-    int2 cd;
+    double xa0, xa1, xa2, xb0, xb1, xb2;      // external dependencies of the row (slot 2, slot 1), polled with the operands
+    int4 cd;
 };
 
 }  // namespace b200

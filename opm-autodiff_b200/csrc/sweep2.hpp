@@ -1,7 +1,8 @@
-// sweep2.hpp -- host-side schedule of the round-2 triangular sweeps (k_sweep2, sweep2.cuh) + a host emulation of the kernel.
+// sweep2.hpp -- host-side schedule of the round-2 triangular sweeps (k_sweep2, kernels.cuh) + a host emulation of the kernel.
 //
 // What changed against the round-1 sweep (analysis.hpp build_sweep / kernels.cuh k_sweep) and why (measured on B200 with
-// tools/microbench/sweep2_proto.cu, fp64lat.cu, dsmem_pingpong.cu; numbers in DESIGN.md):
+// tools/microbench/sweep2_proto.cu, fp64lat.cu, dsmem_pingpong.cu, pollrate.cu and the traces of tools/s2_trace.py; numbers in
+// DESIGN.md):
 //   * a lone warp issues ~1 instruction per 4-5 cycles, so the time of a level was the INSTRUCTION COUNT of a record (operand
 //     fetch + dependent part + stores, ~500 cycles for a 64-row level whatever the layout).  Now the 32-row chunks of consecutive
 //     levels ("steps") of a part go ROUND ROBIN to the consumer warps: while the warps of step l run its dependent part (barrier, 6
@@ -13,10 +14,16 @@
 //     each warp streams ITS OWN records straight from global memory into registers right after it has finished a chunk -- (warps
 //     / chunks per step) step times ahead of their use, which covers the HBM latency -- so the stream of a part is one
 //     independent sequential stream per consumer warp;
-//   * records carry exactly the rows they hold (no lane padding): [pair k][row] 16-byte value pairs, 8 bytes of codes per row,
-//     one 16-byte header per record in a separate array (fetched 32 records at a time, one per lane).
-// The mathematics, the parts (pencils), p-space, the window / external-row value space and the NaN-sentinel dataflow between
-// parts are those of round 1 (analysis.hpp).  Reference semantics: ParallelOverlappingILU0.hpp:867-901.
+//   * records carry exactly the rows they hold (no lane padding): [pair k][row] 16-byte value pairs, 16 bytes of codes per row,
+//     one 16-byte header per record in a separate array (fetched 32 records at a time, one per lane);
+//   * NO helper warps and no external-row ring.  Rows owned by other parts still travel through L2 under the NaN-sentinel
+//     protocol of round 1 (the value is its own ready flag), but the lane that needs a row fetches it ITSELF, together with its
+//     operands, several steps ahead, and folds its contribution into the start value of the row BEFORE it waits for the previous
+//     step -- so an external dependency costs nothing inside the dependent chain, and a row that is not there yet is simply
+//     polled again by the lane that needs it (a helper warp that polled, parked and published for everybody needed 1200-2000
+//     cycles per round, and every round sat between the producer and the consumer of a face row).
+// The mathematics, the parts (pencils), p-space and the shared-memory window of recent rows are those of round 1 (analysis.hpp).
+// Reference semantics: ParallelOverlappingILU0.hpp:867-901.
 #pragma once
 #include "analysis.hpp"
 
@@ -24,34 +31,36 @@ namespace b200 {
 
 constexpr int kS2Barriers = 15;        // named barriers 1..15: barrier 1 + l % 15 separates step l from step l + 1
 constexpr int kS2MaxWarps = 15;        // consumer warps of a CTA (<= kS2Barriers: a barrier is reused only after every warp has passed it)
-constexpr int kS2Reuse = 2;            // an external row parked for step m may be read by the steps m .. m + kS2Reuse - 1 (listed once for them)
 
-// record header (one int4):
+// record header (one int2):
 //   x  first p-space row of the record (rows x + q, lower sweep, or x - q, upper sweep)
-//   y  rows | flags << 8 | barrier to wait on << 16 | barrier to arrive at << 20
-//   z  external rows needed (prefix of the part's list; 0 = nothing new to wait for) | warps on the barrier waited on << 24
-//   w  external rows no step >= this one reads any more (prefix: ring slots free for reuse) | warps on the barrier arrived at << 24
-enum : int { S2_FIRST = 1, S2_LAST = 2, S2_SYNC = 4, S2_ARRIVE = 8, S2_LEAD = 16 };
+//   y  rows (6 bits) | flags << 6 | barrier to wait on << 12 | barrier to arrive at << 16 | warps on the barrier waited on << 20 |
+//      warps on the barrier arrived at << 25
+// codes (one int4 per row): {d0 | d1 << 16, d2 | out << 16, extA, extB}
+//   d_j = 8 x window slot of dependency j (8 x window = the all-zero row: no dependency, or an external one), out = 8 x window
+//   slot of the result; extA / extB = p-space row of an EXTERNAL dependency (a row of another part, or of this part beyond the
+//   window) whose factor block sits in slot 2 / slot 1 of the record, -1 = none
+enum : int { S2_FIRST = 1, S2_LAST = 2, S2_SYNC = 4, S2_ARRIVE = 8, S2_EXT = 16, S2_LEAD = 32 };
+// S2_EXT: some row of the record has an external dependency; S2_LEAD: the warp's first record of the step and chunk 0 (tracing)
 
-struct S2Part { int ncw, nsteps, row0, nrows, stream0, ext0, next, pad; };
+struct S2Part { int ncw, nsteps, row0, nrows, stream0, pad0, pad1, pad2; };
 struct S2Stream { long long vals_off;      // doubles into the sweep's value stream
-                  long long code_off;      // int2 units into the code array
+                  long long code_off;      // int4 units into the code array
                   int hdr_off, nrec; };
 struct S2Build { long long vals_off; int src_off, cnt, first, pad; };
 
 struct Sweep2Plan {
     std::vector<S2Part> parts;
     std::vector<S2Stream> streams;
-    std::vector<int> hdrs;            // 4 per record
-    std::vector<int> codes;           // 2 per row of a record: {d0 | d1 << 16, d2 | out << 16}, each = 8 x slot of the value space
-    std::vector<int> ext;             // p-rows, per part in order of need
+    std::vector<int> hdrs;            // 2 per record
+    std::vector<int> codes;           // 4 per row of a record
     std::vector<S2Build> build;       // one per record
     std::vector<int> src;             // per record: 3 x cnt dependency blocks (p-space block index, -1 none), then cnt pivot blocks (upper)
     std::vector<int> stepChunks;      // host only (emulation, statistics): per part nsteps entries, 32-row chunks of every step
     std::vector<int> stepPtr;         // nparts + 1 offsets into stepChunks
     long long nvals = 0;
     int npairs = 14;                  // value pairs per row: 14 (27 values + pad) lower, 18 (27 + 9) upper
-    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0, nExtRows = 0;
+    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0;
     int maxChunks = 0;
 };
 
@@ -59,18 +68,25 @@ struct Sweep2Options {
     int consumerWarps = kS2MaxWarps;  // warps that take records (round robin over the chunks of consecutive steps)
 };
 
+inline int s2_pack(int cnt, int flags, int sync_id, int arrive_id, int sync_warps, int arrive_warps)
+{
+    return cnt | (flags << 6) | (sync_id << 12) | (arrive_id << 16) | (sync_warps << 20) | (arrive_warps << 25);
+}
+inline int s2_cnt(int y) { return y & 63; }
+inline int s2_flags(int y) { return (y >> 6) & 63; }
+
 namespace detail {
 
 // The steps (level sets) of a part are cut into CHUNKS of <= 32 rows (a lane per row); the chunks of consecutive steps go round
 // robin to the consumer warps, so a warp that has finished its chunk of step l fetches the operands of its next chunk -- of step
 // l + (warps / chunks per step) -- at once, that many step times before they are needed.  A warp has two records of the same
-// step only when a step has more chunks than there are warps, or for rows with more than three dependencies (continuation
-// records; the partial sums stay in registers).
+// step only when a step has more chunks than there are warps, or for rows with more than three dependencies / more than two
+// external ones (continuation records; the partial sums stay in registers).
 inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, const std::vector<int>& glev, const std::vector<int>& partOf,
                          bool lower, const Sweep2Options& opt, Sweep2Plan& S)
 {
-    const int W = A.window, EW = A.extWindow, zslot = W + EW;
-    if (8LL * (zslot + 1) > 65535) throw std::runtime_error("sweep window + external ring exceed the 16-bit slot codes");
+    const int W = A.window, zcode = 8 * W;
+    if (8LL * (W + 1) > 65535) throw std::runtime_error("sweep window exceeds the 16-bit slot codes");
     const int NCW = std::max(1, std::min(opt.consumerWarps, kS2MaxWarps));
     S.npairs = lower ? 14 : 18;
     S.parts.resize(A.nparts);
@@ -87,61 +103,51 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
         auto chunks_of = [&](int st) { return (stepPtr[st + 1] - stepPtr[st] + 31) / 32; };
         auto warps_of = [&](int st) { return std::min(chunks_of(st), NCW); };
         S2Part& P = S.parts[p];
-        P.ncw = NCW; P.nsteps = nsteps; P.row0 = row0; P.nrows = nrows; P.pad = 0;
-        P.stream0 = (int) S.streams.size(); P.ext0 = (int) S.ext.size();
+        P.ncw = NCW; P.nsteps = nsteps; P.row0 = row0; P.nrows = nrows; P.pad0 = P.pad1 = P.pad2 = 0;
+        P.stream0 = (int) S.streams.size();
         // per warp: headers, codes, build refs collected separately, appended stream by stream at the end
         struct WarpStream { std::vector<int> hdr, codes; std::vector<S2Build> build; std::vector<std::vector<int>> src; long long vals = 0; };
         std::vector<WarpStream> ws((size_t) NCW);
-        // external rows: listed in the order the steps need them; a row already listed for one of the last kS2Reuse steps is reused
-        std::vector<std::pair<int, int>> seen;          // (p-row, index in the part's list) of the rows that may be reused, sorted by p-row
-        std::vector<int> listedBefore(1, 0);            // rows listed before step m
-        int next_total = 0;                             // external rows of the part so far
         int base = 0;                                   // warp of chunk 0 of the current step
         for (int st = 0; st < nsteps; ++st) {
             const int pos0 = stepPtr[st], n = stepPtr[st + 1] - pos0;
             const int nchunks = chunks_of(st);
             S.stepChunks.push_back(nchunks);
             S.maxChunks = std::max(S.maxChunks, nchunks);
-            {   // rows listed before step st - kS2Reuse + 1 may not be reused any more
-                const int keep_from = listedBefore[std::max(0, st - kS2Reuse + 1)];
-                size_t o = 0;
-                for (size_t i = 0; i < seen.size(); ++i) if (seen[i].second >= keep_from) seen[o++] = seen[i];
-                seen.resize(o);
-            }
-            const int freed = listedBefore[std::max(0, st - kS2Reuse + 1)];
-            // pass 1: dependencies of every row of the step; external rows get their list index
-            struct RowDeps { std::vector<int> code, src; int piv; };
-            std::vector<RowDeps> rd(n);
+            // pass 1: dependencies of every row of the step, packed into passes of three slots: an external dependency goes to
+            // slot 2, a second one to slot 1, dependencies inside the window fill what is left (the order in which the
+            // contributions of a row are subtracted is free)
+            struct Pass { int code[3], src[3], ext[2]; };
+            std::vector<std::vector<Pass>> rp(n);
             for (int q = 0; q < n; ++q) {
                 const int ps = pos0 + q, gq = g_of(ps), r = A.perm[gq];
+                std::vector<std::pair<int, int>> win, ext;          // (slot code | p-row, source block)
                 for (int k = rows[r]; k < rows[r + 1]; ++k) {
                     const int c = cols[k];
                     if (!(lower ? c < r : c > r)) continue;
-                    const int gd = A.iperm[c];
+                    const int gd = A.iperm[c], sb = A.prow[gq] + (k - rows[r]);
                     int slot = -1;
                     if (partOf[c] == p) {
                         const int pd = lower ? gd - row0 : row0 + nrows - 1 - gd;
                         if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
-                        if (ps - pd <= slack) { slot = pd & (W - 1); S.nWindow++; }
+                        if (ps - pd <= slack) slot = pd & (W - 1);
                     }
-                    if (slot < 0) {
-                        S.nExternal++;
-                        auto it = std::lower_bound(seen.begin(), seen.end(), std::make_pair(gd, -1));
-                        int idx;
-                        if (it != seen.end() && it->first == gd) idx = it->second;
-                        else { idx = next_total++; S.ext.push_back(gd); seen.insert(it, std::make_pair(gd, idx)); }
-                        slot = W + (idx & (EW - 1));
-                    }
-                    rd[q].code.push_back(8 * slot);
-                    rd[q].src.push_back(A.prow[gq] + (k - rows[r]));
+                    if (slot >= 0) { win.emplace_back(8 * slot, sb); S.nWindow++; }
+                    else { ext.emplace_back(gd, sb); S.nExternal++; }
                 }
-                rd[q].piv = A.pdiag[gq];
+                size_t iw = 0, ie = 0;
+                do {
+                    Pass ps2;
+                    for (int j = 0; j < 3; ++j) { ps2.code[j] = zcode; ps2.src[j] = -1; }
+                    ps2.ext[0] = ps2.ext[1] = -1;
+                    bool used[3] = {false, false, false};
+                    if (ie < ext.size()) { ps2.ext[0] = ext[ie].first; ps2.src[2] = ext[ie].second; used[2] = true; ++ie; }
+                    if (ie < ext.size()) { ps2.ext[1] = ext[ie].first; ps2.src[1] = ext[ie].second; used[1] = true; ++ie; }
+                    for (int j = 0; j < 3 && iw < win.size(); ++j)
+                        if (!used[j]) { ps2.code[j] = win[iw].first; ps2.src[j] = win[iw].second; ++iw; }
+                    rp[q].push_back(ps2);
+                } while (iw < win.size() || ie < ext.size());
             }
-            // (a step that adds no external row of its own has nothing new to wait for)
-            const int need = next_total > listedBefore[st] ? next_total : 0;
-            if (next_total - freed > EW) throw std::runtime_error("external-row ring of the triangular sweeps too small for the rows of " + std::to_string(kS2Reuse) + " steps");
-            if (next_total >= (1 << 24)) throw std::runtime_error("too many external rows in one part of the triangular sweeps");
-            listedBefore.push_back(next_total);
             // pass 2: records.  Chunk c of the step belongs to warp (base + c) % NCW.
             const int sync_id = 1 + (st + kS2Barriers - 1) % kS2Barriers, arrive_id = 1 + st % kS2Barriers;
             const int sync_warps = st > 0 ? warps_of(st - 1) + warps_of(st) : 0;
@@ -150,9 +156,7 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
             std::vector<int> npass(nchunks, 1);
             for (int c = 0; c < nchunks; ++c) {
                 const int cnt = std::min(32, n - 32 * c);
-                int nd = 0;
-                for (int q = 0; q < cnt; ++q) nd = std::max(nd, (int) rd[32 * c + q].code.size());
-                npass[c] = std::max(1, (nd + 2) / 3);
+                for (int q = 0; q < cnt; ++q) npass[c] = std::max(npass[c], (int) rp[32 * c + q].size());
                 for (int ps = 0; ps < npass[c]; ++ps) recs[(base + c) % NCW].emplace_back(c, ps);
             }
             for (int wv = 0; wv < NCW; ++wv) {
@@ -165,45 +169,43 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
                     int flags = 0;
                     if (t == 0 && st > 0) flags |= S2_SYNC;
                     if (t == nr - 1 && st < nsteps - 1) flags |= S2_ARRIVE;
-                    if (t == 0 && c == 0) flags |= S2_LEAD;
                     if (ps == 0) flags |= S2_FIRST;
                     if (ps == npass[c] - 1) flags |= S2_LAST;
+                    if (t == 0 && c == 0) flags |= S2_LEAD;
                     const int g0 = g_of(pos0 + 32 * c);
                     S2Build B{};
                     B.vals_off = wsr.vals; B.cnt = cnt; B.first = ps == 0; B.src_off = 0;
                     std::vector<int> src((size_t) (lower ? 3 : 4) * cnt, -1);
                     for (int q = 0; q < cnt; ++q) {
-                        const RowDeps& R = rd[32 * c + q];
-                        int code[3] = {8 * zslot, 8 * zslot, 8 * zslot};
-                        for (int j = 0; j < 3; ++j) {
-                            const int d = 3 * ps + j;
-                            if (d < (int) R.code.size()) { code[j] = R.code[d]; src[(size_t) j * cnt + q] = R.src[d]; }
-                        }
+                        Pass pz;
+                        for (int j = 0; j < 3; ++j) { pz.code[j] = zcode; pz.src[j] = -1; }
+                        pz.ext[0] = pz.ext[1] = -1;
+                        const Pass& R = ps < (int) rp[32 * c + q].size() ? rp[32 * c + q][ps] : pz;
+                        for (int j = 0; j < 3; ++j) src[(size_t) j * cnt + q] = R.src[j];
+                        if (R.ext[0] >= 0) flags |= S2_EXT;
                         const int outc = 8 * ((pos0 + 32 * c + q) & (W - 1));
-                        wsr.codes.push_back(code[0] | (code[1] << 16));
-                        wsr.codes.push_back(code[2] | (outc << 16));
-                        if (!lower) src[(size_t) 3 * cnt + q] = R.piv;
+                        wsr.codes.push_back(R.code[0] | (R.code[1] << 16));
+                        wsr.codes.push_back(R.code[2] | (outc << 16));
+                        wsr.codes.push_back(R.ext[0]);
+                        wsr.codes.push_back(R.ext[1]);
+                        if (!lower) src[(size_t) 3 * cnt + q] = A.pdiag[g_of(pos0 + 32 * c + q)];
                     }
                     wsr.build.push_back(B);
                     wsr.src.push_back(std::move(src));
                     wsr.vals += 2LL * S.npairs * cnt;
                     wsr.hdr.push_back(g0);
-                    wsr.hdr.push_back(cnt | (flags << 8) | (sync_id << 16) | (arrive_id << 20));
-                    wsr.hdr.push_back((t == 0 ? need : 0) | (sync_warps << 24));      // the warp's first record of the step waits for the step's external rows
-                    wsr.hdr.push_back(freed | (arrive_warps << 24));
+                    wsr.hdr.push_back(s2_pack(cnt, flags, sync_id, arrive_id, sync_warps, arrive_warps));
                     S.nrecords++;
                 }
             }
             base = (base + nchunks) % NCW;
         }
-        P.next = next_total;
-        S.nExtRows += next_total;
         S.stepPtr.push_back((int) S.stepChunks.size());
         // append the warp streams
         for (size_t w = 0; w < ws.size(); ++w) {
             S2Stream R{};
-            R.vals_off = S.nvals; R.code_off = (long long) (S.codes.size() / 2); R.hdr_off = (int) (S.hdrs.size() / 4);
-            R.nrec = (int) (ws[w].hdr.size() / 4);
+            R.vals_off = S.nvals; R.code_off = (long long) (S.codes.size() / 4); R.hdr_off = (int) (S.hdrs.size() / 2);
+            R.nrec = (int) (ws[w].hdr.size() / 2);
             S.hdrs.insert(S.hdrs.end(), ws[w].hdr.begin(), ws[w].hdr.end());
             S.codes.insert(S.codes.end(), ws[w].codes.begin(), ws[w].codes.end());
             for (size_t i = 0; i < ws[w].build.size(); ++i) {
@@ -214,7 +216,7 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
                 S.build.push_back(B);
             }
             S.nvals += ws[w].vals;
-            if (S.hdrs.size() / 4 > (size_t) INT_MAX || S.src.size() > (size_t) INT_MAX) throw std::runtime_error("sweep schedule too large");
+            if (S.hdrs.size() / 2 > (size_t) INT_MAX || S.src.size() > (size_t) INT_MAX) throw std::runtime_error("sweep schedule too large");
             S.streams.push_back(R);
         }
     }
@@ -266,23 +268,23 @@ inline void fill_stream2_host(const Sweep2Plan& S, bool lower, const double* LU,
 }
 
 // Host emulation of k_sweep2: interprets the packed streams exactly as the kernel does (per part: steps in order, the warps of a
-// step walk their records; the helper parks external rows in list order under the ring's flow control), round robin over the
-// parts; a step whose external rows have not been produced yet makes its part yield.  Checks the invariants the kernel relies on
-// (barrier ids and counts, ring slots, window slots never read before written, ...).  Returns false on deadlock.
+// step walk their records), round robin over the parts; a step one of whose external rows has not been produced yet makes its
+// part yield.  Checks the invariants the kernel relies on (barrier ids and counts, window slots never read before written, ...).
+// Returns false on deadlock.
 inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, const std::vector<double>& vals, const double* rhs, double* out)
 {
-    const int W = A.window, EW = A.extWindow, zslot = W + EW, NP = S.npairs;
+    const int W = A.window, NP = S.npairs;
     const double NaN = std::nan("");
     for (int i = 0; i < 3 * A.Nb; ++i) out[i] = NaN;
     struct WarpCur { int rec = 0; long long vals = 0, code = 0; double carry[32][3]; };
-    struct PartState { int step = 0, base = 0; std::vector<WarpCur> w; std::vector<double> xs; int parked = 0; bool done = false; };
+    struct PartState { int step = 0, base = 0; std::vector<WarpCur> w; std::vector<double> xs; bool done = false; };
     std::vector<PartState> ps(A.nparts);
     for (int p = 0; p < A.nparts; ++p) {
         const S2Part& P = S.parts[p];
         ps[p].w.resize((size_t) P.ncw);
         for (size_t w = 0; w < ps[p].w.size(); ++w) { ps[p].w[w].vals = S.streams[P.stream0 + w].vals_off; ps[p].w[w].code = S.streams[P.stream0 + w].code_off; }
-        ps[p].xs.assign((size_t) 3 * (zslot + 1), NaN);
-        for (int e = 0; e < 3; ++e) ps[p].xs[(size_t) 3 * zslot + e] = 0.0;
+        ps[p].xs.assign((size_t) 3 * (W + 1), NaN);
+        for (int e = 0; e < 3; ++e) ps[p].xs[(size_t) 3 * W + e] = 0.0;
         ps[p].done = P.nsteps == 0;
     }
     int remaining = 0;
@@ -296,39 +298,39 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
             const int* chunks = S.stepChunks.data() + S.stepPtr[p];
             while (!T.done) {
                 const int st = T.step, nch = chunks[st], nw = std::min(nch, P.ncw);
-                // which external rows does this step need?  (the first record of every warp of the step)
-                int need = 0, freed = -1;
-                for (int k = 0; k < nw; ++k) {
+                // are the external rows of the step there?  (walk the step's records without executing them)
+                bool ready = true;
+                for (int k = 0; k < nw && ready; ++k) {
                     const int wv = (T.base + k) % P.ncw;
                     const S2Stream& R = S.streams[P.stream0 + wv];
                     const WarpCur& c = T.w[wv];
                     if (c.rec >= R.nrec) throw std::runtime_error("emulate2: warp stream ended before the part's last step");
-                    const int* h = S.hdrs.data() + 4 * (size_t) (R.hdr_off + c.rec);
-                    const int flags = (h[1] >> 8) & 255;
-                    if ((flags & S2_SYNC) != (st > 0 ? S2_SYNC : 0)) throw std::runtime_error("emulate2: SYNC flag mismatch");
-                    if (((flags & S2_LEAD) != 0) != (k == 0)) throw std::runtime_error("emulate2: LEAD flag mismatch");
-                    if (st > 0) {
-                        if (((h[1] >> 16) & 15) != 1 + (st - 1) % kS2Barriers) throw std::runtime_error("emulate2: wrong barrier to wait on");
-                        if (((unsigned) h[2] >> 24) != (unsigned) (std::min(chunks[st - 1], P.ncw) + nw)) throw std::runtime_error("emulate2: wrong warp count on the barrier waited on");
+                    {
+                        const int* h = S.hdrs.data() + 2 * (size_t) (R.hdr_off + c.rec);
+                        const int flags = s2_flags(h[1]);
+                        if ((flags & S2_SYNC) != (st > 0 ? S2_SYNC : 0)) throw std::runtime_error("emulate2: SYNC flag mismatch");
+                        if (st > 0) {
+                            if (((h[1] >> 12) & 15) != 1 + (st - 1) % kS2Barriers) throw std::runtime_error("emulate2: wrong barrier to wait on");
+                            if (((h[1] >> 20) & 31) != std::min(chunks[st - 1], P.ncw) + nw) throw std::runtime_error("emulate2: wrong warp count on the barrier waited on");
+                        }
                     }
-                    const int nd = h[2] & 0xffffff, fr = h[3] & 0xffffff;
-                    if (nd) { if (need && nd != need) throw std::runtime_error("emulate2: warps of a step disagree on the external rows"); need = nd; }
-                    if (freed >= 0 && fr != freed) throw std::runtime_error("emulate2: warps of a step disagree on the freed prefix");
-                    freed = fr;
-                }
-                if (need) {
-                    if (need > P.next) throw std::runtime_error("emulate2: external need beyond the part's list");
-                    if (need > freed + EW) throw std::runtime_error("emulate2: ring flow control would deadlock");
-                    // park (the helper's job): in list order, as far as the rows have been produced
-                    bool ready = true;
-                    while (T.parked < need) {
-                        const int k = T.parked, gd = S.ext[P.ext0 + k];
-                        if (std::isnan(out[3 * (size_t) gd])) { ready = false; break; }
-                        for (int e = 0; e < 3; ++e) T.xs[(size_t) 3 * (W + (k & (EW - 1))) + e] = out[3 * (size_t) gd + e];
-                        T.parked++;
+                    long long code = c.code;
+                    for (int rec = c.rec; rec < R.nrec && ready; ++rec) {
+                        const int* h = S.hdrs.data() + 2 * (size_t) (R.hdr_off + rec);
+                        const int cnt = s2_cnt(h[1]), flags = s2_flags(h[1]);
+                        bool any = false;
+                        for (int q = 0; q < cnt && ready; ++q)
+                            for (int j = 0; j < 2; ++j) {
+                                const int er = S.codes[4 * (size_t) (code + q) + 2 + j];
+                                if (er < -1 || er >= A.Nb) throw std::runtime_error("emulate2: bad external row");
+                                if (er >= 0) { any = true; if (std::isnan(out[3 * (size_t) er])) ready = false; }
+                            }
+                        if (any != ((flags & S2_EXT) != 0)) throw std::runtime_error("emulate2: EXT flag mismatch");
+                        code += cnt;
+                        if ((flags & S2_ARRIVE) && st < P.nsteps - 1) break;
                     }
-                    if (!ready) break;      // yield
                 }
+                if (!ready) break;      // yield
                 // run the step: every warp of the step, its records up to and including the one flagged ARRIVE (last step: all that is left)
                 for (int k = 0; k < nw; ++k) {
                     const int wv = (T.base + k) % P.ncw;
@@ -340,14 +342,13 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                             if (st == P.nsteps - 1 && !first_rec) break;
                             throw std::runtime_error("emulate2: warp stream ended inside a step");
                         }
-                        const int* h = S.hdrs.data() + 4 * (size_t) (R.hdr_off + c.rec);
-                        const int g0 = h[0], cnt = h[1] & 255, flags = (h[1] >> 8) & 255;
-                        if (!first_rec && (flags & (S2_SYNC | S2_LEAD))) throw std::runtime_error("emulate2: SYNC / LEAD flag in the middle of a step");
-                        if (!first_rec && (h[2] & 0xffffff)) throw std::runtime_error("emulate2: external wait in the middle of a step");
+                        const int* h = S.hdrs.data() + 2 * (size_t) (R.hdr_off + c.rec);
+                        const int g0 = h[0], cnt = s2_cnt(h[1]), flags = s2_flags(h[1]);
+                        if (!first_rec && (flags & S2_SYNC)) throw std::runtime_error("emulate2: SYNC flag in the middle of a step");
                         if (cnt < 1 || cnt > 32) throw std::runtime_error("emulate2: bad row count");
                         first_rec = false;
                         const double* v = vals.data() + c.vals;
-                        const int* cd = S.codes.data() + 2 * (size_t) c.code;
+                        const int* cd = S.codes.data() + 4 * (size_t) c.code;
                         for (int q = 0; q < cnt; ++q) {
                             const int gq = lower ? g0 + q : g0 - q;
                             if (gq < P.row0 || gq >= P.row0 + P.nrows) throw std::runtime_error("emulate2: row outside the part");
@@ -358,16 +359,19 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                                 acc[cc] = 0.0;
                                 for (int e = 0; e < 3; ++e) acc[cc] += v[s2_vidx(27 + 3 * cc + e, q, cnt)] * rhs[3 * (size_t) gq + e];
                             }
-                            const int d[3] = {cd[2 * q] & 0xffff, (cd[2 * q] >> 16) & 0xffff, cd[2 * q + 1] & 0xffff};
+                            // external dependencies: slot 2 (extA), slot 1 (extB), straight from the result vector
+                            for (int j = 0; j < 2; ++j) {
+                                const int er = cd[4 * q + 2 + j], slot = 2 - j;
+                                if (er < 0) continue;
+                                const int dcode = slot == 2 ? (cd[4 * q + 1] & 0xffff) : ((cd[4 * q] >> 16) & 0xffff);
+                                if (dcode != 8 * W) throw std::runtime_error("emulate2: slot of an external dependency does not point at the zero row");
+                                for (int cc = 0; cc < 3; ++cc)
+                                    for (int e = 0; e < 3; ++e) acc[cc] -= v[s2_vidx(9 * slot + 3 * cc + e, q, cnt)] * out[3 * (size_t) er + e];
+                            }
+                            const int d[3] = {cd[4 * q] & 0xffff, (cd[4 * q] >> 16) & 0xffff, cd[4 * q + 1] & 0xffff};
                             for (int j = 0; j < 3; ++j) {
-                                if (d[j] % 8 || d[j] / 8 > zslot) throw std::runtime_error("emulate2: bad dependency code");
-                                const int slot = d[j] / 8;
-                                if (slot >= W && slot < zslot) {         // parked external row: must be one of the live rows of the ring
-                                    bool live = false;
-                                    for (int kk = std::max(freed, T.parked - EW); kk < T.parked && !live; ++kk) live = (kk & (EW - 1)) == slot - W;
-                                    if (!live) throw std::runtime_error("emulate2: read of a ring slot that holds no live row");
-                                }
-                                const double* x = T.xs.data() + 3 * (size_t) slot;
+                                if (d[j] % 8 || d[j] / 8 > W) throw std::runtime_error("emulate2: bad dependency code");
+                                const double* x = T.xs.data() + 3 * (size_t) (d[j] / 8);
                                 for (int cc = 0; cc < 3; ++cc)
                                     for (int e = 0; e < 3; ++e) {
                                         if (std::isnan(x[e])) throw std::runtime_error("emulate2: read of a value that was not produced yet");
@@ -380,7 +384,7 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                         if (flags & S2_LAST)
                             for (int q = 0; q < cnt; ++q) {
                                 const int gq = lower ? g0 + q : g0 - q;
-                                const int oc = (cd[2 * q + 1] >> 16) & 0xffff;
+                                const int oc = (cd[4 * q + 1] >> 16) & 0xffff;
                                 if (oc % 8 || oc / 8 >= W) throw std::runtime_error("emulate2: bad result slot");
                                 for (int e = 0; e < 3; ++e) { T.xs[(size_t) 3 * (oc / 8) + e] = c.carry[q][e]; out[3 * (size_t) gq + e] = c.carry[q][e]; }
                             }
@@ -390,8 +394,8 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                             continue;
                         }
                         if (flags & S2_ARRIVE) {
-                            if (((h[1] >> 20) & 15) != 1 + st % kS2Barriers) throw std::runtime_error("emulate2: wrong barrier to arrive at");
-                            if (((unsigned) h[3] >> 24) != (unsigned) (nw + std::min(chunks[st + 1], P.ncw))) throw std::runtime_error("emulate2: wrong warp count on the barrier arrived at");
+                            if (((h[1] >> 16) & 15) != 1 + st % kS2Barriers) throw std::runtime_error("emulate2: wrong barrier to arrive at");
+                            if (((h[1] >> 25) & 31) != nw + std::min(chunks[st + 1], P.ncw)) throw std::runtime_error("emulate2: wrong warp count on the barrier arrived at");
                             break;
                         }
                     }

@@ -10,11 +10,15 @@ which = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] in ("lower", "upper") e
 s = synth.full_system(wl) if wl in ("c2", "c3") else synth.small(*[int(t) for t in wl.split("x")])
 be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
 for kv in sys.argv[2:]:
-    if "=" in kv:
+    if "=" in kv and not kv.startswith("late:"):
         k, v = kv.split("=")
         be.set_option(k, float(v))
 be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
 be.ilu0_factorize()
+for kv in sys.argv[2:]:
+    if kv.startswith("late:"):
+        k, v = kv[5:].split("=")
+        be.set_option(k, float(v))
 t_plain, _ = be.time_kernel("ilu_" + which, 5, False)
 be.set_option("sweep_trace", 1)
 t_tr, _ = be.time_kernel("ilu_" + which, 1, False)
@@ -26,31 +30,19 @@ det = out[8192:8192 + 2 * 256 * np_].reshape(np_, 256, 2)
 t0 = summ[:np_, 0].min()
 nst = np.minimum(256, summ[:np_, 5]).astype(int)
 first = np.array([det[p, 0, 0] for p in range(np_)]); last = np.array([det[p, nst[p] - 1, 0] for p in range(np_)])
-waited = np.array([det[p, :nst[p], 1].sum() for p in range(np_)]); nwait = np.array([(det[p, :nst[p], 1] > 300).sum() for p in range(np_)])
 print("%s sweep: %.1f us plain, %.1f us traced, %d parts" % (which, t_plain * 1e3, t_tr * 1e3, np_))
-print("part: first step at / last step at / waited for external rows [us] (steps that waited / steps)")
+print("part: first step at / last step at [us], median step time [us] (steps)")
 order = np.argsort(first)
 for r in range(0, np_, 4):
-    print("   ".join("%3d: %6.1f %6.1f %6.1f (%3d/%3d)" % (p, (first[p] - t0) * 1e-3, (last[p] - t0) * 1e-3, waited[p] * 1e-3, nwait[p], summ[p, 5])
+    print("   ".join("%3d: %6.1f %6.1f %.3f (%3d)" % (p, (first[p] - t0) * 1e-3, (last[p] - t0) * 1e-3, np.median(np.diff(det[p, :nst[p], 0])) * 1e-3 if nst[p] > 1 else 0, summ[p, 5])
                      for p in order[r:r + 4]))
 for p in (int(order[0]), int(order[np_ // 2]), int(np.argmax(last))):
     n = nst[p]
     ts = (det[p, :n, 0] - t0) * 1e-3
     print("part %d: step start times [us]: %s" % (p, " ".join("%.1f" % v for v in ts[:n:max(1, n // 40)])))
-    w = det[p, :n, 1] * 1e-3
-    print("part %d: waits > 0.3 us at steps: %s" % (p, " ".join("%d:%.1f" % (i, w[i]) for i in range(n) if w[i] > 0.3)[:1500]))
-    d = np.diff(ts)
-    print("part %d: step time median %.3f us, p90 %.3f us; without the steps that waited: median %.3f us" % (p, np.median(d), np.percentile(d, 90), np.median(d[w[1:] < 0.1]) if (w[1:] < 0.1).any() else -1))
-
 prof = out[8192 + 2 * 256 * 1024:8192 + 2 * 256 * 1024 + 512].reshape(2, 32, 8)
 for pi, name in ((0, "part 0"), (1, "part %d" % (np_ // 2))):
-    print("%s, cycles per record: [fetch issue | wait for previous step | wait for external rows | dependencies + operands + fma | stores + arrive], records" % name)
+    print("%s, cycles per record: [fetch issue + start value | wait for previous step | external rows | fma | stores + arrive | shared loads of the dependencies], records" % name)
     for w in range(16):
         n = prof[pi, w, 6]
-        if n > 0: print("   warp %2d: %s   %d" % (w, " ".join("%7.1f" % (prof[pi, w, k] / n) for k in range(5)), n))
-
-hst = out[8192 + 2 * 256 * 1024 + 512:8192 + 2 * 256 * 1024 + 512 + 8 * np_].reshape(np_, 8)
-print("per part: median step time [us] | helper: rounds, windows per round, rounds without progress, cycles per round: issue / wait for first poll / park + publish")
-for r in range(0, np_, 3):
-    print("   ".join("%3d: %.3f | %4d %.1f %4d %5.0f %5.0f %5.0f" % (p, np.median(np.diff(det[p, :nst[p], 0])) * 1e-3, hst[p, 0], hst[p, 1] / max(1, hst[p, 0]), hst[p, 2],
-                                                       hst[p, 4] / max(1, hst[p, 0]), hst[p, 5] / max(1, hst[p, 0]), hst[p, 6] / max(1, hst[p, 0])) for p in range(r, min(np_, r + 3))))
+        if n > 0: print("   warp %2d: %s   %d" % (w, " ".join("%7.1f" % (prof[pi, w, k] / n) for k in range(6)), n))
