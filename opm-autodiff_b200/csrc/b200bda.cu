@@ -226,7 +226,7 @@ struct Solver {
     // triangular sweeps: parts (0 = one per SM), consumer warps per CTA, ring slots, bytes per stage, window rows
     int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 0, sweep_helper_sleep = 0;
     // round-2 sweeps (k_sweep2): consumer warps (G x WG per part), helper warps, forced group count / group width (0 = automatic)
-    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1;      // s2_helpers: warps beyond the consumers (they only work in the tails)
+    int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_poll_lead = 15, s2_prefetch = 2;      // s2_helpers: warps beyond the consumers (they only work in the tails)
     bool v2 = false;
     Sweep2Plan L2, U2;
 
@@ -972,6 +972,8 @@ struct Solver {
             a.v2.vals = lower ? d_valL.p : d_valU.p;
             a.v2.window = an.window; a.v2.ncw = s2_cw;
             a.nwarps = s2_cw;              // the SpMV tail's producer warp = the warp after the consumers
+            a.helper_sleep = s2_poll_lead;  // steps before its own a warp starts to poll external rows
+            a.early = s2_prefetch;          // records ahead whose bytes are pulled into L2
         }
         return a;
     }
@@ -1405,6 +1407,8 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
+        else if (k == "s2_prefetch") s->s2_prefetch = std::max(2, std::min(8, (int) value));
+        else if (k == "s2_poll_lead") s->s2_poll_lead = std::max(0, (int) value);
         else if (k == "fuse_ring_warps") { if (s->analysed) throw std::runtime_error("fuse_ring_warps must be set before the first solve"); s->fuse_ring_warps = std::max(1, (int) value); }
         else if (k == "sweep_v2" || k == "s2_cw" || k == "s2_helpers") {
             if (s->analysed) throw std::runtime_error("the sweep schedule must be set before the first solve");
@@ -2043,8 +2047,13 @@ b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* 
         }
         if (max_rel_err) *max_rel_err = den > 0.0 ? num / den : num;
         if (stats) {
-            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, 0,
-                                     0, L.maxChunks, o2.consumerWarps};
+            // part pairs that read each other's rows in the same sweep (a ping-pong: every level pays the hand-over latency)
+            std::sort(L.partEdges.begin(), L.partEdges.end());
+            L.partEdges.erase(std::unique(L.partEdges.begin(), L.partEdges.end()), L.partEdges.end());
+            long long mutual = 0;
+            for (auto& e : L.partEdges) if (e.first < e.second && std::binary_search(L.partEdges.begin(), L.partEdges.end(), std::make_pair(e.second, e.first))) ++mutual;
+            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, L.nOwnExternal,
+                                     mutual, L.maxChunks, o2.consumerWarps};
             memcpy(stats, v, sizeof v);
         }
         return B200_SUCCESS;

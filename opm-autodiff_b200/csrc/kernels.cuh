@@ -639,7 +639,7 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
     const int PW = P.nwarps;                                   // the sweep's producer warp keeps that job
     const int NC = nwarp - 1, ci = warp < PW ? warp : warp - 1;
     const int NR = min(min(NC, kTailMaxCons), F.ring_bytes / (2 * kTailBufBytes));   // consumers fed through the ring
-    const int NU = NR > 0 ? NR : NC;       // warps that take slices: a plain-load warp next to ring-fed ones would be the straggler
+    const int NU = (NR > 0 && !(P.nowait & 32)) ? NR : NC;       // warps that take slices: a plain-load warp next to ring-fed ones would be the straggler
     for (int p = threadIdx.x; p < P.nparts; p += blockDim.x) s_done[p] = 0;
     if (threadIdx.x < 32) { s_red[0][threadIdx.x] = 0.0; s_red[1][threadIdx.x] = 0.0; }
     if (threadIdx.x == 0) {
@@ -1189,7 +1189,8 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
 #pragma unroll
         for (int k = 0; k < NP; ++k) o.v[k] = make_double2(0.0, 0.0);
         o.r0 = o.r1 = o.r2 = 0.0;
-        o.xa0 = o.xa1 = o.xa2 = o.xb0 = o.xb1 = o.xb2 = 0.0;
+        int my_step = -1;                  // step of the current record (headers carry the distance to the warp's previous record)
+        const int poll_lead = max(1, P.helper_sleep);
         // issue the loads of the record described by hd (nothing waits for them here) and advance the stream
         auto fetch = [&](const int2& hd) {
             const int cnt = hd.y & 63;
@@ -1201,12 +1202,9 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                     if (!TRACE || !(P.nowait & 8)) o.v[k] = ldg_stream_f64x2(v);
                 o.cd = ldg_stream_s32x4(cp);
                 if ((hd.y & (S2D_FIRST << 6)) && (!TRACE || !(P.nowait & 16))) {
-                    const double* r = P.rhs + 3 * (size_t) (LOWER ? hd.x + lane : hd.x - lane);
+                    const int g0 = hd.x & 0x3fffffff;
+                    const double* r = P.rhs + 3 * (size_t) (LOWER ? g0 + lane : g0 - lane);
                     o.r0 = r[0]; o.r1 = r[1]; o.r2 = r[2];
-                }
-                if (hd.y & (S2D_EXT << 6)) {                              // first poll of the row's external dependencies
-                    if (o.cd.z >= 0) { const double* x = P.out + 3 * (size_t) o.cd.z; o.xa0 = ld_relaxed(x); o.xa1 = ld_relaxed(x + 1); o.xa2 = ld_relaxed(x + 2); }
-                    if (o.cd.w >= 0) { const double* x = P.out + 3 * (size_t) o.cd.w; o.xb0 = ld_relaxed(x); o.xb1 = ld_relaxed(x + 1); o.xb2 = ld_relaxed(x + 2); }
                 }
             } else o.cd = make_int4(zcode | (zcode << 16), zcode, -1, -1);
             vp += (size_t) (2 * NP) * cnt;
@@ -1217,23 +1215,31 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
         // (~1500 + 700 cycles) per record, i.e. >= 440 cycles per step.  So the bytes of the record AFTER the next one are
         // pulled into L2 at the same time (no registers needed): the loads that follow find them there.
         const unsigned char* pf = reinterpret_cast<const unsigned char*>(V.vals + sd.vals_off);      // start of the record after the next
-        auto prefetch_l2 = [&](int idx) {
+        const int pfd = max(2, min(P.early, 8));       // records ahead of the current one whose bytes are pulled into L2
+        auto prefetch_l2 = [&](int idx, int cur) {     // cur: record whose header batch is in hb
             if (idx >= nrec) return;
             const int j = idx & 31;
-            const int y = __shfl_sync(kFull, (idx >> 5) == ((idx - 1) >> 5) || idx == 0 ? hb.y : hbn.y, j);      // header batch of idx
+            const int y = __shfl_sync(kFull, (idx >> 5) == (cur >> 5) ? hb.y : hbn.y, j);                        // header batch of idx
             const unsigned bytes = 16u * NP * (unsigned) (y & 63);
             if (lane == 0 && bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(bytes) : "memory");
             pf += bytes;
         };
         int2 h = header(0);
-        if (nrec > 0) { prefetch_l2(0); fetch(h); prefetch_l2(1); }
+        my_step += (int) (((unsigned) h.x >> 30) | (((unsigned) h.y >> 30) << 2));
+        if (nrec > 0) { for (int k = 0; k < pfd; ++k) prefetch_l2(k, 0); fetch(h); }
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
         // debugging aid: where the cycles of this warp go (parts 0 and nparts / 2 of a traced launch)
         const bool prof = TRACE && P.trace_cap < 0 && (part == 0 || part == P.nparts / 2);      // trace_cap < 0: per-warp cycle accounting as well (spills: slow)
         long long pc[6] = {0, 0, 0, 0, 0, 0}, c0 = prof ? clock64() : 0;
         for (int i = 0; i < nrec; ++i) {
             const int cnt = h.y & 63, flags = (h.y >> 6) & 63;
+            // everything the dependent part needs besides the dependencies themselves is computed BEFORE the barrier: a lone warp
+            // issues an instruction every 4-5 cycles, so every instruction between bar.sync and bar.arrive is on the level's chain
             const unsigned d0 = (unsigned) o.cd.x & 0xffffu, d1 = (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & 0xffffu, oc = (unsigned) o.cd.y >> 16;
+            const unsigned ax0 = xy + 2 * d0, ax1 = xy + 2 * d1, ax2 = xy + 2 * d2, az0 = z + d0, az1 = z + d1, az2 = z + d2;
+            const unsigned sx = xy + 2 * oc, sz = z + oc;
+            const bool store = (flags & S2D_LAST) && lane < cnt;
+            const int bar_in = (h.y >> 12) & 15, bar_in_n = 32 * ((h.y >> 20) & 31), bar_out = (h.y >> 16) & 15, bar_out_n = 32 * ((h.y >> 25) & 31);
             const double* v = reinterpret_cast<const double*>(o.v);
             // start value: nothing here depends on another row of the part
             if (flags & S2D_FIRST) {
@@ -1246,16 +1252,23 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             }
             if (prof) { const long long c = clock64(); pc[0] += c - c0; c0 = c; }      // fetch issue, header, start value
             if (flags & S2D_EXT) {
-                // external dependencies (rows of other parts: the value is its own ready flag): polled with the operands; poll
-                // again while the sentinel is still there; then fold their contribution into the start value
-                if (P.nowait < 2) {
+                // External dependencies (rows of other parts: the value is its own ready flag).  The rows a step needs are one
+                // level behind it, i.e. their owners produce them about when this part runs the step before: polling them from
+                // the moment the warp is free (several steps early) only loads L2 and the SM's load pipe (15 warps x 5 rows x 3
+                // loads per round trip and SM).  So the warp sleeps until the part is two steps away from its record, then polls
+                // until the sentinel is gone, and folds the rows' contribution into the start value -- all before it waits for
+                // the previous step, outside the dependent chain.
+                double xa0 = 0.0, xa1 = 0.0, xa2 = 0.0, xb0 = 0.0, xb1 = 0.0, xb2 = 0.0;
+                if ((P.nowait & 3) < 2) {
+                    while (ld_volatile_s32(hp + 11) <= my_step - poll_lead) __nanosleep(64);      // until step my_step - poll_lead has started
                     int spins = 0;
+                    bool wa = o.cd.z >= 0, wb = o.cd.w >= 0;
                     while (true) {
-                        const bool wa = o.cd.z >= 0 && (is_sentinel(o.xa0) || is_sentinel(o.xa1) || is_sentinel(o.xa2));
-                        const bool wb = o.cd.w >= 0 && (is_sentinel(o.xb0) || is_sentinel(o.xb1) || is_sentinel(o.xb2));
+                        if (wa) { const double* x = P.out + 3 * (size_t) o.cd.z; xa0 = ld_relaxed(x); xa1 = ld_relaxed(x + 1); xa2 = ld_relaxed(x + 2); }
+                        if (wb) { const double* x = P.out + 3 * (size_t) o.cd.w; xb0 = ld_relaxed(x); xb1 = ld_relaxed(x + 1); xb2 = ld_relaxed(x + 2); }
+                        wa = wa && (is_sentinel(xa0) || is_sentinel(xa1) || is_sentinel(xa2));
+                        wb = wb && (is_sentinel(xb0) || is_sentinel(xb1) || is_sentinel(xb2));
                         if (!__any_sync(kFull, wa || wb)) break;
-                        if (wa) { const double* x = P.out + 3 * (size_t) o.cd.z; o.xa0 = ld_relaxed(x); o.xa1 = ld_relaxed(x + 1); o.xa2 = ld_relaxed(x + 2); }
-                        if (wb) { const double* x = P.out + 3 * (size_t) o.cd.w; o.xb0 = ld_relaxed(x); o.xb1 = ld_relaxed(x + 1); o.xb2 = ld_relaxed(x + 2); }
                         if ((++spins & 255) == 0) {
                             // (~0.3 us per poll round: 2^24 rounds are seconds -- a deadlock, not a slow neighbour)
                             if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || spins > (1 << 24)) {
@@ -1266,19 +1279,19 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                     }
                 }
                 if (o.cd.z >= 0) {
-                    y0 -= fma(v[20], o.xa2, fma(v[19], o.xa1, v[18] * o.xa0));
-                    y1 -= fma(v[23], o.xa2, fma(v[22], o.xa1, v[21] * o.xa0));
-                    y2 -= fma(v[26], o.xa2, fma(v[25], o.xa1, v[24] * o.xa0));
+                    y0 -= fma(v[20], xa2, fma(v[19], xa1, v[18] * xa0));
+                    y1 -= fma(v[23], xa2, fma(v[22], xa1, v[21] * xa0));
+                    y2 -= fma(v[26], xa2, fma(v[25], xa1, v[24] * xa0));
                 }
                 if (o.cd.w >= 0) {
-                    y0 -= fma(v[11], o.xb2, fma(v[10], o.xb1, v[9] * o.xb0));
-                    y1 -= fma(v[14], o.xb2, fma(v[13], o.xb1, v[12] * o.xb0));
-                    y2 -= fma(v[17], o.xb2, fma(v[16], o.xb1, v[15] * o.xb0));
+                    y0 -= fma(v[11], xb2, fma(v[10], xb1, v[9] * xb0));
+                    y1 -= fma(v[14], xb2, fma(v[13], xb1, v[12] * xb0));
+                    y2 -= fma(v[17], xb2, fma(v[16], xb1, v[15] * xb0));
                 }
             }
             if (prof) { const long long c = clock64(); pc[2] += c - c0; c0 = c; }      // external rows
             const bool tr = TRACE && (flags & S2D_LEAD) && lane == 0;      // debugging aid: timeline of the part's steps
-            if (flags & S2D_SYNC) bar_sync_n((h.y >> 12) & 15, 32 * ((h.y >> 20) & 31));    // the previous step is complete
+            if (flags & S2D_SYNC) bar_sync_n(bar_in, bar_in_n);                        // the previous step is complete
             if (prof) {      // (bar.sync does not block at issue: a shared load behind it does)
                 if (ld_volatile_s32(hp + 9) == 12345) pc[5]++;
                 const long long c = clock64(); pc[1] += c - c0; c0 = c;                // waiting for the previous step
@@ -1290,8 +1303,8 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 if (st < 256) P.trace[8192 + 2 * (256 * part + st)] = globaltimer_ns();
             }
             // ---- dependent part
-            const double2 a0 = lds_f64x2(xy + 2 * d0), a1 = lds_f64x2(xy + 2 * d1), a2 = lds_f64x2(xy + 2 * d2);
-            const double b0 = lds_f64(z + d0), b1 = lds_f64(z + d1), b2 = lds_f64(z + d2);
+            const double2 a0 = lds_f64x2(ax0), a1 = lds_f64x2(ax1), a2 = lds_f64x2(ax2);
+            const double b0 = lds_f64(az0), b1 = lds_f64(az1), b2 = lds_f64(az2);
             if (prof) {      // the shared loads have landed
                 if (__double_as_longlong(a0.x + a1.x + a2.x + b0 + b1 + b2) == 0x7ff123456789abcdLL) pc[5]++;
                 const long long c = clock64(); pc[5] += c - c0; c0 = c;
@@ -1306,23 +1319,25 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             const double s1 = fma(v[23], b2, fma(v[22], a2.y, v[21] * a2.x));
             const double s2 = fma(v[26], b2, fma(v[25], a2.y, v[24] * a2.x));
             y0 = ((y0 - p0) - q0) - s0; y1 = ((y1 - p1) - q1) - s1; y2 = ((y2 - p2) - q2) - s2;
-            const bool store = (flags & S2D_LAST) && lane < cnt;
             if (prof) { if (__double_as_longlong(y0) == 0x7ff123456789abcdLL) pc[5]++; const long long c = clock64(); pc[3] += c - c0; c0 = c; }   // dependencies + fma
-            if (store) { sts_f64x2(xy + 2 * oc, y0, y1); sts_f64(z + oc, y2); }
-            if (flags & S2D_ARRIVE) bar_arrive_n((h.y >> 16) & 15, 32 * ((h.y >> 25) & 31));   // this warp's share of the step is in shared memory
+            if (store) { sts_f64x2(sx, y0, y1); sts_f64(sz, y2); }
+            if (flags & S2D_ARRIVE) bar_arrive_n(bar_out, bar_out_n);                  // this warp's share of the step is in shared memory
             if (store && (!TRACE || !(P.nowait & 4))) {
-                const size_t gi = 3 * (size_t) (LOWER ? h.x + lane : h.x - lane);
+                const int g0 = h.x & 0x3fffffff;
+                const size_t gi = 3 * (size_t) (LOWER ? g0 + lane : g0 - lane);
                 st_relaxed(P.out + gi, y0); st_relaxed(P.out + gi + 1, y1); st_relaxed(P.out + gi + 2, y2);
                 if (REARM) { P.rearm[gi] = sentinel(); P.rearm[gi + 1] = sentinel(); P.rearm[gi + 2] = sentinel(); }
             }
             if (prof) { const long long c = clock64(); pc[4] += c - c0; c0 = c; }      // stores, arrive
+            if ((flags & S2D_LEAD) && lane == 0) st_volatile_s32(hp + 11, ld_volatile_s32(hp + 11) + 1);      // steps of the part that have started
             // ---- operands of the next record of this warp: several steps ahead of their use
             if (i + 1 < nrec) {
                 const int j = (i + 1) & 31;
                 if (j == 0) { hb = hbn; hbn = i + 33 + lane < nrec ? __ldg(hdrs + i + 33 + lane) : hzero; }
                 h = header(j);
+                my_step += (int) (((unsigned) h.x >> 30) | (((unsigned) h.y >> 30) << 2));
                 fetch(h);
-                prefetch_l2(i + 2);
+                prefetch_l2(i + pfd, i + 1);
             }
         }
         if (prof && lane == 0) {

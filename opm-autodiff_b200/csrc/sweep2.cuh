@@ -27,7 +27,7 @@ struct S2StreamD { long long vals_off, code_off; int hdr_off, nrec; };
 struct S2BuildD { long long vals_off; int src_off, cnt, first, pad; };
 enum : int { S2D_FIRST = 1, S2D_LAST = 2, S2D_SYNC = 4, S2D_ARRIVE = 8, S2D_EXT = 16, S2D_LEAD = 32 };
 
-constexpr int kS2Header = 128;         // shared: [9] timeout seen, [10] steps traced
+constexpr int kS2Header = 128;         // shared: [9] timeout seen, [10] steps traced, [11] steps of the part that have started
 
 struct Sweep2Args {
     const S2PartD* parts;
@@ -103,7 +103,6 @@ template <bool LOWER>
 struct S2Ops {
     double2 v[LOWER ? 14 : 18];
     double r0, r1, r2;
-    double xa0, xa1, xa2, xb0, xb1, xb2;      // external dependencies of the row (slot 2, slot 1), polled with the operands
     int4 cd;
 };
 

@@ -33,9 +33,10 @@ constexpr int kS2Barriers = 15;        // named barriers 1..15: barrier 1 + l % 
 constexpr int kS2MaxWarps = 15;        // consumer warps of a CTA (<= kS2Barriers: a barrier is reused only after every warp has passed it)
 
 // record header (one int2):
-//   x  first p-space row of the record (rows x + q, lower sweep, or x - q, upper sweep)
+//   x  first p-space row of the record (rows x + q, lower sweep, or x - q, upper sweep), 30 bits | low two bits of `gap` << 30
+//      (gap = steps since the warp's previous record, at most 15: when to start polling external rows)
 //   y  rows (6 bits) | flags << 6 | barrier to wait on << 12 | barrier to arrive at << 16 | warps on the barrier waited on << 20 |
-//      warps on the barrier arrived at << 25
+//      warps on the barrier arrived at << 25 | high two bits of `gap` << 30
 // codes (one int4 per row): {d0 | d1 << 16, d2 | out << 16, extA, extB}
 //   d_j = 8 x window slot of dependency j (8 x window = the all-zero row: no dependency, or an external one), out = 8 x window
 //   slot of the result; extA / extB = p-space row of an EXTERNAL dependency (a row of another part, or of this part beyond the
@@ -60,7 +61,8 @@ struct Sweep2Plan {
     std::vector<int> stepPtr;         // nparts + 1 offsets into stepChunks
     long long nvals = 0;
     int npairs = 14;                  // value pairs per row: 14 (27 values + pad) lower, 18 (27 + 9) upper
-    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0;
+    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0, nOwnExternal = 0;
+    std::vector<std::pair<int, int>> partEdges;      // (owner part, reading part) of every external dependency that crosses parts (host only, statistics)
     int maxChunks = 0;
 };
 
@@ -73,6 +75,8 @@ inline int s2_pack(int cnt, int flags, int sync_id, int arrive_id, int sync_warp
     return cnt | (flags << 6) | (sync_id << 12) | (arrive_id << 16) | (sync_warps << 20) | (arrive_warps << 25);
 }
 inline int s2_cnt(int y) { return y & 63; }
+inline int s2_g0(int x) { return x & 0x3fffffff; }
+inline int s2_gap(int x, int y) { return (int) (((unsigned) x >> 30) | (((unsigned) y >> 30) << 2)); }
 inline int s2_flags(int y) { return (y >> 6) & 63; }
 
 namespace detail {
@@ -109,6 +113,7 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
         struct WarpStream { std::vector<int> hdr, codes; std::vector<S2Build> build; std::vector<std::vector<int>> src; long long vals = 0; };
         std::vector<WarpStream> ws((size_t) NCW);
         int base = 0;                                   // warp of chunk 0 of the current step
+        std::vector<int> lastStep(NCW, -1);             // step of the warp's previous record
         for (int st = 0; st < nsteps; ++st) {
             const int pos0 = stepPtr[st], n = stepPtr[st + 1] - pos0;
             const int nchunks = chunks_of(st);
@@ -133,7 +138,7 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
                         if (ps - pd <= slack) slot = pd & (W - 1);
                     }
                     if (slot >= 0) { win.emplace_back(8 * slot, sb); S.nWindow++; }
-                    else { ext.emplace_back(gd, sb); S.nExternal++; }
+                    else { ext.emplace_back(gd, sb); S.nExternal++; if (partOf[c] == p) S.nOwnExternal++; else S.partEdges.emplace_back(partOf[c], p); }
                 }
                 size_t iw = 0, ie = 0;
                 do {
@@ -193,8 +198,10 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
                     wsr.build.push_back(B);
                     wsr.src.push_back(std::move(src));
                     wsr.vals += 2LL * S.npairs * cnt;
-                    wsr.hdr.push_back(g0);
-                    wsr.hdr.push_back(s2_pack(cnt, flags, sync_id, arrive_id, sync_warps, arrive_warps));
+                    const int gap = std::min(15, st - lastStep[wv]);
+                    lastStep[wv] = st;
+                    wsr.hdr.push_back((int) ((unsigned) g0 | ((unsigned) (gap & 3) << 30)));
+                    wsr.hdr.push_back((int) ((unsigned) s2_pack(cnt, flags, sync_id, arrive_id, sync_warps, arrive_warps) | ((unsigned) (gap >> 2) << 30)));
                     S.nrecords++;
                 }
             }
@@ -343,7 +350,7 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                             throw std::runtime_error("emulate2: warp stream ended inside a step");
                         }
                         const int* h = S.hdrs.data() + 2 * (size_t) (R.hdr_off + c.rec);
-                        const int g0 = h[0], cnt = s2_cnt(h[1]), flags = s2_flags(h[1]);
+                        const int g0 = s2_g0(h[0]), cnt = s2_cnt(h[1]), flags = s2_flags(h[1]);
                         if (!first_rec && (flags & S2_SYNC)) throw std::runtime_error("emulate2: SYNC flag in the middle of a step");
                         if (cnt < 1 || cnt > 32) throw std::runtime_error("emulate2: bad row count");
                         first_rec = false;

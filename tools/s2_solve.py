@@ -8,10 +8,13 @@ s = synth.full_system(wl)
 from tests.helpers import bridge_wells
 for spec in sys.argv[2:] or [""]:
     be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
+    late = {}
     for kv in filter(None, spec.split(",")):
         k, v = kv.split("=")
-        be.set_option(k, float(v))
+        if k == "sweep_nowait": late[k] = float(v)
+        else: be.set_option(k, float(v))
     be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, bridge_wells(s.wells))
+    for k, v in late.items(): be.set_option(k, v)
     res = bridge.BdaResult()
     for _ in range(3): be.solve_resident(res)
     t0 = time.time()
