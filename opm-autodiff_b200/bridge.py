@@ -452,7 +452,7 @@ def sweep_schedule_check_host(rows, cols, parts=0, stage_bytes=0, window=0, seed
 
 
 SWEEP2_STAT_NAMES = ("parts", "lines", "strips", "records_L", "records_U", "multi_record_warp_steps_L", "window_deps_L", "external_deps_L",
-                     "own_external_deps_L", "mutual_part_pairs_L", "max_chunks_per_step", "consumer_warps")
+                     "multi_lane_records_L", "mutual_part_pairs_L", "max_chunks_per_step", "lanes_L")
 
 
 def sweep2_schedule_check_host(rows, cols, parts=0, window=0, ext_window=0, consumer_warps=0, helpers=0, groups=0, wg=0, seed=1,

@@ -227,7 +227,7 @@ struct Solver {
     int sweep_parts = 0, sweep_warps = 8, sweep_groups = 1, sweep_helpers = 2, sweep_slots = 2, sweep_stage_bytes = 0, sweep_window = 0, sweep_ext_window = 0, sweep_helper_sleep = 0;
     // round-2 sweeps (k_sweep2): consumer warps (G x WG per part), helper warps, forced group count / group width (0 = automatic)
     int sweep_v2 = 1, s2_cw = 15, s2_helpers = 1, s2_poll_lead = 15, s2_prefetch = 2;      // s2_helpers: warps beyond the consumers (they only work in the tails)
-    bool v2 = false;
+    bool v2 = false, s2_mlL = false, s2_mlU = false;      // s2_ml*: the sweep's schedule has rows that take several lanes
     Sweep2Plan L2, U2;
 
     cudaStream_t stream = nullptr;
@@ -433,7 +433,12 @@ struct Solver {
         const long long nnzb_in = nnz_ / 9;
         if (rows[Nb] != nnzb_in) throw std::runtime_error("rows[Nb] != nnz / 9");
         AnalysisOptions opt;
-        opt.parts = sweep_parts > 0 ? std::min(sweep_parts, 8 * num_sms) : num_sms;  // every CTA of a sweep must be resident (checked below)
+        // Parts of the sweeps (one CTA each, every CTA resident; checked below).  Automatic: an SM per part from ~270 k block rows;
+        // smaller systems take fewer parts of ~1800 rows -- every part boundary on the dependency path costs a hand-over through
+        // L2 (~1 us), a level inside a part 0.15-0.3 us (measured on B200: 27 k rows best with 16-24 parts, 44 k with 24, 110 k
+        // with 48-74, 262 k with 148; the round-1 kernel takes an SM per part at every size)
+        v2 = sweep_v2 != 0;
+        opt.parts = sweep_parts > 0 ? std::min(sweep_parts, 8 * num_sms) : (v2 ? std::max(8, std::min(num_sms, (int) ((Nb + 900) / 1800))) : num_sms);
         // Stage size of the sweeps' TMA ring.  A part's consumers start when its first stage has landed, so a part that is
         // only one or two stages long (Norne size: 80 KB of factor per part) neither overlaps load and compute nor hands its
         // face rows over early; large parts (C3: 2 MB) want the largest stage that fits (per-stage hand-shakes amortised).
@@ -447,7 +452,6 @@ struct Solver {
         }
         opt.stageBytes = stage_bytes;
         opt.window = sweep_window;
-        v2 = sweep_v2 != 0;
         opt.extWindow = sweep_ext_window > 0 ? sweep_ext_window : 512;
         opt.buildStreams = !v2;
         opt.warps = sweep_warps;
@@ -562,17 +566,19 @@ struct Solver {
             sweep_smem = std::max(need, tail);
             if (sweep_smem > smem_limit) throw std::runtime_error("value space of the triangular sweeps does not fit the shared memory");
             prep(k_sweep2<true, false>); prep(k_sweep2<true, true>); prep(k_sweep2<false, false>); prep(k_sweep2<false, true>);
-            prep(k_sweep2<true, false, -1, true>); prep(k_sweep2<true, true, -1, true>); prep(k_sweep2<false, false, -1, true>); prep(k_sweep2<false, true, -1, true>);
+            prep(k_sweep2<true, false, -1, true, true>); prep(k_sweep2<true, true, -1, true, true>); prep(k_sweep2<false, false, -1, true, true>); prep(k_sweep2<false, true, -1, true, true>);
+            prep(k_sweep2<true, false, -1, false, true>); prep(k_sweep2<true, true, -1, false, true>); prep(k_sweep2<false, false, -1, false, true>); prep(k_sweep2<false, true, -1, false, true>);
+            s2_mlL = L2.nMultiLaneRecords > 0; s2_mlU = U2.nMultiLaneRecords > 0;
             defer_ok = false;
             if (defer_x != 0) {
-                prep(k_sweep2<true, false, 3>);
+                prep(k_sweep2<true, false, 3>); prep(k_sweep2<true, false, 3, false, true>);
                 d_xSync.alloc(2);
                 CUDA_OK(cudaMemsetAsync(d_xSync.p, 0, sizeof(int) * 2, stream));
                 defer_ok = true;
             }
             fused_units = 0;
             if (want_fused) {
-                prep(k_sweep2<false, true, 1>); prep(k_sweep2<false, true, 2>);
+                prep(k_sweep2<false, true, 1>); prep(k_sweep2<false, true, 2>); prep(k_sweep2<false, true, 1, false, true>); prep(k_sweep2<false, true, 2, false, true>);
                 const b200::FusedPlan fp = b200::build_fused(Nb, an.prow, an.pcol, an.partPtr, an.flevPtr, an.flevRows, std::max(1, fuse_unit_slices) * (threads / 32 - 1));
                 fused_units = (int) fp.units.size() / 2;
                 up(d_fUnits, fp.units); up(d_fNeedPtr, fp.needPtr); up(d_fNeed, fp.need);
@@ -998,7 +1004,9 @@ struct Solver {
         const bool rearm = a.rearm != nullptr, trace = a.trace != nullptr;
         auto go = [&](auto kern) { launch_iter(kern, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a); };
         if (v2) {
-            if (trace) { if (rearm) go(k_sweep2<LOWER, true, -1, true>); else go(k_sweep2<LOWER, false, -1, true>); }
+            const bool ml = LOWER ? s2_mlL : s2_mlU;
+            if (trace) { if (rearm) go(k_sweep2<LOWER, true, -1, true, true>); else go(k_sweep2<LOWER, false, -1, true, true>); }
+            else if (ml) { if (rearm) go(k_sweep2<LOWER, true, -1, false, true>); else go(k_sweep2<LOWER, false, -1, false, true>); }
             else { if (rearm) go(k_sweep2<LOWER, true>); else go(k_sweep2<LOWER, false>); }
             return;
         }
@@ -1011,7 +1019,8 @@ struct Solver {
         int id = prof_begin(K_LOWER);
         SweepArgs a = sweep_args(true, rhs, out, nullptr, true);
         a.xu.x = d_x.p; a.xu.y = d_y.p; a.xu.sync = d_xSync.p; a.xu.n = N;
-        if (v2) launch_iter(k_sweep2<true, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2 && s2_mlL) launch_iter(k_sweep2<true, false, 3, false, true>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        else if (v2) launch_iter(k_sweep2<true, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         else launch_iter(k_sweep<true, false, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
@@ -1043,7 +1052,8 @@ struct Solver {
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
         a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
-        if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2 && s2_mlU) launch_iter(k_sweep2<false, true, MODE, false, true>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        else if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         else launch_iter(k_sweep<false, true, false, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
@@ -2052,8 +2062,8 @@ b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* 
             L.partEdges.erase(std::unique(L.partEdges.begin(), L.partEdges.end()), L.partEdges.end());
             long long mutual = 0;
             for (auto& e : L.partEdges) if (e.first < e.second && std::binary_search(L.partEdges.begin(), L.partEdges.end(), std::make_pair(e.second, e.first))) ++mutual;
-            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, L.nOwnExternal,
-                                     mutual, L.maxChunks, o2.consumerWarps};
+            const long long v[12] = {A.nparts, A.nlines, A.nstrips, L.nrecords, U.nrecords, L.nmulti, L.nWindow, L.nExternal, L.nMultiLaneRecords,
+                                     mutual, L.maxChunks, L.nLanes};
             memcpy(stats, v, sizeof v);
         }
         return B200_SUCCESS;

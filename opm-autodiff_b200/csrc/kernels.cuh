@@ -1149,7 +1149,9 @@ __global__ void __launch_bounds__(SPMV >= 0 ? kFusedMaxThreads : 896) k_sweep(co
 // SPMV as k_sweep: -1 sweep only, 1 / 2 go on with the SpMV that follows (fused_spmv_tail), 3 lower sweep + pending x update.
 constexpr int kS2Threads = 512;        // 15 consumer warps + an idle one (tails only) at 128 registers: the register file is handed out in
                                        // units that make 136 and 144 registers x 15 / 14 warps not fit (occupancy query: 0)
-template <bool LOWER, bool REARM, int SPMV = -1, bool TRACE = false>
+// ML: the schedule has rows that take several lanes (more than three dependencies: fault connections, wells folded into the
+// matrix); the other variant carries none of that code (its address masks, lane meta and shuffles cost 15 % on the 1 M-cell grid).
+template <bool LOWER, bool REARM, int SPMV = -1, bool TRACE = false, bool ML = false>
 __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
 {
     extern __shared__ __align__(128) unsigned char sweep_smem[];
@@ -1202,9 +1204,14 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                     if (!TRACE || !(P.nowait & 8)) o.v[k] = ldg_stream_f64x2(v);
                 o.cd = ldg_stream_s32x4(cp);
                 if ((hd.y & (S2D_FIRST << 6)) && (!TRACE || !(P.nowait & 16))) {
-                    const int g0 = hd.x & 0x3fffffff;
-                    const double* r = P.rhs + 3 * (size_t) (LOWER ? g0 + lane : g0 - lane);
-                    o.r0 = r[0]; o.r1 = r[1]; o.r2 = r[2];
+                    // (a record with rows that take several lanes: the row of the lane comes with the codes; its further lanes start from zero)
+                    const bool multi = ML && (hd.y & (S2D_MULTI << 6));
+                    const int meta = multi ? s2d_meta(o.cd) : 0;
+                    const int g0 = hd.x & 0x1fffffff, ord = multi ? (meta & 31) : lane;
+                    if (!(meta & (3 << 5))) {                                    // first lane of its row
+                        const double* r = P.rhs + 3 * (size_t) (LOWER ? g0 + ord : g0 - ord);
+                        o.r0 = r[0]; o.r1 = r[1]; o.r2 = r[2];
+                    } else { o.r0 = 0.0; o.r1 = 0.0; o.r2 = 0.0; }
                 }
             } else o.cd = make_int4(zcode | (zcode << 16), zcode, -1, -1);
             vp += (size_t) (2 * NP) * cnt;
@@ -1235,10 +1242,13 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             const int cnt = h.y & 63, flags = (h.y >> 6) & 63;
             // everything the dependent part needs besides the dependencies themselves is computed BEFORE the barrier: a lone warp
             // issues an instruction every 4-5 cycles, so every instruction between bar.sync and bar.arrive is on the level's chain
-            const unsigned d0 = (unsigned) o.cd.x & 0xffffu, d1 = (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & 0xffffu, oc = (unsigned) o.cd.y >> 16;
+            const unsigned cmask = ML ? 0xfff8u : 0xffffu;
+            const unsigned d0 = (unsigned) o.cd.x & cmask, d1 = ML ? ((unsigned) o.cd.x >> 16) & cmask : (unsigned) o.cd.x >> 16, d2 = (unsigned) o.cd.y & cmask, oc = (unsigned) o.cd.y >> 16;
             const unsigned ax0 = xy + 2 * d0, ax1 = xy + 2 * d1, ax2 = xy + 2 * d2, az0 = z + d0, az1 = z + d1, az2 = z + d2;
             const unsigned sx = xy + 2 * oc, sz = z + oc;
-            const bool store = (flags & S2D_LAST) && lane < cnt;
+            const bool multi = ML && (flags & S2D_MULTI);
+            const int meta = multi ? s2d_meta(o.cd) : 0;                       // rows that take several lanes: row, position and width of the lane
+            const bool store = (flags & S2D_LAST) && lane < cnt && !(meta & (3 << 5));
             const int bar_in = (h.y >> 12) & 15, bar_in_n = 32 * ((h.y >> 20) & 31), bar_out = (h.y >> 16) & 15, bar_out_n = 32 * ((h.y >> 25) & 31);
             const double* v = reinterpret_cast<const double*>(o.v);
             // start value: nothing here depends on another row of the part
@@ -1290,7 +1300,8 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 }
             }
             if (prof) { const long long c = clock64(); pc[2] += c - c0; c0 = c; }      // external rows
-            const bool tr = TRACE && (flags & S2D_LEAD) && lane == 0;      // debugging aid: timeline of the part's steps
+            const bool lead = (h.x >> 29) & 1;                              // this record counts the part's steps
+            const bool tr = TRACE && lead && lane == 0;                     // debugging aid: timeline of the part's steps
             if (flags & S2D_SYNC) bar_sync_n(bar_in, bar_in_n);                        // the previous step is complete
             if (prof) {      // (bar.sync does not block at issue: a shared load behind it does)
                 if (ld_volatile_s32(hp + 9) == 12345) pc[5]++;
@@ -1319,17 +1330,25 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
             const double s1 = fma(v[23], b2, fma(v[22], a2.y, v[21] * a2.x));
             const double s2 = fma(v[26], b2, fma(v[25], a2.y, v[24] * a2.x));
             y0 = ((y0 - p0) - q0) - s0; y1 = ((y1 - p1) - q1) - s1; y2 = ((y2 - p2) - q2) - s2;
+            if (multi && (flags & S2D_LAST)) {
+                // rows that take several lanes: add the partial sums of the row's lanes (pairs (0, 1) and (2, 3), then 0 += 2)
+                const int k = (meta >> 5) & 3, nsec = (meta >> 7) & 3;
+                double t0 = __shfl_down_sync(kFull, y0, 1), t1 = __shfl_down_sync(kFull, y1, 1), t2 = __shfl_down_sync(kFull, y2, 1);
+                if (!(k & 1) && k + 1 <= nsec) { y0 += t0; y1 += t1; y2 += t2; }
+                t0 = __shfl_down_sync(kFull, y0, 2); t1 = __shfl_down_sync(kFull, y1, 2); t2 = __shfl_down_sync(kFull, y2, 2);
+                if (k == 0 && nsec >= 2) { y0 += t0; y1 += t1; y2 += t2; }
+            }
             if (prof) { if (__double_as_longlong(y0) == 0x7ff123456789abcdLL) pc[5]++; const long long c = clock64(); pc[3] += c - c0; c0 = c; }   // dependencies + fma
             if (store) { sts_f64x2(sx, y0, y1); sts_f64(sz, y2); }
             if (flags & S2D_ARRIVE) bar_arrive_n(bar_out, bar_out_n);                  // this warp's share of the step is in shared memory
             if (store && (!TRACE || !(P.nowait & 4))) {
-                const int g0 = h.x & 0x3fffffff;
-                const size_t gi = 3 * (size_t) (LOWER ? g0 + lane : g0 - lane);
+                const int g0 = h.x & 0x1fffffff, ord = multi ? (meta & 31) : lane;
+                const size_t gi = 3 * (size_t) (LOWER ? g0 + ord : g0 - ord);
                 st_relaxed(P.out + gi, y0); st_relaxed(P.out + gi + 1, y1); st_relaxed(P.out + gi + 2, y2);
                 if (REARM) { P.rearm[gi] = sentinel(); P.rearm[gi + 1] = sentinel(); P.rearm[gi + 2] = sentinel(); }
             }
             if (prof) { const long long c = clock64(); pc[4] += c - c0; c0 = c; }      // stores, arrive
-            if ((flags & S2D_LEAD) && lane == 0) st_volatile_s32(hp + 11, ld_volatile_s32(hp + 11) + 1);      // steps of the part that have started
+            if (lead && lane == 0) st_volatile_s32(hp + 11, ld_volatile_s32(hp + 11) + 1);      // steps of the part that have started
             // ---- operands of the next record of this warp: several steps ahead of their use
             if (i + 1 < nrec) {
                 const int j = (i + 1) & 31;

@@ -25,7 +25,7 @@ namespace b200 {
 struct S2PartD { int ncw, nsteps, row0, nrows, stream0, pad0, pad1, pad2; };
 struct S2StreamD { long long vals_off, code_off; int hdr_off, nrec; };
 struct S2BuildD { long long vals_off; int src_off, cnt, first, pad; };
-enum : int { S2D_FIRST = 1, S2D_LAST = 2, S2D_SYNC = 4, S2D_ARRIVE = 8, S2D_EXT = 16, S2D_LEAD = 32 };
+enum : int { S2D_FIRST = 1, S2D_LAST = 2, S2D_SYNC = 4, S2D_ARRIVE = 8, S2D_EXT = 16, S2D_MULTI = 32 };
 
 constexpr int kS2Header = 128;         // shared: [9] timeout seen, [10] steps traced, [11] steps of the part that have started
 
@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(256) k_fill_stream2(const S2BuildD* __restrict
         for (int k = 0; k < NP; ++k) *reinterpret_cast<double2*>(out + k * ps) = make_double2(v[2 * k], v[2 * k + 1]);
     }
 }
+
+// meta bits of a lane (rows that take several lanes): row within the record (5 bits) | position within the row << 5 | further lanes << 7,
+// kept in the low three bits (always zero in a slot code) of the three dependency codes
+__device__ __forceinline__ int s2d_meta(const int4& cd) { return (cd.x & 7) | ((cd.x >> 13) & 0x38) | ((cd.y & 7) << 6); }
 
 // the operands of one record in registers
 template <bool LOWER>

@@ -33,16 +33,26 @@ constexpr int kS2Barriers = 15;        // named barriers 1..15: barrier 1 + l % 
 constexpr int kS2MaxWarps = 15;        // consumer warps of a CTA (<= kS2Barriers: a barrier is reused only after every warp has passed it)
 
 // record header (one int2):
-//   x  first p-space row of the record (rows x + q, lower sweep, or x - q, upper sweep), 30 bits | low two bits of `gap` << 30
-//      (gap = steps since the warp's previous record, at most 15: when to start polling external rows)
+//   x  first p-space row of the record (rows x + q, lower sweep, or x - q, upper sweep), 29 bits | lead << 29 (the warp's first
+//      record of the step, chunk 0: it counts the part's steps) | low two bits of `gap` << 30 (gap = steps since the warp's
+//      previous record, at most 15: the warp tracks the step of its record with it)
 //   y  rows (6 bits) | flags << 6 | barrier to wait on << 12 | barrier to arrive at << 16 | warps on the barrier waited on << 20 |
 //      warps on the barrier arrived at << 25 | high two bits of `gap` << 30
-// codes (one int4 per row): {d0 | d1 << 16, d2 | out << 16, extA, extB}
+// codes (one int4 per LANE): {d0 | d1 << 16, d2 | out << 16, extA, extB}
 //   d_j = 8 x window slot of dependency j (8 x window = the all-zero row: no dependency, or an external one), out = 8 x window
 //   slot of the result; extA / extB = p-space row of an EXTERNAL dependency (a row of another part, or of this part beyond the
-//   window) whose factor block sits in slot 2 / slot 1 of the record, -1 = none
-enum : int { S2_FIRST = 1, S2_LAST = 2, S2_SYNC = 4, S2_ARRIVE = 8, S2_EXT = 16, S2_LEAD = 32 };
-// S2_EXT: some row of the record has an external dependency; S2_LEAD: the warp's first record of the step and chunk 0 (tracing)
+//   window) whose factor block sits in slot 2 / slot 1 of the lane, -1 = none;
+//   the low three bits of d0, d1, d2 (always zero in a slot code) carry meta bits 0-2, 3-5, 6-8:
+//   meta = row of the lane within the record (5 bits) | position of the lane within its row << 5 | further lanes of the row << 7.
+// A block row with more than three dependencies (or more than two external ones) takes SEVERAL LANES of the record (at most
+// kS2RowLanes): every lane subtracts its own three blocks from its own start value (the rhs for the first lane, zero for the
+// others) and the partial sums are added with two warp shuffles before the store.  (Continuation records -- the first version
+// -- put the second record's operand fetch, a full memory round trip, on the chain of every level that had such a row: 1.2 us
+// instead of 0.25 us per level on the Norne-size system with its fault connections.)  Rows with more than 3 x kS2RowLanes
+// dependencies still take continuation records (every lane keeps its partial sum in registers between them).
+constexpr int kS2RowLanes = 4;
+enum : int { S2_FIRST = 1, S2_LAST = 2, S2_SYNC = 4, S2_ARRIVE = 8, S2_EXT = 16, S2_MULTI = 32 };
+// S2_EXT: some lane of the record has an external dependency; S2_MULTI: some row of the record takes several lanes
 
 struct S2Part { int ncw, nsteps, row0, nrows, stream0, pad0, pad1, pad2; };
 struct S2Stream { long long vals_off;      // doubles into the sweep's value stream
@@ -54,14 +64,14 @@ struct Sweep2Plan {
     std::vector<S2Part> parts;
     std::vector<S2Stream> streams;
     std::vector<int> hdrs;            // 2 per record
-    std::vector<int> codes;           // 4 per row of a record
+    std::vector<int> codes;           // 4 per lane of a record
     std::vector<S2Build> build;       // one per record
-    std::vector<int> src;             // per record: 3 x cnt dependency blocks (p-space block index, -1 none), then cnt pivot blocks (upper)
-    std::vector<int> stepChunks;      // host only (emulation, statistics): per part nsteps entries, 32-row chunks of every step
+    std::vector<int> src;             // per record: 3 x cnt dependency blocks (p-space block index, -1 none), then cnt pivot blocks (upper); cnt = lanes
+    std::vector<int> stepChunks;      // host only (emulation, statistics): per part nsteps entries, chunks (<= 32 lanes) of every step
     std::vector<int> stepPtr;         // nparts + 1 offsets into stepChunks
     long long nvals = 0;
     int npairs = 14;                  // value pairs per row: 14 (27 values + pad) lower, 18 (27 + 9) upper
-    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0, nOwnExternal = 0;
+    long long nrecords = 0, nmulti = 0, nExternal = 0, nWindow = 0, nOwnExternal = 0, nMultiLaneRecords = 0, nLanes = 0;
     std::vector<std::pair<int, int>> partEdges;      // (owner part, reading part) of every external dependency that crosses parts (host only, statistics)
     int maxChunks = 0;
 };
@@ -75,22 +85,28 @@ inline int s2_pack(int cnt, int flags, int sync_id, int arrive_id, int sync_warp
     return cnt | (flags << 6) | (sync_id << 12) | (arrive_id << 16) | (sync_warps << 20) | (arrive_warps << 25);
 }
 inline int s2_cnt(int y) { return y & 63; }
-inline int s2_g0(int x) { return x & 0x3fffffff; }
+inline int s2_g0(int x) { return x & 0x1fffffff; }
+inline int s2_lead(int x) { return (x >> 29) & 1; }
 inline int s2_gap(int x, int y) { return (int) (((unsigned) x >> 30) | (((unsigned) y >> 30) << 2)); }
 inline int s2_flags(int y) { return (y >> 6) & 63; }
+inline int s2_meta(const int* cd) { return (cd[0] & 7) | (((cd[0] >> 16) & 7) << 3) | ((cd[1] & 7) << 6); }
+inline int s2_ord(int meta) { return meta & 31; }
+inline int s2_k(int meta) { return (meta >> 5) & 3; }
+inline int s2_nsec(int meta) { return (meta >> 7) & 3; }
 
 namespace detail {
 
-// The steps (level sets) of a part are cut into CHUNKS of <= 32 rows (a lane per row); the chunks of consecutive steps go round
-// robin to the consumer warps, so a warp that has finished its chunk of step l fetches the operands of its next chunk -- of step
-// l + (warps / chunks per step) -- at once, that many step times before they are needed.  A warp has two records of the same
-// step only when a step has more chunks than there are warps, or for rows with more than three dependencies / more than two
-// external ones (continuation records; the partial sums stay in registers).
+// The steps (level sets) of a part are cut into CHUNKS of <= 32 lanes (a lane per row and three dependencies); the chunks of
+// consecutive steps go round robin to the consumer warps, so a warp that has finished its chunk of step l fetches the operands
+// of its next chunk -- of step l + (warps / chunks per step) -- at once, that many step times before they are needed.  A warp
+// has two records of the same step only when a step has more chunks than there are warps, or for rows with more than
+// 3 x kS2RowLanes dependencies (continuation records; the partial sums stay in registers).
 inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, const std::vector<int>& glev, const std::vector<int>& partOf,
                          bool lower, const Sweep2Options& opt, Sweep2Plan& S)
 {
     const int W = A.window, zcode = 8 * W;
     if (8LL * (W + 1) > 65535) throw std::runtime_error("sweep window exceeds the 16-bit slot codes");
+    if (A.Nb >= (1 << 29)) throw std::runtime_error("too many block rows for the sweep record headers");
     const int NCW = std::max(1, std::min(opt.consumerWarps, kS2MaxWarps));
     S.npairs = lower ? 14 : 18;
     S.parts.resize(A.nparts);
@@ -104,7 +120,51 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
         for (int pos = 1; pos <= nrows; ++pos)
             if (pos == nrows || glev[A.perm[g_of(pos)]] != glev[A.perm[g_of(pos - 1)]]) stepPtr.push_back(pos);
         const int nsteps = (int) stepPtr.size() - 1;
-        auto chunks_of = [&](int st) { return (stepPtr[st + 1] - stepPtr[st] + 31) / 32; };
+        // pass 0: the dependencies of every row, grouped three to a lane (an external dependency sits in slot 2 of its lane; the order
+        // in which the contributions of a row are subtracted is free), and the chunks (<= 32 lanes, whole rows) of every step
+        struct Group { int code[3], src[3], ext[2]; };
+        struct RowPlan { std::vector<Group> groups; int lanes, passes; };
+        std::vector<RowPlan> rplan(nrows);
+        for (int ps = 0; ps < nrows; ++ps) {
+            const int gq = g_of(ps), r = A.perm[gq];
+            std::vector<std::pair<int, int>> win, ext;          // (slot code | p-row, source block)
+            for (int k = rows[r]; k < rows[r + 1]; ++k) {
+                const int c = cols[k];
+                if (!(lower ? c < r : c > r)) continue;
+                const int gd = A.iperm[c], sb = A.prow[gq] + (k - rows[r]);
+                int slot = -1;
+                if (partOf[c] == p) {
+                    const int pd = lower ? gd - row0 : row0 + nrows - 1 - gd;
+                    if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
+                    if (ps - pd <= slack) slot = pd & (W - 1);
+                }
+                if (slot >= 0) { win.emplace_back(8 * slot, sb); S.nWindow++; }
+                else { ext.emplace_back(gd, sb); S.nExternal++; if (partOf[c] == p) S.nOwnExternal++; else S.partEdges.emplace_back(partOf[c], p); }
+            }
+            RowPlan& R = rplan[ps];
+            size_t iw = 0, ie = 0;
+            do {
+                Group g;
+                for (int j = 0; j < 3; ++j) { g.code[j] = zcode; g.src[j] = -1; }
+                g.ext[0] = g.ext[1] = -1;
+                int free_slots = 3;
+                if (ie < ext.size()) { g.ext[0] = ext[ie].first; g.src[2] = ext[ie].second; ++ie; free_slots = 2; }
+                if (ie < ext.size()) { g.ext[1] = ext[ie].first; g.src[1] = ext[ie].second; ++ie; free_slots = 1; }
+                for (int j = 0; j < free_slots && iw < win.size(); ++j, ++iw) { g.code[j] = win[iw].first; g.src[j] = win[iw].second; }
+                R.groups.push_back(g);
+            } while (iw < win.size() || ie < ext.size());
+            R.lanes = std::min(kS2RowLanes, (int) R.groups.size());
+            R.passes = ((int) R.groups.size() + R.lanes - 1) / R.lanes;
+        }
+        std::vector<std::vector<int>> stepChunkStart(nsteps);      // first row (position) of every chunk of the step
+        for (int st = 0; st < nsteps; ++st) {
+            int lanes = 0;
+            for (int ps = stepPtr[st]; ps < stepPtr[st + 1]; ++ps) {
+                if (stepChunkStart[st].empty() || lanes + rplan[ps].lanes > 32) { stepChunkStart[st].push_back(ps); lanes = 0; }
+                lanes += rplan[ps].lanes;
+            }
+        }
+        auto chunks_of = [&](int st) { return (int) stepChunkStart[st].size(); };
         auto warps_of = [&](int st) { return std::min(chunks_of(st), NCW); };
         S2Part& P = S.parts[p];
         P.ncw = NCW; P.nsteps = nsteps; P.row0 = row0; P.nrows = nrows; P.pad0 = P.pad1 = P.pad2 = 0;
@@ -115,92 +175,66 @@ inline void build_sweep2(const Analysis& A, const int* rows, const int* cols, co
         int base = 0;                                   // warp of chunk 0 of the current step
         std::vector<int> lastStep(NCW, -1);             // step of the warp's previous record
         for (int st = 0; st < nsteps; ++st) {
-            const int pos0 = stepPtr[st], n = stepPtr[st + 1] - pos0;
             const int nchunks = chunks_of(st);
             S.stepChunks.push_back(nchunks);
             S.maxChunks = std::max(S.maxChunks, nchunks);
-            // pass 1: dependencies of every row of the step, packed into passes of three slots: an external dependency goes to
-            // slot 2, a second one to slot 1, dependencies inside the window fill what is left (the order in which the
-            // contributions of a row are subtracted is free)
-            struct Pass { int code[3], src[3], ext[2]; };
-            std::vector<std::vector<Pass>> rp(n);
-            for (int q = 0; q < n; ++q) {
-                const int ps = pos0 + q, gq = g_of(ps), r = A.perm[gq];
-                std::vector<std::pair<int, int>> win, ext;          // (slot code | p-row, source block)
-                for (int k = rows[r]; k < rows[r + 1]; ++k) {
-                    const int c = cols[k];
-                    if (!(lower ? c < r : c > r)) continue;
-                    const int gd = A.iperm[c], sb = A.prow[gq] + (k - rows[r]);
-                    int slot = -1;
-                    if (partOf[c] == p) {
-                        const int pd = lower ? gd - row0 : row0 + nrows - 1 - gd;
-                        if (pd >= ps) throw std::runtime_error("internal: dependency not earlier in processing order");
-                        if (ps - pd <= slack) slot = pd & (W - 1);
-                    }
-                    if (slot >= 0) { win.emplace_back(8 * slot, sb); S.nWindow++; }
-                    else { ext.emplace_back(gd, sb); S.nExternal++; if (partOf[c] == p) S.nOwnExternal++; else S.partEdges.emplace_back(partOf[c], p); }
-                }
-                size_t iw = 0, ie = 0;
-                do {
-                    Pass ps2;
-                    for (int j = 0; j < 3; ++j) { ps2.code[j] = zcode; ps2.src[j] = -1; }
-                    ps2.ext[0] = ps2.ext[1] = -1;
-                    bool used[3] = {false, false, false};
-                    if (ie < ext.size()) { ps2.ext[0] = ext[ie].first; ps2.src[2] = ext[ie].second; used[2] = true; ++ie; }
-                    if (ie < ext.size()) { ps2.ext[1] = ext[ie].first; ps2.src[1] = ext[ie].second; used[1] = true; ++ie; }
-                    for (int j = 0; j < 3 && iw < win.size(); ++j)
-                        if (!used[j]) { ps2.code[j] = win[iw].first; ps2.src[j] = win[iw].second; ++iw; }
-                    rp[q].push_back(ps2);
-                } while (iw < win.size() || ie < ext.size());
-            }
-            // pass 2: records.  Chunk c of the step belongs to warp (base + c) % NCW.
             const int sync_id = 1 + (st + kS2Barriers - 1) % kS2Barriers, arrive_id = 1 + st % kS2Barriers;
             const int sync_warps = st > 0 ? warps_of(st - 1) + warps_of(st) : 0;
             const int arrive_warps = st < nsteps - 1 ? warps_of(st) + warps_of(st + 1) : 0;
             std::vector<std::vector<std::pair<int, int>>> recs(NCW);     // per warp: (chunk, pass)
-            std::vector<int> npass(nchunks, 1);
+            std::vector<int> npass(nchunks, 1), chunkEnd(nchunks);
             for (int c = 0; c < nchunks; ++c) {
-                const int cnt = std::min(32, n - 32 * c);
-                for (int q = 0; q < cnt; ++q) npass[c] = std::max(npass[c], (int) rp[32 * c + q].size());
-                for (int ps = 0; ps < npass[c]; ++ps) recs[(base + c) % NCW].emplace_back(c, ps);
+                chunkEnd[c] = c + 1 < nchunks ? stepChunkStart[st][c + 1] : stepPtr[st + 1];
+                for (int ps = stepChunkStart[st][c]; ps < chunkEnd[c]; ++ps) npass[c] = std::max(npass[c], rplan[ps].passes);
+                for (int pz = 0; pz < npass[c]; ++pz) recs[(base + c) % NCW].emplace_back(c, pz);
             }
             for (int wv = 0; wv < NCW; ++wv) {
                 WarpStream& wsr = ws[wv];
                 const int nr = (int) recs[wv].size();
                 if (nr > 1) S.nmulti++;
                 for (int t = 0; t < nr; ++t) {
-                    const int c = recs[wv][t].first, ps = recs[wv][t].second;
-                    const int cnt = std::min(32, n - 32 * c);
+                    const int c = recs[wv][t].first, pz = recs[wv][t].second;
+                    const int ps0 = stepChunkStart[st][c], ps1 = chunkEnd[c];
+                    int cnt = 0;
+                    for (int ps = ps0; ps < ps1; ++ps) cnt += rplan[ps].lanes;
                     int flags = 0;
                     if (t == 0 && st > 0) flags |= S2_SYNC;
                     if (t == nr - 1 && st < nsteps - 1) flags |= S2_ARRIVE;
-                    if (ps == 0) flags |= S2_FIRST;
-                    if (ps == npass[c] - 1) flags |= S2_LAST;
-                    if (t == 0 && c == 0) flags |= S2_LEAD;
-                    const int g0 = g_of(pos0 + 32 * c);
+                    if (pz == 0) flags |= S2_FIRST;
+                    if (pz == npass[c] - 1) flags |= S2_LAST;
+                    const int g0 = g_of(ps0);
                     S2Build B{};
-                    B.vals_off = wsr.vals; B.cnt = cnt; B.first = ps == 0; B.src_off = 0;
+                    B.vals_off = wsr.vals; B.cnt = cnt; B.first = pz == 0; B.src_off = 0;
                     std::vector<int> src((size_t) (lower ? 3 : 4) * cnt, -1);
-                    for (int q = 0; q < cnt; ++q) {
-                        Pass pz;
-                        for (int j = 0; j < 3; ++j) { pz.code[j] = zcode; pz.src[j] = -1; }
-                        pz.ext[0] = pz.ext[1] = -1;
-                        const Pass& R = ps < (int) rp[32 * c + q].size() ? rp[32 * c + q][ps] : pz;
-                        for (int j = 0; j < 3; ++j) src[(size_t) j * cnt + q] = R.src[j];
-                        if (R.ext[0] >= 0) flags |= S2_EXT;
-                        const int outc = 8 * ((pos0 + 32 * c + q) & (W - 1));
-                        wsr.codes.push_back(R.code[0] | (R.code[1] << 16));
-                        wsr.codes.push_back(R.code[2] | (outc << 16));
-                        wsr.codes.push_back(R.ext[0]);
-                        wsr.codes.push_back(R.ext[1]);
-                        if (!lower) src[(size_t) 3 * cnt + q] = A.pdiag[g_of(pos0 + 32 * c + q)];
+                    for (int ps = ps0; ps < ps1; ++ps) if (rplan[ps].lanes > 1) flags |= S2_MULTI;
+                    int lane = 0;
+                    for (int ps = ps0; ps < ps1; ++ps) {
+                        const RowPlan& R = rplan[ps];
+                        for (int k = 0; k < R.lanes; ++k, ++lane) {
+                            Group gz;
+                            for (int j = 0; j < 3; ++j) { gz.code[j] = zcode; gz.src[j] = -1; }
+                            gz.ext[0] = gz.ext[1] = -1;
+                            const int gi = pz * R.lanes + k;
+                            const Group& Gr = gi < (int) R.groups.size() ? R.groups[gi] : gz;
+                            for (int j = 0; j < 3; ++j) src[(size_t) j * cnt + lane] = Gr.src[j];
+                            if (Gr.ext[0] >= 0) flags |= S2_EXT;
+                            const int outc = k == 0 ? 8 * (ps & (W - 1)) : zcode;
+                            const int meta = (flags & S2_MULTI) ? (ps - ps0) | (k << 5) | ((R.lanes - 1) << 7) : 0;      // (a lane per row otherwise: nothing to say)
+                            wsr.codes.push_back((Gr.code[0] | (meta & 7)) | ((Gr.code[1] | ((meta >> 3) & 7)) << 16));
+                            wsr.codes.push_back((Gr.code[2] | ((meta >> 6) & 7)) | (outc << 16));
+                            wsr.codes.push_back(Gr.ext[0]);
+                            wsr.codes.push_back(Gr.ext[1]);
+                            if (!lower) src[(size_t) 3 * cnt + lane] = A.pdiag[g_of(ps)];
+                        }
                     }
+                    if (flags & S2_MULTI) S.nMultiLaneRecords++;
+                    S.nLanes += cnt;
                     wsr.build.push_back(B);
                     wsr.src.push_back(std::move(src));
                     wsr.vals += 2LL * S.npairs * cnt;
                     const int gap = std::min(15, st - lastStep[wv]);
                     lastStep[wv] = st;
-                    wsr.hdr.push_back((int) ((unsigned) g0 | ((unsigned) (gap & 3) << 30)));
+                    wsr.hdr.push_back((int) ((unsigned) g0 | ((unsigned) (t == 0 && c == 0) << 29) | ((unsigned) (gap & 3) << 30)));
                     wsr.hdr.push_back((int) ((unsigned) s2_pack(cnt, flags, sync_id, arrive_id, sync_warps, arrive_warps) | ((unsigned) (gap >> 2) << 30)));
                     S.nrecords++;
                 }
@@ -356,26 +390,32 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                         first_rec = false;
                         const double* v = vals.data() + c.vals;
                         const int* cd = S.codes.data() + 4 * (size_t) c.code;
+                        bool multi = false;
                         for (int q = 0; q < cnt; ++q) {
-                            const int gq = lower ? g0 + q : g0 - q;
+                            const int meta = s2_meta(cd + 4 * q), ord = (flags & S2_MULTI) ? s2_ord(meta) : q, k = s2_k(meta), nsec = s2_nsec(meta);
+                            if (!(flags & S2_MULTI) && meta) throw std::runtime_error("emulate2: lane meta in a record without multi-lane rows");
+                            if (k > nsec || nsec >= kS2RowLanes || (k > 0 && (q == 0 || s2_meta(cd + 4 * (q - 1)) != ((meta & ~(3 << 5)) | ((k - 1) << 5)))))
+                                throw std::runtime_error("emulate2: bad lane meta");
+                            if (nsec > 0) multi = true;
+                            const int gq = lower ? g0 + ord : g0 - ord;
                             if (gq < P.row0 || gq >= P.row0 + P.nrows) throw std::runtime_error("emulate2: row outside the part");
                             double acc[3];
                             if (!(flags & S2_FIRST)) for (int e = 0; e < 3; ++e) acc[e] = c.carry[q][e];
+                            else if (k > 0) for (int e = 0; e < 3; ++e) acc[e] = 0.0;
                             else if (lower) for (int e = 0; e < 3; ++e) acc[e] = rhs[3 * (size_t) gq + e];
                             else for (int cc = 0; cc < 3; ++cc) {
                                 acc[cc] = 0.0;
                                 for (int e = 0; e < 3; ++e) acc[cc] += v[s2_vidx(27 + 3 * cc + e, q, cnt)] * rhs[3 * (size_t) gq + e];
                             }
                             // external dependencies: slot 2 (extA), slot 1 (extB), straight from the result vector
+                            const int d[3] = {cd[4 * q] & 0xfff8, (cd[4 * q] >> 16) & 0xfff8, cd[4 * q + 1] & 0xfff8};
                             for (int j = 0; j < 2; ++j) {
                                 const int er = cd[4 * q + 2 + j], slot = 2 - j;
                                 if (er < 0) continue;
-                                const int dcode = slot == 2 ? (cd[4 * q + 1] & 0xffff) : ((cd[4 * q] >> 16) & 0xffff);
-                                if (dcode != 8 * W) throw std::runtime_error("emulate2: slot of an external dependency does not point at the zero row");
+                                if (d[slot] != 8 * W) throw std::runtime_error("emulate2: slot of an external dependency does not point at the zero row");
                                 for (int cc = 0; cc < 3; ++cc)
                                     for (int e = 0; e < 3; ++e) acc[cc] -= v[s2_vidx(9 * slot + 3 * cc + e, q, cnt)] * out[3 * (size_t) er + e];
                             }
-                            const int d[3] = {cd[4 * q] & 0xffff, (cd[4 * q] >> 16) & 0xffff, cd[4 * q + 1] & 0xffff};
                             for (int j = 0; j < 3; ++j) {
                                 if (d[j] % 8 || d[j] / 8 > W) throw std::runtime_error("emulate2: bad dependency code");
                                 const double* x = T.xs.data() + 3 * (size_t) (d[j] / 8);
@@ -387,14 +427,32 @@ inline bool emulate_sweep2(const Analysis& A, const Sweep2Plan& S, bool lower, c
                             }
                             for (int e = 0; e < 3; ++e) c.carry[q][e] = acc[e];
                         }
-                        // stores happen after every row of the record has read its dependencies (the kernel: all lanes in lock step)
-                        if (flags & S2_LAST)
+                        if (multi != ((flags & S2_MULTI) != 0)) throw std::runtime_error("emulate2: MULTI flag mismatch");
+                        // stores happen after every lane of the record has read its dependencies (the kernel: all lanes in lock step);
+                        // the lanes of a row add their partial sums as the kernel's two shuffle rounds do
+                        if (flags & S2_LAST) {
+                            double fin[32][3];
+                            for (int q = 0; q < cnt; ++q) for (int e = 0; e < 3; ++e) fin[q][e] = c.carry[q][e];
+                            for (int q = 0; q < cnt; ++q) {            // round 1: (0, 1), (2, 3)
+                                const int meta = s2_meta(cd + 4 * q), k = s2_k(meta), nsec = s2_nsec(meta);
+                                if (!(k & 1) && k + 1 <= nsec) for (int e = 0; e < 3; ++e) fin[q][e] += c.carry[q + 1][e];
+                            }
+                            for (int q = 0; q < cnt; ++q) {            // round 2: 0 += 2
+                                const int meta = s2_meta(cd + 4 * q), k = s2_k(meta), nsec = s2_nsec(meta);
+                                if (k == 0 && nsec >= 2) {
+                                    const int m2 = s2_meta(cd + 4 * (q + 2)), k2 = s2_k(m2), n2 = s2_nsec(m2);
+                                    for (int e = 0; e < 3; ++e) fin[q][e] += c.carry[q + 2][e] + ((!(k2 & 1) && k2 + 1 <= n2) ? c.carry[q + 3][e] : 0.0);
+                                }
+                            }
                             for (int q = 0; q < cnt; ++q) {
-                                const int gq = lower ? g0 + q : g0 - q;
+                                const int meta = s2_meta(cd + 4 * q), ord = (flags & S2_MULTI) ? s2_ord(meta) : q, k = s2_k(meta);
+                                if (k != 0) continue;
+                                const int gq = lower ? g0 + ord : g0 - ord;
                                 const int oc = (cd[4 * q + 1] >> 16) & 0xffff;
                                 if (oc % 8 || oc / 8 >= W) throw std::runtime_error("emulate2: bad result slot");
-                                for (int e = 0; e < 3; ++e) { T.xs[(size_t) 3 * (oc / 8) + e] = c.carry[q][e]; out[3 * (size_t) gq + e] = c.carry[q][e]; }
+                                for (int e = 0; e < 3; ++e) { T.xs[(size_t) 3 * (oc / 8) + e] = fin[q][e]; out[3 * (size_t) gq + e] = fin[q][e]; }
                             }
+                        }
                         c.vals += 2LL * NP * cnt; c.code += cnt; c.rec++;
                         if (st == P.nsteps - 1) {
                             if (flags & S2_ARRIVE) throw std::runtime_error("emulate2: ARRIVE flag on the last step");

@@ -122,7 +122,7 @@ def test_round2_emulated_sweeps_match_sequential_substitution(built, shape, part
     err, st = bridge.sweep2_schedule_check_host(rows, cols, parts, window, ext, cw, helpers, groups, wg, seed=3, relax=0.9)
     assert err < 1e-11
     assert 1 <= st["parts"] <= max(1, parts)
-    assert st["consumer_warps"] == (min(cw, 15) if cw else 15)
+    assert st["lanes_L"] >= len(rows) - 1
     assert st["window_deps_L"] + st["external_deps_L"] == (len(cols) - (len(rows) - 1)) // 2
 
 

@@ -1,0 +1,17 @@
+import sys, time
+sys.path.insert(0, '/root/repo')
+from opm_autodiff_b200 import bridge, synth
+for shape in [(48,48,48),(64,64,64),(30,30,30)]:
+    s = synth.small(*shape)
+    for parts in (16, 24, 37, 48, 74, 100, 148):
+        be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
+        be.set_option("sweep_parts", parts)
+        be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
+        res = bridge.BdaResult()
+        for _ in range(2): be.solve_resident(res)
+        t0 = time.time()
+        for _ in range(5): be.solve_resident(res)
+        dt = (time.time() - t0) / 5
+        lo = 1e3 * be.time_kernel("ilu_lower", 10, False)[0]
+        print("%s Nb %d parts %3d: %.2f ms per solve, it %.1f, lower %.1f us" % (shape, s.Nb, parts, dt*1e3, res.it, lo), flush=True)
+        del be
