@@ -339,6 +339,15 @@ class B200SolverBackend:
         self._chk(lib().b200_well_apply(self._h, np.ascontiguousarray(x, dtype=np.float64).reshape(-1), y))
         return y
 
+    def host_register(self, arr: np.ndarray) -> None:
+        """Page-lock a caller-owned array (matrix values, right-hand side, solution vector) for the copies of solve_system /
+        get_result; the caller keeps it alive until host_unregister or the solver is destroyed (b200_host_register)."""
+        assert arr.flags["C_CONTIGUOUS"]
+        self._chk(lib().b200_host_register(self._h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray) -> None:
+        self._chk(lib().b200_host_unregister(self._h, arr.ctypes.data_as(C.c_void_p)))
+
     def ilu0_factorize(self) -> SolverStatus:
         st = lib().b200_ilu0_factorize(self._h)
         if st == SolverStatus.BDA_SOLVER_UNKNOWN_ERROR:

@@ -397,6 +397,15 @@ class DistSolver:
             bridge.WellContributions.from_arrays(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv)
         self.N = 3 * ls.n_owned
         self.nnz = 9 * ls.nnzb
+        self._registered = []
+
+    def register_host_buffers(self, x: Optional[np.ndarray] = None) -> None:
+        """Page-lock the slab's values and right-hand side (and the caller's solution vector): what the glue code of a Flow
+        rank does once, since those buffers live as long as the simulator (b200_host_register)."""
+        for a in (self.ls.vals, self.ls.b, x):
+            if a is not None and a.size:
+                self.be.host_register(a)
+                self._registered.append(a)
 
     def solve_system(self, res=None):
         res = res or self.bridge.BdaResult()
