@@ -67,7 +67,12 @@ def _rank_main(rank, world, port, shape, faults, out, blocks=False):
         td.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,faults", [(2, (12, 10, 8), ((6, 1),)), (4, (9, 7, 12), ())])
+# (tiny slabs of 2-4 planes, then realistic ones: 16 planes per rank at 40 x 36 x 32 / 2, 12 at 48^3 / 4, 8 at 64^3 / 8,
+# wells inside the slabs, against the oracle's own partitioned solve = the reference's `mpirun -np N` semantics,
+# PreconditionerFactory.hpp:237-252, WellOperators.hpp:200-214)
+@pytest.mark.parametrize("world,shape,faults", [(2, (12, 10, 8), ((6, 1),)), (4, (9, 7, 12), ()),
+                                                (2, (40, 36, 32), ((20, 1),)), (4, (48, 48, 48), ()), (8, (64, 64, 64), ()),
+                                                (8, (20, 16, 24), ((9, 1),))])
 def test_multi_gpu_solve_matches_partitioned_oracle(mods, world, shape, faults):
     bridge, dist, synth, oracle = mods
     import torch
