@@ -691,13 +691,11 @@ struct Solver {
     // Multisegment wells: everything the two apply kernels need, in one piece (persistent device buffers).
     void upload_mswells(const Wells* w)
     {
-        const bool had = nms > 0;
         nms = 0; ms_blocks = 0; ms_rows = 0; ms_ncells = 0; ms_dinv_entries = 0;
-        if (had) ++ms_epoch;
-        if (!w || w->ms.empty()) return;
+        if (!w || w->ms.empty()) return;       // (the iteration graph's signature carries the well count)
         if (dist.enabled && dist.world > 1)
             throw std::runtime_error("multisegment wells are not supported on several ranks yet");
-        ++ms_epoch;
+        const MsWellsD before = msD;
         nms = (int) w->ms.size();
         std::vector<int> zoff(nms + 1, 0), rowoff(nms + 1, 0), rowptr(1, 0), bcol, uz_of_block;
         std::vector<long long> doff(nms, 0);
@@ -752,6 +750,9 @@ struct Solver {
         msD.nwells = nms; msD.zoff = d_msZoff.p; msD.rowoff = d_msRowoff.p; msD.doff = d_msDoff.p; msD.rowptr = d_msRowptr.p;
         msD.bcol = d_msBcol.p; msD.B = d_msB.p; msD.C = d_msC.p; msD.Dinv = d_msDinv.p; msD.z1 = d_msZ1.p; msD.z2 = d_msZ2.p;
         msD.ncells = ms_ncells; msD.ucell = d_msUcell.p; msD.uptr = d_msUptr.p; msD.ublock = d_msUblock.p; msD.uz = d_msUz.p;
+        // Flow rebuilds its WellContributions every Newton step: the captured iteration graph (kernel arguments = msD) stays
+        // valid as long as the buffers and counts are the same -- the values were refreshed in place above
+        if (memcmp(&before, &msD, sizeof(MsWellsD)) != 0) ++ms_epoch;
     }
 
     void upload_wells(const Wells* w)
@@ -1261,6 +1262,11 @@ struct Solver {
     {
         if (!have_system) throw std::runtime_error("no system uploaded");
         const double t0 = wall();
+        // verbosity >= 3: per-phase timings as the reference's backends print them (BdaSolver.hpp:47-51,
+        // openclSolverBackend.cpp:451-459): every kernel of this solve is timed with CUDA events (no graph replay)
+        const bool phase_times = verbosity >= 3 && !profile;
+        double ms_before[K_COUNT];
+        if (phase_times) { profile = true; for (int k = 0; k < K_COUNT; ++k) ms_before[k] = stats[k].ms; }
         CUDA_OK(cudaEventRecord(ev_a, stream));
         permute_values();
         factorize();
@@ -1312,6 +1318,21 @@ struct Solver {
         if (verbosity > 0)
             fprintf(stderr, "[b200bda] converged %d, it %.1f, reduction %.3e, factor %.3f ms, krylov %.3f ms\n", S.converged, it,
                     res->reduction, ms_f, ms_k);
+        if (phase_times) {
+            profile = false;
+            auto d = [&](int k) { return (stats[k].ms - ms_before[k]) * 1e-3; };
+            const double prec = d(K_LOWER) + d(K_UPPER) + d(K_UPPER_SPMV), spmv_s = d(K_SPMV) + d(K_SPMV_GHOST) + d(K_HALO_PUSH), well = d(K_WELL);
+            const double dec = d(K_PERMUTE) + d(K_FACTOR) + d(K_SLICES);
+            const double rest = d(K_VEC_P) + d(K_VEC_XR1) + d(K_VEC_XR2) + d(K_INIT) + d(K_UNPERMUTE) + d(K_ALLREDUCE) + d(K_FINISH) + d(K_MISC);
+            fprintf(stderr, "b200Solver::create_preconditioner: %g s\n"
+                            "b200Solver::ilu_apply:   %g s%s\n"
+                            "wellContributions::apply:  %g s\n"
+                            "b200Solver::spmv:        %g s\n"
+                            "b200Solver::rest:        %g s\n"
+                            "b200Solver::total_solve: %g s\n",
+                    dec, prec, d(K_UPPER_SPMV) > 0.0 ? " (the upper sweep's launch also runs the SpMV that follows it)" : "", well, spmv_s, rest,
+                    res->elapsed);
+        }
         if (S.trsv_timeout) throw std::runtime_error("triangular-solve dataflow wait timed out");
     }
 
@@ -1479,6 +1500,10 @@ b200_status b200_solve_system(b200_solver* s, int N, int nnz, int dim, const dou
         double t_an = 0.0;
         double t_copy = s->upload(N, nnz, dim, vals, rows, cols, b, wells, &t_an);
         in_analysis = false;
+        if (s->verbosity >= 3) {      // cusparseSolverBackend.cu:340-344, openclSolverBackend.cpp:625-629
+            if (t_an > 0.0) fprintf(stderr, "b200Solver::analyse_matrix(): %g s\n", t_an);
+            fprintf(stderr, "b200Solver::copy_system_to_gpu(): %g s\n", t_copy);
+        }
         b200_status r = solve_common(s, res, t_an, t_copy);
         res->elapsed = wall() - t0;
         return r;

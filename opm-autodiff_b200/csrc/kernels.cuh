@@ -190,7 +190,7 @@ __device__ __forceinline__ void finish_xr2(Scalars* S, double rr, double rtr)
     S->rho = S->rho_new; S->rho_new = rtr;
     S->norm = sqrt(rr); S->it_half += 1;
     if (S->norm < S->tol * S->norm0 || S->norm < 1e-30) { S->converged = 1; S->done = 1; }
-    else if (fabs(S->rho) <= 1e-80 || fabs(S->omega) <= 1e-80 || !(S->norm == S->norm)) { S->breakdown = 1; S->done = 1; }
+    else if (fabs(S->rho_new) <= 1e-80 || fabs(S->omega) <= 1e-80 || !(S->norm == S->norm)) { S->breakdown = 1; S->done = 1; }      // the rho of the NEXT iteration (Dune: abs(rho) <= EPSILON right after it is computed)
     else if (S->it_half >= S->max_half) S->done = 1;
 }
 // PHASE 0: after k_init, 1: after k_vec_xr1, 2: after k_vec_xr2 (multi-GPU only, one thread)
