@@ -119,10 +119,8 @@ struct Dist {
     std::vector<void*> rank_base;           // IPC-mapped block of every rank (own block: the local pointer)
     MailD mail{};                           // mail flags / values of every rank
     bool mail_ready = false;
-    unsigned mail_seq = 0;
     bool use_p2p_allreduce = true;
     std::vector<HaloPeerD> peers;
-    unsigned epoch = 0;
     bool peers_ready = false;
 };
 
@@ -251,6 +249,7 @@ struct Solver {
     DevBuf<HaloPeerD> d_peers;
     DevBuf<int> d_send_prow, d_grow, d_gptr, d_gcol, d_gsrc;
     DevBuf<unsigned> d_push_tickets;
+    DevBuf<unsigned> d_dist_ctr;               // device-side counters: [0] all-reduce sequence number, [1] halo epoch, [2] ticket
 
     DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows, d_facPtr, d_facOps;
     DevBuf<int> d_sellPtr, d_sellOver, d_sellCol, d_sellSrc;     // sliced-ELL copy of A for the SpMV (analysis.hpp SellPlan)
@@ -562,7 +561,7 @@ struct Solver {
             // the SpMV tail streams SELL slices through the same dynamic shared memory: two chunk buffers per ring-fed consumer warp
             // (the shared-memory carve-out is taken from the L1: with the whole 227 KB handed to the tail's ring the sweeps ran 40 % slower --
             // their strided rhs loads and record headers live in L1 -- so only `fuse_ring_warps` consumers are ring-fed)
-            const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * kTailBufBytes * std::min({kTailMaxCons, threads / 32 - 1, std::max(1, fuse_ring_warps)})) : 0;
+            const size_t tail = want_fused ? std::min<size_t>(smem_limit, (size_t) 2 * std::max(1, std::min(fuse_chunk, kTailChunk)) * (2304 + 128) * std::min({kTailMaxCons, threads / 32 - 1, std::max(1, fuse_ring_warps)})) : 0;
             sweep_smem = std::max(need, tail);
             if (sweep_smem > smem_limit) throw std::runtime_error("value space of the triangular sweeps does not fit the shared memory");
             prep(k_sweep2<true, false>); prep(k_sweep2<true, true>); prep(k_sweep2<false, false>); prep(k_sweep2<false, true>);
@@ -1051,7 +1050,7 @@ struct Solver {
         a.f.prow = d_prow.p; a.f.pcol = d_pcol.p; a.f.A = d_A.p; a.f.y = y; a.f.d1 = d1;
         a.f.units = reinterpret_cast<const int2*>(d_fUnits.p); a.f.need_ptr = d_fNeedPtr.p; a.f.need = d_fNeed.p;
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
-        a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem;
+        a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem; a.f.chunk = fuse_chunk;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
         if (v2 && s2_mlU) launch_iter(k_sweep2<false, true, MODE, false, true>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         else if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
@@ -1064,6 +1063,7 @@ struct Solver {
     bool sweep_early = false;
     int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
+    int fuse_chunk = 4;                // option: slots of a SELL slice per chunk buffer of the SpMV tail (1..4)
     int fuse_ring_warps = 8;           // option (round-2 sweeps): warps of the SpMV tail fed through the shared-memory ring (19 KB each)
     DevBuf<long long> d_fDbg;
     template <int MODE>
@@ -1129,9 +1129,8 @@ struct Solver {
     {
         if (!dist.enabled) return;
         if (dist.world > 1 && dist.use_p2p_allreduce && dist.mail_ready) {
-            ++dist.mail_seq;
             int id = prof_begin(K_ALLREDUCE);
-            k_allreduce_p2p<PHASE><<<1, 64, 0, stream>>>(dist.mail, dist.rank, dist.world, dist.mail_seq, d_S.p, tolerance, 2 * maxit);
+            k_allreduce_p2p<PHASE><<<1, 64, 0, stream>>>(dist.mail, dist.rank, dist.world, d_dist_ctr.p, d_S.p, tolerance, 2 * maxit);
             prof_end(id);
             return;
         }
@@ -1146,29 +1145,26 @@ struct Solver {
     void halo_push(const double* y, bool check_done)
     {
         if (!dist.enabled) return;
-        ++dist.epoch;
         if (dist.nneigh == 0) return;
         if (!dist.peers_ready) throw std::runtime_error("multi-GPU solver: peers not connected (b200_dist_connect_peer)");
         int maxsend = 0;
         for (int n = 0; n < dist.nneigh; ++n) maxsend = std::max(maxsend, dist.send_ptr[n + 1] - dist.send_ptr[n]);
         const int bx = std::max(1, std::min(128, (3 * maxsend + 511) / 512));
         int id = prof_begin(K_HALO_PUSH);
-        k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, stream>>>(d_peers.p, d_send_prow.p, y, dist.epoch, d_push_tickets.p, d_S.p,
+        k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, stream>>>(d_peers.p, d_send_prow.p, y, d_dist_ctr.p + 1, d_push_tickets.p, d_S.p,
                                                                 check_done ? 1 : 0);
         prof_end(id);
     }
-    const double* ghost_x() const
-    {
-        return reinterpret_cast<const double*>(d_halo.p + kHaloRecvOffset) + (size_t) (dist.epoch & 1u) * 3 * (size_t) dist.n_ghost;
-    }
+    const double* ghost_x0() const { return reinterpret_cast<const double*>(d_halo.p + kHaloRecvOffset); }      // parity 0; parity 1 follows 3 n_ghost doubles later
     template <int MODE>
     void spmv_ghost(double* y, const double* d1, bool check_done)
     {
         if (!dist.enabled || dist.nneigh == 0 || dist.gnrows == 0) return;
         int id = prof_begin(K_SPMV_GHOST);
         const int blocks = blocks_for(3ll * dist.gnrows, kVecThreads, num_sms * 2);
-        k_spmv_ghost<MODE><<<blocks, kVecThreads, 0, stream>>>(dist.gnrows, d_grow.p, d_gptr.p, d_gcol.p, d_gsrc.p, d_stage.p, ghost_x(),
-                                                               reinterpret_cast<const unsigned*>(d_halo.p), dist.nneigh, dist.epoch, y,
+        k_spmv_ghost<MODE><<<blocks, kVecThreads, 0, stream>>>(dist.gnrows, d_grow.p, d_gptr.p, d_gcol.p, d_gsrc.p, d_stage.p, ghost_x0(),
+                                                               3ll * dist.n_ghost, reinterpret_cast<const unsigned*>(d_halo.p), dist.nneigh,
+                                                               d_dist_ctr.p + 1, d_dist_ctr.p + 2, y,
                                                                d1, d_S.p, d_partials.p, d_ticket.p, check_done ? 1 : 0);
         prof_end(id);
     }
@@ -1221,7 +1217,8 @@ struct Solver {
     IterSig iter_sig{};
     void run_iteration()
     {
-        if (!use_graph || profile || dist.enabled || sweep_trace) { enqueue_iteration(); return; }
+        // (several GPUs: graph replay needs the peer-memory all-reduce -- NCCL calls are not captured here)
+        if (!use_graph || profile || sweep_trace || (dist.enabled && dist.world > 1 && !(dist.use_p2p_allreduce && dist.mail_ready))) { enqueue_iteration(); return; }
         IterSig sig{};
         sig.a[0] = d_B.p; sig.a[1] = d_C.p; sig.a[2] = d_Dinv.p; sig.a[3] = d_ucell.p; sig.a[4] = d_wptr.p; sig.a[5] = d_z2.p;
         sig.n[0] = nwells; sig.n[1] = nucells; sig.n[2] = nwblocks; sig.n[3] = sweep_helper_sleep + (fused_now() ? 1 << 20 : 0) + (defer_now() ? 1 << 21 : 0);
@@ -1440,6 +1437,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "sweep_nowait") s->sweep_nowait = (int) value;
         else if (k == "s2_prefetch") s->s2_prefetch = std::max(2, std::min(8, (int) value));
         else if (k == "s2_poll_lead") s->s2_poll_lead = std::max(0, (int) value);
+        else if (k == "fuse_chunk") { if (s->analysed) throw std::runtime_error("fuse_chunk must be set before the first solve"); s->fuse_chunk = std::max(1, std::min(4, (int) value)); }
         else if (k == "fuse_ring_warps") { if (s->analysed) throw std::runtime_error("fuse_ring_warps must be set before the first solve"); s->fuse_ring_warps = std::max(1, (int) value); }
         else if (k == "sweep_v2" || k == "s2_cw" || k == "s2_helpers") {
             if (s->analysed) throw std::runtime_error("the sweep schedule must be set before the first solve");
@@ -1764,6 +1762,8 @@ b200_status b200_dist_set_halo(b200_solver* s, int n_ghost, int n_neigh, const i
         CUDA_OK(cudaMemset(s->d_halo.p, 0, bytes));
         s->d_push_tickets.alloc(64);
         CUDA_OK(cudaMemset(s->d_push_tickets.p, 0, 64 * sizeof(unsigned)));
+        s->d_dist_ctr.alloc(4);
+        CUDA_OK(cudaMemset(s->d_dist_ctr.p, 0, 4 * sizeof(unsigned)));
         D.rank_base.assign(D.world, nullptr);
         D.rank_base[D.rank] = s->d_halo.p;
         D.peers.assign(n_neigh, HaloPeerD{});

@@ -511,6 +511,7 @@ struct FusedSpmv {
     int ring_bytes;                // dynamic shared memory of the launch: ring of SELL slices once the part is swept
     long long* dbg;                // debugging aid (may be null): per part {part done, exit, units taken, time spent waiting for parts} [ns]
     int Nb, nunits;
+    int chunk;                     // slots of a slice per chunk buffer (0: kTailChunk)
 };
 
 // Deferred solution update run by idle CTAs of a lower sweep (k_sweep<true, ..., SPMV = 3>): x += pend * y, y re-armed
@@ -638,7 +639,9 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int PW = P.nwarps;                                   // the sweep's producer warp keeps that job
     const int NC = nwarp - 1, ci = warp < PW ? warp : warp - 1;
-    const int NR = min(min(NC, kTailMaxCons), F.ring_bytes / (2 * kTailBufBytes));   // consumers fed through the ring
+    const int tc = max(1, min(F.chunk > 0 ? F.chunk : kTailChunk, kTailChunk));          // slots of a slice per chunk buffer
+    const int bufBytes = tc * (2304 + 128);
+    const int NR = min(min(NC, kTailMaxCons), F.ring_bytes / (2 * bufBytes));   // consumers fed through the ring
     const int NU = (NR > 0 && !(P.nowait & 32)) ? NR : NC;       // warps that take slices: a plain-load warp next to ring-fed ones would be the straggler
     for (int p = threadIdx.x; p < P.nparts; p += blockDim.x) s_done[p] = 0;
     if (threadIdx.x < 32) { s_red[0][threadIdx.x] = 0.0; s_red[1][threadIdx.x] = 0.0; }
@@ -682,13 +685,13 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
             while (__any_sync(kFull, active)) {
                 bool issued = false;
                 if (active) {
-                    const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                    const int b2 = cnt & 1, n = min(tc, w - k0);
                     if (cnt < 2 || mbar_test(&s_empty[lane][b2], ((cnt >> 1) - 1) & 1)) {
-                        unsigned char* buf = ring + (size_t) (2 * lane + b2) * kTailBufBytes;
+                        unsigned char* buf = ring + (size_t) (2 * lane + b2) * bufBytes;
                         mbar_expect_tx(&s_full[lane][b2], (unsigned) n * (2304 + 128));
                         bulk_g2s(buf, F.sval + (size_t) (s0 + k0) * 288, (unsigned) n * 2304, &s_full[lane][b2]);
-                        bulk_g2s(buf + kTailChunk * 2304, F.scol + (size_t) (s0 + k0) * 32, (unsigned) n * 128, &s_full[lane][b2]);
-                        ++cnt; k0 += kTailChunk; issued = true;
+                        bulk_g2s(buf + tc * 2304, F.scol + (size_t) (s0 + k0) * 32, (unsigned) n * 128, &s_full[lane][b2]);
+                        ++cnt; k0 += tc; issued = true;
                         if (k0 >= w) { j += NU; active = next_slice(); }
                     }
                 }
@@ -720,14 +723,14 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
             const int row = 32 * slice + lane;
             double y0 = 0.0, y1 = 0.0, y2 = 0.0;
             if (ci < NR) {
-                for (int k0 = 0; k0 < w; k0 += kTailChunk, ++cnt) {
-                    const int b2 = cnt & 1, n = min(kTailChunk, w - k0);
+                for (int k0 = 0; k0 < w; k0 += tc, ++cnt) {
+                    const int b2 = cnt & 1, n = min(tc, w - k0);
                     const long long tf0 = F.dbg && threadIdx.x == 0 ? now_ns() : 0;
                     mbar_wait(&s_full[ci][b2], (cnt >> 1) & 1);
                     if (F.dbg && threadIdx.x == 0) { t_full += now_ns() - tf0; ++n_chunks; }
-                    const unsigned char* buf = ring + (size_t) (2 * ci + b2) * kTailBufBytes;
+                    const unsigned char* buf = ring + (size_t) (2 * ci + b2) * bufBytes;
                     const double* vs = reinterpret_cast<const double*>(buf) + lane;
-                    const int* cs = reinterpret_cast<const int*>(buf + kTailChunk * 2304) + lane;
+                    const int* cs = reinterpret_cast<const int*>(buf + tc * 2304) + lane;
                     double xr[kTailChunk][3];
 #pragma unroll
                     for (int k = 0; k < kTailChunk; ++k)
@@ -1933,10 +1936,14 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
 
 // grid (blocks per neighbour, neighbours).  tickets: one counter per neighbour (self-resetting).
 __global__ void __launch_bounds__(256) k_halo_push(const HaloPeerD* __restrict__ peers, const int* __restrict__ send_prow,
-                                                   const double* __restrict__ y, unsigned epoch, unsigned* tickets, Scalars* S,
+                                                   const double* __restrict__ y, const unsigned* epoch_ctr, unsigned* tickets, Scalars* S,
                                                    int check_done)
 {
     if (check_done && S->done) return;
+    // The exchange's epoch lives on the device (one past the last COMPLETED exchange; k_spmv_ghost, which consumes the exchange,
+    // bumps it): no kernel argument changes from launch to launch, so the iteration can be replayed from a CUDA graph on several
+    // GPUs too.  Every rank runs the same launch sequence and takes the same `done` decisions: the counters stay in step.
+    const unsigned epoch = *epoch_ctr + 1u;
     const HaloPeerD P = peers[blockIdx.y];
     double* dst = P.recv + (epoch & 1u) * P.parity_stride;
     const int n3 = 3 * (P.send_end - P.send_begin);
@@ -1961,12 +1968,15 @@ __global__ void __launch_bounds__(256) k_halo_push(const HaloPeerD* __restrict__
 template <int MODE>
 __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int* __restrict__ grow, const int* __restrict__ gptr,
                                                             const int* __restrict__ gcol, const int* __restrict__ gsrc,
-                                                            const double* __restrict__ stage, const double* __restrict__ ghost_x,
-                                                            const unsigned* flags, int nneigh, unsigned epoch, double* y,
+                                                            const double* __restrict__ stage, const double* __restrict__ ghost_x0,
+                                                            long long ghost_parity_stride, const unsigned* flags, int nneigh,
+                                                            unsigned* epoch_ctr, unsigned* bump_ticket, double* y,
                                                             const double* __restrict__ d1, Scalars* S, double* partials,
                                                             unsigned* ticket, int check_done)
 {
     if (check_done && S->done) return;
+    const unsigned epoch = *epoch_ctr + 1u;                       // the exchange k_halo_push has just started (see there)
+    const double* __restrict__ ghost_x = ghost_x0 + (size_t) (epoch & 1u) * ghost_parity_stride;
     if (threadIdx.x < nneigh) {
         long long spins = 0;
         while ((int) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
@@ -1997,6 +2007,13 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int
         if (grid_reduce<2>(acc, partials, ticket, tot)) {
             if (MODE == 1) S->h += tot[0];
             if (MODE == 2) { S->tr += tot[0]; S->tt += tot[1]; }
+            *epoch_ctr = epoch;                                    // last block: the exchange is consumed
+        }
+    } else {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(bump_ticket, 1u) == gridDim.x - 1) { *bump_ticket = 0; *epoch_ctr = epoch; }
         }
     }
 }
@@ -2016,10 +2033,16 @@ constexpr int kHaloRecvOffset = 4864;
 struct MailD { unsigned* flags[64]; double* vals[64]; };   // mapped mail flags / values of every rank (own included)
 
 template <int PHASE>
-__global__ void __launch_bounds__(64) k_allreduce_p2p(const MailD M, int rank, int world, unsigned seq, Scalars* S, double tol, int max_half)
+__global__ void __launch_bounds__(64) k_allreduce_p2p(const MailD M, int rank, int world, unsigned* seq_ctr, Scalars* S, double tol, int max_half)
 {
     __shared__ double got[64][4];
+    __shared__ unsigned s_seq;
     const int r = threadIdx.x;
+    // the sequence number lives on the device (no kernel argument changes between launches: graph replay); it advances with
+    // every launch, skipped or not, on every rank alike
+    if (r == 0) { s_seq = *seq_ctr + 1u; *seq_ctr = s_seq; }
+    __syncthreads();
+    const unsigned seq = s_seq;
     if (PHASE != 0 && PHASE != 5 && S->done) return;
     const int par = seq & 1u;
     if (r < world) {
