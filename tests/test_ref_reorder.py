@@ -95,5 +95,5 @@ def test_graph_colouring_is_valid_but_a_weaker_preconditioner(R):
     col = oracle.solve(rr, rc, rv, rb, tol=1e-10, maxit=400)
     x = np.zeros_like(col.x).reshape(-1, 3)
     x[fr] = col.x.reshape(-1, 3)
-    assert col.converged and relerr(x.reshape(-1), nat.x) < 1e-6    # same system, same answer ...
+    assert col.converged and relerr(x.reshape(-1), nat.x) < 1e-5    # same system, same answer (two 1e-10 residual solves) ...
     assert col.it > 1.1 * nat.it                                    # ... but outside the +-10 % iteration bound
