@@ -360,7 +360,7 @@ def run_b200_single(args):
     peak, peak_src = measured_peak()
     kernels = {}
     total_ms = 0.0
-    for k in ("permute", "ilu_factor", "ilu_lower", "ilu_upper", "ilu_upper_spmv", "spmv", "well_apply", "vec_p", "vec_xr1", "vec_xr2", "init", "unpermute"):
+    for k in ("permute", "ilu_factor", "ilu_stream", "ilu_lower", "ilu_upper", "ilu_upper_spmv", "spmv", "well_apply", "vec_p", "vec_xr1", "vec_xr2", "init", "unpermute"):
         n, ms, by = be.kernel_stats(k)
         if n:
             kernels[k] = {"launches": n, "ms_total": round(ms, 4), "us_per_launch": round(1e3 * ms / n, 3),

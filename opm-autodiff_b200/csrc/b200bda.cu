@@ -229,6 +229,8 @@ struct Solver {
     Sweep2Plan L2, U2;
 
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_aux = nullptr;         // multi-GPU: the halo push runs beside the well apply (fork / join by events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = 0;
     int vec_blocks = 0;
     int spmv_blocks_cap = kMaxPartials;
@@ -249,6 +251,7 @@ struct Solver {
     DevBuf<HaloPeerD> d_peers;
     DevBuf<int> d_send_prow, d_grow, d_gptr, d_gcol, d_gsrc;
     DevBuf<unsigned> d_push_tickets;
+    DevBuf<MailD> d_mail;                      // device copy of dist.mail for the all-reduce run inside producer kernels
     DevBuf<unsigned> d_dist_ctr;               // device-side counters: [0] all-reduce sequence number, [1] halo epoch, [2] ticket
 
     DevBuf<int> d_prow, d_pcol, d_pdiag, d_srcblk, d_perm, d_flevRows, d_facPtr, d_facOps;
@@ -268,8 +271,14 @@ struct Solver {
     int fused_units = 0;
     int fuse_spmv = 1;                 // option
     bool fac_plan = false;
+    // one-launch factorisation (k_ilu_factor_flow): a record per row in level order, a ready flag per row
+    DevBuf<int> d_facRec;              // k_ilu_factor_plan3: a record per row, level order, levels padded to whole triples
+    std::vector<int> fac3_ptr;         // first triple of every level (+ end)
+    int fac_warps = 4;                 // option: warps per CTA of k_ilu_factor_plan3 (1..16), read at upload
+    int fac_rows3 = 1;                 // option: 1 = three rows per warp (k_ilu_factor_plan3), 0 = one (k_ilu_factor_plan)
+    size_t fac3_smem = 0;
+    bool fac3_ready() const { return fac_plan && fac_rows3 && !fac3_ptr.empty(); }
     cudaGraphExec_t fac_graph_exec = nullptr;
-    double fac_graph_relax = 0.0;
     DevBuf<StageD> d_stagesL, d_stagesU;
     DevBuf<PartD> d_partsL, d_partsU;
     DevBuf<BuildD> d_buildL, d_buildU;
@@ -336,6 +345,9 @@ struct Solver {
         for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (cudaEvent_t e : {ev_a, ev_b, ev_c, ev_d, ev_t0, ev_t1}) if (e) cudaEventDestroy(e);
         if (h_S) cudaFreeHost(h_S);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (stream_aux) cudaStreamDestroy(stream_aux);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -383,7 +395,8 @@ struct Solver {
             case K_LOWER: return 76.0 * nnzL + 52.0 * nb;
             case K_UPPER: return 76.0 * (nz - nnzL) + 52.0 * nb;
             case K_UPPER_SPMV: return 76.0 * (nz - nnzL) + 52.0 * nb + 76.0 * nz + 52.0 * nb;     // the sweep and the product it also runs
-            case K_FACTOR: return 148.0 * nz + 8.0 * nb;
+            case K_FACTOR: return (148.0 * nz + 8.0 * nb) / std::max(1, an.nflev);      // per level launch
+            case K_SLICES: return 0.5 * (72.0 * nz + 76.0 * nz + 52.0 * nb);             // factor read, stream written (two fills)
             case K_VEC_P: return 96.0 * nb;
             case K_VEC_XR1: return (defer_now() ? 72.0 : 144.0) * nb;      // deferred x update: r, v read, r written
             case K_VEC_XR2: return (defer_now() ? 96.0 : 168.0) * nb;
@@ -410,6 +423,9 @@ struct Solver {
                             std::to_string(prop.minor) + "; this library is built for sm_100a only");
         num_sms = prop.multiProcessorCount;
         CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&stream_aux, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         CUDA_OK(cudaMallocHost((void**) &h_S, sizeof(Scalars)));
         memset(h_S, 0, sizeof(Scalars));
         d_S.alloc(1);
@@ -525,6 +541,25 @@ struct Solver {
         }
         fac_plan = an.facMaxRow <= kFacMaxRow && an.facMaxOps <= kFacMaxOps;
         if (fac_plan) { up(d_facPtr, an.facPtr); up(d_facOps, an.facOps); }
+        fac3_ptr.clear();
+        if (fac_plan) {
+            std::vector<int> recs;
+            recs.reserve((size_t) 4 * (Nb + 3 * an.nflev));
+            fac3_ptr.push_back(0);
+            for (int l = 0; l < an.nflev; ++l) {
+                for (int p = an.flevPtr[l]; p < an.flevPtr[l + 1]; ++p) {
+                    const int i = an.flevRows[p], rs = an.prow[i];
+                    recs.push_back(i); recs.push_back(rs); recs.push_back(an.facPtr[i]);
+                    recs.push_back((an.prow[i + 1] - rs) | ((an.pdiag[i] - rs) << 8) | ((an.facPtr[i + 1] - an.facPtr[i]) << 16));
+                }
+                while ((recs.size() / 4) % 3) { recs.push_back(-1); recs.push_back(0); recs.push_back(0); recs.push_back(0); }
+                fac3_ptr.push_back((int) (recs.size() / 12));
+            }
+            up(d_facRec, recs);
+            fac3_smem = (size_t) fac_warps * 3 * ((size_t) (an.facMaxRow + an.facMaxOps) * 72 + (size_t) an.facMaxOps * 8);
+            CUDA_OK(cudaFuncSetAttribute(k_ilu_factor_plan3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fac3_smem));
+            CUDA_OK(cudaStreamSynchronize(stream));            // recs is a temporary
+        }
         auto upraw = [&](void* d, const void* h, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream)); };
         const bool want_fused = feature_on(fuse_spmv) && sell_slices && an.nparts <= kMaxSweepParts;
         const size_t smem_limit = smem_optin - (want_fused ? 2560 : 0);      // static shared memory of the fused SpMV tail
@@ -878,16 +913,27 @@ struct Solver {
         prof_end(id);
     }
 
-    // ILU0 of the resident A: one kernel per level set + the two stream fills.  The launch sequence only depends on the
-    // pattern, so it is captured once into a CUDA graph and replayed per solve (298 launches for C3: the launch gaps are a
-    // third of the factorisation time); with per-kernel profiling on, the kernels are launched one by one.
-    void factorize_launches(bool count)
+    // ILU0 of the resident A: one kernel per level set, chained by programmatic dependent launch, + the two stream fills.
+    // The level launches only depend on the pattern, so they are captured once into a CUDA graph and replayed per solve
+    // (298 launches for C3).  With per-kernel profiling on, the chain is timed as ONE entry (events between the levels would
+    // break the programmatic chain and time the event gaps, not the kernels): launches = levels, ms = the whole chain.
+    void factorize_levels()
     {
         CUDA_OK(cudaMemsetAsync(&d_S.p->singular, 0, sizeof(int), stream));
         for (int l = 0; l < an.nflev; ++l) {
             int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
-            int id = count ? prof_begin(K_FACTOR) : -1;
-            if (fac_plan && fac_pdl && l > 0) {
+            if (fac3_ready()) {
+                const int t0 = fac3_ptr[l], nt = fac3_ptr[l + 1] - t0;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((nt + fac_warps - 1) / fac_warps); cfg.blockDim = dim3(32 * fac_warps); cfg.stream = stream;
+                cfg.dynamicSmemBytes = fac3_smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = (fac_pdl && l > 0) ? 1 : 0;
+                CUDA_OK(cudaLaunchKernelEx(&cfg, k_ilu_factor_plan3, reinterpret_cast<const int4*>(d_facRec.p) + 3 * (size_t) t0, nt,
+                                           reinterpret_cast<const int2*>(d_facOps.p), (const double*) d_A.p, d_LU.p, an.facMaxRow, an.facMaxOps, d_S.p));
+            } else if (fac_plan && fac_pdl && l > 0) {
                 // programmatic dependent launch on the previous level: the launch gap and the prologue hide behind it
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((nrows + kFacWarps - 1) / kFacWarps); cfg.blockDim = dim3(32 * kFacWarps); cfg.stream = stream;
@@ -903,41 +949,44 @@ struct Solver {
                     d_prow.p, d_pdiag.p, d_facPtr.p, reinterpret_cast<const int2*>(d_facOps.p), d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
             else
                 k_ilu_factor_level<<<(nrows + 7) / 8, 256, 0, stream>>>(d_prow.p, d_pcol.p, d_pdiag.p, d_A.p, d_LU.p, d_flevRows.p + row0, nrows, d_S.p);
-            prof_end(id);
         }
+    }
+    void fill_streams()
+    {
         if (v2) {
-            int id2 = count ? prof_begin(K_SLICES) : -1;
+            int id2 = prof_begin(K_SLICES);
             if (!L2.build.empty())
                 k_fill_stream2<true><<<blocks_for((long long) L2.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
                     d_s2buildL.p, (int) L2.build.size(), d_s2srcL.p, d_LU.p, d_valL.p, 1.0);
             prof_end(id2);
-            id2 = count ? prof_begin(K_SLICES) : -1;
+            id2 = prof_begin(K_SLICES);
             if (!U2.build.empty())
                 k_fill_stream2<false><<<blocks_for((long long) U2.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
                     d_s2buildU.p, (int) U2.build.size(), d_s2srcU.p, d_LU.p, d_valU.p, relaxation);
             prof_end(id2);
             return;
         }
-        int id = count ? prof_begin(K_SLICES) : -1;
+        int id = prof_begin(K_SLICES);
         k_fill_stream<true><<<blocks_for((long long) an.L.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
             d_buildL.p, (int) an.L.build.size(), d_srcL.p, d_LU.p, d_valL.p, 1.0);
         prof_end(id);
-        id = count ? prof_begin(K_SLICES) : -1;
+        id = prof_begin(K_SLICES);
         k_fill_stream<false><<<blocks_for((long long) an.U.build.size() * 32, 256, num_sms * 8), 256, 0, stream>>>(
             d_buildU.p, (int) an.U.build.size(), d_srcU.p, d_LU.p, d_valU.p, relaxation);
         prof_end(id);
     }
     void factorize()
     {
-        if (!use_graph || profile) {
-            factorize_launches(true);
+        const int id = prof_begin(K_FACTOR);
+        stats[K_FACTOR].launches += an.nflev - 1; launch_count += an.nflev - 1;
+        if (!use_graph) {
+            factorize_levels();
         } else {
-            if (!fac_graph_exec || fac_graph_relax != relaxation) {
-                if (fac_graph_exec) { cudaGraphExecDestroy(fac_graph_exec); fac_graph_exec = nullptr; }
+            if (!fac_graph_exec) {
                 cudaGraph_t g = nullptr;
                 CUDA_OK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 try {
-                    factorize_launches(false);
+                    factorize_levels();
                 } catch (...) {
                     cudaStreamEndCapture(stream, &g);
                     if (g) cudaGraphDestroy(g);
@@ -946,12 +995,11 @@ struct Solver {
                 CUDA_OK(cudaStreamEndCapture(stream, &g));
                 CUDA_OK(cudaGraphInstantiate(&fac_graph_exec, g, 0));
                 cudaGraphDestroy(g);
-                fac_graph_relax = relaxation;
             }
             CUDA_OK(cudaGraphLaunch(fac_graph_exec, stream));
-            stats[K_FACTOR].launches += an.nflev; stats[K_SLICES].launches += 2;
-            launch_count += an.nflev + 2;
         }
+        prof_end(id);
+        fill_streams();
         have_factor = true;
     }
 
@@ -1124,10 +1172,22 @@ struct Solver {
     }
     // Sum the scalars of one Krylov phase over the ranks and run its epilogue.  PHASE as k_allreduce_p2p.
     // Peer-memory mailboxes when every rank is mapped (default), else NCCL + k_finish.
+    // The exchange of a phase runs in the epilogue of the kernel that completes its local sums (mail_allreduce: k_vec_xr1,
+    // k_vec_xr2, and k_spmv_ghost on ranks that have ghost columns); a launch of its own only where there is no such kernel.
+    int fuse_allreduce = 1;            // option
+    bool mail_on() const { return dist.enabled && dist.world > 1 && dist.use_p2p_allreduce && dist.mail_ready; }
+    bool ghost_on() const { return dist.enabled && dist.nneigh > 0 && dist.gnrows > 0; }
+    DistRedD dist_red() const
+    {
+        DistRedD D = {};
+        if (mail_on() && fuse_allreduce) { D.mail = d_mail.p; D.seq = d_dist_ctr.p; D.rank = dist.rank; D.world = dist.world; D.tol = tolerance; D.max_half = 2 * maxit; }
+        return D;
+    }
     template <int PHASE>
     void reduce_phase()
     {
         if (!dist.enabled) return;
+        if (mail_on() && fuse_allreduce && (PHASE == 2 || PHASE == 4 || ((PHASE == 1 || PHASE == 3) && ghost_on()))) return;
         if (dist.world > 1 && dist.use_p2p_allreduce && dist.mail_ready) {
             int id = prof_begin(K_ALLREDUCE);
             k_allreduce_p2p<PHASE><<<1, 64, 0, stream>>>(dist.mail, dist.rank, dist.world, d_dist_ctr.p, d_S.p, tolerance, 2 * maxit);
@@ -1141,7 +1201,11 @@ struct Solver {
         if (PHASE == 4) { allreduce_sum(d_S.p->red, 2); finish<2>(); }
         if (PHASE == 5) allreduce(&d_S.p->singular, 1, kNcclInt32, kNcclMax);
     }
-    // boundary entries of y (p-space) -> the neighbours' receive blocks; one epoch per exchange
+    // boundary entries of y (p-space) -> the neighbours' receive blocks; one epoch per exchange.  The push only reads y and the
+    // exchange counters, so it runs on a side stream beside the kernels that follow the sweep (the well apply, or the separate
+    // SpMV) and is joined before k_spmv_ghost, the consumer of the exchange (halo_join).
+    int halo_side = 1;                 // option
+    bool halo_forked = false;
     void halo_push(const double* y, bool check_done)
     {
         if (!dist.enabled) return;
@@ -1150,10 +1214,24 @@ struct Solver {
         int maxsend = 0;
         for (int n = 0; n < dist.nneigh; ++n) maxsend = std::max(maxsend, dist.send_ptr[n + 1] - dist.send_ptr[n]);
         const int bx = std::max(1, std::min(128, (3 * maxsend + 511) / 512));
+        cudaStream_t st = stream;
+        halo_forked = halo_side && !profile;
+        if (halo_forked) {
+            CUDA_OK(cudaEventRecord(ev_fork, stream));
+            CUDA_OK(cudaStreamWaitEvent(stream_aux, ev_fork, 0));
+            st = stream_aux;
+        }
         int id = prof_begin(K_HALO_PUSH);
-        k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, stream>>>(d_peers.p, d_send_prow.p, y, d_dist_ctr.p + 1, d_push_tickets.p, d_S.p,
-                                                                check_done ? 1 : 0);
+        k_halo_push<<<dim3(bx, dist.nneigh), 256, 0, st>>>(d_peers.p, d_send_prow.p, y, d_dist_ctr.p + 1, d_push_tickets.p, d_S.p,
+                                                            check_done ? 1 : 0);
         prof_end(id);
+        if (halo_forked) CUDA_OK(cudaEventRecord(ev_join, stream_aux));
+    }
+    void halo_join()
+    {
+        if (!halo_forked) return;
+        CUDA_OK(cudaStreamWaitEvent(stream, ev_join, 0));
+        halo_forked = false;
     }
     const double* ghost_x0() const { return reinterpret_cast<const double*>(d_halo.p + kHaloRecvOffset); }      // parity 0; parity 1 follows 3 n_ghost doubles later
     template <int MODE>
@@ -1165,7 +1243,8 @@ struct Solver {
         k_spmv_ghost<MODE><<<blocks, kVecThreads, 0, stream>>>(dist.gnrows, d_grow.p, d_gptr.p, d_gcol.p, d_gsrc.p, d_stage.p, ghost_x0(),
                                                                3ll * dist.n_ghost, reinterpret_cast<const unsigned*>(d_halo.p), dist.nneigh,
                                                                d_dist_ctr.p + 1, d_dist_ctr.p + 2, y,
-                                                               d1, d_S.p, d_partials.p, d_ticket.p, check_done ? 1 : 0);
+                                                               d1, d_S.p, d_partials.p, d_ticket.p, check_done ? 1 : 0,
+                                                               MODE != 0 ? dist_red() : DistRedD{});
         prof_end(id);
     }
 
@@ -1186,10 +1265,11 @@ struct Solver {
             spmv<1>(d_y.p, d_v.p, d_rt.p);
         }
         wells_apply<1>(d_y.p, d_v.p, d_rt.p);
+        halo_join();
         spmv_ghost<1>(d_v.p, d_rt.p, true);
         reduce_phase<1>();
         id = prof_begin(K_VEC_XR1);
-        launch_iter(k_vec_xr1, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
+        launch_iter(k_vec_xr1, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_v.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0, dist_red());
         prof_end(id);
         reduce_phase<2>();
         if (defer_now()) trsv_lower_xupdate(d_r.p, d_w.p); else trsv_lower(d_r.p, d_w.p, true);
@@ -1202,10 +1282,11 @@ struct Solver {
             spmv<2>(d_y.p, d_t.p, d_r.p);
         }
         wells_apply<2>(d_y.p, d_t.p, d_r.p);
+        halo_join();
         spmv_ghost<2>(d_t.p, d_r.p, true);
         reduce_phase<3>();
         id = prof_begin(K_VEC_XR2);
-        launch_iter(k_vec_xr2, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0);
+        launch_iter(k_vec_xr2, dim3(vec_blocks), dim3(kVecThreads), 0, d_x.p, d_y.p, d_r.p, d_t.p, d_rt.p, N, d_S.p, d_partials.p, d_ticket.p, dm, defer_now() ? 1 : 0, dist_red());
         prof_end(id);
         reduce_phase<4>();
     }
@@ -1225,6 +1306,8 @@ struct Solver {
         sig.n[4] = nms; sig.n[5] = ms_epoch;
         sig.a[6] = d_item.p; sig.a[7] = d_itemC.p;
         sig.n[3] += (flat_ok && wells_flat) ? 1 << 22 : 0;
+        sig.n[3] += (mail_on() && fuse_allreduce) ? 1 << 23 : 0;
+        sig.n[3] += halo_side ? 1 << 24 : 0;
         if (!iter_graph_exec || sig != iter_sig) {
             if (iter_graph_exec) { cudaGraphExecDestroy(iter_graph_exec); iter_graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -1447,6 +1530,10 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
             else s->s2_helpers = std::max(1, v);
         }
         else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
+        else if (k == "fuse_allreduce") s->fuse_allreduce = (int) value;
+        else if (k == "halo_side") s->halo_side = (int) value;
+        else if (k == "fac_warps") s->fac_warps = std::max(1, std::min(kFac3MaxWarps, (int) value));
+        else if (k == "fac_rows3") { s->fac_rows3 = (int) value; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
         else if (k == "fac_pdl") { s->fac_pdl = value != 0.0; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
         else if (k == "sweep_early") { if (s->analysed) throw std::runtime_error("sweep_early must be set before the first solve"); s->sweep_early_opt = std::max(0, std::min(2, (int) value)); }
         else if (k == "defer_x") { if (s->analysed) throw std::runtime_error("defer_x must be set before the first solve"); s->defer_x = std::max(0, std::min(2, (int) value)); }
@@ -1804,6 +1891,8 @@ b200_status b200_dist_map_rank(b200_solver* s, int rank, const unsigned char* ip
                 D.mail.flags[r] = reinterpret_cast<unsigned*>(b + 256);
                 D.mail.vals[r] = reinterpret_cast<double*>(b + 768);
             }
+            s->d_mail.alloc(1);
+            CUDA_OK(cudaMemcpy(s->d_mail.p, &D.mail, sizeof(MailD), cudaMemcpyHostToDevice));
             D.mail_ready = true;
         }
         return B200_SUCCESS;
@@ -1849,6 +1938,7 @@ b200_status b200_dist_spmv(b200_solver* s, const double* x, double* y)
         s->to_device_p(x, s->d_tmp2.p);
         s->halo_push(s->d_tmp2.p, false);
         s->spmv<0>(s->d_tmp2.p, s->d_t.p, nullptr);
+        s->halo_join();
         s->spmv_ghost<0>(s->d_t.p, nullptr, false);
         s->to_host_nat(s->d_t.p, y);
         return B200_SUCCESS;
@@ -2211,9 +2301,9 @@ b200_status b200_time_kernel(b200_solver* s, const char* which, int reps, int fl
                 case K_VEC_P: s->stats[K_VEC_P].launches++; s->launch_count++;
                     k_vec_p<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_tmp2.p, s->d_p.p, s->d_v.p, N, s->d_S.p); break;
                 case K_VEC_XR1: s->stats[K_VEC_XR1].launches++; s->launch_count++;
-                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0); break;
+                    k_vec_xr1<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_v.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0, DistRedD{}); break;
                 case K_VEC_XR2: s->stats[K_VEC_XR2].launches++; s->launch_count++;
-                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0); break;
+                    k_vec_xr2<<<s->vec_blocks, kVecThreads, 0, s->stream>>>(s->d_x.p, s->d_y.p, s->d_r.p, s->d_t.p, s->d_rt.p, N, s->d_S.p, s->d_partials.p, s->d_ticket.p, 0, 0, DistRedD{}); break;
                 case K_WELL: s->wells_apply<0>(s->d_y.p, s->d_t.p, nullptr); break;
                 default: throw std::runtime_error(std::string("kernel '") + which + "' cannot be timed in isolation");
             }

@@ -193,6 +193,57 @@ __device__ __forceinline__ void finish_xr2(Scalars* S, double rr, double rtr)
     else if (fabs(S->rho_new) <= 1e-80 || fabs(S->omega) <= 1e-80 || !(S->norm == S->norm)) { S->breakdown = 1; S->done = 1; }      // the rho of the NEXT iteration (Dune: abs(rho) <= EPSILON right after it is computed)
     else if (S->it_half >= S->max_half) S->done = 1;
 }
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Multi-GPU all-reduce of a phase's scalars over peer-memory mailboxes (layout: k_allreduce_p2p below), run by ONE thread:
+// the thread of the producing kernel that has just summed the local partials (the last block of its grid reduction), so the
+// exchange needs no launch of its own.  Stores to the `world` mailboxes are posted, one system fence, the flags, then the
+// contributions are added in rank order -- every rank gets the same bits.
+struct MailD { unsigned* flags[64]; double* vals[64]; };   // mapped mail flags / values of every rank (own included)
+struct DistRedD { const MailD* mail; unsigned* seq; int rank, world; double tol; int max_half; };      // mail == nullptr: not fused
+template <int NV>
+__device__ __noinline__ void mail_allreduce(const DistRedD D, Scalars* S, double (&v)[NV])
+{
+    const MailD* M = D.mail;
+    const unsigned seq = *D.seq + 1u;
+    *D.seq = seq;
+    const size_t slot = (size_t) (seq & 1u) * 64;
+    for (int r = 0; r < D.world; ++r) {
+        double* dst = M->vals[r] + (slot + D.rank) * 4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dst[k] = v[k];
+    }
+    __threadfence_system();
+    for (int r = 0; r < D.world; ++r) st_relaxed_sys(M->flags[r] + slot + D.rank, seq);
+    double t[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) t[k] = 0.0;
+    for (int r = 0; r < D.world; ++r) {
+        const unsigned* mine = M->flags[D.rank] + slot + r;
+        long long spins = 0;
+        while (ld_acquire_sys(mine) != seq) {
+            if ((++spins & 1023) == 0 && spins > (1ll << 26)) { S->trsv_timeout = 1; break; }
+        }
+        const double* src = M->vals[D.rank] + (slot + r) * 4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) t[k] += __ldcg(src + k);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = t[k];
+}
+
 // PHASE 0: after k_init, 1: after k_vec_xr1, 2: after k_vec_xr2 (multi-GPU only, one thread)
 template <int PHASE>
 __global__ void k_finish(Scalars* S, double tol, int max_half)
@@ -373,6 +424,87 @@ __global__ void __launch_bounds__(32 * kFacWarps) k_ilu_factor_plan(const int* _
     }
     __syncwarp();
     for (int f = lane; f < (re - rs) * 9; f += 32) LU[(size_t) rs * 9 + f] = row[f];
+}
+
+// Round 2: the same elimination with THREE rows per warp -- nine lanes per row, one lane per scalar of a 3x3 block -- instead
+// of one (where 9 of the 32 lanes did the arithmetic and a large level was bound by warp throughput: 5.8 us per level on C3's
+// 7500-row levels against 2 us on small ones).  rec (built by the host, level order, every level padded to whole triples):
+//   rec[p] = { row i (-1: padding), first block of the row, first op, blocks | diagonal offset << 8 | ops << 16 }
+// The launches stay one per level set, chained by programmatic dependent launch: a single resident launch in which rows wait
+// for rows through L2 (per-row flags with release/acquire, or the sentinel-armed factor as its own flag) was measured at
+// 4.4-8 us per level -- the L2 hand-over between SMs costs more than a PDL-chained launch.
+constexpr int kFac3MaxWarps = 16;
+__global__ void __launch_bounds__(32 * kFac3MaxWarps) k_ilu_factor_plan3(const int4* __restrict__ rec, int ntriples, const int2* __restrict__ facOps,
+                                                                     const double* __restrict__ A, double* LU, int maxRow, int maxOps, Scalars* S)
+{
+    extern __shared__ __align__(16) unsigned char fac3_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = lane / 9, e = lane - 9 * slot, er = e / 3, ec = e - 3 * er;
+    const bool lane_on = slot < 3;
+    const size_t per = (size_t) (maxRow + maxOps) * 72 + (size_t) maxOps * 8;
+    double* row = reinterpret_cast<double*>(fac3_smem + (size_t) (3 * w + (lane_on ? slot : 0)) * per);
+    double* up = row + maxRow * 9;
+    int2* sop = reinterpret_cast<int2*>(up + maxOps * 9);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int t = blockIdx.x * (blockDim.x >> 5) + w;
+    if (t >= ntriples) return;
+    const int4 r = lane_on ? __ldg(rec + 3 * (size_t) t + slot) : make_int4(-1, 0, 0, 0);
+    const int i = r.x, rs = r.y, o0 = r.z, nblk = r.w & 255, di = (r.w >> 8) & 255, nops = r.w >> 16;
+    // everything that does not depend on earlier levels: the plan and the row of A (no level writes them)
+    for (int o = e; o < nops; o += 9) sop[o] = __ldg(facOps + o0 + o);
+    for (int b0 = 0; b0 < nblk; b0 += 8) {              // eight loads in flight per lane, not one round trip per block
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = b0 + k < nblk ? __ldg(A + (size_t) (rs + b0 + k) * 9 + e) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (b0 + k < nblk) row[(b0 + k) * 9 + e] = v[k];
+    }
+    __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // upstream blocks: pivots and U blocks of the rows this one eliminates with (earlier levels, final)
+    for (int ob = 0; ob < nops; ob += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ob + k < nops ? __ldcg(LU + (size_t) sop[ob + k].x * 9 + e) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (ob + k < nops) up[(ob + k) * 9 + e] = v[k];
+    }
+    __syncwarp();
+    int o = 0;
+    while (__any_sync(kFull, o < nops)) {
+        const bool act = o < nops;
+        const int code = act ? sop[o].y : 0;
+        const int toff = code & 255, nupd = code >> 8;
+        // L_ij = A_ij * inv(A_jj)
+        double lij = 0.0;
+        if (act) {
+            const double* a = row + toff * 9 + er * 3;
+            const double* d = up + o * 9 + ec;
+            lij = a[0] * d[0] + a[1] * d[3] + a[2] * d[6];
+        }
+        __syncwarp();
+        if (act) row[toff * 9 + e] = lij;
+        __syncwarp();
+        // A_ik -= L_ij * U_jk for the blocks present in both rows: distinct targets, this lane's scalar of each
+        for (int u = 0; u < nupd; ++u) {
+            const int tgt = -(sop[o + 1 + u].y + 1);
+            const double* l = row + toff * 9 + er * 3;
+            const double* uu = up + (o + 1 + u) * 9 + ec;
+            row[tgt * 9 + e] -= l[0] * uu[0] + l[1] * uu[3] + l[2] * uu[6];
+        }
+        __syncwarp();
+        if (act) o += 1 + nupd;
+    }
+    if (e == 0 && i >= 0) {
+        double inv[9];
+        if (!inv3(row + di * 9, inv)) S->singular = 1;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) row[di * 9 + k] = inv[k];
+    }
+    __syncwarp();
+    for (int bk = 0; bk < nblk; ++bk) LU[(size_t) (rs + bk) * 9 + e] = row[bk * 9 + e];
 }
 
 // ---- triangular solves: pencil-pipelined sweeps -----------------------------------------------------
@@ -1501,7 +1633,7 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_p(const double* __restrict_
 // x += alpha y; r -= alpha v; norm = ||r||; y is re-armed (its last reader).  alpha = rho_new / h.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ v, int N, Scalars* S, double* partials,
-                                                         unsigned* ticket, int dist, int defer)
+                                                         unsigned* ticket, int dist, int defer, const DistRedD D)
 {
     pdl_enter();
     if (S->done) return;
@@ -1525,7 +1657,8 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
     if (grid_reduce<1>(acc, partials, ticket, tot)) {
         S->alpha = alpha;
         if (defer) { S->pend = alpha; S->pend_on = 1; }
-        if (dist) S->red[0] = tot[0];
+        if (dist && D.mail) { mail_allreduce<1>(D, S, tot); finish_xr1(S, tot[0]); }
+        else if (dist) S->red[0] = tot[0];
         else finish_xr1(S, tot[0]);
     }
 }
@@ -1533,7 +1666,8 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr1(double* __restrict__ x,
 // x += omega y; r -= omega t; norm = ||r||; rho <- rho_new <- <rt, r>.  omega = tr / tt.
 __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x, double* __restrict__ y, double* __restrict__ r,
                                                          const double* __restrict__ t, const double* __restrict__ rt, int N,
-                                                         Scalars* S, double* partials, unsigned* ticket, int dist, int defer)
+                                                         Scalars* S, double* partials, unsigned* ticket, int dist, int defer,
+                                                         const DistRedD D)
 {
     pdl_enter();
     if (S->done) return;
@@ -1553,7 +1687,8 @@ __global__ void __launch_bounds__(kVecThreads) k_vec_xr2(double* __restrict__ x,
     if (grid_reduce<2>(acc, partials, ticket, tot)) {
         S->omega = omega;
         if (defer) { S->pend = omega; S->pend_on = 1; }
-        if (dist) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
+        if (dist && D.mail) { mail_allreduce<2>(D, S, tot); finish_xr2(S, tot[0], tot[1]); }
+        else if (dist) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
         else finish_xr2(S, tot[0], tot[1]);
     }
 }
@@ -1923,16 +2058,6 @@ struct HaloPeerD {
     int send_begin, send_end;    // my entries of send_prow
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // grid (blocks per neighbour, neighbours).  tickets: one counter per neighbour (self-resetting).
 __global__ void __launch_bounds__(256) k_halo_push(const HaloPeerD* __restrict__ peers, const int* __restrict__ send_prow,
@@ -1972,7 +2097,7 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int
                                                             long long ghost_parity_stride, const unsigned* flags, int nneigh,
                                                             unsigned* epoch_ctr, unsigned* bump_ticket, double* y,
                                                             const double* __restrict__ d1, Scalars* S, double* partials,
-                                                            unsigned* ticket, int check_done)
+                                                            unsigned* ticket, int check_done, const DistRedD D)
 {
     if (check_done && S->done) return;
     const unsigned epoch = *epoch_ctr + 1u;                       // the exchange k_halo_push has just started (see there)
@@ -2005,9 +2130,15 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int
     if (MODE != 0) {
         double tot[2];
         if (grid_reduce<2>(acc, partials, ticket, tot)) {
-            if (MODE == 1) S->h += tot[0];
-            if (MODE == 2) { S->tr += tot[0]; S->tt += tot[1]; }
             *epoch_ctr = epoch;                                    // last block: the exchange is consumed
+            if (MODE == 1) tot[0] += S->h;
+            if (MODE == 2) { tot[0] += S->tr; tot[1] += S->tt; }
+            if (D.mail) {                                          // this launch completes the local sums: all-reduce them here
+                if (MODE == 1) { double one[1] = {tot[0]}; mail_allreduce<1>(D, S, one); tot[0] = one[0]; }
+                else mail_allreduce<2>(D, S, tot);
+            }
+            if (MODE == 1) S->h = tot[0];
+            if (MODE == 2) { S->tr = tot[0]; S->tt = tot[1]; }
         }
     } else {
         __syncthreads();
@@ -2030,7 +2161,6 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int
 // PHASE 0: after k_init (red[0]); 1: after the first SpMV (h); 2: after k_vec_xr1 (red[0]); 3: after the second SpMV
 // (tr, tt); 4: after k_vec_xr2 (red[0..1]); 5: singular flag of the factorisation (max).
 constexpr int kHaloRecvOffset = 4864;
-struct MailD { unsigned* flags[64]; double* vals[64]; };   // mapped mail flags / values of every rank (own included)
 
 template <int PHASE>
 __global__ void __launch_bounds__(64) k_allreduce_p2p(const MailD M, int rank, int world, unsigned* seq_ctr, Scalars* S, double tol, int max_half)
@@ -2039,11 +2169,11 @@ __global__ void __launch_bounds__(64) k_allreduce_p2p(const MailD M, int rank, i
     __shared__ unsigned s_seq;
     const int r = threadIdx.x;
     // the sequence number lives on the device (no kernel argument changes between launches: graph replay); it advances with
-    // every launch, skipped or not, on every rank alike
+    // every exchange, here or in a producer's epilogue (mail_allreduce), on every rank alike
+    if (PHASE != 0 && PHASE != 5 && S->done) return;         // (every rank takes this branch alike: done comes from reduced sums)
     if (r == 0) { s_seq = *seq_ctr + 1u; *seq_ctr = s_seq; }
     __syncthreads();
     const unsigned seq = s_seq;
-    if (PHASE != 0 && PHASE != 5 && S->done) return;
     const int par = seq & 1u;
     if (r < world) {
         double v[4] = {0.0, 0.0, 0.0, 0.0};

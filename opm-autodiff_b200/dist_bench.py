@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-KERNELS = ("permute", "ilu_factor", "ilu_lower", "ilu_upper", "ilu_upper_spmv", "spmv", "spmv_ghost", "halo_push", "allreduce", "finish",
+KERNELS = ("permute", "ilu_factor", "ilu_stream", "ilu_lower", "ilu_upper", "ilu_upper_spmv", "spmv", "spmv_ghost", "halo_push", "allreduce", "finish",
            "well_apply", "vec_p", "vec_xr1", "vec_xr2", "init", "unpermute")
 
 
@@ -45,6 +45,9 @@ def measure(cfg, args, steps, warmup, tol, maxit, ClockSampler, measured_peak, t
     ls = dist.block_system(cfg, rank, world) if blocks else dist.slab_system(cfg, rank, world)
     t_gen = time.perf_counter() - t0
     ds = dist.DistSolver(ls, local, maxit=maxit, tolerance=tol)
+    for kv in filter(None, os.environ.get("B200_OPTIONS", "").split(",")):      # experiment knob: "option=value,..."
+        k, v = kv.split("=")
+        ds.be.set_option(k, float(v))
     res = bridge.BdaResult()
 
     # ---- e2e: host buffers, H2D of values + rhs and D2H of x inside the timed region --------------------
