@@ -727,8 +727,8 @@ struct Solver {
     {
         nms = 0; ms_blocks = 0; ms_rows = 0; ms_ncells = 0; ms_dinv_entries = 0;
         if (!w || w->ms.empty()) return;       // (the iteration graph's signature carries the well count)
-        if (dist.enabled && dist.world > 1)
-            throw std::runtime_error("multisegment wells are not supported on several ranks yet");
+        // (several ranks: a well lives inside one rank, as the standard wells do -- its apply and the patch of the local dot
+        //  products need no exchange; the all-reduce that follows carries the patched sums)
         const MsWellsD before = msD;
         nms = (int) w->ms.size();
         std::vector<int> zoff(nms + 1, 0), rowoff(nms + 1, 0), rowptr(1, 0), bcol, uz_of_block;

@@ -264,15 +264,17 @@ class MSWellData:
         return D
 
 
-def add_mswells(system: System, nwells: int, nseg: int, seed: int = 4242, share_cells: bool = True):
+def add_mswells(system: System, nwells: int, nseg: int, seed: int = 4242, share_cells: bool = True, cell_range=None):
     """Synthetic multisegment wells on a whole system (single-GPU use), in place: every well is a tree of `nseg` segments
     (segment s > 0 drains into a random earlier one; D couples a segment with its outlet, 4x4 blocks, as
     MultisegmentWell_impl.hpp:636-643 describes), segment 0 is the top segment without perforations (unless it is the only one), the others perforate
     0-2 cells (one segment per cell inside a well; with share_cells two wells may meet in a cell).  The perforation
     conductance goes on A's diagonal and b is updated so that x_true stays the solution:
-    b += A_add x_true - sum_w C^T D^-1 B x_true.  Returns the list of MSWellData."""
+    b += A_add x_true - sum_w C^T D^-1 B x_true.  cell_range = (lo, hi) perforates only block rows lo <= c < hi (the rows of one
+    rank: a well does not span ranks, as with the reference's default AllowDistributedWells = false).  Returns the list of MSWellData."""
     rng = np.random.default_rng(seed)
     Nb = system.Nb
+    c_lo, c_hi = cell_range if cell_range is not None else (0, Nb)
     cs = np.array([1e-7, 1.0, 1.0])
     E = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0.3, 0.3, 0.3]], dtype=np.float64)
     wr = 0.25
@@ -288,11 +290,11 @@ def add_mswells(system: System, nwells: int, nseg: int, seed: int = 4242, share_
         if nseg > 1 and nperf_seg.sum() == 0:
             nperf_seg[-1] = 1
         nblk = int(nperf_seg.sum())
-        cells = rng.choice(Nb, size=nblk, replace=False).astype(np.int64)
+        cells = c_lo + rng.choice(c_hi - c_lo, size=nblk, replace=False).astype(np.int64)
         if share_cells and w > 0 and nblk > 0 and len(prev_cells) > 0:
             cells[0] = prev_cells[0]                    # two wells meet in one cell
             if len(set(cells.tolist())) != nblk:
-                cells = rng.choice(Nb, size=nblk, replace=False).astype(np.int64)
+                cells = c_lo + rng.choice(c_hi - c_lo, size=nblk, replace=False).astype(np.int64)
         prev_cells = cells
         Brow = np.concatenate([[0], np.cumsum(nperf_seg)]).astype(np.uint32)
         T = 0.5 + 1.5 * rng.random(nblk)

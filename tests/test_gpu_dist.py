@@ -130,3 +130,70 @@ def test_four_gpu_block_partition_matches_partitioned_oracle(mods):
         assert conv and abs(it - ref.it) <= max(1.0, 0.1 * ref.it) and it2 == it
         x[3 * r0:3 * r1] = xl
     assert relerr(x, ref.x) < 1e-6
+
+
+def _mswell_case(synth, dist, world, shape):
+    """The whole system with standard wells + two multisegment wells inside every rank's rows (global column ids)."""
+    cfg = synth.GridConfig("t", *shape, seed=5, faults=(), nwells=4, nperf=3)
+    s = synth.full_system(cfg)
+    ranges = dist.slab_ranges(shape[2], shape[0] * shape[1], world)
+    per_rank = [synth.add_mswells(s, 2, 6, seed=31 + r, cell_range=ranges[r]) for r in range(world)]
+    return s, ranges, per_rank
+
+
+def _rank_main_ms(rank, world, port, shape, out):
+    import copy
+    import torch
+    import torch.distributed as td
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from opm_autodiff_b200 import dist, synth
+        from tests.helpers import add_bridge_mswells
+        s, ranges, per_rank = _mswell_case(synth, dist, world, shape)
+        ls = dist.partition_global(s.rows, s.cols, s.vals, s.b, ranges, s.x_true, s.wells)[rank]
+        ds = dist.DistSolver(ls, rank, maxit=200, tolerance=1e-10)
+        mine = []
+        for m in per_rank[rank]:                        # this rank's multisegment wells with LOCAL column ids
+            m = copy.copy(m)
+            m.BcolIndices = (np.asarray(m.BcolIndices, np.int64) - ranges[rank][0]).astype(np.uint32)
+            mine.append(m)
+        add_bridge_mswells(ds.wc, mine)
+        res = ds.solve_system()
+        x = ds.get_result()
+        res2 = ds.solve_resident()
+        out[rank] = (ls.row0, ls.row1, res.converged, res.it, x, res2.it, ds.get_result())
+        td.barrier()
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (12, 10, 8)), (4, (24, 20, 16))])
+def test_multi_gpu_solve_with_multisegment_wells(mods, world, shape):
+    """Standard + multisegment wells in the operator of a partitioned solve: every well lives inside one rank (the reference's
+    default, AllowDistributedWells = false, ebos/eclbasevanguard.hh:148-150), its apply and the patch of the dot products stay
+    rank-local, the all-reduce carries the patched sums.  Against the oracle's partitioned solve with the same wells."""
+    bridge, dist, synth, oracle = mods
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    from tests.helpers import oracle_mswells
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank_main_ms, args=(world, _free_port(), shape, out), nprocs=world, join=True)
+    s, ranges, per_rank = _mswell_case(synth, dist, world, shape)
+    om = oracle_mswells([m for ms in per_rank for m in ms])
+    part_ptr = np.array([r[0] for r in ranges] + [s.Nb], np.int32)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200, part_ptr=part_ptr, mswells=om)
+    assert ref.converged
+    x = np.zeros(3 * s.Nb)
+    for rank in range(world):
+        r0, r1, conv, it, xl, it2, xl2 = out[rank]
+        assert conv and abs(it - ref.it) <= max(1.0, 0.1 * ref.it) and it2 == it
+        assert np.array_equal(xl, xl2)
+        x[3 * r0:3 * r1] = xl
+    assert relerr(x, ref.x) < 1e-6
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells), om) < 1e-8

@@ -1,9 +1,12 @@
+"""Sweep time against the number of parts for given grid shapes (GPU box tool).
+usage: python tools/s2_parts_exp.py 100x100x13 100x100x25 ..."""
 import sys, time
 sys.path.insert(0, '/root/repo')
 from opm_autodiff_b200 import bridge, synth
-for shape in [(48,48,48),(64,64,64),(30,30,30)]:
+shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(48, 48, 48), (64, 64, 64), (30, 30, 30)]
+for shape in shapes:
     s = synth.small(*shape)
-    for parts in (16, 24, 37, 48, 74, 100, 148):
+    for parts in (0, 16, 24, 37, 48, 74, 100, 148):
         be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
         be.set_option("sweep_parts", parts)
         be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
@@ -13,5 +16,6 @@ for shape in [(48,48,48),(64,64,64),(30,30,30)]:
         for _ in range(5): be.solve_resident(res)
         dt = (time.time() - t0) / 5
         lo = 1e3 * be.time_kernel("ilu_lower", 10, False)[0]
-        print("%s Nb %d parts %3d: %.2f ms per solve, it %.1f, lower %.1f us" % (shape, s.Nb, parts, dt*1e3, res.it, lo), flush=True)
+        up = 1e3 * be.time_kernel("ilu_upper", 10, False)[0]
+        print("%s Nb %d parts %3d: %.2f ms per solve, it %.1f, lower %.1f upper %.1f us" % (shape, s.Nb, parts, dt*1e3, res.it, lo, up), flush=True)
         del be
