@@ -1335,6 +1335,12 @@ struct Solver {
         if (nwells) stats[K_WELL].launches += 2;
         if (nms) stats[K_WELL].launches += 4;
         launch_count += (fused_now() ? 7 : 9) + (nwells ? 2 : 0) + (nms ? 4 : 0);
+        if (dist.enabled && dist.world > 1) {      // the multi-GPU kernels of the replayed iteration
+            const int push = dist.nneigh > 0 ? 2 : 0, ghost = ghost_on() ? 2 : 0;
+            const int ar = fuse_allreduce ? (ghost_on() ? 0 : 2) : 4;      // all-reduce launches of their own (the others run inside their producers)
+            stats[K_HALO_PUSH].launches += push; stats[K_SPMV_GHOST].launches += ghost; stats[K_ALLREDUCE].launches += ar;
+            launch_count += push + ghost + ar;
+        }
     }
 
     // permutation + ILU0 + BiCGSTAB on the resident system
