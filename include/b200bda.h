@@ -92,6 +92,19 @@ void b200_destroy(b200_solver* s);
  *                 (automatic = on at every size)
  *   "sweep_early" sweep helper warps fetch a stage's external rows one stage ahead
  *   "p2p_allreduce"  multi-GPU: 1 peer-memory mailboxes, 0 NCCL + finish kernel                    default 1
+ *   "fuse_allreduce" multi-GPU: the mailbox exchange runs inside the kernel that completes the local sums      default 1
+ *   "halo_side"   multi-GPU: the halo push runs on a side stream beside the well apply (joined before k_spmv_ghost)  default 1
+ *   Round-2 sweeps and factorisation (set before the first solve):
+ *   "sweep_v2"    1: k_sweep2 (a lane per block row, operands from global memory into registers); 0: the round-1 kernel  default 1
+ *   "sweep_autotune"  1: below the size where every SM gets a part, the analysis times a lower + upper sweep for a few part
+ *                 counts around the rule's value and keeps the fastest (once per pattern); 0: the rule's value -- part
+ *                 counts differ in rounding only, so pin it for bit-reproducible runs across processes             default 1
+ *   "s2_cw", "s2_poll_lead", "s2_prefetch"   consumer warps per part (<= 15), steps before its own at which a warp starts
+ *                 to poll rows of other parts, records ahead pulled into L2                              default 15, 15, 2
+ *   "fuse_ring_warps", "fuse_chunk"  ring-fed warps and slots per chunk of the SpMV tail                       default 8, 4
+ *   "fac_rows3"   1: factorisation with three rows per warp (k_ilu_factor_plan3), 0: one row per warp         default 1
+ *   "fac_warps"   warps per CTA of k_ilu_factor_plan3                                                      default 4
+ *   "fac_pdl"     level launches of the factorisation chained by programmatic dependent launch               default 1
  * Unknown keys return B200_UNKNOWN_ERROR. */
 b200_status b200_set_option(b200_solver* s, const char* key, double value);
 

@@ -442,6 +442,94 @@ struct Solver {
                     num_sms, smem_optin, vec_blocks, kVecThreads);
     }
 
+    // Part count of the round-2 sweeps below the size where every SM gets a part: measured, not guessed.  The best count depends
+    // on how the parts factor into strips x bands for the grid at hand (100 x 100 x 13: 55 us with 44 parts, 69 with 40, 65 with
+    // 72), so the analysis builds the plan for a few counts around the rule's value and times one lower + one upper sweep of
+    // each on the device (zero factor values: the dataflow, which is all that is timed, does not depend on them).  Once per
+    // pattern; ~0.1-0.3 s per candidate at these sizes.  Different counts give the same factors and solves up to rounding (a
+    // row adds its other-part dependencies first), so `sweep_autotune = 0` pins the rule's value for bit-reproducible runs
+    // across processes.
+    int sweep_autotune = 1;            // option
+    int autotune_parts(const int* r_, const int* c_, AnalysisOptions opt, int p0)
+    {
+        std::vector<int> cand;
+        for (double f : {1.0, 0.62, 0.72, 0.82, 0.91, 1.12, 1.3}) {
+            const int p = std::max(8, std::min(num_sms, (int) std::lround(f * p0)));
+            if (std::find(cand.begin(), cand.end(), p) == cand.end()) cand.push_back(p);
+        }
+        const int threads = sweep_threads();
+        DevBuf<double> rhs, out;
+        rhs.alloc(N + 8); out.alloc(N + 8);
+        CUDA_OK(cudaMemsetAsync(rhs.p, 0, sizeof(double) * (N + 8), stream));
+        double armed;
+        { const unsigned long long bits = b200::kSentinel; std::memcpy(&armed, &bits, sizeof armed); }
+        cudaEvent_t e0, e1;
+        CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+        int best = p0;
+        double best_us = 1e30, p0_us = 1e30;
+        for (int p : cand) {
+            opt.parts = p;
+            const b200::Analysis a = b200::analyse(Nb, r_, c_, opt);
+            Sweep2Options o2;
+            o2.consumerWarps = s2_cw;
+            Sweep2Plan L, U;
+            build_sweep2_plans(a, r_, c_, o2, L, U);
+            const size_t smem = kS2Header + 24 * (size_t) (a.window + 1);
+            if (smem > smem_optin || a.nparts > num_sms) continue;
+            struct Dev { DevBuf<S2PartD> parts; DevBuf<S2StreamD> streams; DevBuf<int> hdrs, codes; DevBuf<double> vals; } dl, du;
+            auto upl = [&](Sweep2Plan& P2, Dev& d) {
+                d.parts.alloc(P2.parts.size()); d.streams.alloc(P2.streams.size());
+                d.hdrs.alloc(P2.hdrs.size() + 4 * 64); d.codes.alloc(P2.codes.size() + 4); d.vals.alloc((size_t) P2.nvals + 2);
+                CUDA_OK(cudaMemcpyAsync(d.parts.p, P2.parts.data(), sizeof(S2Part) * P2.parts.size(), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaMemcpyAsync(d.streams.p, P2.streams.data(), sizeof(S2Stream) * P2.streams.size(), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaMemcpyAsync(d.hdrs.p, P2.hdrs.data(), sizeof(int) * P2.hdrs.size(), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaMemcpyAsync(d.codes.p, P2.codes.data(), sizeof(int) * P2.codes.size(), cudaMemcpyHostToDevice, stream));
+                CUDA_OK(cudaMemsetAsync(d.vals.p, 0, sizeof(double) * ((size_t) P2.nvals + 2), stream));
+            };
+            upl(L, dl); upl(U, du);
+            auto args = [&](Dev& d, bool ml) {
+                SweepArgs sa = {};
+                sa.rhs = rhs.p; sa.out = out.p; sa.rearm = nullptr; sa.S = d_S.p;
+                sa.nparts = a.nparts; sa.window = a.window; sa.nwarps = s2_cw; sa.helper_sleep = s2_poll_lead; sa.early = s2_prefetch;
+                sa.v2.parts = d.parts.p; sa.v2.streams = d.streams.p; sa.v2.hdrs = reinterpret_cast<const int2*>(d.hdrs.p);
+                sa.v2.codes = reinterpret_cast<const int4*>(d.codes.p); sa.v2.vals = d.vals.p; sa.v2.window = a.window; sa.v2.ncw = s2_cw;
+                (void) ml;
+                return sa;
+            };
+            const bool mlL = L.nMultiLaneRecords > 0, mlU = U.nMultiLaneRecords > 0;
+            auto launch = [&](bool lower) {
+                const SweepArgs sa = args(lower ? dl : du, lower ? mlL : mlU);
+                k_fill<<<blocks_for(N, 256, num_sms * 8), 256, 0, stream>>>(out.p, armed, N);
+                CUDA_OK(cudaEventRecord(e0, stream));
+                auto go = [&](auto kern) {
+                    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+                    kern<<<a.nparts, threads, smem, stream>>>(sa);
+                };
+                if (lower) { if (mlL) go(k_sweep2<true, false, -1, false, true>); else go(k_sweep2<true, false>); }
+                else { if (mlU) go(k_sweep2<false, false, -1, false, true>); else go(k_sweep2<false, false>); }
+                CUDA_OK(cudaEventRecord(e1, stream));
+                CUDA_OK(cudaEventSynchronize(e1));
+                CUDA_OK(cudaGetLastError());
+                float ms = 0.f;
+                CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+                return 1e3 * (double) ms;
+            };
+            double us = 1e30;
+            for (int rep = 0; rep < 4; ++rep) {
+                const double t = launch(true) + launch(false);
+                if (rep > 0) us = std::min(us, t);          // the first pass warms the caches
+            }
+            CUDA_OK(cudaMemcpy(h_S, d_S.p, sizeof(Scalars), cudaMemcpyDeviceToHost));
+            if (h_S->trsv_timeout) throw std::runtime_error("triangular-sweep dataflow wait timed out while tuning the part count");
+            if (verbosity > 0) fprintf(stderr, "[b200bda] part-count tuning: %d parts (%d asked) %.1f us per lower + upper sweep\n", a.nparts, p, us);
+            if (p == p0) p0_us = us;
+            if (us < best_us) { best_us = us; best = p; }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (best != p0 && best_us > 0.97 * p0_us) best = p0;       // within the noise: keep the rule's value
+        return best;
+    }
+
     void analyse(int N_, long long nnz_, const int* rows, const int* cols)
     {
         Nb = N_ / 3; N = N_; nnz_stage = nnz_;
@@ -480,7 +568,9 @@ struct Solver {
             L2 = Sweep2Plan(); U2 = Sweep2Plan();
             build_sweep2_plans(an, r_, c_, o2, L2, U2);
         };
+        const bool tune = v2 && sweep_autotune && sweep_parts <= 0 && opt.parts < num_sms && Nb >= 4096;
         if (!dist.enabled) {
+            if (tune) opt.parts = autotune_parts(rows, cols, opt, opt.parts);
             an = b200::analyse(Nb, rows, cols, opt);
             if (v2) build_v2(rows, cols);
         } else {
@@ -502,6 +592,7 @@ struct Solver {
                 sq_rows[r + 1] = (int) sq_cols.size();
                 if (any) { grow_nat.push_back(r); gptr.push_back((int) gcol.size()); }
             }
+            if (tune) opt.parts = autotune_parts(sq_rows.data(), sq_cols.data(), opt, opt.parts);
             an = b200::analyse(Nb, sq_rows.data(), sq_cols.data(), opt);
             if (v2) build_v2(sq_rows.data(), sq_cols.data());
             for (auto& b : an.srcblk) b = sq_src[b];            // p-space block -> block of the caller's array
@@ -1537,6 +1628,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         }
         else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "fuse_allreduce") s->fuse_allreduce = (int) value;
+        else if (k == "sweep_autotune") s->sweep_autotune = (int) value;
         else if (k == "halo_side") s->halo_side = (int) value;
         else if (k == "fac_warps") s->fac_warps = std::max(1, std::min(kFac3MaxWarps, (int) value));
         else if (k == "fac_rows3") { s->fac_rows3 = (int) value; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }

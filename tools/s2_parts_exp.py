@@ -6,8 +6,9 @@ from opm_autodiff_b200 import bridge, synth
 shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(48, 48, 48), (64, 64, 64), (30, 30, 30)]
 for shape in shapes:
     s = synth.small(*shape)
-    for parts in (0, 16, 24, 37, 48, 74, 100, 148):
-        be = bridge.B200SolverBackend(0, 2000, 1e-10, 0)
+    import os
+    for parts in [int(v) for v in os.environ.get('PARTS', '0,16,24,37,48,74,100,148').split(',')]:
+        be = bridge.B200SolverBackend(int(os.environ.get("VERB", "0")), 2000, 1e-10, 0)
         be.set_option("sweep_parts", parts)
         be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
         res = bridge.BdaResult()
