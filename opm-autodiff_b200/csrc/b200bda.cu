@@ -241,6 +241,7 @@ struct Solver {
     DevBuf<long long> d_trace;
 
     bool analysed = false, have_system = false, have_factor = false;
+    bool poisoned = false;                     // a dataflow wait timed out: the solver refuses further solves
     int N = 0, Nb = 0;
     long long nnz = 0, nnzb = 0;              // owned x owned part (what ILU0 and the big SpMV see)
     long long nnz_stage = 0;                   // the caller's array (owned x (owned + ghost))
@@ -1107,6 +1108,7 @@ struct Solver {
         a.nwarps = sweep_warps; a.nhalo = sweep_helpers; a.helper_sleep = sweep_helper_sleep;
         a.check_done = check_done ? 1 : 0;
         a.nowait = sweep_nowait; a.early = sweep_early ? 1 : 0;
+        if (sweep_trace && an.nparts > 148) throw std::runtime_error("sweep_trace: the trace buffer holds 148 parts");
         a.trace = sweep_trace ? d_trace.p : nullptr;
         a.trace_cap = kTraceCap;
         if (v2) {
@@ -1438,6 +1440,7 @@ struct Solver {
     void solve_resident(b200_result* res)
     {
         if (!have_system) throw std::runtime_error("no system uploaded");
+        if (poisoned) throw std::runtime_error("this solver saw a dataflow wait time out and is unusable: create a new one");
         const double t0 = wall();
         // verbosity >= 3: per-phase timings as the reference's backends print them (BdaSolver.hpp:47-51,
         // openclSolverBackend.cpp:451-459): every kernel of this solve is timed with CUDA events (no graph replay)
@@ -1510,7 +1513,11 @@ struct Solver {
                     dec, prec, d(K_UPPER_SPMV) > 0.0 ? " (the upper sweep's launch also runs the SpMV that follows it)" : "", well, spmv_s, rest,
                     res->elapsed);
         }
-        if (S.trsv_timeout) throw std::runtime_error("triangular-solve dataflow wait timed out");
+        if (S.trsv_timeout) {
+            // the dataflow counters (and, on several GPUs, the exchange epochs of the ranks) may be out of step now
+            poisoned = true;
+            throw std::runtime_error("triangular-solve dataflow wait timed out");
+        }
     }
 
     // natural-order host vector -> p-space device vector and back (kernel-level API)

@@ -48,6 +48,14 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
 {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// Waits of the dataflow (rows of other parts, peers' flags) give up on ELAPSED TIME, not on spin counts: under MPS, time
+// slicing or a debugger a count fires spuriously.  4 s without progress is a deadlock, not a slow neighbour.
+constexpr long long kWaitTimeoutNs = 4000000000LL;
+__device__ __forceinline__ long long wall_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// one register instead of two where registers are short (k_sweep2): the low word wraps every 4.29 s, differences of two reads
+// taken less than that apart are exact
+constexpr unsigned kWaitTimeoutLoNs = 3000000000u;
+__device__ __forceinline__ unsigned wall_lo_ns() { unsigned t; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t)); return t; }
 __device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long) __double_as_longlong(v) == kSentinel; }
 __device__ __forceinline__ double sentinel() { return __longlong_as_double((long long) kSentinel); }
 
@@ -232,9 +240,12 @@ __device__ __noinline__ void mail_allreduce(const DistRedD D, Scalars* S, double
     for (int k = 0; k < NV; ++k) t[k] = 0.0;
     for (int r = 0; r < D.world; ++r) {
         const unsigned* mine = M->flags[D.rank] + slot + r;
-        long long spins = 0;
+        long long spins = 0, t0 = 0;
         while (ld_acquire_sys(mine) != seq) {
-            if ((++spins & 1023) == 0 && spins > (1ll << 26)) { S->trsv_timeout = 1; break; }
+            if ((++spins & 1023) == 0) {
+                if (t0 == 0) t0 = wall_ns();
+                else if (wall_ns() - t0 > kWaitTimeoutNs) { S->trsv_timeout = 1; break; }
+            }
         }
         const double* src = M->vals[D.rank] + (slot + r) * 4;
 #pragma unroll
@@ -1407,6 +1418,7 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                 if ((P.nowait & 3) < 2) {
                     while (ld_volatile_s32(hp + 11) <= my_step - poll_lead) __nanosleep(64);      // until step my_step - poll_lead has started
                     int spins = 0;
+                    unsigned t0 = 0;
                     bool wa = o.cd.z >= 0, wb = o.cd.w >= 0;
                     while (true) {
                         if (wa) { const double* x = P.out + 3 * (size_t) o.cd.z; xa0 = ld_relaxed(x); xa1 = ld_relaxed(x + 1); xa2 = ld_relaxed(x + 2); }
@@ -1415,8 +1427,9 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
                         wb = wb && (is_sentinel(xb0) || is_sentinel(xb1) || is_sentinel(xb2));
                         if (!__any_sync(kFull, wa || wb)) break;
                         if ((++spins & 255) == 0) {
-                            // (~0.3 us per poll round: 2^24 rounds are seconds -- a deadlock, not a slow neighbour)
-                            if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || spins > (1 << 24)) {
+                            // (elapsed time, not a spin count: kWaitTimeoutNs without the row is a deadlock, not a slow neighbour)
+                            if (t0 == 0) t0 = wall_lo_ns();
+                            else if (ld_volatile_s32(hp + 9) || *((volatile int*) &P.S->trsv_timeout) || wall_lo_ns() - t0 > kWaitTimeoutLoNs) {
                                 P.S->trsv_timeout = 1; st_volatile_s32(hp + 9, 1);
                                 break;
                             }
@@ -2103,11 +2116,11 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_ghost(int nrows, const int
     const unsigned epoch = *epoch_ctr + 1u;                       // the exchange k_halo_push has just started (see there)
     const double* __restrict__ ghost_x = ghost_x0 + (size_t) (epoch & 1u) * ghost_parity_stride;
     if (threadIdx.x < nneigh) {
-        long long spins = 0;
+        long long spins = 0, t0 = 0;
         while ((int) (ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-            if ((++spins & 1023) == 0 && (spins > (1ll << 24) || *((volatile int*) &S->trsv_timeout))) {
-                S->trsv_timeout = 1;
-                break;
+            if ((++spins & 1023) == 0) {
+                if (t0 == 0) t0 = wall_ns();
+                else if (wall_ns() - t0 > kWaitTimeoutNs || *((volatile int*) &S->trsv_timeout)) { S->trsv_timeout = 1; break; }
             }
         }
     }
@@ -2188,9 +2201,12 @@ __global__ void __launch_bounds__(64) k_allreduce_p2p(const MailD M, int rank, i
         __threadfence_system();
         st_release_sys(M.flags[r] + par * 64 + rank, seq);
         const unsigned* mine = M.flags[rank] + par * 64 + r;
-        long long spins = 0;
+        long long spins = 0, t0 = 0;
         while (ld_acquire_sys(mine) != seq) {
-            if ((++spins & 1023) == 0 && spins > (1ll << 26)) { S->trsv_timeout = 1; break; }
+            if ((++spins & 1023) == 0) {
+                if (t0 == 0) t0 = wall_ns();
+                else if (wall_ns() - t0 > kWaitTimeoutNs) { S->trsv_timeout = 1; break; }
+            }
         }
         const double* src = M.vals[rank] + ((size_t) par * 64 + r) * 4;
 #pragma unroll
