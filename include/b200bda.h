@@ -101,6 +101,8 @@ void b200_destroy(b200_solver* s);
  *                 counts differ in rounding only, so pin it for bit-reproducible runs across processes             default 1
  *   "s2_cw", "s2_poll_lead", "s2_prefetch"   consumer warps per part (<= 15), steps before its own at which a warp starts
  *                 to poll rows of other parts, records ahead pulled into L2                              default 15, 15, 2
+ *   "tail_all_sms"  sweeps with a tail (SpMV, x update) launch one CTA per SM even when the schedule has fewer parts; the CTAs
+ *                 beyond the parts only work on the tail.  0 never, 1 when the parts take at most half of the SMs, 2 always  default 1
  *   "fuse_ring_warps", "fuse_chunk"  ring-fed warps and slots per chunk of the SpMV tail                       default 8, 4
  *   "fac_rows3"   1: factorisation with three rows per warp (k_ilu_factor_plan3), 0: one row per warp         default 1
  *   "fac_warps"   warps per CTA of k_ilu_factor_plan3                                                      default 4

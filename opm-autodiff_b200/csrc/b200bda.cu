@@ -1160,11 +1160,17 @@ struct Solver {
         int id = prof_begin(K_LOWER);
         SweepArgs a = sweep_args(true, rhs, out, nullptr, true);
         a.xu.x = d_x.p; a.xu.y = d_y.p; a.xu.sync = d_xSync.p; a.xu.n = N;
-        if (v2 && s2_mlL) launch_iter(k_sweep2<true, false, 3, false, true>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
-        else if (v2) launch_iter(k_sweep2<true, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2 && s2_mlL) launch_iter(k_sweep2<true, false, 3, false, true>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
+        else if (v2) launch_iter(k_sweep2<true, false, 3>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
         else launch_iter(k_sweep<true, false, false, 3>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
+    // round-2 sweeps with a tail (SpMV, x update): one CTA per SM even when the schedule has fewer parts -- the CTAs beyond the
+    // parts skip the sweep and work on the tail (each CTA fills an SM: 512 threads x 128 registers, so all are resident)
+    // Measured (one B200): 45 parts (130 k rows) 8.82 -> 8.38 ms per solve, 56 parts (110 k) 9.73 -> 9.18, 86 parts (250 k)
+    // 11.87 -> 12.06: automatic (1) = only when the parts take at most half of the SMs; 2 = always, 0 = never.
+    int tail_all_sms = 1;              // option
+    int tail_grid() const { return (tail_all_sms == 2 || (tail_all_sms == 1 && 2 * an.nparts <= num_sms)) ? std::max(an.nparts, num_sms) : an.nparts; }
     bool defer_now() const { return defer_ok && !sweep_trace; }
     int defer_x = 1;                   // option
     bool defer_ok = false;             // the tail kernel fits (set by the analysis)
@@ -1193,8 +1199,8 @@ struct Solver {
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
         a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem; a.f.chunk = fuse_chunk;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
-        if (v2 && s2_mlU) launch_iter(k_sweep2<false, true, MODE, false, true>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
-        else if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
+        if (v2 && s2_mlU) launch_iter(k_sweep2<false, true, MODE, false, true>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
+        else if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
         else launch_iter(k_sweep<false, true, false, MODE>, dim3(an.nparts), dim3(sweep_threads()), sweep_smem, a);
         prof_end(id);
     }
@@ -1635,6 +1641,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         }
         else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "fuse_allreduce") s->fuse_allreduce = (int) value;
+        else if (k == "tail_all_sms") { s->tail_all_sms = (int) value; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "sweep_autotune") s->sweep_autotune = (int) value;
         else if (k == "halo_side") s->halo_side = (int) value;
         else if (k == "fac_warps") s->fac_warps = std::max(1, std::min(kFac3MaxWarps, (int) value));

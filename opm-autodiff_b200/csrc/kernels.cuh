@@ -797,10 +797,13 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
     long long t_wait = 0, t_full = 0, t_top = 0;
     int n_units = 0, n_chunks = 0;
     auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-    if (F.dbg && threadIdx.x == 0) F.dbg[4 * part] = now_ns();
+    const bool has_part = part < P.nparts;                     // (round-2 kernel: CTAs beyond the parts only run the tail)
+    if (F.dbg && threadIdx.x == 0 && has_part) F.dbg[4 * part] = now_ns();
     if (threadIdx.x == 0) {
-        __threadfence();
-        st_release_gpu_s32(F.sync + 2 + part, 1);
+        if (has_part) {
+            __threadfence();
+            st_release_gpu_s32(F.sync + 2 + part, 1);
+        }
         s_unit[0] = atomicAdd(F.sync, 1);
     }
     if (warp == PW) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -935,7 +938,7 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
         }
     }
     if (threadIdx.x == 0) {
-        if (F.dbg) { F.dbg[4 * part + 1] = now_ns(); F.dbg[4 * part + 2] = n_units; F.dbg[4 * part + 3] = t_wait;
+        if (F.dbg && has_part) { F.dbg[4 * part + 1] = now_ns(); F.dbg[4 * part + 2] = n_units; F.dbg[4 * part + 3] = t_wait;
             if (part % 12 == 0) printf("    part %d warp 0: %d units, %d chunks, %.1f us waiting for chunks, %.1f us at the unit barrier, %.1f us waiting for parts, NR %d\n", part, n_units, n_chunks, t_full * 1e-3, t_top * 1e-3, t_wait * 1e-3, NR); }
         __threadfence();
         s_last = atomicAdd(F.sync + 1, 1) == (int) gridDim.x - 1;
@@ -1304,11 +1307,15 @@ __global__ void __launch_bounds__(kS2Threads) k_sweep2(const SweepArgs P)
     pdl_enter();
     if (P.check_done && P.S->done) return;
     const int part = blockIdx.x;
-    if (part >= P.nparts) return;
+    // CTAs beyond the parts (launched only by the variants with a tail, when the schedule has fewer parts than the device has
+    // SMs): nothing to sweep, they go straight to the tail -- the SpMV / x update then runs on every SM, not on the parts' SMs only
+    const bool has_part = part < P.nparts;
+    if (!has_part && SPMV == -1) return;
     const bool xupd = SPMV == 3 && P.S->pend_on != 0;
     const double xupd_coef = SPMV == 3 ? P.S->pend : 0.0;
     const Sweep2Args& V = P.v2;
-    const S2PartD pr = V.parts[part];
+    S2PartD pr = {};
+    if (has_part) pr = V.parts[part];
     int* hp = reinterpret_cast<int*>(sweep_smem);
     const int W = V.window;
     double* xyp = reinterpret_cast<double*>(sweep_smem + kS2Header);      // window of recent rows, components 0 and 1: 16 bytes per slot

@@ -10,6 +10,9 @@ for shape in shapes:
     for parts in [int(v) for v in os.environ.get('PARTS', '0,16,24,37,48,74,100,148').split(',')]:
         be = bridge.B200SolverBackend(int(os.environ.get("VERB", "0")), 2000, 1e-10, 0)
         be.set_option("sweep_parts", parts)
+        for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+            k, v = kv.split("=")
+            be.set_option(k, float(v))
         be.upload_system(3 * s.Nb, 9 * s.nnzb, 3, s.vals, s.rows, s.cols, s.b, None)
         res = bridge.BdaResult()
         for _ in range(2): be.solve_resident(res)
