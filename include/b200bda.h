@@ -73,6 +73,7 @@ void b200_destroy(b200_solver* s);
  *                 Off by default -- the library does not own that memory; see also b200_host_register.            default 0
  *   "wells_flat"  1: standard wells that fit one CTA (<= 1024 perforations, <= 128 wells) use the apply kernel with
  *                 host-resolved index chains (k_wells_flat); 0: always the general kernel                 default 1
+ *   "wells_cluster"  1: the flat well apply runs on a thread-block cluster of 8 CTAs (k_wells_cluster)        default 1
  *   "use_graph"   1: replay the factorisation launches and the BiCGSTAB iteration body as CUDA graphs  default 1
  *   "lookahead"   iterations enqueued per convergence read-back (the device stops by itself)      default 2
  *   "profile"     1: time every kernel with CUDA events (no graphs), see b200_kernel_stats         default 0

@@ -304,6 +304,7 @@ struct Solver {
     DevBuf<double> d_B, d_C, d_Dinv, d_z2;
     // standard wells, index chains resolved on the host (k_wells_flat): used when the wells fit one CTA
     int wells_flat = 1;                // option: 0 never, 1 when they fit
+    int wells_cluster = 1;             // option: the flat apply on a cluster of 8 CTAs (k_wells_cluster) instead of one CTA
     bool flat_ok = false;
     DevBuf<int4> d_item;
     DevBuf<double> d_itemC;
@@ -1242,6 +1243,11 @@ struct Solver {
         mswells_apply<MODE>(x, y, d1);
         if (nwells == 0) return;
         int id = prof_begin(K_WELL);
+        if (flat_ok && wells_flat && wells_cluster) {
+            launch_iter(k_wells_cluster<MODE>, dim3(kWellClCtas), dim3(kWellClThreads), 0, flatD, x, y, d1, d_S.p);
+            prof_end(id);
+            return;
+        }
         if (flat_ok && wells_flat) {
             launch_iter(k_wells_flat<MODE>, dim3(1), dim3(1024), 0, flatD, x, y, d1, d_S.p);
             prof_end(id);
@@ -1405,6 +1411,7 @@ struct Solver {
         sig.n[4] = nms; sig.n[5] = ms_epoch;
         sig.a[6] = d_item.p; sig.a[7] = d_itemC.p;
         sig.n[3] += (flat_ok && wells_flat) ? 1 << 22 : 0;
+        sig.n[3] += wells_cluster ? 1 << 25 : 0;
         sig.n[3] += (mail_on() && fuse_allreduce) ? 1 << 23 : 0;
         sig.n[3] += halo_side ? 1 << 24 : 0;
         if (!iter_graph_exec || sig != iter_sig) {
@@ -1624,6 +1631,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "lookahead") s->lookahead = std::max(1, (int) value);
         else if (k == "profile") s->profile = value != 0.0;
         else if (k == "wells_flat") s->wells_flat = value != 0.0 ? 1 : 0;
+        else if (k == "wells_cluster") s->wells_cluster = value != 0.0 ? 1 : 0;
         else if (k == "spmv_sell") { if (s->analysed) throw std::runtime_error("spmv_sell must be set before the first solve"); s->spmv_sell = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_spmv") { if (s->analysed) throw std::runtime_error("fuse_spmv must be set before the first solve"); s->fuse_spmv = std::max(0, std::min(2, (int) value)); }
         else if (k == "fuse_debug") s->fuse_debug = (int) value;

@@ -1959,6 +1959,153 @@ __global__ void __launch_bounds__(1024) k_wells_flat(WellsFlatD W, const double*
     }
 }
 
+// The same apply on a CLUSTER of 8 CTAs x 128 threads (round 2): one SM cannot pull the ~600 KB of cold sectors of a
+// 1000-perforation well set faster than ~15 us, eight can.  Thread T = 128 * rank + t of the cluster does exactly what thread T
+// of k_wells_flat does; what that kernel keeps in one CTA's shared memory is read here through distributed shared memory from
+// the CTA that owns it (perforation p: CTA p / 128; well row 4 w + r: CTA (4 w + r) / 128), eight loads in flight per thread, in the
+// same summation order -- y is bit-identical to k_wells_flat, the dot-product patch is summed in a different (fixed) order.
+constexpr int kWellClCtas = 8, kWellClThreads = 128;
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local, unsigned rank)
+{
+    unsigned a = smem_u32(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+template <int MODE>
+__global__ void __cluster_dims__(kWellClCtas, 1, 1) __launch_bounds__(kWellClThreads)
+k_wells_cluster(WellsFlatD W, const double* __restrict__ x, double* y, const double* __restrict__ d1, Scalars* S)
+{
+    pdl_enter();
+    constexpr int kItems = 3, kAll = kWellClCtas * kWellClThreads;      // == the 1024 threads of k_wells_flat
+    __shared__ double part[kWellClThreads * 4];
+    __shared__ double z1s[kWellClThreads];
+    __shared__ double z2s[kWellClThreads];
+    __shared__ double sm[2][kWellClThreads / 32];
+    const unsigned rank = cluster_ctarank();
+    const int tl = threadIdx.x, t = (int) rank * kWellClThreads + tl, lane = tl & 31, warp = tl >> 5;
+    // ---- loads that depend on nothing computed here
+    const bool hasp = t < W.nblocks;
+    int col = 0;
+    double b[12];
+    if (hasp) {
+        col = W.bcol[t];
+        const double2* bp = reinterpret_cast<const double2*>(W.B + (size_t) t * 12);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double2 v = bp[i]; b[2 * i] = v.x; b[2 * i + 1] = v.y; }
+    }
+    const bool hasw = t < 4 * W.nwells;
+    double dinv[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned wb = 0, we = 0;
+    if (hasw) {
+        const int w = t >> 2;
+        wb = W.wptr[w]; we = W.wptr[w + 1];
+        const double2* dp = reinterpret_cast<const double2*>(W.Dinv + (size_t) t * 4);
+        const double2 v0 = dp[0], v1 = dp[1];
+        dinv[0] = v0.x; dinv[1] = v0.y; dinv[2] = v1.x; dinv[3] = v1.y;
+    }
+    int4 it[kItems];
+    double ic[kItems][4], yold[kItems], dd1[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        const int q = t + k * kAll;
+        it[k] = make_int4(0, 0, 0, 0);
+        yold[k] = 0.0; dd1[k] = 0.0;
+        if (q < W.nitems) {
+            it[k] = W.item[q];
+            const double2* cp = reinterpret_cast<const double2*>(W.itemC + (size_t) q * 4);
+            const double2 v0 = cp[0], v1 = cp[1];
+            ic[k][0] = v0.x; ic[k][1] = v0.y; ic[k][2] = v1.x; ic[k][3] = v1.y;
+        }
+    }
+    const int done = MODE != 0 ? S->done : 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+        if (t + k * kAll < W.nitems) {
+            yold[k] = y[it[k].x];
+            if (MODE != 0) dd1[k] = d1[it[k].x];
+        }
+    if (done) return;                      // (every thread of every CTA alike: no cluster barrier has been entered yet)
+    // ---- phase 1
+    if (hasp) {
+        const double* xp = x + 3 * (size_t) col;
+        const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) part[tl * 4 + r] = b[3 * r] * x0 + b[3 * r + 1] * x1 + b[3 * r + 2] * x2;
+    }
+    cluster_sync_all();
+    if (hasw) {
+        const int r = t & 3;
+        double z = 0.0;
+        for (unsigned p0 = wb; p0 < we; p0 += 8) {
+            double v[8];
+#pragma unroll
+            for (unsigned k = 0; k < 8; ++k) {
+                const unsigned p = p0 + k;
+                v[k] = p < we ? ld_dsmem_f64(part + (p & (kWellClThreads - 1)) * 4 + r, p / kWellClThreads) : 0.0;
+            }
+#pragma unroll
+            for (unsigned k = 0; k < 8; ++k)
+                if (p0 + k < we) z += v[k];
+        }
+        z1s[tl] = z;
+    }
+    __syncthreads();                       // the four rows of a well sit in one CTA (128 is a multiple of 4)
+    if (hasw) {
+        const double* zz = z1s + (tl & ~3);
+        z2s[tl] = dinv[0] * zz[0] + dinv[1] * zz[1] + dinv[2] * zz[2] + dinv[3] * zz[3];
+    }
+    cluster_sync_all();
+    // ---- phase 2
+    double acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+        if (t + k * kAll >= W.nitems) continue;
+        const int zi = it[k].w;                                  // 4 * well: its four rows are thread rows zi .. zi + 3 of the cluster
+        const unsigned owner = (unsigned) zi / kWellClThreads;
+        const double* zl = z2s + (zi & (kWellClThreads - 1));
+        const double z0 = ld_dsmem_f64(zl, owner), z1 = ld_dsmem_f64(zl + 1, owner), z2v = ld_dsmem_f64(zl + 2, owner), z3 = ld_dsmem_f64(zl + 3, owner);
+        double delta = ic[k][0] * z0 + ic[k][1] * z1 + ic[k][2] * z2v + ic[k][3] * z3;
+        if (it[k].y > 1) {
+            const int c = it[k].x % 3;
+            for (int e = it[k].z + 1, ee = it[k].z + it[k].y; e < ee; ++e) {
+                const double* cb = W.C + (size_t) W.ublock[e] * 12 + c;
+                const int zj = 4 * W.uwell[e];
+                const unsigned ow = (unsigned) zj / kWellClThreads;
+                const double* zq = z2s + (zj & (kWellClThreads - 1));
+                delta += cb[0] * ld_dsmem_f64(zq, ow) + cb[3] * ld_dsmem_f64(zq + 1, ow) + cb[6] * ld_dsmem_f64(zq + 2, ow) + cb[9] * ld_dsmem_f64(zq + 3, ow);
+            }
+        }
+        const double now = yold[k] - delta;
+        y[it[k].x] = now;
+        if (MODE == 1) acc[0] += dd1[k] * (now - yold[k]);
+        if (MODE == 2) { acc[0] += dd1[k] * (now - yold[k]); acc[1] += now * now - yold[k] * yold[k]; }
+    }
+    if (MODE != 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) sm[i][warp] = v;
+        }
+    }
+    cluster_sync_all();                    // every CTA's partial sums are in its shared memory
+    if (MODE != 0 && rank == 0 && tl == 0) {
+        double a = 0.0, bsum = 0.0;
+        for (unsigned q = 0; q < (unsigned) kWellClCtas; ++q)
+            for (int w = 0; w < kWellClThreads / 32; ++w) { a += ld_dsmem_f64(&sm[0][w], q); bsum += ld_dsmem_f64(&sm[1][w], q); }
+        if (MODE == 1) S->h += a;
+        if (MODE == 2) { S->tr += a; S->tt += bsum; }
+    }
+    cluster_sync_all();                    // no CTA leaves while its shared memory may still be read
+}
+
 // ---- multisegment wells ---------------------------------------------------------------------------
 //
 // y -= C^T (D^-1 (B x)) for multisegment wells (bda/MultisegmentWellContribution.cpp:70-110).  The reference copies x and y
