@@ -769,7 +769,6 @@ inline Analysis analyse(int Nb, const int* rows, const int* cols, const Analysis
 // Returns false if a full round makes no progress (the schedule would deadlock on the device).
 inline void fill_stream_host(const SweepPlan& S, bool lower, const double* LU, double relax, std::vector<double>& vals)
 {
-    const int NF = S.nfields;
     vals.assign((size_t) std::max<long long>(S.nvals, 1), 0.0);
     for (const BuildRef& B : S.build)
         for (int l = 0; l < 32; ++l) {
