@@ -3,6 +3,7 @@
 // link with -lb200bda.  Flow selects it with --accelerator-mode=b200 once the two string-chain
 // branches of INTEGRATION.md are in BdaBridge.cpp:65-120 and WellContributions.cpp:31-49.
 #pragma once
+#include <cstddef>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -61,6 +62,18 @@ public:
     void get_result(double* x) override
     {
         if (b200_get_result(handle_, x) != B200_SUCCESS) throw std::logic_error(b200_last_error());
+    }
+
+    /// Page-lock a caller-owned buffer that outlives the solves -- Flow's matrix values, right-hand side and solution vector --
+    /// so that the copies run at PCIe speed (b200_host_register).  The library never pins memory on its own:
+    /// the glue code that knows the buffers' lifetime (BdaBridge) calls this once and unregisters before they are freed or resized.
+    void registerHostBuffer(void* p, std::size_t bytes)
+    {
+        if (b200_host_register(handle_, p, bytes) != B200_SUCCESS) throw std::logic_error(b200_last_error());
+    }
+    void unregisterHostBuffer(void* p)
+    {
+        if (b200_host_unregister(handle_, p) != B200_SUCCESS) throw std::logic_error(b200_last_error());
     }
 
     const b200_result& lastResult() const { return last_; }

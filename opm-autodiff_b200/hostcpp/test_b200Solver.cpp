@@ -56,9 +56,17 @@ int main(int argc, char** argv)
         }
         bda::BdaResult result;
         const int N = A.Nb * 3, nnz = (int) A.cols.size() * 9;
-        bda::SolverStatus st = backend->solve_system(N, nnz, 3, A.vals.data(), A.rows.data(), A.cols.data(), rhs.data(), wellContribs, result);
         std::vector<double> x((size_t) N, 0.0);
+        // the glue code page-locks the buffers that live as long as the simulator, once
+        auto* b200 = static_cast<bda::b200SolverBackend<3>*>(backend.get());
+        b200->registerHostBuffer(A.vals.data(), sizeof(double) * (size_t) nnz);
+        b200->registerHostBuffer(rhs.data(), sizeof(double) * (size_t) N);
+        b200->registerHostBuffer(x.data(), sizeof(double) * (size_t) N);
+        bda::SolverStatus st = backend->solve_system(N, nnz, 3, A.vals.data(), A.rows.data(), A.cols.data(), rhs.data(), wellContribs, result);
         backend->get_result(x.data());
+        b200->unregisterHostBuffer(x.data());
+        b200->unregisterHostBuffer(rhs.data());
+        b200->unregisterHostBuffer(A.vals.data());
         std::printf("status %d converged %d iterations %d reduction %.6e\n", (int) st, (int) result.converged, result.iterations, result.reduction);
         for (double v : x) std::printf("%.17g\n", v);
         return st == bda::SolverStatus::BDA_SOLVER_SUCCESS ? 0 : 1;
