@@ -197,3 +197,25 @@ def test_gloo_world2_block_jacobi_bicgstab_matches_partitioned_oracle(mods):
         x[3 * r0:3 * r1] = xl
     assert relerr(x, ref.x) < 1e-9
     assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells)) < 1e-9
+
+
+def test_rank_local_multisegment_wells_keep_x_true(mods):
+    """synth.add_mswells(cell_range=...) -- the generator of the multi-GPU multisegment-well test -- perforates only the rows
+    of one rank, keeps x_true the solution of the whole operator (A - sum C^T D^-1 B) x = b, and the oracle's partitioned
+    solve with those wells converges to it."""
+    dist, synth, oracle = mods
+    from tests.helpers import oracle_mswells
+    cfg = synth.GridConfig("t", 12, 10, 8, seed=5, faults=(), nwells=4, nperf=3)
+    s = synth.full_system(cfg)
+    world = 2
+    ranges = dist.slab_ranges(8, 120, world)
+    per_rank = [synth.add_mswells(s, 2, 6, seed=31 + r, cell_range=ranges[r]) for r in range(world)]
+    for r, ms in enumerate(per_rank):
+        for m in ms:
+            c = np.asarray(m.BcolIndices, np.int64)
+            assert c.size and c.min() >= ranges[r][0] and c.max() < ranges[r][1]
+    om = oracle_mswells([m for ms in per_rank for m in ms])
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, s.x_true, oracle_wells(s.wells), om) < 1e-12
+    part_ptr = np.array([a for a, _ in ranges] + [s.Nb], np.int32)
+    ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=200, part_ptr=part_ptr, mswells=om)
+    assert ref.converged and relerr(ref.x, s.x_true) < 1e-5
