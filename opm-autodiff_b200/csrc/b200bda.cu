@@ -1198,7 +1198,7 @@ struct Solver {
         a.f.prow = d_prow.p; a.f.pcol = d_pcol.p; a.f.A = d_A.p; a.f.y = y; a.f.d1 = d1;
         a.f.units = reinterpret_cast<const int2*>(d_fUnits.p); a.f.need_ptr = d_fNeedPtr.p; a.f.need = d_fNeed.p;
         a.f.sync = d_fSync.p; a.f.partials = d_fPartials.p; a.f.Nb = Nb; a.f.nunits = fused_units;
-        a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem; a.f.chunk = fuse_chunk;
+        a.f.dbg = nullptr; a.f.ring_bytes = (int) sweep_smem; a.f.chunk = fuse_chunk; a.f.prefetch = fuse_prefetch;
         if (fuse_debug > 0) { --fuse_debug; d_fDbg.alloc((size_t) 4 * an.nparts); a.f.dbg = d_fDbg.p; }
         if (v2 && s2_mlU) launch_iter(k_sweep2<false, true, MODE, false, true>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
         else if (v2) launch_iter(k_sweep2<false, true, MODE>, dim3(tail_grid()), dim3(sweep_threads()), sweep_smem, a);
@@ -1212,6 +1212,8 @@ struct Solver {
     int sweep_early_opt = 1;           // option "sweep_early"
     int fuse_unit_slices = 2;          // option: SELL slices per consumer warp and unit
     int fuse_chunk = 4;                // option: slots of a SELL slice per chunk buffer of the SpMV tail (1..4)
+    int fuse_prefetch = 0;             // option: the tail's producer warp pulls a unit's SELL slices into L2 when the unit starts
+                                       // (measured on C3: 243 -> 257 us per upper sweep + SpMV launch -- the requests compete with the sweeps' own)
     int fuse_ring_warps = 8;           // option (round-2 sweeps): warps of the SpMV tail fed through the shared-memory ring (19 KB each)
     DevBuf<long long> d_fDbg;
     template <int MODE>
@@ -1649,6 +1651,7 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         }
         else if (k == "iter_pdl") { s->iter_pdl = value != 0.0; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "fuse_allreduce") s->fuse_allreduce = (int) value;
+        else if (k == "fuse_prefetch") { s->fuse_prefetch = (int) value; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "tail_all_sms") { s->tail_all_sms = (int) value; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "sweep_autotune") s->sweep_autotune = (int) value;
         else if (k == "halo_side") s->halo_side = (int) value;

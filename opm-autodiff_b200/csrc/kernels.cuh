@@ -655,6 +655,7 @@ struct FusedSpmv {
     long long* dbg;                // debugging aid (may be null): per part {part done, exit, units taken, time spent waiting for parts} [ns]
     int Nb, nunits;
     int chunk;                     // slots of a slice per chunk buffer (0: kTailChunk)
+    int prefetch;                  // 1: the producer warp pulls the whole unit into L2 when the unit starts
 };
 
 // Deferred solution update run by idle CTAs of a lower sweep (k_sweep<true, ..., SPMV = 3>): x += pend * y, y re-armed
@@ -817,6 +818,20 @@ __device__ __forceinline__ void fused_spmv_tail(const SweepArgs& P, int part, un
         if (u >= F.nunits) break;
         const int2 un = __ldg(F.units + u);
         if (warp == PW) {                                      // ---- producer: lane c feeds consumer c
+            // The ring holds 2 x ~10 KB per consumer: at HBM latency that is ~40 GB/s per SM, what a full machine needs -- but
+            // while the sweep still runs only the idle SMs work on the product and HBM has bandwidth to spare.  So the unit's
+            // slices (consecutive in the SELL arrays, ~0.5 MB) are requested into L2 at once: the ring's copies then see L2
+            // latency, and an idle SM takes units several times faster.  MEASURED: slower (C3: 243 -> 257 us per launch, the
+            // requests compete with the operand streams of the parts that are still sweeping) -- off by default.
+            if (F.prefetch) {
+                for (int jj = lane; jj < un.y; jj += 32) {
+                    const int q0 = __ldg(F.sptr + un.x + jj), qw = __ldg(F.sptr + un.x + jj + 1) - q0;
+                    if (qw > 0) {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(F.sval + (size_t) q0 * 288), "r"((unsigned) qw * 2304u) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(F.scol + (size_t) q0 * 32), "r"((unsigned) qw * 128u) : "memory");
+                    }
+                }
+            }
             // one converged loop with non-blocking barrier tests: lanes that slept in private wait loops would serialise
             // (nine lanes x 200 ns of sleep per poll round = the whole ring starves)
             int j = lane, k0 = 0, s0 = 0, w = 0;
