@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=12, help="BiCGSTAB iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short C2 measurement reported under \"also\"")
+    ap.add_argument("--reorder", default="none", choices=["none", "graph_coloring"],
+                    help="one GPU: the opt-in colour ordering (ILU0 of the colour-permuted matrix: another preconditioner, more "
+                         "iterations; reported separately, never the headline)")
     ap.add_argument("--partition", default="slabs", choices=["slabs", "blocks"],
                     help="N > 1: z-slabs (default: they cut only the weak vertical couplings) or y-z blocks (fewer levels per rank)")
     return ap.parse_args()
@@ -309,6 +312,8 @@ def run_b200_single(args):
     wc = bridge.WellContributions("b200", False) if w is None else \
         bridge.WellContributions.from_arrays(w.val_pointers, w.Bcols, w.Ccols, w.B, w.C, w.Dinv)
     be = bridge.B200SolverBackend(0, MAXIT, TOL, 0)
+    if args.reorder == "graph_coloring":
+        be.set_option("reorder", 1)
     res = bridge.BdaResult()
     x = np.zeros(N)
 
@@ -427,7 +432,7 @@ def run_b200_single(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg.name, "cells": cfg.ncells, "nnz_blocks": system.nnzb, "wells": cfg.nwells,
-                   "perforations_per_well": cfg.nperf if cfg.nwells else 0, "tolerance": TOL, "relaxation": 1.0,
+                   "perforations_per_well": cfg.nperf if cfg.nwells else 0, "tolerance": TOL, "relaxation": 1.0, "reorder": args.reorder,
                    "iterations": gpu_it, "levels": res.num_levels, "x_error_vs_generator": xerr,
                    "l2": "inputs larger than L2 (matrix %.0f MB + factor %.0f MB vs 126 MB L2), no flush needed"
                          % (system.vals.nbytes / 1e6, system.vals.nbytes / 1e6) if system.vals.nbytes > 2.5e8

@@ -95,6 +95,8 @@ void b200_destroy(b200_solver* s);
  *   "p2p_allreduce"  multi-GPU: 1 peer-memory mailboxes, 0 NCCL + finish kernel                    default 1
  *   "fuse_allreduce" multi-GPU: the mailbox exchange runs inside the kernel that completes the local sums      default 1
  *   "halo_side"   multi-GPU: the halo push runs on a side stream beside the well apply (joined before k_spmv_ghost)  default 1
+ *   "reorder"     0: natural order, the level sets of the reference's level scheduling (default); 1: graph colouring (see
+ *                 b200_graph_coloring_host / b200_get_reorder), opt-in, set before the first solve.  "reorder_seed": its seed  default 0, 1
  *   Round-2 sweeps and factorisation (set before the first solve):
  *   "sweep_v2"    1: k_sweep2 (a lane per block row, operands from global memory into registers); 0: the round-1 kernel  default 1
  *   "sweep_autotune"  1: below the size where every SM gets a part, the analysis times a lower + upper sweep for a few part
@@ -257,6 +259,20 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
 b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int window, int ext_window,
                                             int consumer_warps, int helpers, int groups, int wg, unsigned int seed, double relax,
                                             double* max_rel_err, long long* stats);
+
+/* Opt-in multi-colour ordering (the reference's --opencl-ilu-reorder=graph_coloring: Reorder.cpp:58-172 colorBlockedNodes,
+ * :209-222 colorsToReordering, called from BILU0.cpp:86-91 with maxRowsPerColor = maxColsPerColor = Nb).  Host only: colours
+ * the block rows so that connected rows differ, returns the colour-major order (to_order[natural row] = position,
+ * from_order[position] = natural row), the rows per colour (room for 256, may be NULL) and the number of colours.  The
+ * reference seeds its random weights from std::random_device (Reorder.cpp:35-43); here `seed` makes the result reproducible. */
+b200_status b200_graph_coloring_host(int Nb, const int* rows, const int* cols, unsigned int seed, int* to_order, int* from_order,
+                                     int* rows_per_color, int* ncolors);
+
+/* The ordering a solver created with option "reorder" = 1 works in (valid after its first solve).  Such a solver takes ILU0 of
+ * the colour-permuted matrix -- another, weaker preconditioner (+30-50 % iterations on grid problems), as the reference's OpenCL
+ * backend does with graph_coloring -- and sweeps level by level (k_trsv_level, one launch per colour); vals / b / x stay in the
+ * caller's order.  Not available on several ranks. */
+b200_status b200_get_reorder(b200_solver* s, int* to_order, int* from_order, int* ncolors);
 
 /* Host-only replay of the ILU0 elimination plan the device kernel executes (no device needed): LU in the caller's pattern
  * with the inverse pivot in the diagonal slot, as ParallelOverlappingILU0.hpp:440-494 leaves it.  max_row / max_ops (may be

@@ -123,6 +123,8 @@ def lib():
                                                      np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
         L.b200_sweep2_schedule_check_host.argtypes = [ip, _i32p, _i32p, ip, ip, ip, ip, ip, ip, ip, C.c_uint, C.c_double,
                                                       C.POINTER(C.c_double), np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+        L.b200_graph_coloring_host.argtypes = [ip, _i32p, _i32p, C.c_uint, _i32p, _i32p, _i32p, C.POINTER(C.c_int)]
+        L.b200_get_reorder.argtypes = [vp, _i32p, _i32p, C.POINTER(C.c_int)]
         L.b200_host_register.argtypes = [vp, vp, C.c_size_t]
         L.b200_host_unregister.argtypes = [vp, vp]
         L.b200_time_kernel.argtypes = [vp, C.c_char_p, ip, ip, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -154,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "b200_wells_destroy", "b200_wells_set_block_size", "b200_wells_add_num_blocks", "b200_wells_alloc",
     "b200_wells_add_matrix", "b200_wells_get_num_wells", "b200_wells_add_multisegment", "b200_wells_get_multisegment_inverse", "b200_spmv", "b200_well_apply",
     "b200_ilu0_factorize", "b200_ilu0_apply", "b200_get_ilu0", "b200_get_level_schedule",
-    "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_sweep2_schedule_check_host", "b200_host_register", "b200_host_unregister", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
+    "b200_level_schedule_host", "b200_sweep_schedule_check_host", "b200_sweep2_schedule_check_host", "b200_graph_coloring_host", "b200_get_reorder", "b200_host_register", "b200_host_unregister", "b200_time_kernel", "b200_kernel_stats", "b200_reset_stats",
     "b200_launch_count", "b200_timer_start", "b200_timer_stop", "b200_device_available", "b200_version",
     "b200_dist_unique_id", "b200_dist_init", "b200_dist_set_halo", "b200_dist_map_rank", "b200_dist_connect_peer", "b200_dist_spmv",
     "b200_dist_rank", "b200_dist_world", "b200_get_sweep_trace", "b200_factor_plan_check_host",
@@ -371,6 +373,14 @@ class B200SolverBackend:
         self._chk(lib().b200_get_level_schedule(self._h, to, fr, rpl, C.byref(n)))
         return to, fr, rpl[:n.value].copy()
 
+    def get_reorder(self):
+        """(toOrder, fromOrder, colours) of a solver created with option reorder = 1, after its first solve."""
+        Nb = self.N // 3
+        to, fr = np.zeros(Nb, np.int32), np.zeros(Nb, np.int32)
+        n = C.c_int(0)
+        self._chk(lib().b200_get_reorder(self._h, to, fr, C.byref(n)))
+        return to, fr, n.value
+
     def time_kernel(self, which: str, reps: int = 20, flush_l2: bool = True):
         ms, by = C.c_double(0), C.c_double(0)
         self._chk(lib().b200_time_kernel(self._h, which.encode(), int(reps), int(flush_l2), C.byref(ms), C.byref(by)))
@@ -478,6 +488,19 @@ def sweep2_schedule_check_host(rows, cols, parts=0, window=0, ext_window=0, cons
     return err.value, dict(zip(SWEEP2_STAT_NAMES, (int(v) for v in stats)))
 
 
+def graph_coloring_host(rows, cols, seed=1):
+    """Host-only multi-colour ordering (coloring.hpp, restating Reorder.cpp:58-172,209-222): returns (toOrder, fromOrder,
+    rowsPerColor)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    Nb = len(rows) - 1
+    to, fr, rpc = np.zeros(Nb, np.int32), np.zeros(Nb, np.int32), np.zeros(256, np.int32)
+    nc = C.c_int(0)
+    if lib().b200_graph_coloring_host(Nb, rows, cols, seed, to, fr, rpc, C.byref(nc)) != 0:
+        raise RuntimeError(last_error())
+    return to, fr, rpc[:nc.value].copy()
+
+
 def factor_plan_check_host(rows, cols, vals):
     """Host-only replay of the device's ILU0 elimination plan: returns (LU [nnzb,3,3], longest row, longest plan)."""
     rows = np.ascontiguousarray(rows, dtype=np.int32)
@@ -578,9 +601,16 @@ class BdaBridge:
         self._h_cols = None
         self._diag_indices = None
         self.last_result = BdaResult()
+        if opencl_ilu_reorder not in ("none", "level_scheduling", "graph_coloring"):
+            # BdaBridge.cpp:72-80
+            raise ValueError("Error invalid argument for --opencl-ilu-reorder, usage: '--opencl-ilu-reorder=[level_scheduling|graph_coloring]'")
         if accelerator_mode == "b200":
             self.use_gpu = True
             self.backend = B200SolverBackend(linear_solver_verbosity, maxit, tolerance, deviceID)
+            # natural-order ILU0 ("none" / "level_scheduling": the level sets only schedule the same factorisation) is the default;
+            # "graph_coloring" is the opt-in colour ordering of the reference's OpenCL backend (another preconditioner)
+            if opencl_ilu_reorder == "graph_coloring":
+                self.backend.set_option("reorder", 1)
         elif accelerator_mode == "none":
             self.use_gpu = False
         else:

@@ -18,6 +18,7 @@
 
 #include "analysis.hpp"
 #include "sweep2.hpp"
+#include "coloring.hpp"
 #include "kernels.cuh"
 
 namespace b200 {
@@ -451,6 +452,12 @@ struct Solver {
     // pattern; ~0.1-0.3 s per candidate at these sizes.  Different counts give the same factors and solves up to rounding (a
     // row adds its other-part dependencies first), so `sweep_autotune = 0` pins the rule's value for bit-reproducible runs
     // across processes.
+    // Opt-in multi-colour ordering (coloring.hpp; the reference's --opencl-ilu-reorder=graph_coloring): ILU0 of the colour-permuted
+    // matrix, level-synchronous sweeps (k_trsv_level, one launch per colour).  A different preconditioner: never the default.
+    int reorder = 0;                   // option: 0 natural order (level scheduling), 1 graph colouring; set before the first solve
+    unsigned reorder_seed = 1;         // option: seed of the colouring's random weights (the reference seeds from random_device)
+    bool level_sweeps = false;         // the sweeps run level by level (set by the analysis with reorder = 1)
+    b200::ColorOrder color;
     int sweep_autotune = 1;            // option
     int autotune_parts(const int* r_, const int* c_, AnalysisOptions opt, int p0)
     {
@@ -570,8 +577,25 @@ struct Solver {
             L2 = Sweep2Plan(); U2 = Sweep2Plan();
             build_sweep2_plans(an, r_, c_, o2, L2, U2);
         };
-        const bool tune = v2 && sweep_autotune && sweep_parts <= 0 && opt.parts < num_sms && Nb >= 4096;
-        if (!dist.enabled) {
+        const bool tune = v2 && sweep_autotune && sweep_parts <= 0 && opt.parts < num_sms && Nb >= 4096 && reorder == 0;
+        level_sweeps = false;
+        if (reorder != 0 && dist.enabled) throw std::runtime_error("the colour ordering is not available on several ranks");
+        if (reorder != 0) {
+            // colour the rows, permute the PATTERN (P A P^T) and analyse that: the level sets of the permuted matrix are the
+            // colours.  The value, right-hand-side and solution permutations cost nothing extra -- they are composed into the
+            // maps the device gathers / scatters with anyway (srcblk, perm).
+            color = b200::graph_coloring(Nb, rows, cols, reorder_seed);
+            std::vector<int> crows, ccols, csrc;
+            b200::permute_pattern(Nb, rows, cols, color, crows, ccols, csrc);
+            opt.buildStreams = false;
+            opt.parts = 1;
+            an = b200::analyse(Nb, crows.data(), ccols.data(), opt);
+            for (auto& b : an.srcblk) b = csrc[b];                                  // p-space block -> block of the caller's array
+            for (int q = 0; q < Nb; ++q) an.perm[q] = color.fromOrder[an.perm[q]];    // p-space row -> the caller's row
+            for (int q = 0; q < Nb; ++q) an.iperm[an.perm[q]] = q;
+            level_sweeps = true;
+            if (verbosity > 0) fprintf(stderr, "[b200bda] graph colouring: %d colours, %d level sets of the permuted matrix\n", color.ncolors, an.nflev);
+        } else if (!dist.enabled) {
             if (tune) opt.parts = autotune_parts(rows, cols, opt, opt.parts);
             an = b200::analyse(Nb, rows, cols, opt);
             if (v2) build_v2(rows, cols);
@@ -664,7 +688,11 @@ struct Solver {
             CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, threads, sweep_smem));
             occ = std::min(occ, o);
         };
-        if (v2) {
+        if (level_sweeps) {
+            // no pencil schedule: the sweeps run level by level from the BSR factor, SpMV and vector kernels are the separate ones
+            defer_ok = false; fused_units = 0; occ = 1; sweep_smem = 0;
+            d_valL.alloc(2); d_valU.alloc(2);
+        } else if (v2) {
             static_assert(sizeof(S2PartD) == sizeof(S2Part) && sizeof(S2StreamD) == sizeof(S2Stream) &&
                           sizeof(S2BuildD) == sizeof(S2Build), "device/host round-2 sweep descriptor mismatch");
             auto up2 = [&](Sweep2Plan& P2, DevBuf<S2PartD>& dp, DevBuf<S2StreamD>& ds, DevBuf<S2BuildD>& dbu, DevBuf<int>& dh,
@@ -772,7 +800,7 @@ struct Solver {
         }
         }
         if (occ < 1) throw CudaError("triangular-sweep kernel does not fit on an SM");
-        if (an.nparts > occ * num_sms)
+        if (!level_sweeps && an.nparts > occ * num_sms)
             throw std::runtime_error("triangular sweeps: " + std::to_string(an.nparts) + " parts cannot all be resident (" +
                                      std::to_string(occ) + " CTAs per SM fit); lower sweep_parts or the stage size");
         if (verbosity > 0 && !v2)
@@ -1046,6 +1074,7 @@ struct Solver {
     }
     void fill_streams()
     {
+        if (level_sweeps) return;          // the level-synchronous sweeps read the BSR factor itself
         if (v2) {
             int id2 = prof_begin(K_SLICES);
             if (!L2.build.empty())
@@ -1176,15 +1205,29 @@ struct Solver {
     int defer_x = 1;                   // option
     bool defer_ok = false;             // the tail kernel fits (set by the analysis)
     DevBuf<int> d_xSync;
+    // level-synchronous sweep (colour ordering): one launch per level set, ascending for L, descending for U
+    template <bool LOWER>
+    void trsv_levels(const double* rhs, double* out, bool check_done)
+    {
+        for (int n = 0; n < an.nflev; ++n) {
+            const int l = LOWER ? n : an.nflev - 1 - n;
+            const int row0 = an.flevPtr[l], nrows = an.flevPtr[l + 1] - row0;
+            const int warps = (nrows + 9) / 10;
+            launch_iter(k_trsv_level<LOWER>, dim3((warps + 7) / 8), dim3(256), 0, d_prow.p, d_pcol.p, d_pdiag.p, d_LU.p, rhs, out,
+                        d_flevRows.p + row0, nrows, LOWER ? 1.0 : relaxation, d_S.p, check_done ? 1 : 0);
+        }
+    }
     void trsv_lower(const double* rhs, double* out, bool check_done)
     {
         int id = prof_begin(K_LOWER);
+        if (level_sweeps) { trsv_levels<true>(rhs, out, check_done); prof_end(id); return; }
         launch_sweep<true>(sweep_args(true, rhs, out, nullptr, check_done));
         prof_end(id);
     }
     void trsv_upper(const double* rhs, double* out, double* rearm, bool check_done)
     {
         int id = prof_begin(K_UPPER);
+        if (level_sweeps) { trsv_levels<false>(rhs, out, check_done); prof_end(id); return; }
         launch_sweep<false>(sweep_args(false, rhs, out, rearm, check_done));
         prof_end(id);
     }
@@ -1414,6 +1457,7 @@ struct Solver {
         sig.a[6] = d_item.p; sig.a[7] = d_itemC.p;
         sig.n[3] += (flat_ok && wells_flat) ? 1 << 22 : 0;
         sig.n[3] += wells_cluster ? 1 << 25 : 0;
+        sig.n[3] += level_sweeps ? 1 << 26 : 0;
         sig.n[3] += (mail_on() && fuse_allreduce) ? 1 << 23 : 0;
         sig.n[3] += halo_side ? 1 << 24 : 0;
         if (!iter_graph_exec || sig != iter_sig) {
@@ -1654,6 +1698,8 @@ b200_status b200_set_option(b200_solver* s, const char* key, double value)
         else if (k == "fuse_prefetch") { s->fuse_prefetch = (int) value; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "tail_all_sms") { s->tail_all_sms = (int) value; if (s->iter_graph_exec) { cudaGraphExecDestroy(s->iter_graph_exec); s->iter_graph_exec = nullptr; } }
         else if (k == "sweep_autotune") s->sweep_autotune = (int) value;
+        else if (k == "reorder") { if (s->analysed) throw std::runtime_error("reorder must be set before the first solve"); s->reorder = value != 0.0 ? 1 : 0; }
+        else if (k == "reorder_seed") { if (s->analysed) throw std::runtime_error("reorder_seed must be set before the first solve"); s->reorder_seed = (unsigned) value; }
         else if (k == "halo_side") s->halo_side = (int) value;
         else if (k == "fac_warps") s->fac_warps = std::max(1, std::min(kFac3MaxWarps, (int) value));
         else if (k == "fac_rows3") { s->fac_rows3 = (int) value; if (s->fac_graph_exec) { cudaGraphExecDestroy(s->fac_graph_exec); s->fac_graph_exec = nullptr; } }
@@ -2263,6 +2309,34 @@ b200_status b200_sweep_schedule_check_host(int Nb, const int* rows, const int* c
 // factor and runs the host emulation of k_sweep2 against the sequential natural-order solves.
 // stats (12): parts, lines, strips, records L, records U, empty records L, window deps L, external deps L, external rows L,
 // helper blocks L, max groups, max group width.
+// Opt-in colour ordering: the colouring alone, on the host (no device needed)
+b200_status b200_graph_coloring_host(int Nb, const int* rows, const int* cols, unsigned seed, int* to_order, int* from_order,
+                                     int* rows_per_color, int* ncolors)
+{
+    return guarded([&]() -> b200_status {
+        if (Nb <= 0 || !rows || !cols || !to_order || !from_order || !ncolors) throw std::runtime_error("null argument");
+        const b200::ColorOrder o = b200::graph_coloring(Nb, rows, cols, seed);
+        std::copy(o.toOrder.begin(), o.toOrder.end(), to_order);
+        std::copy(o.fromOrder.begin(), o.fromOrder.end(), from_order);
+        if (rows_per_color) std::copy(o.rowsPerColor.begin(), o.rowsPerColor.end(), rows_per_color);
+        *ncolors = o.ncolors;
+        return B200_SUCCESS;
+    });
+}
+
+// the ordering a solver with option reorder = 1 works in (after its first solve): to_order / from_order as above
+b200_status b200_get_reorder(b200_solver* s, int* to_order, int* from_order, int* ncolors)
+{
+    return guarded([&]() -> b200_status {
+        if (!s || !ncolors) throw std::runtime_error("null argument");
+        if (!s->analysed || !s->level_sweeps) throw std::runtime_error("no colour ordering: set option reorder = 1 before the first solve");
+        if (to_order) std::copy(s->color.toOrder.begin(), s->color.toOrder.end(), to_order);
+        if (from_order) std::copy(s->color.fromOrder.begin(), s->color.fromOrder.end(), from_order);
+        *ncolors = s->color.ncolors;
+        return B200_SUCCESS;
+    });
+}
+
 b200_status b200_sweep2_schedule_check_host(int Nb, const int* rows, const int* cols, int parts, int window, int ext_window,
                                             int consumer_warps, int helpers, int groups, int wg, unsigned seed, double relax,
                                             double* max_rel_err, long long* stats)

@@ -518,6 +518,53 @@ __global__ void __launch_bounds__(32 * kFac3MaxWarps) k_ilu_factor_plan3(const i
     for (int bk = 0; bk < nblk; ++bk) LU[(size_t) (rs + bk) * 9 + e] = row[bk * 9 + e];
 }
 
+// ---- triangular solves, level-synchronous (opt-in multi-colour ordering only) ---------------------------------------------
+//
+// With the colour ordering (coloring.hpp) the level sets are the ~15 colours: tens of thousands of independent rows each, no
+// chain to pipeline.  One launch per level (chained by programmatic dependent launch inside the iteration's graph), three
+// lanes per block row straight from the BSR factor: lane c of a row owns component c.
+//   lower:  w_i = d_i - sum_{j < i} L_ij w_j                     (unit diagonal)
+//   upper:  y_i = relax * Dinv_i (w_i - sum_{j > i} U_ij y_j)    (inverse pivot stored, ParallelOverlappingILU0.hpp:867-901)
+// Rows of earlier levels were written by earlier launches: plain loads.
+template <bool LOWER>
+__global__ void __launch_bounds__(256) k_trsv_level(const int* __restrict__ prow, const int* __restrict__ pcol, const int* __restrict__ pdiag,
+                                                    const double* __restrict__ LU, const double* __restrict__ rhs, double* out,
+                                                    const int* __restrict__ rowlist, int nrows, double relax, const Scalars* S, int check_done)
+{
+    pdl_enter();
+    if (check_done && S->done) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int q = lane / 3, c = lane - 3 * q;                   // ten rows per warp, lanes 30 and 31 idle
+    const int slot = (t >> 5) * 10 + q;
+    const bool on = q < 10 && slot < nrows;
+    double acc = 0.0;
+    int i = 0, di = 0;
+    if (on) {
+        i = rowlist[slot];
+        di = pdiag[i];
+        const int k0 = LOWER ? prow[i] : di + 1, k1 = LOWER ? di : prow[i + 1];
+        acc = rhs[3 * (size_t) i + c];
+        for (int k = k0; k < k1; ++k) {
+            const double* a = LU + (size_t) k * 9 + 3 * c;
+            const double* x = out + 3 * (size_t) pcol[k];
+            acc -= a[0] * x[0] + a[1] * x[1] + a[2] * x[2];
+        }
+    }
+    if (LOWER) {
+        if (on) out[3 * (size_t) i + c] = acc;
+        return;
+    }
+    // y = relax * Dinv t: the three components of t sit in the three lanes of the row
+    const int base = 3 * q;
+    const double t0 = __shfl_sync(kFull, acc, base < 30 ? base : 0), t1 = __shfl_sync(kFull, acc, base < 30 ? base + 1 : 0),
+                 t2 = __shfl_sync(kFull, acc, base < 30 ? base + 2 : 0);
+    if (on) {
+        const double* d = LU + (size_t) di * 9 + 3 * c;
+        out[3 * (size_t) i + c] = relax * (d[0] * t0 + d[1] * t1 + d[2] * t2);
+    }
+}
+
 // ---- triangular solves: pencil-pipelined sweeps -----------------------------------------------------
 //
 // Device mirrors of analysis.hpp's StageRef / PartRef / BuildRef (layout checked by static_assert in

@@ -78,3 +78,33 @@ def relerr(a, b):
     a = np.asarray(a).reshape(-1)
     b = np.asarray(b).reshape(-1)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def permute_system(rows, cols, vals, b, to, fr, wells=None):
+    """P A P^T, P b (and the wells' columns) for an ordering to[natural row] = position, fr[position] = natural row, columns of
+    every row sorted ascending -- what reorderBlockedMatrixByPattern / reorderBlockedVectorByPattern do (Reorder.cpp:179-233)."""
+    import copy
+    rows, cols = np.asarray(rows), np.asarray(cols)
+    vals = np.asarray(vals).reshape(-1, 3, 3)
+    Nb = len(rows) - 1
+    prow = np.zeros(Nb + 1, np.int32)
+    pcol = np.zeros(len(cols), np.int32)
+    pval = np.zeros_like(vals)
+    out = 0
+    for p in range(Nb):
+        r = fr[p]
+        k = np.arange(rows[r], rows[r + 1])
+        c = np.asarray(to)[cols[k]]
+        o = np.argsort(c, kind="stable")
+        n = len(k)
+        pcol[out:out + n] = c[o]
+        pval[out:out + n] = vals[k[o]]
+        out += n
+        prow[p + 1] = out
+    pb = np.asarray(b).reshape(-1, 3)[np.asarray(fr)].reshape(-1)
+    pw = None
+    if wells is not None:
+        pw = copy.copy(wells)
+        pw.Bcols = np.asarray(to)[np.asarray(wells.Bcols)].astype(np.int32)
+        pw.Ccols = np.asarray(to)[np.asarray(wells.Ccols)].astype(np.int32)
+    return prow, pcol, pval.reshape(-1), pb, pw

@@ -574,3 +574,42 @@ def test_well_values_change_under_a_cached_structure(mods):
             be.get_result(xs)
             ref = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(w), tol=1e-10, maxit=200)
             assert res.converged == ref.converged and relerr(xs, ref.x) <= 1e-6
+
+
+@pytest.mark.parametrize("shape,faults,nwells,nperf,sell", [((12, 10, 8), ((6, 1),), 3, 4, 0), ((30, 24, 20), ((10, 1),), 4, 6, 2)])
+def test_opt_in_graph_colouring_matches_the_oracle_on_the_permuted_system(mods, shape, faults, nwells, nperf, sell):
+    """SURVEY a19, opt-in: BdaBridge(..., opencl_ilu_reorder="graph_coloring") (BdaBridge.cpp:72-80, BILU0.cpp:86-91) takes ILU0
+    of the colour-permuted matrix -- another preconditioner, so the parity target is the oracle's solve of P A P^T with the
+    ordering the solver reports (b200_get_reorder): x to 1e-6 in the caller's order, half-step iterations within 10 %, and
+    the colouring needs MORE iterations than natural order (why it is not the default).  vals / b / x stay in the caller's
+    order; the sweeps run level by level (one launch per colour)."""
+    bridge, synth, oracle = mods
+    from tests.helpers import permute_system
+    s = synth.small(*shape, faults=faults, nwells=nwells, nperf=nperf)
+    br = bridge.BdaBridge("b200", "", 0, 400, 1e-10, 0, 0, "graph_coloring")
+    br.backend.set_option("spmv_sell", sell)
+    res = bridge.InverseOperatorResult()
+    wc = bridge_wells(s.wells)
+    br.solve_system(bridge.BsrMatrix(s.rows, s.cols, s.vals.copy()), s.b, wc, res)
+    x = np.zeros(3 * s.Nb)
+    br.get_result(x)
+    to, fr, nc = br.backend.get_reorder()
+    assert 2 <= nc <= 256 and np.array_equal(fr[to], np.arange(s.Nb))
+    prow, pcol, pval, pb, pw = permute_system(s.rows, s.cols, s.vals, s.b, to, fr, s.wells)
+    ref = oracle.solve(prow, pcol, pval, pb, oracle_wells(pw), tol=1e-10, maxit=400)
+    xr = np.zeros(3 * s.Nb).reshape(-1, 3)
+    xr[fr] = ref.x.reshape(-1, 3)
+    assert res.converged and ref.converged
+    assert relerr(x, xr.reshape(-1)) <= 1e-6
+    nat = oracle.solve(s.rows, s.cols, s.vals, s.b, oracle_wells(s.wells), tol=1e-10, maxit=400)
+    assert abs(res.iterations - int(ref.it)) <= max(1, 0.1 * ref.it) and ref.it >= nat.it
+    assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells)) < 2e-10
+    # the plain ILU0 apply in that ordering: v = (LU)^-1 d of the permuted matrix, in the caller's order
+    d = np.random.default_rng(5).normal(size=3 * s.Nb)
+    v = br.backend.ilu0_apply(d)
+    LUo, diag, st = oracle.ilu0(prow, pcol, pval)
+    assert st == 0
+    vr = oracle.ilu0_apply(prow, pcol, diag, LUo, d.reshape(-1, 3)[fr].reshape(-1))
+    vv = np.zeros_like(xr)
+    vv[fr] = np.asarray(vr).reshape(-1, 3)
+    assert relerr(v, vv.reshape(-1)) < 1e-9

@@ -97,3 +97,50 @@ def test_graph_colouring_is_valid_but_a_weaker_preconditioner(R):
     x[fr] = col.x.reshape(-1, 3)
     assert col.converged and relerr(x.reshape(-1), nat.x) < 1e-5    # same system, same answer (two 1e-10 residual solves) ...
     assert col.it > 1.1 * nat.it                                    # ... but outside the +-10 % iteration bound
+
+
+def test_own_graph_colouring_against_the_compiled_reference(R):
+    """coloring.hpp (the opt-in ordering of option reorder = 1) restates colorBlockedNodes + colorsToReordering with a seed
+    instead of std::random_device: valid (connected rows differ), colour-major with natural order inside a colour, the
+    reference's per-colour limit (scalar rows per colour < Nb, BILU0.cpp:89), reproducible, and as many colours as the
+    compiled reference needs on the same grid, give or take the randomness of either."""
+    from opm_autodiff_b200 import bridge, synth
+    s = synth.small(16, 14, 12, faults=((7, 1),))
+    Nb = s.Nb
+    to, fr, rpc = bridge.graph_coloring_host(s.rows, s.cols, seed=3)
+    nc = len(rpc)
+    assert 2 <= nc <= 256 and rpc.sum() == Nb
+    assert np.array_equal(np.sort(to), np.arange(Nb)) and np.array_equal(fr[to], np.arange(Nb))
+    colour = np.repeat(np.arange(nc), rpc)[to]
+    for i in range(Nb):
+        for k in range(s.rows[i], s.rows[i + 1]):
+            assert s.cols[k] == i or colour[s.cols[k]] != colour[i]
+    for c in range(nc):                                               # natural order inside a colour
+        members = fr[rpc[:c].sum():rpc[:c + 1].sum()]
+        assert np.all(np.diff(members) > 0)
+    assert 3 * rpc.max() + 2 <= Nb + 3                                # rowsInColor + block_size - 1 >= maxRowsPerColor stops a colour
+    to2, fr2, rpc2 = bridge.graph_coloring_host(s.rows, s.cols, seed=3)
+    assert np.array_equal(to, to2) and np.array_equal(rpc, rpc2)      # seeded: reproducible
+    to3, _, _ = bridge.graph_coloring_host(s.rows, s.cols, seed=4)
+    assert not np.array_equal(to, to3)
+    rto, rfr, rrpc = np.zeros(Nb, np.int32), np.zeros(Nb, np.int32), np.zeros(Nb, np.int32)
+    rnc = R.ref_graph_coloring(Nb, np.ascontiguousarray(s.rows, np.int32).copy(), np.ascontiguousarray(s.cols, np.int32).copy(), rto, rfr, rrpc)
+    assert 0.6 * rnc <= nc <= 1.6 * rnc
+
+
+def test_own_colouring_gives_the_reference_permuted_solve(R):
+    """The permutation helpers used by the GPU test agree with the compiled reorderBlockedMatrixByPattern, and the oracle's
+    solve of the colour-permuted system -- the parity target of the opt-in GPU path -- needs more iterations than natural
+    order but converges to the same solution."""
+    from opm_autodiff_b200 import bridge, synth
+    from tests.helpers import permute_system
+    s = synth.small(12, 10, 8)
+    to, fr, rpc = bridge.graph_coloring_host(s.rows, s.cols, seed=1)
+    prow, pcol, pval, pb, _ = permute_system(s.rows, s.cols, s.vals, s.b, to, fr)
+    rr, rc, rv = _reorder(R, s.rows, s.cols, s.vals, to, fr)
+    assert np.array_equal(prow, rr) and np.array_equal(pcol, rc) and np.array_equal(pval.reshape(-1), np.asarray(rv).reshape(-1))
+    nat = oracle.solve(s.rows, s.cols, s.vals, s.b, tol=1e-10, maxit=400)
+    col = oracle.solve(prow, pcol, pval, pb, tol=1e-10, maxit=400)
+    x = np.zeros_like(col.x).reshape(-1, 3)
+    x[fr] = col.x.reshape(-1, 3)
+    assert col.converged and relerr(x.reshape(-1), nat.x) < 1e-5 and col.it >= nat.it
