@@ -545,10 +545,22 @@ __global__ void __launch_bounds__(256) k_trsv_level(const int* __restrict__ prow
         di = pdiag[i];
         const int k0 = LOWER ? prow[i] : di + 1, k1 = LOWER ? di : prow[i + 1];
         acc = rhs[3 * (size_t) i + c];
-        for (int k = k0; k < k1; ++k) {
-            const double* a = LU + (size_t) k * 9 + 3 * c;
-            const double* x = out + 3 * (size_t) pcol[k];
-            acc -= a[0] * x[0] + a[1] * x[1] + a[2] * x[2];
+        for (int kb = k0; kb < k1; kb += 4) {                   // four blocks' loads in flight, summed in column order
+            int cc[4];
+            double a[4][3], x[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cc[u] = kb + u < k1 ? pcol[kb + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cc[u] >= 0) {
+                    const double* ap = LU + (size_t) (kb + u) * 9 + 3 * c;
+                    const double* xp = out + 3 * (size_t) cc[u];
+                    a[u][0] = ap[0]; a[u][1] = ap[1]; a[u][2] = ap[2];
+                    x[u][0] = xp[0]; x[u][1] = xp[1]; x[u][2] = xp[2];
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cc[u] >= 0) acc -= a[u][0] * x[u][0] + a[u][1] * x[u][1] + a[u][2] * x[u][2];
         }
     }
     if (LOWER) {
