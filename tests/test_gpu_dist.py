@@ -197,3 +197,55 @@ def test_multi_gpu_solve_with_multisegment_wells(mods, world, shape):
         x[3 * r0:3 * r1] = xl
     assert relerr(x, ref.x) < 1e-6
     assert oracle.true_residual(s.rows, s.cols, s.vals, s.b, x, oracle_wells(s.wells), om) < 1e-8
+
+
+def _rank_main_c4(rank, world, port, golden, out):
+    import torch
+    import torch.distributed as td
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from opm_autodiff_b200 import dist, synth
+        cfg = synth.CONFIGS["c4"]
+        ls = dist.slab_system(cfg, rank, world)                      # every rank generates only its own rows
+        ds = dist.DistSolver(ls, rank, maxit=200, tolerance=1e-10)
+        res = ds.solve_system()
+        x = ds.get_result().reshape(-1, 3)
+        rows = np.asarray(golden["sample_rows"], np.int64)
+        mine = (rows >= ls.row0) & (rows < ls.row1)
+        xs = np.asarray(golden["sample_x"], np.float64)[mine]
+        got = x[rows[mine] - ls.row0]
+        out[rank] = (bool(res.converged), float(res.it), float(np.sum((got - xs) ** 2)), float(np.sum(xs ** 2)), int(mine.sum()),
+                     float(np.sum(x ** 2)))
+        td.barrier()
+    finally:
+        td.destroy_process_group()
+
+
+def test_c4_eight_gpu_solve_matches_the_partitioned_oracle_fingerprint(mods):
+    """BASELINE.json's C4 (250 x 200 x 200 = 10 M cells, 200 wells) on 8 row slabs against the CPU oracle's 8-partition solve of
+    the same system (tools/c4_golden.py, run once on a CPU box: tests/golden/c4_n8_oracle.json holds its iteration count, the
+    norm of its solution and the solution at 4000 sampled block rows): iterations within 10 %, the sampled solution to 1e-6."""
+    import json
+    bridge, dist, synth, oracle = mods
+    import torch
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    path = os.path.join(os.path.dirname(__file__), "golden", "c4_n8_oracle.json")
+    golden = json.load(open(path))
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rank_main_c4, args=(8, _free_port(), golden, out), nprocs=8, join=True)
+    err2 = sum(out[r][2] for r in range(8))
+    ref2 = sum(out[r][3] for r in range(8))
+    assert sum(out[r][4] for r in range(8)) == len(golden["sample_rows"])
+    assert all(out[r][0] for r in range(8))
+    it = out[0][1]
+    assert all(out[r][1] == it for r in range(8))
+    assert abs(it - golden["iterations"]) <= max(1.0, 0.1 * golden["iterations"])
+    assert np.sqrt(err2 / ref2) <= 1e-6
+    assert abs(np.sqrt(sum(out[r][5] for r in range(8))) / golden["x_norm"] - 1.0) < 1e-6
+    print("C4 on 8 GPUs: %.1f iterations (oracle %.1f), sampled |x - x_ref| / |x_ref| = %.2e" % (it, golden["iterations"], np.sqrt(err2 / ref2)))
